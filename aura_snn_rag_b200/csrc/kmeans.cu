@@ -1,0 +1,414 @@
+// Centroid index maintenance: K2 assign, K3 update, K1 online assign, CSR inverted lists.
+// Replaces hippocampal.py:345-377 (rebuild_centroids: cdist + argmin + a Python loop of C masked
+// means with a host sync each + a second cdist/argmin + a C-iteration count loop) and :218-230
+// (per-write nearest-centroid + running mean).
+//
+// This file holds the CUDA-core (fp32 FMA) formulation: exact fp32 arithmetic, any d / C / M.
+// The tcgen05 formulation of the assign GEMM lives in gemm_sm100.cu; this one stays as the
+// exact-fp32 path for small problems and for re-checking rows whose two best centroids are
+// closer than the tensor-core rounding.
+#include "aura_common.cuh"
+
+namespace aura {
+
+// ------------------------------------------------------------------ K2: assign (SIMT tiled)
+// score(x, c) = ||c||^2 - 2 x.c   (||x||^2 is constant per row; same expansion torch.cdist uses
+// for M or C > 25, hippocampal.py:358,370).  argmin over c, first minimum on ties (ATen CPU argmin).
+static constexpr int AS_BM = 64, AS_BN = 64, AS_BK = 16, AS_THREADS = 256;
+
+template <bool BF16>
+__global__ void __launch_bounds__(AS_THREADS) kmeans_assign_kernel(const void* __restrict__ rows, long long n_rows, int d,
+                                                                    const float* __restrict__ cent, int n_cent,
+                                                                    const float* __restrict__ cent_sq,
+                                                                    int* __restrict__ assign, float* __restrict__ cid_f32,
+                                                                    int cid_stride, float* __restrict__ best_out) {
+  __shared__ float As[AS_BK][AS_BM + 4];
+  __shared__ float Bs[AS_BK][AS_BN + 4];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;  // 16 x 16 threads, 4x4 micro-tile each
+  const long long row0 = (long long)blockIdx.x * AS_BM;
+  float best[4];
+  int arg[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { best[i] = INFINITY; arg[i] = 0x7fffffff; }
+
+  for (int c0 = 0; c0 < n_cent; c0 += AS_BN) {
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int k0 = 0; k0 < d; k0 += AS_BK) {
+      // cooperative loads: 64 x 16 of each operand, 4 elements per thread
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int e = threadIdx.x + t * AS_THREADS;  // 0..1023
+        const int r = e >> 4, kk = e & 15;
+        const long long gr = row0 + r;
+        float va = 0.f, vb = 0.f;
+        if (gr < n_rows && k0 + kk < d) {
+          va = BF16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(rows)[(size_t)gr * d + k0 + kk])
+                    : reinterpret_cast<const float*>(rows)[(size_t)gr * d + k0 + kk];
+        }
+        if (c0 + r < n_cent && k0 + kk < d) vb = cent[(size_t)(c0 + r) * d + k0 + kk];
+        As[kk][r] = va;
+        Bs[kk][r] = vb;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int kk = 0; kk < AS_BK; ++kk) {
+        float a[4], b[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+      }
+      __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c = c0 + tx * 4 + j;
+        if (c < n_cent) {
+          const float s = fmaf(-2.f, acc[i][j], cent_sq[c]);
+          if (s < best[i] || (s == best[i] && c < arg[i])) { best[i] = s; arg[i] = c; }
+        }
+      }
+  }
+  // reduce across the 16 threads (tx) that share rows: they are 16 consecutive lanes
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(FULL, best[i], o);
+      const int oa = __shfl_xor_sync(FULL, arg[i], o);
+      if (ob < best[i] || (ob == best[i] && oa < arg[i])) { best[i] = ob; arg[i] = oa; }
+    }
+    const long long gr = row0 + ty * 4 + i;
+    if (tx == 0 && gr < n_rows) {
+      assign[gr] = arg[i];
+      if (cid_f32) cid_f32[(size_t)gr * cid_stride] = (float)arg[i];   // float ids, hippocampal.py:376
+      if (best_out) best_out[gr] = best[i];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) row_sq_norm_kernel(const float* __restrict__ x, int n, int d, float* __restrict__ out) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= n) return;
+  float ss = 0.f;
+  for (int e = lane; e < d; e += 32) { const float v = x[(size_t)w * d + e]; ss = fmaf(v, v, ss); }
+  ss = warp_sum(ss);
+  if (lane == 0) out[w] = ss;
+}
+
+// ------------------------------------------------------------------ CSR inverted lists (counting sort)
+__global__ void __launch_bounds__(256) hist_kernel(const int* __restrict__ cid, long long n, int n_lists,
+                                                   int* __restrict__ counts) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int c = cid[i];
+    if (c >= 0 && c < n_lists) atomicAdd(&counts[c], 1);
+  }
+}
+// single CTA exclusive scan of counts[0..n_lists) -> offsets[0..n_lists], cursor := offsets
+__global__ void __launch_bounds__(1024) scan_offsets_kernel(const int* __restrict__ counts, int n_lists,
+                                                            int* __restrict__ offsets, int* __restrict__ cursor) {
+  __shared__ int warp_tot[32];
+  __shared__ int carry_s;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int base = 0; base < n_lists; base += 1024) {
+    const int i = base + threadIdx.x;
+    const int v = i < n_lists ? counts[i] : 0;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc += t; }
+    if (lane == 31) warp_tot[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+      int w = warp_tot[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(FULL, w, o); if (lane >= o) w += t; }
+      warp_tot[lane] = w;  // inclusive
+    }
+    __syncthreads();
+    const int excl = carry_s + (warp ? warp_tot[warp - 1] : 0) + inc - v;
+    if (i < n_lists) { offsets[i] = excl; cursor[i] = excl; }
+    __syncthreads();
+    if (threadIdx.x == 1023) carry_s = excl + v;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) offsets[n_lists] = carry_s;
+}
+__global__ void __launch_bounds__(256) scatter_kernel(const int* __restrict__ cid, long long n, int n_lists,
+                                                      int* __restrict__ cursor, int* __restrict__ list_rows) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int c = cid[i];
+    if (c >= 0 && c < n_lists) list_rows[atomicAdd(&cursor[c], 1)] = (int)i;
+  }
+}
+
+// ------------------------------------------------------------------ K3: per-list sums (fp64) + finalize
+// One CTA per (list, 256-column chunk): thread = column, loop over the list's rows.  fp64
+// accumulation makes the sum independent of the (unordered) CSR row order in all but
+// astronomically rare rounding cases, and is at least as accurate as the fp32 mean of :363.
+template <bool BF16>
+__global__ void __launch_bounds__(256) list_sums_kernel(const void* __restrict__ rows, int d,
+                                                        const int* __restrict__ list_offsets,
+                                                        const int* __restrict__ list_rows, double* __restrict__ sums) {
+  const int c = blockIdx.x;
+  const int col = blockIdx.y * 256 + threadIdx.x;
+  if (col >= d) return;
+  const int b = list_offsets[c], e = list_offsets[c + 1];
+  double acc = 0.0;
+  int i = b;
+  for (; i + 4 <= e; i += 4) {
+    float v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const size_t off = (size_t)list_rows[i + u] * d + col;
+      v[u] = BF16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(rows)[off])
+                  : reinterpret_cast<const float*>(rows)[off];
+    }
+    acc += (double)v[0]; acc += (double)v[1]; acc += (double)v[2]; acc += (double)v[3];
+  }
+  for (; i < e; ++i) {
+    const size_t off = (size_t)list_rows[i] * d + col;
+    acc += (double)(BF16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(rows)[off])
+                         : reinterpret_cast<const float*>(rows)[off]);
+  }
+  sums[(size_t)c * d + col] = acc;
+}
+
+// centroid[c] = sums[c] / count[c]  when count[c] > 0, else left untouched (empty cluster keeps its
+// sampled seed, hippocampal.py:362).  counts are the per-list sizes (possibly all-reduced).
+__global__ void __launch_bounds__(256) finalize_centroids_kernel(const double* __restrict__ sums,
+                                                                 const long long* __restrict__ counts, int n_cent, int d,
+                                                                 float* __restrict__ cent) {
+  const size_t n = (size_t)n_cent * d;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const long long cnt = counts[i / d];
+    if (cnt > 0) cent[i] = (float)(sums[i] / (double)cnt);
+  }
+}
+
+__global__ void offsets_to_counts_kernel(const int* __restrict__ offsets, int n_lists, long long* __restrict__ counts_i64,
+                                         float* __restrict__ counts_f32) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_lists) {
+    const int c = offsets[i + 1] - offsets[i];
+    if (counts_i64) counts_i64[i] = c;
+    if (counts_f32) counts_f32[i] = (float)c;
+  }
+}
+
+template <bool BF16>
+__global__ void __launch_bounds__(256) gather_seed_rows_kernel(const void* __restrict__ rows, int d,
+                                                               const long long* __restrict__ seeds, int n_seeds,
+                                                               float* __restrict__ cent) {
+  const int s = blockIdx.x;
+  if (s >= n_seeds) return;
+  const size_t r = (size_t)seeds[s];
+  for (int e = threadIdx.x; e < d; e += blockDim.x)
+    cent[(size_t)s * d + e] = BF16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(rows)[r * d + e])
+                                   : reinterpret_cast<const float*>(rows)[r * d + e];
+}
+
+// ------------------------------------------------------------------ K1: online assign (one write)
+// dist_c = ||centroid_c - f||_2 (direct form, as torch.norm(centroids_view - features, dim=1), :223),
+// c* = first argmin; count[c*] += 1; eta = 1/max(count,1); centroid[c*] = (1-eta) centroid + eta f.
+// Grid of CTAs over centroids; the last CTA to finish reduces the per-CTA minima and applies the
+// update, so one write = one launch and consecutive writes serialise on the stream (the sequential
+// semantics of :218-230 are preserved exactly).
+template <bool BF16>
+__global__ void __launch_bounds__(256) online_assign_kernel(const void* __restrict__ rows, long long row, int d,
+                                                            float* __restrict__ cent, int n_live,
+                                                            float* __restrict__ counts, int* __restrict__ cid_i32,
+                                                            float* __restrict__ cid_f32, int cid_stride,
+                                                            u64* __restrict__ partial, unsigned* __restrict__ counter) {
+  __shared__ u64 warp_best[8];
+  __shared__ int s_last;
+  __shared__ int s_arg;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int gw = blockIdx.x * 8 + warp, tw = gridDim.x * 8;
+  u64 best = 0ull;  // max of key(-dist, c)  ==  min dist, lower c on ties
+  for (int c = gw; c < n_live; c += tw) {
+    float ss = 0.f;
+    for (int e = lane; e < d; e += 32) {
+      const float f = BF16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(rows)[(size_t)row * d + e])
+                           : reinterpret_cast<const float*>(rows)[(size_t)row * d + e];
+      const float t = cent[(size_t)c * d + e] - f;
+      ss = fmaf(t, t, ss);
+    }
+    ss = warp_sum(ss);
+    const u64 key = make_key(-sqrtf(ss), (unsigned)c);
+    best = key > best ? key : best;
+  }
+  if (lane == 0) warp_best[warp] = best;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    u64 b = 0ull;
+    for (int w = 0; w < 8; ++w) b = warp_best[w] > b ? warp_best[w] : b;
+    partial[blockIdx.x] = b;
+    __threadfence();
+    s_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (threadIdx.x == 0) {
+    u64 b = 0ull;
+    for (unsigned i = 0; i < gridDim.x; ++i) { const u64 p = partial[i]; b = p > b ? p : b; }
+    const int c = (int)key_row(b);
+    s_arg = c;
+    counts[c] += 1.0f;                                   // :225
+    cid_i32[row] = c;
+    if (cid_f32) cid_f32[(size_t)row * cid_stride] = (float)c;  // :230
+    *counter = 0u;
+  }
+  __syncthreads();
+  const int c = s_arg;
+  const float eta = 1.0f / fmaxf(counts[c], 1.0f);       // :227
+  for (int e = threadIdx.x; e < d; e += blockDim.x) {
+    const float f = BF16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(rows)[(size_t)row * d + e])
+                         : reinterpret_cast<const float*>(rows)[(size_t)row * d + e];
+    cent[(size_t)c * d + e] = (1.0f - eta) * cent[(size_t)c * d + e] + eta * f;  // :228
+  }
+}
+
+static int blocks_for(long long n, int per) {
+  long long g = (n + per - 1) / per;
+  const long long cap = (long long)sm_count() * 8;
+  return (int)(g < 1 ? 1 : g > cap ? cap : g);
+}
+
+}  // namespace aura
+using namespace aura;
+
+extern "C" size_t aura_kmeans_assign_workspace_bytes(int n_centroids) { return (size_t)n_centroids * 4 + 256; }
+
+extern "C" int aura_kmeans_assign(const void* rows, int dtype, int64_t n_rows, int d, const float* centroids,
+                                  int n_centroids, int32_t* assign, float* cid_f32, int cid_stride, float* best_score,
+                                  void* workspace, size_t workspace_bytes, void* stream) {
+  AURA_REQUIRE(dtype == AURA_F32 || dtype == AURA_BF16, AURA_ERR_INVALID_ARG, "aura_kmeans_assign: bad dtype %d", dtype);
+  AURA_REQUIRE(n_rows >= 0 && d >= 1 && n_centroids >= 1, AURA_ERR_INVALID_ARG,
+               "aura_kmeans_assign: n_rows=%lld d=%d n_centroids=%d", (long long)n_rows, d, n_centroids);
+  if (n_rows == 0) return AURA_OK;
+  AURA_REQUIRE(rows && centroids && assign && workspace, AURA_ERR_INVALID_ARG, "aura_kmeans_assign: null pointer");
+  AURA_REQUIRE(workspace_bytes >= aura_kmeans_assign_workspace_bytes(n_centroids), AURA_ERR_WORKSPACE,
+               "aura_kmeans_assign: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  float* csq = reinterpret_cast<float*>(workspace);
+  row_sq_norm_kernel<<<(n_centroids + 7) / 8, 256, 0, st>>>(centroids, n_centroids, d, csq);
+  const long long g = (n_rows + AS_BM - 1) / AS_BM;
+  AURA_REQUIRE(g < 0x7fffffffll, AURA_ERR_UNSUPPORTED, "aura_kmeans_assign: too many rows");
+  if (dtype == AURA_BF16)
+    kmeans_assign_kernel<true><<<(int)g, AS_THREADS, 0, st>>>(rows, n_rows, d, centroids, n_centroids, csq, assign,
+                                                              cid_f32, cid_stride, best_score);
+  else
+    kmeans_assign_kernel<false><<<(int)g, AS_THREADS, 0, st>>>(rows, n_rows, d, centroids, n_centroids, csq, assign,
+                                                               cid_f32, cid_stride, best_score);
+  AURA_CUDA_OK(cudaGetLastError());
+  return AURA_OK;
+}
+
+extern "C" size_t aura_ivf_build_lists_workspace_bytes(int n_lists) { return (size_t)n_lists * 8 + 256; }
+
+extern "C" int aura_ivf_build_lists(const int32_t* cid, int64_t n_rows, int n_lists, int32_t* list_offsets,
+                                    int32_t* list_rows, void* workspace, size_t workspace_bytes, void* stream) {
+  AURA_REQUIRE(n_rows >= 0 && n_rows < 0x7fffffffll && n_lists >= 1, AURA_ERR_INVALID_ARG,
+               "aura_ivf_build_lists: n_rows=%lld n_lists=%d", (long long)n_rows, n_lists);
+  AURA_REQUIRE(list_offsets && workspace && (n_rows == 0 || (cid && list_rows)), AURA_ERR_INVALID_ARG,
+               "aura_ivf_build_lists: null pointer");
+  AURA_REQUIRE(workspace_bytes >= aura_ivf_build_lists_workspace_bytes(n_lists), AURA_ERR_WORKSPACE,
+               "aura_ivf_build_lists: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  int* counts = reinterpret_cast<int*>(workspace);
+  int* cursor = counts + n_lists;
+  AURA_CUDA_OK(cudaMemsetAsync(counts, 0, (size_t)n_lists * 4, st));
+  if (n_rows > 0) hist_kernel<<<blocks_for(n_rows, 256), 256, 0, st>>>(cid, n_rows, n_lists, counts);
+  scan_offsets_kernel<<<1, 1024, 0, st>>>(counts, n_lists, list_offsets, cursor);
+  if (n_rows > 0) scatter_kernel<<<blocks_for(n_rows, 256), 256, 0, st>>>(cid, n_rows, n_lists, cursor, list_rows);
+  AURA_CUDA_OK(cudaGetLastError());
+  return AURA_OK;
+}
+
+extern "C" int aura_kmeans_seed(const void* rows, int dtype, int d, const int64_t* seed_rows, int n_seeds,
+                                float* centroids, void* stream) {
+  AURA_REQUIRE(dtype == AURA_F32 || dtype == AURA_BF16, AURA_ERR_INVALID_ARG, "aura_kmeans_seed: bad dtype %d", dtype);
+  if (n_seeds <= 0) return AURA_OK;
+  AURA_REQUIRE(rows && seed_rows && centroids && d >= 1, AURA_ERR_INVALID_ARG, "aura_kmeans_seed: null pointer");
+  if (dtype == AURA_BF16)
+    gather_seed_rows_kernel<true><<<n_seeds, 256, 0, (cudaStream_t)stream>>>(rows, d, reinterpret_cast<const long long*>(seed_rows), n_seeds, centroids);
+  else
+    gather_seed_rows_kernel<false><<<n_seeds, 256, 0, (cudaStream_t)stream>>>(rows, d, reinterpret_cast<const long long*>(seed_rows), n_seeds, centroids);
+  AURA_CUDA_OK(cudaGetLastError());
+  return AURA_OK;
+}
+
+extern "C" int aura_kmeans_list_sums(const void* rows, int dtype, int d, const int32_t* list_offsets,
+                                     const int32_t* list_rows, int n_lists, double* sums, int64_t* counts, void* stream) {
+  AURA_REQUIRE(dtype == AURA_F32 || dtype == AURA_BF16, AURA_ERR_INVALID_ARG, "aura_kmeans_list_sums: bad dtype %d", dtype);
+  AURA_REQUIRE(n_lists >= 1 && d >= 1 && rows && list_offsets && list_rows && sums && counts, AURA_ERR_INVALID_ARG,
+               "aura_kmeans_list_sums: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 g(n_lists, (d + 255) / 256);
+  if (dtype == AURA_BF16) list_sums_kernel<true><<<g, 256, 0, st>>>(rows, d, list_offsets, list_rows, sums);
+  else list_sums_kernel<false><<<g, 256, 0, st>>>(rows, d, list_offsets, list_rows, sums);
+  offsets_to_counts_kernel<<<(n_lists + 255) / 256, 256, 0, st>>>(list_offsets, n_lists, reinterpret_cast<long long*>(counts), nullptr);
+  AURA_CUDA_OK(cudaGetLastError());
+  return AURA_OK;
+}
+
+extern "C" int aura_kmeans_finalize(const double* sums, const int64_t* counts, int n_centroids, int d, float* centroids,
+                                    void* stream) {
+  AURA_REQUIRE(n_centroids >= 1 && d >= 1 && sums && counts && centroids, AURA_ERR_INVALID_ARG,
+               "aura_kmeans_finalize: bad argument");
+  finalize_centroids_kernel<<<blocks_for((long long)n_centroids * d, 256), 256, 0, (cudaStream_t)stream>>>(
+      sums, reinterpret_cast<const long long*>(counts), n_centroids, d, centroids);
+  AURA_CUDA_OK(cudaGetLastError());
+  return AURA_OK;
+}
+
+extern "C" int aura_ivf_list_counts(const int32_t* list_offsets, int n_lists, float* counts_f32, void* stream) {
+  AURA_REQUIRE(n_lists >= 1 && list_offsets && counts_f32, AURA_ERR_INVALID_ARG, "aura_ivf_list_counts: bad argument");
+  offsets_to_counts_kernel<<<(n_lists + 255) / 256, 256, 0, (cudaStream_t)stream>>>(list_offsets, n_lists, nullptr, counts_f32);
+  AURA_CUDA_OK(cudaGetLastError());
+  return AURA_OK;
+}
+
+extern "C" size_t aura_online_assign_workspace_bytes(void) { return (size_t)sm_count() * 2 * 8 + 256; }
+
+extern "C" int aura_online_assign(const void* rows, int dtype, int d, int64_t first_row, int n_writes, float* centroids,
+                                  int n_live, float* counts, int32_t* cid_i32, float* cid_f32, int cid_stride,
+                                  void* workspace, size_t workspace_bytes, void* stream) {
+  AURA_REQUIRE(dtype == AURA_F32 || dtype == AURA_BF16, AURA_ERR_INVALID_ARG, "aura_online_assign: bad dtype %d", dtype);
+  AURA_REQUIRE(d >= 1 && n_live >= 1 && first_row >= 0 && n_writes >= 0, AURA_ERR_INVALID_ARG,
+               "aura_online_assign: d=%d n_live=%d first_row=%lld n_writes=%d", d, n_live, (long long)first_row, n_writes);
+  if (n_writes == 0) return AURA_OK;
+  AURA_REQUIRE(rows && centroids && counts && cid_i32 && workspace, AURA_ERR_INVALID_ARG, "aura_online_assign: null pointer");
+  AURA_REQUIRE(workspace_bytes >= aura_online_assign_workspace_bytes(), AURA_ERR_WORKSPACE,
+               "aura_online_assign: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned* counter = reinterpret_cast<unsigned*>(workspace);
+  u64* partial = reinterpret_cast<u64*>(reinterpret_cast<unsigned char*>(workspace) + 256);
+  AURA_CUDA_OK(cudaMemsetAsync(counter, 0, 4, st));
+  int grid = (n_live + 7) / 8;
+  const int cap = sm_count() * 2;
+  if (grid > cap) grid = cap;
+  for (int w = 0; w < n_writes; ++w) {
+    if (dtype == AURA_BF16)
+      online_assign_kernel<true><<<grid, 256, 0, st>>>(rows, first_row + w, d, centroids, n_live, counts, cid_i32,
+                                                       cid_f32 ? cid_f32 + (size_t)0 : nullptr, cid_stride, partial, counter);
+    else
+      online_assign_kernel<false><<<grid, 256, 0, st>>>(rows, first_row + w, d, centroids, n_live, counts, cid_i32,
+                                                        cid_f32, cid_stride, partial, counter);
+  }
+  AURA_CUDA_OK(cudaGetLastError());
+  return AURA_OK;
+}

@@ -1,0 +1,71 @@
+// aura_topk_merge - k-way merge of per-shard top-k blocks (the step after the NCCL all-gather
+// of a row-sharded bank).  One CTA per query: load n_lists*k_in (score,idx) pairs,
+// bitonic-sort the 64-bit ranking keys in shared memory, emit the best k_out.
+// Indices here are GLOBAL int64 rows; ties are broken on the lower global row, which is the
+// same rule every local top-k uses, so sharded results equal single-GPU results exactly.
+#include "aura_common.cuh"
+
+namespace aura {
+
+// 96-bit ranking (score, idx64) does not fit a u64 key, so sort (orderable score, slot) keys and
+// break score ties on the idx by a second compare inside the comparator.
+__global__ void __launch_bounds__(256) topk_merge_kernel(const float* __restrict__ in_score,
+                                                         const long long* __restrict__ in_idx, int n_in, int k_out,
+                                                         float* __restrict__ out_score, long long* __restrict__ out_idx,
+                                                         int n2) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  u64* keys = reinterpret_cast<u64*>(smem);
+  const float* sc = in_score + (size_t)blockIdx.x * n_in;
+  const long long* ix = in_idx + (size_t)blockIdx.x * n_in;
+  for (int i = threadIdx.x; i < n2; i += blockDim.x) {
+    u64 key = 0ull;
+    if (i < n_in && ix[i] >= 0) key = ((u64)f32_orderable(sc[i]) << 32) | (u64)(0xFFFFFFFFu - (unsigned)i);
+    keys[i] = key;
+  }
+  // bitonic sort, descending by (score, then lower idx)
+  for (int size = 2; size <= n2; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      __syncthreads();
+      for (int t = threadIdx.x; t < (n2 >> 1); t += blockDim.x) {
+        const int lo = 2 * t - (t & (stride - 1)), hi = lo + stride;
+        const bool desc = ((lo & size) == 0);
+        const u64 a = keys[lo], b = keys[hi];
+        bool a_before_b;  // does a rank ahead of b?
+        const unsigned sa = (unsigned)(a >> 32), sb = (unsigned)(b >> 32);
+        if (sa != sb) a_before_b = sa > sb;
+        else if (a == 0ull || b == 0ull) a_before_b = a > b;
+        else a_before_b = ix[key_row(a)] < ix[key_row(b)];
+        if (a_before_b != desc) { keys[lo] = b; keys[hi] = a; }
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < k_out; i += blockDim.x) {
+    const u64 key = i < n2 ? keys[i] : 0ull;
+    out_score[(size_t)blockIdx.x * k_out + i] = key ? sc[key_row(key)] : -INFINITY;
+    out_idx[(size_t)blockIdx.x * k_out + i] = key ? ix[key_row(key)] : -1ll;
+  }
+}
+
+}  // namespace aura
+using namespace aura;
+
+extern "C" int aura_topk_merge(const float* in_score, const int64_t* in_idx, int n_queries, int n_lists, int k_in,
+                               int k_out, float* out_score, int64_t* out_idx, void* stream) {
+  AURA_REQUIRE(n_queries >= 0 && n_lists >= 1 && k_in >= 1 && k_out >= 1, AURA_ERR_INVALID_ARG,
+               "aura_topk_merge: n_queries=%d n_lists=%d k_in=%d k_out=%d", n_queries, n_lists, k_in, k_out);
+  if (n_queries == 0) return AURA_OK;
+  AURA_REQUIRE(in_score && in_idx && out_score && out_idx, AURA_ERR_INVALID_ARG, "aura_topk_merge: null pointer");
+  const long long n_in = (long long)n_lists * k_in;
+  int n2 = 2;
+  while (n2 < n_in) n2 <<= 1;
+  AURA_REQUIRE((size_t)n2 * 8 <= (size_t)max_smem_optin() - 1024, AURA_ERR_UNSUPPORTED,
+               "aura_topk_merge: n_lists*k_in=%lld does not fit shared memory", n_in);
+  const size_t smem = (size_t)n2 * 8;
+  AURA_CUDA_OK(cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  topk_merge_kernel<<<n_queries, 256, smem, (cudaStream_t)stream>>>(in_score, reinterpret_cast<const long long*>(in_idx),
+                                                                    (int)n_in, k_out, out_score,
+                                                                    reinterpret_cast<long long*>(out_idx), n2);
+  AURA_CUDA_OK(cudaGetLastError());
+  return AURA_OK;
+}

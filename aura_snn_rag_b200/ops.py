@@ -1,0 +1,137 @@
+"""Tensor-level wrappers over the C ABI: pointer/stream plumbing only, no arithmetic.
+
+torch is used for device memory and streams; every computation happens inside
+libaura_hippo.so.  All functions require CUDA tensors and raise otherwise.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import AURA_BF16, AURA_F32, AURA_MAX_K, check
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _dtype_code(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return AURA_F32
+    if t.dtype == torch.bfloat16:
+        return AURA_BF16
+    raise TypeError(f"memory bank rows must be float32 or bfloat16, got {t.dtype}")
+
+
+def _dev(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise _lib.AuraLibraryError(f"{name} must be a CUDA tensor: the retrieval path has no CPU implementation")
+    if not t.is_contiguous():
+        raise ValueError(f"{name} must be contiguous")
+    return t
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+_workspaces = {}
+
+
+def _workspace(nbytes: int, device: torch.device, tag: str = "ws") -> torch.Tensor:
+    """Per-(device, stream) scratch, grown on demand (the library never allocates)."""
+    key = (device.index, _stream(), tag)
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+def row_inv_norms(rows: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    rows = _dev(rows, "rows")
+    n, d = rows.shape
+    if out is None:
+        out = torch.empty(n, dtype=torch.float32, device=rows.device)
+    check(_lib.load().aura_row_inv_norms(rows.data_ptr(), _dtype_code(rows), n, d, out.data_ptr(), _stream()),
+          "aura_row_inv_norms")
+    return out
+
+
+def row_terms(metadata: torch.Tensor, inv_norm: torch.Tensor, now: float, n_rows: int,
+              locations: Optional[torch.Tensor] = None, query_loc: Optional[torch.Tensor] = None,
+              scale: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None):
+    metadata = _dev(metadata, "metadata")
+    dev = metadata.device
+    if scale is None:
+        scale = torch.empty(n_rows, dtype=torch.float32, device=dev)
+    if bias is None:
+        bias = torch.empty(n_rows, dtype=torch.float32, device=dev)
+    sd = 0
+    if query_loc is not None:
+        locations = _dev(locations, "locations")
+        query_loc = _dev(query_loc.to(device=dev, dtype=torch.float32), "query_loc")
+        sd = locations.shape[1]
+    check(_lib.load().aura_row_terms(metadata.data_ptr(), _ptr(locations) if query_loc is not None else None, sd,
+                                     _ptr(query_loc), float(now), inv_norm.data_ptr(), n_rows, scale.data_ptr(),
+                                     bias.data_ptr(), _stream()), "aura_row_terms")
+    return scale, bias
+
+
+def decay_strength(metadata: torch.Tensor, n_rows: int, rate: float) -> None:
+    metadata = _dev(metadata, "metadata")
+    check(_lib.load().aura_decay_strength(metadata.data_ptr(), n_rows, float(rate), _stream()), "aura_decay_strength")
+
+
+def scan_topk(rows: torch.Tensor, queries: torch.Tensor, k: int, scale: Optional[torch.Tensor],
+              bias: Optional[torch.Tensor] = None, n_rows: Optional[int] = None, row_base: int = 0,
+              out_idx: Optional[torch.Tensor] = None, out_score: Optional[torch.Tensor] = None
+              ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Exact scan + fused top-k.  queries [B,d] fp32 (raw; normalised inside).  Returns (idx[B,k], score[B,k])."""
+    rows = _dev(rows, "rows")
+    queries = _dev(queries, "queries")
+    if queries.dtype != torch.float32:
+        raise TypeError("queries must be float32")
+    if queries.dim() == 1:
+        queries = queries.unsqueeze(0)
+    b, d = queries.shape
+    if rows.shape[1] != d:
+        raise ValueError(f"query dim {d} != bank dim {rows.shape[1]}")
+    n = rows.shape[0] if n_rows is None else int(n_rows)
+    if not (1 <= k <= AURA_MAX_K):
+        raise ValueError(f"k={k} outside [1,{AURA_MAX_K}]")
+    dev = rows.device
+    if out_idx is None:
+        out_idx = torch.empty(b, k, dtype=torch.int64, device=dev)
+    if out_score is None:
+        out_score = torch.empty(b, k, dtype=torch.float32, device=dev)
+    lib = _lib.load()
+    nbytes = lib.aura_scan_topk_workspace_bytes(n, d, b, k)
+    ws = _workspace(nbytes, dev)
+    check(lib.aura_scan_topk(rows.data_ptr(), _dtype_code(rows), n, d, queries.data_ptr(), b, _ptr(scale), _ptr(bias),
+                             k, row_base, out_idx.data_ptr(), out_score.data_ptr(), ws.data_ptr(), ws.numel(),
+                             _stream()), "aura_scan_topk")
+    return out_idx, out_score
+
+
+def topk_merge(scores: torch.Tensor, idx: torch.Tensor, n_lists: int, k_in: int, k_out: int):
+    scores = _dev(scores, "scores")
+    idx = _dev(idx, "idx")
+    b = scores.shape[0]
+    out_s = torch.empty(b, k_out, dtype=torch.float32, device=scores.device)
+    out_i = torch.empty(b, k_out, dtype=torch.int64, device=scores.device)
+    check(_lib.load().aura_topk_merge(scores.data_ptr(), idx.data_ptr(), b, n_lists, k_in, k_out, out_s.data_ptr(),
+                                      out_i.data_ptr(), _stream()), "aura_topk_merge")
+    return out_s, out_i
+
+
+def gather_rows(rows: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    rows = _dev(rows, "rows")
+    idx = _dev(idx, "idx")
+    d = rows.shape[1]
+    out = torch.empty(*idx.shape, d, dtype=torch.float32, device=rows.device)
+    check(_lib.load().aura_gather_rows(rows.data_ptr(), _dtype_code(rows), d, idx.data_ptr(), idx.numel(),
+                                       out.data_ptr(), _stream()), "aura_gather_rows")
+    return out
