@@ -24,6 +24,14 @@ void set_error(const char* fmt, ...);
 int  cuda_fail(cudaError_t e, const char* what);
 int  sm_count();
 int  max_smem_optin();
+void note_launches(int n);  // kernels launched by this library in this process (aura_kernel_launches)
+
+// scan_topk.cu: shared launcher of aura_scan_topk (probes == nullptr) and aura_ivf_search
+size_t scan_workspace_bytes(int n_queries, int k);
+int launch_scan(const void* rows, int dtype, long long n_rows, int d, const float* queries, int n_queries,
+                const float* scale, const float* bias, int k, long long row_base, long long* out_idx, float* out_score,
+                void* workspace, const long long* probes, int nprobe, int n_lists, const int* list_offsets,
+                const int* list_rows, long long expected_rows, cudaStream_t st);
 
 #define AURA_CUDA_OK(expr)                                                        \
   do {                                                                            \
@@ -130,6 +138,45 @@ __device__ __forceinline__ int next_pow2(int v) {
   int p = 1;
   while (p < v) p <<= 1;
   return p;
+}
+
+// ---- shared tail: CTA merge + cross-CTA final merge ------------------------------------------
+template <int KPL>
+__device__ __forceinline__ void publish_cta_topk(const WarpTopK<KPL>& tk, int warp, int lane, int n_warps,
+                                                 u64* merge, int k, u64* dst) {
+  constexpr int KC = 32 * KPL;
+  const int n2 = next_pow2(n_warps * KC);
+  __syncthreads();
+  if (warp < n_warps) tk.store(merge + warp * KC, lane);
+  for (int i = n_warps * KC + threadIdx.x; i < n2; i += blockDim.x) merge[i] = 0ull;
+  block_bitonic_sort_desc(merge, n2);
+  for (int i = threadIdx.x; i < k; i += blockDim.x) dst[i] = merge[i];
+  __syncthreads();
+}
+
+// Merge n_lists sorted-or-not lists of k keys (list l at src + l*list_stride) into out (last CTA).
+__device__ __forceinline__ void final_merge_write(const u64* src, int n_lists, size_t list_stride, int k, u64* merge,
+                                                  int merge_cap, long long row_base, long long* out_idx,
+                                                  float* out_score) {
+  int have = 0, list = 0;
+  while (list < n_lists) {
+    const int lists_fit = max(1, (merge_cap - have) / k);
+    const int take = min(lists_fit, n_lists - list);
+    __syncthreads();
+    for (int i = threadIdx.x; i < take * k; i += blockDim.x)
+      merge[have + i] = src[(size_t)(list + i / k) * list_stride + (i % k)];
+    const int n2 = next_pow2(max(have + take * k, 2));
+    for (int i = have + take * k + threadIdx.x; i < n2; i += blockDim.x) merge[i] = 0ull;
+    block_bitonic_sort_desc(merge, n2);
+    list += take;
+    have = min(k, n2);
+  }
+  for (int i = threadIdx.x; i < k; i += blockDim.x) {
+    const u64 key = merge[i];
+    out_idx[i] = key ? row_base + (long long)key_row(key) : -1ll;
+    out_score[i] = key ? key_score(key) : -INFINITY;
+  }
+  __syncthreads();
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

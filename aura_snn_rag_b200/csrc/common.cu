@@ -2,12 +2,16 @@
 // version.  (C ABI: include/aura_hippo.h.)
 #include <stdarg.h>
 #include <stdio.h>
+#include <atomic>
 
 #include "aura_common.cuh"
 
 namespace aura {
 
 static thread_local char g_err[512] = "";
+static std::atomic<unsigned long long> g_launches{0};
+void note_launches(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+unsigned long long launches() { return g_launches.load(std::memory_order_relaxed); }
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -48,3 +52,4 @@ int max_smem_optin() {
 
 extern "C" int aura_version(void) { return AURA_HIPPO_VERSION; }
 extern "C" const char* aura_last_error_string(void) { return aura::g_err; }
+extern "C" uint64_t aura_kernel_launches(void) { return aura::launches(); }

@@ -314,6 +314,7 @@ extern "C" int aura_kmeans_assign(const void* rows, int dtype, int64_t n_rows, i
     kmeans_assign_kernel<false><<<(int)g, AS_THREADS, 0, st>>>(rows, n_rows, d, centroids, n_centroids, csq, assign,
                                                                cid_f32, cid_stride, best_score);
   AURA_CUDA_OK(cudaGetLastError());
+  note_launches(2);
   return AURA_OK;
 }
 
@@ -335,6 +336,7 @@ extern "C" int aura_ivf_build_lists(const int32_t* cid, int64_t n_rows, int n_li
   scan_offsets_kernel<<<1, 1024, 0, st>>>(counts, n_lists, list_offsets, cursor);
   if (n_rows > 0) scatter_kernel<<<blocks_for(n_rows, 256), 256, 0, st>>>(cid, n_rows, n_lists, cursor, list_rows);
   AURA_CUDA_OK(cudaGetLastError());
+  note_launches(n_rows > 0 ? 3 : 1);
   return AURA_OK;
 }
 
@@ -348,6 +350,7 @@ extern "C" int aura_kmeans_seed(const void* rows, int dtype, int d, const int64_
   else
     gather_seed_rows_kernel<false><<<n_seeds, 256, 0, (cudaStream_t)stream>>>(rows, d, reinterpret_cast<const long long*>(seed_rows), n_seeds, centroids);
   AURA_CUDA_OK(cudaGetLastError());
+  note_launches(1);
   return AURA_OK;
 }
 
@@ -362,6 +365,7 @@ extern "C" int aura_kmeans_list_sums(const void* rows, int dtype, int d, const i
   else list_sums_kernel<false><<<g, 256, 0, st>>>(rows, d, list_offsets, list_rows, sums);
   offsets_to_counts_kernel<<<(n_lists + 255) / 256, 256, 0, st>>>(list_offsets, n_lists, reinterpret_cast<long long*>(counts), nullptr);
   AURA_CUDA_OK(cudaGetLastError());
+  note_launches(2);
   return AURA_OK;
 }
 
@@ -372,6 +376,7 @@ extern "C" int aura_kmeans_finalize(const double* sums, const int64_t* counts, i
   finalize_centroids_kernel<<<blocks_for((long long)n_centroids * d, 256), 256, 0, (cudaStream_t)stream>>>(
       sums, reinterpret_cast<const long long*>(counts), n_centroids, d, centroids);
   AURA_CUDA_OK(cudaGetLastError());
+  note_launches(1);
   return AURA_OK;
 }
 
@@ -379,6 +384,7 @@ extern "C" int aura_ivf_list_counts(const int32_t* list_offsets, int n_lists, fl
   AURA_REQUIRE(n_lists >= 1 && list_offsets && counts_f32, AURA_ERR_INVALID_ARG, "aura_ivf_list_counts: bad argument");
   offsets_to_counts_kernel<<<(n_lists + 255) / 256, 256, 0, (cudaStream_t)stream>>>(list_offsets, n_lists, nullptr, counts_f32);
   AURA_CUDA_OK(cudaGetLastError());
+  note_launches(1);
   return AURA_OK;
 }
 
@@ -410,5 +416,6 @@ extern "C" int aura_online_assign(const void* rows, int dtype, int d, int64_t fi
                                                         cid_f32, cid_stride, partial, counter);
   }
   AURA_CUDA_OK(cudaGetLastError());
+  note_launches(n_writes);
   return AURA_OK;
 }

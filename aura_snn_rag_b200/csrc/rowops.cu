@@ -85,6 +85,41 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const void* rows, int 
   }
 }
 
+// One CTA per new row: convert + store the features, compute the inverse norm from the values AS
+// STORED (bf16 banks normalise their rounded rows), write location and metadata {1, t, -1, 0}.
+template <bool BF16>
+__global__ void __launch_bounds__(256) bank_write_kernel(void* rows, int d, long long first_row,
+                                                         const float* __restrict__ feats, float* locations, int sd,
+                                                         const float* __restrict__ location, float* metadata,
+                                                         float timestamp, float* inv_norm) {
+  __shared__ float warp_ss[8];
+  const long long r = first_row + blockIdx.x;
+  const float* f = feats + (size_t)blockIdx.x * d;
+  float ss = 0.f;
+  for (int e = threadIdx.x; e < d; e += blockDim.x) {
+    float v = f[e];
+    if (BF16) {
+      const __nv_bfloat16 b = __float2bfloat16_rn(v);
+      reinterpret_cast<__nv_bfloat16*>(rows)[(size_t)r * d + e] = b;
+      v = __bfloat162float(b);
+    } else {
+      reinterpret_cast<float*>(rows)[(size_t)r * d + e] = v;
+    }
+    ss = fmaf(v, v, ss);
+  }
+  ss = warp_sum(ss);
+  if ((threadIdx.x & 31) == 0) warp_ss[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += warp_ss[w];
+    inv_norm[r] = 1.0f / fmaxf(sqrtf(t), 1e-12f);
+    reinterpret_cast<float4*>(metadata)[r] = make_float4(1.0f, timestamp, -1.0f, 0.0f);  // :215,:232
+  }
+  if (locations != nullptr && threadIdx.x < sd)
+    locations[(size_t)r * sd + threadIdx.x] = location ? location[threadIdx.x] : 0.f;  // :212
+}
+
 static int grid_for(long long work_items, int per_block) {
   long long g = (work_items + per_block - 1) / per_block;
   const long long cap = (long long)sm_count() * 16;
@@ -103,6 +138,7 @@ extern "C" int aura_row_inv_norms(const void* rows, int dtype, int64_t n_rows, i
   if (dtype == AURA_BF16) inv_norm_kernel<true><<<g, 256, 0, (cudaStream_t)stream>>>(rows, n_rows, d, inv_norm);
   else inv_norm_kernel<false><<<g, 256, 0, (cudaStream_t)stream>>>(rows, n_rows, d, inv_norm);
   AURA_CUDA_OK(cudaGetLastError());
+  note_launches(1);
   return AURA_OK;
 }
 
@@ -118,6 +154,7 @@ extern "C" int aura_row_terms(const float* metadata, const float* locations, int
   row_terms_kernel<<<grid_for(n_rows, 256), 256, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const float4*>(metadata), locations, spatial_dims, query_loc, now, inv_norm, n_rows, scale, bias);
   AURA_CUDA_OK(cudaGetLastError());
+  note_launches(1);
   return AURA_OK;
 }
 
@@ -127,6 +164,7 @@ extern "C" int aura_decay_strength(float* metadata, int64_t n_rows, float rate, 
   AURA_REQUIRE(metadata, AURA_ERR_INVALID_ARG, "aura_decay_strength: null pointer");
   decay_kernel<<<grid_for(n_rows, 256), 256, 0, (cudaStream_t)stream>>>(metadata, n_rows, 1.0f - rate);
   AURA_CUDA_OK(cudaGetLastError());
+  note_launches(1);
   return AURA_OK;
 }
 
@@ -141,5 +179,28 @@ extern "C" int aura_gather_rows(const void* rows, int dtype, int d, const int64_
   else
     gather_rows_kernel<false><<<g, 256, 0, (cudaStream_t)stream>>>(rows, d, reinterpret_cast<const long long*>(idx), n_idx, out);
   AURA_CUDA_OK(cudaGetLastError());
+  note_launches(1);
+  return AURA_OK;
+}
+
+extern "C" int aura_bank_write(void* rows, int dtype, int d, int64_t first_row, int n_new, const float* features,
+                               float* locations, int spatial_dims, const float* location, float* metadata,
+                               float timestamp, float* inv_norm, void* stream) {
+  AURA_REQUIRE(dtype == AURA_F32 || dtype == AURA_BF16, AURA_ERR_INVALID_ARG, "aura_bank_write: bad dtype %d", dtype);
+  AURA_REQUIRE(d >= 1 && first_row >= 0 && n_new >= 0 && spatial_dims >= 0 && spatial_dims <= 256, AURA_ERR_INVALID_ARG,
+               "aura_bank_write: d=%d first_row=%lld n_new=%d spatial_dims=%d", d, (long long)first_row, n_new,
+               spatial_dims);
+  if (n_new == 0) return AURA_OK;
+  AURA_REQUIRE(rows && features && metadata && inv_norm, AURA_ERR_INVALID_ARG, "aura_bank_write: null pointer");
+  AURA_REQUIRE((reinterpret_cast<uintptr_t>(metadata) & 15) == 0, AURA_ERR_INVALID_ARG,
+               "aura_bank_write: metadata must be 16-byte aligned");
+  if (dtype == AURA_BF16)
+    bank_write_kernel<true><<<n_new, 256, 0, (cudaStream_t)stream>>>(rows, d, first_row, features, locations,
+                                                                     spatial_dims, location, metadata, timestamp, inv_norm);
+  else
+    bank_write_kernel<false><<<n_new, 256, 0, (cudaStream_t)stream>>>(rows, d, first_row, features, locations,
+                                                                      spatial_dims, location, metadata, timestamp, inv_norm);
+  AURA_CUDA_OK(cudaGetLastError());
+  note_launches(1);
   return AURA_OK;
 }

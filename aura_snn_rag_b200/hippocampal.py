@@ -1,0 +1,370 @@
+"""Drop-in `HippocampalFormation` whose memory bank + centroid index run in libaura_hippo.so.
+
+Mirrors the public surface of the reference class (src/core/hippocampal.py:31-377): constructor
+signature (:41-49), the 13 registered buffers with the same names / shapes (state-dict
+compatible), `create_episodic_memory` (:195-243), `retrieve_similar_memories` (:245-319),
+`decay_memories` / `decay` (:321-343), `rebuild_centroids` (:345-377), the spatial / temporal
+context helpers (:120-193) and the attributes callers touch directly (`memory_count`,
+`id_to_idx`, `episodic_memories`, `centroids_k`, `centroids_update_interval`, `_index_ready`).
+
+What is different underneath
+* every O(M) or O(M*d) step is one hand-written sm_100a kernel behind the C ABI
+  (include/aura_hippo.h); torch supplies device memory and streams only;
+* there is NO CPU path: constructing the module without CUDA raises (the reference silently falls
+  back to CPU, :53);
+* inverted lists (CSR) replace the per-query mask passes (:264-268); per-row inverse norms and
+  score terms replace the per-query re-normalisation of the whole bank (:278);
+* result rows of the centroid path are bank rows (the reference maps candidate-local positions
+  through id_to_idx, :307-317 - a bug); `k` is clamped to the candidate
+  count; `location=` works together with the centroid path.  Scores are the reference's.
+* batched / tensor-valued entry points exist next to the reference API: `retrieve_batch`,
+  `exact_topk`, `create_episodic_memories`.
+"""
+from __future__ import annotations
+
+import time
+from dataclasses import dataclass
+from typing import Any, Dict, List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import ops
+from ._lib import AURA_MAX_K, AuraLibraryError
+from .idtable import IdTable
+
+
+@dataclass
+class EpisodicMemory:
+    """Per-memory metadata record, as hippocampal.py:23-29."""
+    memory_id: str
+    feature_idx: int
+    timestamp: float
+    strength: float = 1.0
+
+
+class HippocampalFormation(nn.Module):
+    def __init__(self,
+                 spatial_dimensions: int = 2,
+                 n_place_cells: int = 2000,
+                 n_time_cells: int = 100,
+                 n_grid_cells: int = 200,
+                 max_memories: int = 100000,
+                 feature_dim: int = 768,
+                 device: str = 'cuda',
+                 use_centroid_index: bool = True,
+                 *,
+                 centroids_k: int = 256,
+                 centroid_rows: Optional[int] = None,
+                 nprobe: int = 8,
+                 bank_dtype: torch.dtype = torch.float32,
+                 track_ids: bool = True):
+        super().__init__()
+        if not torch.cuda.is_available():
+            raise AuraLibraryError("HippocampalFormation (B200 build) needs a CUDA device: the retrieval path has "
+                                   "no CPU implementation")
+        dev = torch.device(device)
+        if dev.type != 'cuda':
+            raise AuraLibraryError(f"device={device!r}: the retrieval path has no CPU implementation")
+        if dev.index is None:
+            dev = torch.device('cuda', torch.cuda.current_device())
+        if bank_dtype not in (torch.float32, torch.bfloat16):
+            raise TypeError("bank_dtype must be torch.float32 or torch.bfloat16")
+        self.spatial_dims = spatial_dimensions
+        self.device = dev
+        f32 = dict(device=dev, dtype=torch.float32)
+
+        # place / grid / time cells (hippocampal.py:55-82): small state, same buffer names
+        self.register_buffer('place_centers', torch.rand(n_place_cells, spatial_dimensions, **f32) * 20 - 10)
+        self.register_buffer('place_radii', torch.rand(n_place_cells, 1, **f32) * 1.5 + 0.5)
+        self.place_max_rate = 20.0
+        spacings = torch.logspace(0, 2, n_grid_cells, base=2.0, **f32).unsqueeze(1)
+        self.register_buffer('grid_spacings', spacings)
+        self.register_buffer('grid_orientations', torch.rand(n_grid_cells, 1, **f32) * (torch.pi / 3))
+        self.register_buffer('grid_phases', torch.rand(n_grid_cells, spatial_dimensions, **f32) * spacings)
+        self.grid_max_rate = 25.0
+        intervals = torch.logspace(0, 3, n_time_cells, base=10.0, **f32).unsqueeze(1)
+        self.register_buffer('time_intervals', intervals)
+        self.register_buffer('time_widths', intervals * 0.3)
+
+        # memory bank (hippocampal.py:84-99)
+        self.max_memories = int(max_memories)
+        self.memory_count = 0
+        self.register_buffer('memory_features', torch.zeros(max_memories, feature_dim, device=dev, dtype=bank_dtype))
+        self.register_buffer('memory_locations', torch.zeros(max_memories, spatial_dimensions, **f32))
+        self.register_buffer('memory_metadata', torch.zeros(max_memories, 4, **f32))
+        self.episodic_memories: Dict[str, EpisodicMemory] = {}
+        self.track_ids = bool(track_ids)
+        self._ids = IdTable()
+        self.current_location = torch.zeros(spatial_dimensions, **f32)
+        self.last_event_time = time.time()
+        self.register_buffer('k_const', 4 * torch.pi / torch.sqrt(torch.tensor(3.0, **f32)))
+
+        # centroid index (hippocampal.py:112-118); knobs stay plain mutable attributes
+        self.use_centroid_index = use_centroid_index
+        self.centroids_k = int(centroids_k)
+        self.centroids_update_interval = 512
+        self.nprobe = int(nprobe)                       # reference literal 8 (:262)
+        rows = int(centroid_rows) if centroid_rows is not None else max(256, self.centroids_k)
+        self.register_buffer('centroids', torch.zeros(rows, feature_dim, **f32))
+        self.register_buffer('centroid_counts', torch.zeros(rows, **f32))
+        self._index_ready = False
+
+        # derived index state (not part of the reference's state dict)
+        self.register_buffer('_inv_norm', torch.zeros(max_memories, **f32), persistent=False)
+        self.register_buffer('_cid', torch.full((max_memories,), -1, device=dev, dtype=torch.int32), persistent=False)
+        self.register_buffer('_list_offsets', torch.zeros(rows + 1, device=dev, dtype=torch.int32), persistent=False)
+        self.register_buffer('_list_rows', torch.zeros(max_memories, device=dev, dtype=torch.int32), persistent=False)
+        self.register_buffer('_scale', torch.zeros(max_memories, **f32), persistent=False)
+        self.register_buffer('_bias', torch.zeros(max_memories, **f32), persistent=False)
+        self._lists_dirty = True
+        self._terms_key = None        # (fp32 now, location key, version) the cached _scale/_bias belong to
+        self._version = 0             # bumped by every write / decay
+
+    # ------------------------------------------------------------------ reference attribute surface
+    @property
+    def id_to_idx(self) -> Dict[str, int]:
+        return self._ids.id_to_idx
+
+    # ------------------------------------------------------------------ spatial / temporal context
+    def _to_dev_f32(self, x) -> torch.Tensor:
+        if isinstance(x, np.ndarray):
+            x = torch.from_numpy(x)
+        return x.to(device=self.device, dtype=torch.float32, non_blocking=True)
+
+    def update_spatial_state(self, new_location, dt: float = 0.1) -> None:
+        """hippocampal.py:120-132."""
+        loc = self._to_dev_f32(new_location)
+        self.current_location = loc if loc.dim() == 1 else loc[0]
+
+    def get_spatial_context(self) -> Dict[str, Any]:
+        """Place / grid cell rates at the current location (hippocampal.py:134-179); not on the hot path."""
+        loc = self.current_location.unsqueeze(0)
+        dist = torch.norm(loc - self.place_centers, dim=1, keepdim=True)
+        sigma = self.place_radii / 3.0
+        place = self.place_max_rate * torch.exp(-(dist ** 2) / (2 * sigma ** 2)) * (dist <= self.place_radii).float()
+        c, s = torch.cos(self.grid_orientations), torch.sin(self.grid_orientations)
+        x, y = loc[0, 0], loc[0, 1]
+        rot = torch.cat([c * x - s * y, s * x + c * y], dim=1) - self.grid_phases
+        kk = self.k_const / self.grid_spacings
+        a, b = rot[:, 0:1], rot[:, 1:2]
+        waves = torch.cos(kk * a) + torch.cos(kk * (-0.5 * a + 0.866 * b)) + torch.cos(kk * (-0.5 * a - 0.866 * b))
+        grid = self.grid_max_rate * torch.relu(waves / 3.0 + 0.5)
+        return {"current_location": self.current_location, "place_cells": place.flatten(),
+                "grid_cells": grid.flatten(), "n_memories": self.memory_count}
+
+    def get_temporal_context(self) -> Dict[str, Any]:
+        """Time-cell rates (hippocampal.py:181-193)."""
+        elapsed = time.time() - self.last_event_time
+        diff = elapsed - self.time_intervals
+        rates = 15.0 * torch.exp(-(diff ** 2) / (2 * (self.time_widths / 3) ** 2))
+        return {"time_cells": rates.flatten(), "elapsed": elapsed}
+
+    # ------------------------------------------------------------------ writes
+    def _centroid_buffer_rows(self) -> int:
+        return self.centroids.shape[0]
+
+    def create_episodic_memory(self, memory_id: str, event_id: str, features,
+                               associated_experts: Optional[List[str]] = None, *,
+                               seed_rows: Optional[torch.Tensor] = None) -> None:
+        """One-shot write + online k-means step (hippocampal.py:195-243).
+
+        `seed_rows` (extension) is handed to a rebuild this write triggers, so that tests can replay the
+        reference's randperm draw; None draws torch.randperm on the device like the reference.
+        """
+        if self.memory_count >= self.max_memories:
+            idx = self.memory_count % self.max_memories     # full-bank quirk kept: always row 0 (:200-202)
+        else:
+            idx = self.memory_count
+            self.memory_count += 1
+        feats = self._to_dev_f32(features).detach().reshape(1, -1).contiguous()
+        now = time.time()
+        ops.bank_write(self.memory_features, idx, feats, self.memory_metadata, self._inv_norm, now,
+                       self.memory_locations, self.current_location.contiguous())
+        if self.use_centroid_index and self._index_ready:
+            live = min(self.centroids_k, self._centroid_buffer_rows())          # :220
+            ops.online_assign(self.memory_features, idx, 1, self.centroids, live, self.centroid_counts, self._cid,
+                              self.memory_metadata[:, 2], 4)
+        else:
+            self._cid[idx:idx + 1].fill_(-1)
+        self._lists_dirty = True
+        self._version += 1
+        if self.track_ids:
+            self.episodic_memories[memory_id] = EpisodicMemory(memory_id=memory_id, feature_idx=idx, timestamp=now)
+            self._ids.set(memory_id, idx)
+        if (self.use_centroid_index and self.memory_count % self.centroids_update_interval == 0
+                and self.memory_count > self.centroids_k):              # :242-243
+            self.rebuild_centroids(seed_rows=seed_rows)
+
+    def create_episodic_memories(self, features, memory_ids: Optional[Sequence[str]] = None) -> Tuple[int, int]:
+        """Bulk append of N rows: same semantics as N calls of
+        `create_episodic_memory` with one timestamp, including the sequential online-assign order and the
+        periodic rebuild points.  Returns the [first, last+1) row range written.  The bank must have room
+        (no FIFO overwrite in bulk mode)."""
+        feats = self._to_dev_f32(features).detach()
+        if feats.dim() == 1:
+            feats = feats.unsqueeze(0)
+        feats = feats.contiguous()
+        n = feats.shape[0]
+        first = self.memory_count
+        if first + n > self.max_memories:
+            raise ValueError(f"bulk write of {n} rows does not fit: {first} of {self.max_memories} rows used")
+        if memory_ids is not None and len(memory_ids) != n:
+            raise ValueError("memory_ids length differs from the number of rows")
+        now = time.time()
+        ops.bank_write(self.memory_features, first, feats, self.memory_metadata, self._inv_norm, now,
+                       self.memory_locations, self.current_location.contiguous())
+        self._cid[first:first + n].fill_(-1)
+        done = 0
+        interval = self.centroids_update_interval
+        while done < n:
+            # rows up to the next rebuild point are assigned online (if the index is ready), then rebuild
+            count = self.memory_count
+            nxt = (count // interval + 1) * interval
+            step = min(n - done, nxt - count)
+            if self.use_centroid_index and self._index_ready:
+                live = min(self.centroids_k, self._centroid_buffer_rows())
+                ops.online_assign(self.memory_features, first + done, step, self.centroids, live,
+                                  self.centroid_counts, self._cid, self.memory_metadata[:, 2], 4)
+            self.memory_count += step
+            done += step
+            if (self.use_centroid_index and self.memory_count % interval == 0
+                    and self.memory_count > self.centroids_k):
+                self.rebuild_centroids()
+        self._lists_dirty = True
+        self._version += 1
+        if self.track_ids and memory_ids is not None:
+            for j, mid in enumerate(memory_ids):
+                self.episodic_memories[mid] = EpisodicMemory(memory_id=mid, feature_idx=first + j, timestamp=now)
+                self._ids.set(mid, first + j)
+        return first, first + n
+
+    def decay_memories(self, decay_rate: float = 0.01) -> None:
+        """strength *= (1 - rate) over live rows (hippocampal.py:321-334)."""
+        if self.memory_count == 0:
+            return
+        ops.decay_strength(self.memory_metadata, self.memory_count, decay_rate)
+        self._version += 1
+
+    def decay(self, rate: float = 0.01) -> None:
+        self.decay_memories(decay_rate=rate)
+
+    # ------------------------------------------------------------------ index build
+    def rebuild_centroids(self, seed_rows: Optional[torch.Tensor] = None) -> None:
+        """Sample k seeds, one Lloyd step, re-assign, counts (hippocampal.py:345-377)."""
+        if self.memory_count == 0 or not self.use_centroid_index:
+            return
+        m = self.memory_count
+        k = min(self.centroids_k, m)
+        rows_c = self._centroid_buffer_rows()
+        if k > rows_c:
+            raise ValueError(f"centroids_k={self.centroids_k} exceeds the centroid buffer ({rows_c} rows); "
+                             "pass centroids_k / centroid_rows to the constructor")
+        if seed_rows is None:
+            seed_rows = torch.randperm(m, device=self.device)[:k]          # :354
+        seeds = seed_rows.to(device=self.device, dtype=torch.int64)[:k].contiguous()
+        bank = self.memory_features
+        ops.kmeans_seed(bank, seeds, self.centroids)                          # :355
+        ops.kmeans_assign(bank, m, self.centroids, k, self._cid)              # :358-359
+        ops.ivf_build_lists(self._cid, m, rows_c, self._list_offsets, self._list_rows)
+        sums = torch.empty(rows_c, bank.shape[1], device=self.device, dtype=torch.float64)
+        counts = torch.empty(rows_c, device=self.device, dtype=torch.int64)
+        ops.kmeans_list_sums(bank, self._list_offsets, self._list_rows, rows_c, sums, counts)
+        ops.kmeans_finalize(sums, counts, k, self.centroids)                  # :360-363 (empty keeps its seed)
+        if k < self.centroids_k and k < rows_c:
+            self.centroids[k:].zero_()                                        # :366-367
+        ops.kmeans_assign(bank, m, self.centroids, k, self._cid, self.memory_metadata[:, 2], 4)   # :370-371,:376
+        ops.ivf_build_lists(self._cid, m, rows_c, self._list_offsets, self._list_rows)
+        counts_f = torch.zeros(max(self.centroids_k, 1), device=self.device, dtype=torch.float32)
+        full = torch.empty(rows_c, device=self.device, dtype=torch.float32)
+        ops.ivf_list_counts(self._list_offsets, rows_c, full)
+        counts_f[:min(rows_c, counts_f.numel())] = full[:counts_f.numel()]
+        self.centroid_counts = counts_f                                       # rebinding quirk kept (:369,:374)
+        self._lists_dirty = False
+        self._index_ready = True
+
+    def _ensure_lists(self) -> None:
+        if self._lists_dirty:
+            ops.ivf_build_lists(self._cid, self.memory_count, self._centroid_buffer_rows(), self._list_offsets,
+                                self._list_rows)
+            self._lists_dirty = False
+
+    # ------------------------------------------------------------------ queries
+    def _row_terms(self, location) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Per-row scale / bias of the combined score (hippocampal.py:282-303), cached while the fp32
+        clock value, the query location and the bank contents are unchanged."""
+        now32 = float(np.float32(time.time()))          # the reference subtracts in fp32 (:296)
+        loc = None
+        loc_key = None
+        if location is not None:
+            loc = self._to_dev_f32(location).reshape(-1).contiguous()
+            loc_key = tuple(loc.tolist())
+        key = (now32, loc_key, self._version, self.memory_count)
+        if key != self._terms_key:
+            ops.row_terms(self.memory_metadata, self._inv_norm, now32, self.memory_count, self.memory_locations, loc,
+                          self._scale, self._bias)
+            self._terms_key = key
+        return self._scale, self._bias
+
+    def _centroid_path(self) -> bool:
+        return bool(self.use_centroid_index and self._index_ready and self.memory_count > self.centroids_k)   # :259
+
+    def _queries(self, q) -> torch.Tensor:
+        q = self._to_dev_f32(q).detach()
+        if q.dim() == 1:
+            q = q.unsqueeze(0)
+        return q.contiguous()
+
+    def retrieve_batch(self, queries, k: int = 5, location=None, gather: bool = False, force_exact: bool = False):
+        """Batched form of `retrieve_similar_memories`: queries [B,d] -> (rows int64 [B,k'], scores fp32 [B,k'])
+        with k' = min(k, memory_count); missing results are row -1 / score -inf.  `gather=True` also returns the
+        fp32 feature rows [B,k',d] (zeros for missing), replacing memory_augmented_layer.py:124-128."""
+        q = self._queries(queries)
+        m = self.memory_count
+        if m == 0:
+            e = torch.empty(q.shape[0], 0, device=self.device)
+            return (e.long(), e, e.unsqueeze(-1)) if gather else (e.long(), e)
+        kk = min(int(k), m)                                                     # :306
+        if not (1 <= kk <= AURA_MAX_K):
+            raise ValueError(f"k={k} outside [1,{AURA_MAX_K}]")
+        scale, bias = self._row_terms(location)
+        if self._centroid_path() and not force_exact:
+            self._ensure_lists()
+            nprobe = min(self.nprobe, self.centroids_k, self._centroid_buffer_rows())   # :262
+            idx, score = ops.ivf_search(self.memory_features, m, q, self.centroids, nprobe, self._list_offsets,
+                                        self._list_rows, kk, scale, bias)
+        else:
+            idx, score = ops.scan_topk(self.memory_features, q, kk, scale, bias, n_rows=m)
+        if gather:
+            return idx, score, ops.gather_rows(self.memory_features, idx)
+        return idx, score
+
+    def retrieve_similar_memories(self, query_features, location=None, k: int = 5) -> List[Tuple[Union[str, int], float]]:
+        """List[(memory_id, combined score)], best first (hippocampal.py:245-319)."""
+        if self.memory_count == 0:
+            return []                                                           # :251-252
+        idx, score = self.retrieve_batch(query_features, k=k, location=location)
+        rows = idx[0].tolist()
+        scores = score[0].tolist()
+        out: List[Tuple[Union[str, int], float]] = []
+        for r, s in zip(rows, scores):
+            if r < 0:
+                break
+            if not self.track_ids:
+                out.append((r, s))
+                continue
+            owner = self._ids.owner(r)
+            if owner is not None:                                               # :316
+                out.append((owner, s))
+        return out
+
+    def exact_topk(self, queries, k: int = 10, gather: bool = False):
+        """Pure cosine exact top-k, no temporal / strength terms (.tmp_infer_old.py:40-49)."""
+        q = self._queries(queries)
+        m = self.memory_count
+        kk = min(int(k), m)
+        idx, score = ops.scan_topk(self.memory_features, q, kk, self._inv_norm, None, n_rows=m)
+        if gather:
+            return ops.gather_rows(self.memory_features, idx), score, idx
+        return idx, score

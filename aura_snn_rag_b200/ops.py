@@ -135,3 +135,129 @@ def gather_rows(rows: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
     check(_lib.load().aura_gather_rows(rows.data_ptr(), _dtype_code(rows), d, idx.data_ptr(), idx.numel(),
                                        out.data_ptr(), _stream()), "aura_gather_rows")
     return out
+
+
+# ---------------------------------------------------------------------------- bank write
+def bank_write(rows: torch.Tensor, first_row: int, features: torch.Tensor, metadata: torch.Tensor,
+               inv_norm: torch.Tensor, timestamp: float, locations: Optional[torch.Tensor] = None,
+               location: Optional[torch.Tensor] = None) -> None:
+    """Write features [n,d] (fp32, CUDA) into bank rows first_row.. plus metadata / location / inv_norm."""
+    rows = _dev(rows, "rows")
+    features = _dev(features, "features")
+    if features.dtype != torch.float32:
+        raise TypeError("features must be float32")
+    if features.dim() == 1:
+        features = features.unsqueeze(0)
+    n, d = features.shape
+    if d != rows.shape[1]:
+        raise ValueError(f"feature dim {d} != bank dim {rows.shape[1]}")
+    if first_row < 0 or first_row + n > rows.shape[0]:
+        raise IndexError(f"rows [{first_row},{first_row + n}) outside the bank of {rows.shape[0]}")
+    sd = 0 if locations is None else locations.shape[1]
+    check(_lib.load().aura_bank_write(rows.data_ptr(), _dtype_code(rows), d, first_row, n, features.data_ptr(),
+                                      _ptr(locations), sd, _ptr(location), metadata.data_ptr(), float(timestamp),
+                                      inv_norm.data_ptr(), _stream()), "aura_bank_write")
+
+
+# ---------------------------------------------------------------------------- centroid index
+def kmeans_seed(rows: torch.Tensor, seed_rows: torch.Tensor, centroids: torch.Tensor) -> None:
+    rows = _dev(rows, "rows")
+    seed_rows = _dev(seed_rows, "seed_rows")
+    if seed_rows.dtype != torch.int64:
+        raise TypeError("seed_rows must be int64")
+    check(_lib.load().aura_kmeans_seed(rows.data_ptr(), _dtype_code(rows), rows.shape[1], seed_rows.data_ptr(),
+                                       seed_rows.numel(), centroids.data_ptr(), _stream()), "aura_kmeans_seed")
+
+
+def kmeans_assign(rows: torch.Tensor, n_rows: int, centroids: torch.Tensor, n_centroids: int, assign: torch.Tensor,
+                  cid_f32: Optional[torch.Tensor] = None, cid_stride: int = 1,
+                  best: Optional[torch.Tensor] = None) -> None:
+    """assign[i] (int32) = nearest of centroids[:n_centroids]; optional float id written at cid_f32[i*cid_stride]."""
+    rows = _dev(rows, "rows")
+    lib = _lib.load()
+    ws = _workspace(lib.aura_kmeans_assign_workspace_bytes(n_centroids), rows.device, "assign")
+    check(lib.aura_kmeans_assign(rows.data_ptr(), _dtype_code(rows), n_rows, rows.shape[1], centroids.data_ptr(),
+                                 n_centroids, assign.data_ptr(), _ptr(cid_f32), cid_stride, _ptr(best), ws.data_ptr(),
+                                 ws.numel(), _stream()), "aura_kmeans_assign")
+
+
+def ivf_build_lists(cid: torch.Tensor, n_rows: int, n_lists: int, list_offsets: torch.Tensor,
+                    list_rows: torch.Tensor) -> None:
+    cid = _dev(cid, "cid")
+    lib = _lib.load()
+    ws = _workspace(lib.aura_ivf_build_lists_workspace_bytes(n_lists), cid.device, "lists")
+    check(lib.aura_ivf_build_lists(cid.data_ptr(), n_rows, n_lists, list_offsets.data_ptr(), list_rows.data_ptr(),
+                                   ws.data_ptr(), ws.numel(), _stream()), "aura_ivf_build_lists")
+
+
+def kmeans_list_sums(rows: torch.Tensor, list_offsets: torch.Tensor, list_rows: torch.Tensor, n_lists: int,
+                     sums: torch.Tensor, counts: torch.Tensor) -> None:
+    rows = _dev(rows, "rows")
+    check(_lib.load().aura_kmeans_list_sums(rows.data_ptr(), _dtype_code(rows), rows.shape[1], list_offsets.data_ptr(),
+                                            list_rows.data_ptr(), n_lists, sums.data_ptr(), counts.data_ptr(),
+                                            _stream()), "aura_kmeans_list_sums")
+
+
+def kmeans_finalize(sums: torch.Tensor, counts: torch.Tensor, n_centroids: int, centroids: torch.Tensor) -> None:
+    check(_lib.load().aura_kmeans_finalize(sums.data_ptr(), counts.data_ptr(), n_centroids, centroids.shape[1],
+                                           centroids.data_ptr(), _stream()), "aura_kmeans_finalize")
+
+
+def ivf_list_counts(list_offsets: torch.Tensor, n_lists: int, counts_f32: torch.Tensor) -> None:
+    check(_lib.load().aura_ivf_list_counts(list_offsets.data_ptr(), n_lists, counts_f32.data_ptr(), _stream()),
+          "aura_ivf_list_counts")
+
+
+def online_assign(rows: torch.Tensor, first_row: int, n_writes: int, centroids: torch.Tensor, n_live: int,
+                  counts: torch.Tensor, cid_i32: torch.Tensor, cid_f32: Optional[torch.Tensor] = None,
+                  cid_stride: int = 1) -> None:
+    rows = _dev(rows, "rows")
+    lib = _lib.load()
+    ws = _workspace(lib.aura_online_assign_workspace_bytes(), rows.device, "online")
+    check(lib.aura_online_assign(rows.data_ptr(), _dtype_code(rows), rows.shape[1], first_row, n_writes,
+                                 centroids.data_ptr(), n_live, counts.data_ptr(), cid_i32.data_ptr(), _ptr(cid_f32),
+                                 cid_stride, ws.data_ptr(), ws.numel(), _stream()), "aura_online_assign")
+
+
+def ivf_coarse(queries: torch.Tensor, centroids: torch.Tensor, nprobe: int) -> torch.Tensor:
+    queries = _dev(queries, "queries")
+    centroids = _dev(centroids, "centroids")
+    if queries.dim() == 1:
+        queries = queries.unsqueeze(0)
+    b, d = queries.shape
+    c = centroids.shape[0]
+    probes = torch.empty(b, nprobe, dtype=torch.int64, device=queries.device)
+    lib = _lib.load()
+    ws = _workspace(lib.aura_ivf_coarse_workspace_bytes(b, c), queries.device, "coarse")
+    check(lib.aura_ivf_coarse(queries.data_ptr(), b, d, centroids.data_ptr(), c, nprobe, probes.data_ptr(),
+                              ws.data_ptr(), ws.numel(), _stream()), "aura_ivf_coarse")
+    return probes
+
+
+def ivf_search(rows: torch.Tensor, n_rows: int, queries: torch.Tensor, centroids: torch.Tensor, nprobe: int,
+               list_offsets: torch.Tensor, list_rows: torch.Tensor, k: int, scale: Optional[torch.Tensor],
+               bias: Optional[torch.Tensor] = None, row_base: int = 0, return_probes: bool = False):
+    """Centroid-path query: coarse probes + scan of the probed lists.  Returns (idx[B,k], score[B,k][, probes])."""
+    rows = _dev(rows, "rows")
+    queries = _dev(queries, "queries")
+    if queries.dtype != torch.float32:
+        raise TypeError("queries must be float32")
+    if queries.dim() == 1:
+        queries = queries.unsqueeze(0)
+    b, d = queries.shape
+    if rows.shape[1] != d or centroids.shape[1] != d:
+        raise ValueError("query / bank / centroid dims differ")
+    if not (1 <= k <= AURA_MAX_K):
+        raise ValueError(f"k={k} outside [1,{AURA_MAX_K}]")
+    c = centroids.shape[0]
+    dev = rows.device
+    out_idx = torch.empty(b, k, dtype=torch.int64, device=dev)
+    out_score = torch.empty(b, k, dtype=torch.float32, device=dev)
+    probes = torch.empty(b, nprobe, dtype=torch.int64, device=dev) if return_probes else None
+    lib = _lib.load()
+    ws = _workspace(lib.aura_ivf_search_workspace_bytes(b, c, k), dev)
+    check(lib.aura_ivf_search(rows.data_ptr(), _dtype_code(rows), n_rows, d, queries.data_ptr(), b,
+                              centroids.data_ptr(), c, nprobe, list_offsets.data_ptr(), list_rows.data_ptr(),
+                              _ptr(scale), _ptr(bias), k, row_base, out_idx.data_ptr(), out_score.data_ptr(),
+                              _ptr(probes), ws.data_ptr(), ws.numel(), _stream()), "aura_ivf_search")
+    return (out_idx, out_score, probes) if return_probes else (out_idx, out_score)

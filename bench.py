@@ -1,0 +1,373 @@
+#!/usr/bin/env python
+"""bench.py - queries/sec of the episodic-memory retrieval hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B]
+
+Workload (N=1): BASELINE.json configs[1], "C2" - 1 000 000 memories x 768 fp32, exact brute-force
+top-10.  One step = one batch of B (default 1024) queries against the whole bank.  The same JSON
+line also carries the single-query leg of C2 (`single_query`), which is the HBM-bound case.
+N>1: the same bank row-sharded over N ranks (strong scaling), local top-k -> NCCL all-gather ->
+k-way merge on every rank (aura_snn_rag_b200/sharded.py).
+
+Timing: W >= 3 warm-up steps, then K steps between CUDA events on the launching stream, bracketed
+by barrier + synchronize, max over ranks.  The bank (3.07 GB) is far larger than L2 (126 MB), so no
+explicit L2 flush is needed between steps (`config.l2`).  `value` = inputs resident in HBM;
+`e2e` = the same steps through the public Python API with the query batch in pinned host memory
+(H2D inside the timed region) and the result rows / scores read back to the host (D2H inside).
+
+`--impl reference`: the reference's CPU algorithm for the same path - the pinned CPU port
+oracle/hippo_oracle.py (the reference is pure Python/torch and does not travel to the GPU box) -
+on all host threads, one bounded sample of the workload per step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_ROWS, DIM, TOPK = 1_000_000, 768, 10
+SEED_DATA, SEED_QUERY = 1234, 4321
+METRIC = "queries/sec at recall@10>=ref (exact top-10, 1M x 768 fp32)"
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return {"hbm_gbs": float(p["hbm_gbs"]), "bf16_tflops": float(p["bf16_tflops"]),
+                "bf16_tflops_sustained": float(p.get("bf16_tflops_sustained", p["bf16_tflops"])), "source": "measured"}
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------ data
+def make_bank(n_rows, d, device, seed, dtype=torch.float32, chunk=131072):
+    """iid N(0,1) rows generated on the device in chunks (SURVEY.md 8d distribution G)."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    bank = torch.empty(n_rows, d, device=device, dtype=dtype)
+    for r0 in range(0, n_rows, chunk):
+        r1 = min(n_rows, r0 + chunk)
+        bank[r0:r1] = torch.randn(r1 - r0, d, device=device, generator=g).to(dtype)
+    return bank
+
+
+def make_queries(bank_rows_fn, n_total, b, d, seed):
+    """queries = stored row + 0.1 N(0,1), generated on the host (CPU generator)."""
+    g = torch.Generator().manual_seed(seed)
+    pick = torch.randint(0, n_total, (b,), generator=g)
+    noise = 0.1 * torch.randn(b, d, generator=g)
+    return pick, noise
+
+
+# ------------------------------------------------------------------------------------------ reference arm
+def oracle_bank(bank_cpu):
+    from oracle.hippo_oracle import OracleHippocampus
+    n, d = bank_cpu.shape
+    clock = [1.79e9]
+    o = OracleHippocampus(max_memories=n, feature_dim=d, use_centroid_index=False, time_fn=lambda: clock[0])
+    o.memory_features = bank_cpu
+    o.memory_metadata[:, 0] = 1.0
+    o.memory_metadata[:, 1] = clock[0]
+    o.memory_count = n
+    return o
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    g = torch.Generator().manual_seed(SEED_DATA)
+    bank = torch.randn(N_ROWS, DIM, generator=g)
+    o = oracle_bank(bank)
+    gq = torch.Generator().manual_seed(SEED_QUERY)
+    per_step = args.ref_queries_per_step
+    total = (args.steps + args.warmup) * per_step
+    pick = torch.randint(0, N_ROWS, (total,), generator=gq)
+    queries = bank[pick] + 0.1 * torch.randn(total, DIM, generator=gq)
+    qi = 0
+    for _ in range(args.warmup):
+        for _ in range(per_step):
+            o.retrieve_rows(queries[qi], k=TOPK); qi += 1
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        for _ in range(per_step):
+            o.retrieve_rows(queries[qi], k=TOPK); qi += 1
+    dt = time.perf_counter() - t0
+    qps = args.steps * per_step / dt
+    line = {"impl": "reference", "metric": METRIC, "value": qps, "unit": "queries/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "C2: 1M x 768 fp32 exact top-10", "rows": N_ROWS, "d": DIM, "k": TOPK,
+                       "batch": per_step},
+            "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": threads, "kind": "port",
+                             "sample": f"{per_step} single-query retrieve_similar_memories calls per step through the "
+                                       "oracle port of hippocampal.py:245-319 (the reference has no batched entry "
+                                       "point; it re-normalises the whole bank per query)"},
+            "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------ our arm
+def cuda_time_steps(fn, steps, stream_sync, barrier):
+    barrier(); stream_sync()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(steps):
+        fn(i)
+    ev1.record()
+    stream_sync(); barrier()
+    return ev0.elapsed_time(ev1)  # ms
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    from aura_snn_rag_b200 import _lib, ops
+    from aura_snn_rag_b200.hippocampal import HippocampalFormation
+    from aura_snn_rag_b200.sharded import ShardedBank, shard_range
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus != world and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the retrieval path has no CPU implementation")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    peaks = load_peaks()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    def sync():
+        torch.cuda.current_stream().synchronize()
+
+    B, K, W = args.batch, args.steps, max(3, args.warmup)
+    lo, hi = shard_range(N_ROWS, rank, world)
+
+    # ---- bank: written through the public API (bulk write), index disabled = exact path of C2
+    hf = HippocampalFormation(n_place_cells=8, n_time_cells=4, n_grid_cells=4, max_memories=hi - lo, feature_dim=DIM,
+                              device=f"cuda:{local_rank}", use_centroid_index=False, track_ids=False)
+    g = torch.Generator(device=dev).manual_seed(SEED_DATA)
+    chunk = 65536
+    # every rank draws the full stream and keeps its own rows, so the global bank does not depend on N
+    for r0 in range(0, N_ROWS, chunk):
+        r1 = min(N_ROWS, r0 + chunk)
+        blk = torch.randn(r1 - r0, DIM, device=dev, generator=g)
+        a, b = max(r0, lo), min(r1, hi)
+        if a < b:
+            hf.create_episodic_memories(blk[a - r0:b - r0])
+    sync()
+    bank = hf.memory_features
+    shard = ShardedBank(bank, lo, scale=hf._inv_norm)
+
+    # ---- queries: distinct batch per step, pinned host copies for the e2e leg
+    gq = torch.Generator().manual_seed(SEED_QUERY)
+    n_batches = K + W
+    pick = torch.randint(0, N_ROWS, (n_batches, B), generator=gq)
+    noise = 0.1 * torch.randn(n_batches, B, DIM, generator=gq)
+    # stored rows are looked up on the owning rank, then summed across ranks (setup only)
+    q_dev = torch.zeros(n_batches, B, DIM, device=dev)
+    own = (pick >= lo) & (pick < hi)
+    q_dev[own.to(dev)] = bank[(pick[own] - lo).to(dev)]
+    if world > 1:
+        dist.all_reduce(q_dev)
+    q_dev += noise.to(dev)
+    q_host = q_dev.cpu().pin_memory()
+    out_idx_host = torch.empty(B, TOPK, dtype=torch.int64).pin_memory()
+    out_score_host = torch.empty(B, TOPK, dtype=torch.float32).pin_memory()
+
+    # ---- leg 1: resident inputs
+    def step_resident(i):
+        shard.search(q_dev[(W + i) % n_batches], TOPK)
+
+    for i in range(W):
+        shard.search(q_dev[i], TOPK)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = lib.aura_kernel_launches()
+    ms = cuda_time_steps(step_resident, K, sync, barrier)
+    launches = lib.aura_kernel_launches() - l0
+
+    # ---- leg 2: end to end through the public API, host buffers
+    def step_e2e(i):
+        q = q_host[(W + i) % n_batches]          # pinned host memory; the API call does the H2D copy
+        if world == 1:
+            idx, score = hf.exact_topk(q, TOPK)
+        else:
+            idx, score = shard.search(q, TOPK)
+        out_idx_host.copy_(idx, non_blocking=True)
+        out_score_host.copy_(score, non_blocking=True)
+        sync()
+
+    for i in range(2):
+        step_e2e(i)
+    ms_e2e = cuda_time_steps(step_e2e, K, sync, barrier)
+    clocks = sampler.stop() if rank == 0 else None
+
+    t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = t.tolist()
+
+    # ---- correctness guard on the timed configuration: the perturbed stored row must be top-1
+    idx, score = shard.search(q_dev[0], TOPK)
+    hit = float((idx[:, 0].cpu() == pick[0]).float().mean())
+
+    extra = {}
+    if world == 1:
+        # ---- single-query leg of C2 (HBM-bound): one query per launch
+        nq = 40
+        for i in range(5):
+            ops.scan_topk(bank, q_dev[0, i:i + 1], TOPK, hf._inv_norm)
+        evs = []
+        sync()
+        for i in range(nq):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); ops.scan_topk(bank, q_dev[1, i:i + 1], TOPK, hf._inv_norm); e1.record()
+            evs.append((e0, e1))
+        sync()
+        ts = sorted(a.elapsed_time(b) for a, b in evs)
+        sq_ms = sum(ts) / len(ts)
+        sq_bytes = N_ROWS * DIM * 4
+        extra["single_query"] = {
+            "value": 1e3 / sq_ms, "unit": "queries/s", "ms_per_query": sq_ms, "ms_min": ts[0],
+            "roofline": {"bound": "hbm", "achieved": sq_bytes / sq_ms / 1e6, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": sq_bytes / sq_ms / 1e6 / peaks["hbm_gbs"], "frac_of_nominal_8TBs": sq_bytes / sq_ms / 1e6 / 8000.0,
+                         "traffic": None, "kernel": "scan_topk_kernel<f32,QB=1>", "peak_source": peaks["source"]}}
+
+    if rank == 0:
+        qps = B * K / (ms / 1e3)
+        step_ms = ms / K
+        flops = 2.0 * B * N_ROWS * DIM
+        alg_bytes = N_ROWS * DIM * 4
+        # batch kernel: CUDA-core streaming scan, QB queries per pass -> bank re-read B/QB times.  The bound that
+        # applies to the step is the tensor pipe (2*B*N*d flop); achieved is reported against it.
+        tf = flops / (step_ms / 1e3) / 1e12
+        roof = {"bound": "tensor", "achieved": tf, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                "frac": tf / peaks["bf16_tflops_sustained"], "traffic": None, "kernel": args.kernel_name,
+                "algorithmic_flops_per_launch": flops, "algorithmic_bytes_per_launch": alg_bytes,
+                "peak_source": peaks["source"] + " (bf16 sustained)"}
+        line = {"metric": METRIC, "value": qps, "unit": "queries/s", "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "C2: 1M x 768 fp32 exact brute-force top-10, batch of B queries per step",
+                           "rows": N_ROWS, "d": DIM, "k": TOPK, "batch": B, "sharding": f"rows/{world}",
+                           "l2": "bank 3.07 GB >> 126 MB L2, distinct query batch per step; no flush needed"},
+                "e2e": {"value": B * K / (ms_e2e / 1e3), "unit": "queries/s", "ms_per_step": ms_e2e / K,
+                        "h2d_bytes_per_step": B * DIM * 4, "d2h_bytes_per_step": B * TOPK * 12},
+                "gpu_launches": int(launches), "roofline": roof, "clocks": clocks, "top1_hit_rate": hit}
+        line.update(extra)
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(bank, q_dev, args)
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def cpu_baseline(bank_dev, q_dev, args):
+    """The oracle port of the reference's exact path, timed on the host cores on a bounded sample."""
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    bank_cpu = bank_dev.cpu()
+    o = oracle_bank(bank_cpu)
+    qs = q_dev[0, :args.cpu_queries + 1].cpu()
+    o.retrieve_rows(qs[0], k=TOPK)  # warm-up (page-in, thread pool)
+    t0 = time.perf_counter()
+    for i in range(args.cpu_queries):
+        o.retrieve_rows(qs[1 + i], k=TOPK)
+    dt = time.perf_counter() - t0
+    return {"value": args.cpu_queries / dt, "unit": "queries/s", "cores": threads, "kind": "port",
+            "sample": f"{args.cpu_queries} sequential single queries of the same workload through the oracle port of "
+                      f"retrieve_similar_memories (hippocampal.py:245-319), {dt:.1f} s"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=1024)
+    ap.add_argument("--cpu-queries", type=int, default=24)
+    ap.add_argument("--ref-queries-per-step", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--kernel-name", default="scan_topk_kernel<f32,QB=8> (CUDA-core streaming scan)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -46,6 +46,8 @@ enum { AURA_F32 = 0, AURA_BF16 = 1 };
 
 int aura_version(void);
 const char* aura_last_error_string(void);
+/* number of CUDA kernels this library has launched in this process (bench accounting only) */
+uint64_t aura_kernel_launches(void);
 
 /* ---- per-row terms maintained at write time / per query -------------------------------- */
 
@@ -76,6 +78,69 @@ size_t aura_scan_topk_workspace_bytes(int64_t n_rows, int d, int n_queries, int 
 int aura_scan_topk(const void* rows, int dtype, int64_t n_rows, int d, const float* queries, int n_queries,
                    const float* scale, const float* bias, int k, int64_t row_base, int64_t* out_idx,
                    float* out_score, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- memory-bank write (hippocampal.py:207-215) --------------------------------------------
+ * Append/overwrite n_new consecutive bank rows starting at first_row from fp32 `features`
+ * [n_new, d] (device): converts to the bank dtype, writes locations[row] = location (may be NULL
+ * -> zeros), metadata[row] = {1.0, timestamp, -1, 0} and inv_norm[row]. One launch. */
+int aura_bank_write(void* rows, int dtype, int d, int64_t first_row, int n_new, const float* features,
+                    float* locations, int spatial_dims, const float* location, float* metadata, float timestamp,
+                    float* inv_norm, void* stream);
+
+/* ---- centroid index: build (hippocampal.py:345-377) -------------------------------------------
+ * aura_kmeans_seed     centroids[s] = rows[seed_rows[s]]                      (:354-355; the caller
+ *                      supplies randperm(M)[:k], CPU and CUDA generators differ)
+ * aura_kmeans_assign   assign[i] = argmin_c ||rows[i] - centroid_c||  via ||c||^2 - 2 x.c, first
+ *                      minimum on ties (:358-359,:370-371); optionally also writes the id as float
+ *                      into cid_f32[i*cid_stride] (metadata[:,2], :376) and the best score.
+ * aura_ivf_build_lists counting sort of the assignments into CSR inverted lists (replaces the
+ *                      P float-equality mask passes + nonzero of :264-268).
+ * aura_kmeans_list_sums / aura_kmeans_finalize   per-cluster mean, empty clusters keep their seed
+ *                      (:360-363); sums are fp64 so a sharded build can all-reduce them.
+ * aura_ivf_list_counts counts[c] = |list c| as fp32 (:372-374). */
+int aura_kmeans_seed(const void* rows, int dtype, int d, const int64_t* seed_rows, int n_seeds, float* centroids,
+                     void* stream);
+size_t aura_kmeans_assign_workspace_bytes(int n_centroids);
+int aura_kmeans_assign(const void* rows, int dtype, int64_t n_rows, int d, const float* centroids, int n_centroids,
+                       int32_t* assign, float* cid_f32, int cid_stride, float* best_score, void* workspace,
+                       size_t workspace_bytes, void* stream);
+size_t aura_ivf_build_lists_workspace_bytes(int n_lists);
+int aura_ivf_build_lists(const int32_t* cid, int64_t n_rows, int n_lists, int32_t* list_offsets, int32_t* list_rows,
+                         void* workspace, size_t workspace_bytes, void* stream);
+int aura_kmeans_list_sums(const void* rows, int dtype, int d, const int32_t* list_offsets, const int32_t* list_rows,
+                          int n_lists, double* sums, int64_t* counts, void* stream);
+int aura_kmeans_finalize(const double* sums, const int64_t* counts, int n_centroids, int d, float* centroids,
+                         void* stream);
+int aura_ivf_list_counts(const int32_t* list_offsets, int n_lists, float* counts_f32, void* stream);
+
+/* ---- centroid index: one-shot writes (hippocampal.py:218-230) ------------------------------
+ * For each of the n_writes rows first_row .. first_row+n_writes-1, IN ORDER:
+ *   c* = argmin_{c < n_live} ||centroid_c - row||_2 (direct form, first minimum);
+ *   counts[c*] += 1; eta = 1/max(counts[c*],1); centroid_c* = (1-eta) centroid_c* + eta row;
+ *   cid_i32[row] = c*; cid_f32[row*cid_stride] = c*.
+ * Sequential semantics are preserved (write i sees the centroid moved by write i-1). */
+size_t aura_online_assign_workspace_bytes(void);
+int aura_online_assign(const void* rows, int dtype, int d, int64_t first_row, int n_writes, float* centroids,
+                       int n_live, float* counts, int32_t* cid_i32, float* cid_f32, int cid_stride, void* workspace,
+                       size_t workspace_bytes, void* stream);
+
+/* ---- centroid index: query (hippocampal.py:257-307) ------------------------------------------
+ * aura_ivf_coarse: probes[b, 0..nprobe) = the nprobe centroid rows nearest to query b by
+ *   ||centroid_c - q||_2 over ALL n_centroid_rows rows of the buffer (zeroed tail rows included,
+ *   as :261 does), nearest first, ties to the lower row (:262).
+ * aura_ivf_search: coarse + scan of the probed inverted lists with the same score/top-k as
+ *   aura_scan_topk.  A query whose probed lists are all empty scans every row (:269-270).
+ *   Returned indices are bank rows (the reference returns candidate-local positions, :307-317:
+ *   a documented bug this library does not reproduce). */
+size_t aura_ivf_coarse_workspace_bytes(int n_queries, int n_centroid_rows);
+int aura_ivf_coarse(const float* queries, int n_queries, int d, const float* centroids, int n_centroid_rows, int nprobe,
+                    int64_t* probes, void* workspace, size_t workspace_bytes, void* stream);
+size_t aura_ivf_search_workspace_bytes(int n_queries, int n_centroid_rows, int k);
+int aura_ivf_search(const void* rows, int dtype, int64_t n_rows, int d, const float* queries, int n_queries,
+                    const float* centroids, int n_centroid_rows, int nprobe, const int32_t* list_offsets,
+                    const int32_t* list_rows, const float* scale, const float* bias, int k, int64_t row_base,
+                    int64_t* out_idx, float* out_score, int64_t* out_probes, void* workspace, size_t workspace_bytes,
+                    void* stream);
 
 /* ---- k-way merge of per-shard top-k blocks (after the NCCL all-gather) ----------
  * in_score/in_idx: [n_queries, n_lists * k_in] (any order inside a row); out: [n_queries, k_out]. */
