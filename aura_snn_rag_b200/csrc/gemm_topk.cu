@@ -1,0 +1,524 @@
+// K6 / K7 - dense contractions on the 5th-generation tensor cores with a fused per-row top-L epilogue.
+//
+//   aura_batch_topk    (K6)  batched exact search: queries [B,d] x bank [N,d]
+//                            (hippocampal.py:272-307 for a block of queries; the reference loops over
+//                            the batch, memory_augmented_layer.py:113-128)
+//   aura_allpairs_topk (K7)  cognitive map: bank x bank cosine, top-k neighbours per row, self excluded
+//                            (documented in training_recipes.md:292-308, never implemented upstream)
+//
+// One kernel serves both: C[128 x 256] tiles of A[rows_a, d] . B[rows_b, d]^T, both operands K-major.
+//   * TMA (cp.async.bulk.tensor.2d, SWIZZLE_128B) streams 128-byte K-slabs of A (16 KB) and B (32 KB) into a ring;
+//   * one elected thread issues tcgen05.mma (kind::tf32 straight from an fp32 bank, kind::f16 for a bf16 bank),
+//     M=128, N=256, accumulating over K in TMEM; two accumulator stages (2 x 256 columns = all of TMEM) so the
+//     epilogue of tile t overlaps the MMAs of tile t+1;
+//   * 4 epilogue warps read the accumulator with tcgen05.ld (thread = one A row, 32 columns per load), apply the
+//     per-B-row affine terms (scale, bias) and keep a per-A-row top-L list in shared memory behind a register
+//     threshold, so the common case per element is LDS + FFMA + compare.  C is never written to memory.
+//   * A-row tiles x column groups are distributed over a persistent grid; CTAs that share a column range run
+//     concurrently so each B tile is fetched from HBM once and re-read from L2.
+//
+// Exactness (K6): tensor-core scores are only used to SHORTLIST.  The finish kernel merges the per-CTA lists,
+// re-scores the L best candidates of every query in exact fp32 (the same arithmetic, in the same order, as the
+// streaming scan kernel) and certifies the result: every row outside the shortlist has approximate score
+// <= s_L, hence exact score <= s_L + eps; if the exact k-th best beats that, the top-k is provably the exact
+// one, otherwise the query is flagged and the caller re-runs it through the exact scan.
+#include <stdlib.h>
+
+#include "tc_common.cuh"
+
+namespace aura {
+
+static constexpr int GT_BM = 128;            // A rows per tile (TMEM lanes)
+static constexpr int GT_BN = 256;            // B rows per tile (TMEM columns per accumulator stage)
+static constexpr int GT_SLAB = 128;          // bytes of K per pipeline stage (one swizzle atom row)
+static constexpr int GT_A_BYTES = GT_BM * GT_SLAB;   // 16 KB
+static constexpr int GT_B_BYTES = GT_BN * GT_SLAB;   // 32 KB
+static constexpr int GT_STAGE_BYTES = GT_A_BYTES + GT_B_BYTES;
+static constexpr int GT_MAX_STAGES = 4;
+static constexpr int GT_THREADS = 192;       // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
+static constexpr int GT_MAX_L = 64;
+
+struct GemmTopkArgs {
+  int n_atiles, n_ctiles, n_groups;
+  long long n_a_rows, n_b_rows;
+  long long a_row_first;      // global row id of A row 0 (all-pairs: position of the A block inside B)
+  int k_blocks;               // ceil(d / elements per slab)
+  int L;                      // list length per A row
+  int n_stages;
+  int exclude_self;
+  const float* scale;         // per B row, may be null (1)
+  const float* bias;          // per B row, may be null (0)
+  u64* partial;               // [n_atiles * n_groups][L][128]
+};
+
+// thread-private top-L list living in shared memory: list[s*128 + te], the slot of the minimum in min_pos[te]
+__device__ __noinline__ float list_insert(u64* list, int* min_pos, int te, int L, u64 key) {
+  int pos = min_pos[te];
+  const u64 cur = list[pos * GT_BM + te];
+  if (key > cur) {
+    list[pos * GT_BM + te] = key;
+    u64 m = ~0ull;
+#pragma unroll 4
+    for (int s = 0; s < L; ++s) {
+      const u64 v = list[s * GT_BM + te];
+      if (v < m) { m = v; pos = s; }
+    }
+    min_pos[te] = pos;
+    return m ? key_score(m) : -INFINITY;
+  }
+  return cur ? key_score(cur) : -INFINITY;
+}
+
+template <bool TF32>
+__global__ void __launch_bounds__(GT_THREADS, 1)
+gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                 const GemmTopkArgs a) {
+  extern __shared__ unsigned char smem_raw[];
+  // 1024-byte aligned carve-up (SWIZZLE_128B atoms are 1024 B)
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int S = a.n_stages;
+  unsigned char* ring = smem;
+  u64* list = reinterpret_cast<u64*>(ring + (size_t)S * GT_STAGE_BYTES);
+  float2* sbuf = reinterpret_cast<float2*>(list + (size_t)a.L * GT_BM);   // [2][GT_BN] (scale, bias)
+  int* min_pos = reinterpret_cast<int*>(sbuf + 2 * GT_BN);                // [128]
+  uint64_t* full = reinterpret_cast<uint64_t*>(min_pos + GT_BM);
+  uint64_t* empty = full + GT_MAX_STAGES;
+  uint64_t* tfull = empty + GT_MAX_STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int ELEMS_PER_SLAB = TF32 ? 32 : 64;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4); }
+    fence_mbar_init();
+    tc::tma_prefetch_desc(&tmap_a);
+    tc::tma_prefetch_desc(&tmap_b);
+  }
+  if (warp == 1) { tc::tmem_alloc(tmem_slot, 512); tc::tmem_relinquish(); }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int n_items = a.n_atiles * a.n_groups;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      const uint64_t pol_b = l2_policy_evict_first();   // bank tiles stream through
+      const uint64_t pol_a = l2_policy_evict_last();    // the A block is re-read for every column tile
+      int stage = 0; unsigned phase = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int atile = item % a.n_atiles, group = item / a.n_atiles;
+        const int ct0 = (int)(((long long)a.n_ctiles * group) / a.n_groups);
+        const int ct1 = (int)(((long long)a.n_ctiles * (group + 1)) / a.n_groups);
+        for (int ct = ct0; ct < ct1; ++ct) {
+          for (int kb = 0; kb < a.k_blocks; ++kb) {
+            tc::mbar_wait_guarded(&empty[stage], phase ^ 1u);
+            unsigned char* sa = ring + (size_t)stage * GT_STAGE_BYTES;
+            mbar_arrive_expect_tx(&full[stage], GT_STAGE_BYTES);
+            tc::tma_load_2d(sa, &tmap_a, kb * ELEMS_PER_SLAB, atile * GT_BM, &full[stage], pol_a);
+            tc::tma_load_2d(sa + GT_A_BYTES, &tmap_b, kb * ELEMS_PER_SLAB, ct * GT_BN, &full[stage], pol_b);
+            if (++stage == S) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = tc::make_idesc(TF32 ? 2 : 1, GT_BM, GT_BN);
+      int stage = 0; unsigned phase = 0;
+      unsigned tile_n = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int group = item / a.n_atiles;
+        const int ct0 = (int)(((long long)a.n_ctiles * group) / a.n_groups);
+        const int ct1 = (int)(((long long)a.n_ctiles * (group + 1)) / a.n_groups);
+        for (int ct = ct0; ct < ct1; ++ct, ++tile_n) {
+          const unsigned acc = tile_n & 1u, acc_phase = (tile_n >> 1) & 1u;
+          tc::mbar_wait_guarded(&tempty[acc], acc_phase ^ 1u);     // epilogue has drained this accumulator
+          tc::tc_fence_after();
+          const uint32_t d_tmem = tmem_base + acc * GT_BN;
+          for (int kb = 0; kb < a.k_blocks; ++kb) {
+            tc::mbar_wait_guarded(&full[stage], phase);
+            tc::tc_fence_after();
+            const unsigned char* sa = ring + (size_t)stage * GT_STAGE_BYTES;
+            const uint64_t da = tc::make_smem_desc_sw128(sa);
+            const uint64_t db = tc::make_smem_desc_sw128(sa + GT_A_BYTES);
+#pragma unroll
+            for (int j = 0; j < GT_SLAB / 32; ++j)    // 32 bytes of K per instruction: advance the start address
+              tc::umma<TF32>(d_tmem, da + (uint64_t)(2 * j), db + (uint64_t)(2 * j), idesc, (kb | j) != 0 ? 1u : 0u);
+            tc::umma_commit(&empty[stage]);           // frees the smem slot once these MMAs have read it
+            if (++stage == S) { stage = 0; phase ^= 1u; }
+          }
+          tc::umma_commit(&tfull[acc]);               // accumulator complete
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue: 4 warps, thread = one A row =====================
+    const int quarter = warp & 3;                   // TMEM lane quarter this warp may access
+    const int te = quarter * 32 + lane;             // A row inside the tile
+    const int et = threadIdx.x - 64;                // 0..127 among epilogue threads
+    unsigned tile_n = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int atile = item % a.n_atiles, group = item / a.n_atiles;
+      const int ct0 = (int)(((long long)a.n_ctiles * group) / a.n_groups);
+      const int ct1 = (int)(((long long)a.n_ctiles * (group + 1)) / a.n_groups);
+      for (int s = 0; s < a.L; ++s) list[s * GT_BM + te] = 0ull;
+      min_pos[te] = 0;
+      float thr = -INFINITY;
+      const long long my_row = a.a_row_first + (long long)atile * GT_BM + te;   // global id of this A row
+      for (int ct = ct0; ct < ct1; ++ct, ++tile_n) {
+        const unsigned acc = tile_n & 1u, acc_phase = (tile_n >> 1) & 1u;
+        const long long col0 = (long long)ct * GT_BN;
+        // stage the per-column terms of this tile (invalid columns -> NaN score, never selected)
+        float2* sb = sbuf + acc * GT_BN;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int c = et + h * 128;
+          const long long gc = col0 + c;
+          float2 t;
+          if (gc < a.n_b_rows) { t.x = a.scale ? a.scale[gc] : 1.f; t.y = a.bias ? a.bias[gc] : 0.f; }
+          else { t.x = 0.f; t.y = __int_as_float(0x7fc00000); }
+          sb[c] = t;
+        }
+        tc::named_bar_sync(1, 128);
+        tc::mbar_wait_guarded(&tfull[acc], acc_phase);
+        tc::tc_fence_after();
+        const bool diag = a.exclude_self && my_row >= col0 && my_row < col0 + GT_BN;
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * GT_BN;
+#pragma unroll 1
+        for (int c0 = 0; c0 < GT_BN; c0 += 32) {
+          float v[32];
+          tc::tmem_ld_32x32(taddr + c0, v);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float2 t = sb[c0 + j];
+            const float s = fmaf(v[j], t.x, t.y);
+            if (s >= thr) {
+              const long long gc = col0 + c0 + j;
+              if (!(diag && gc == my_row)) thr = list_insert(list, min_pos, te, a.L, make_key(s, (unsigned)gc));
+            }
+          }
+        }
+        tc::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[acc]);
+      }
+      // flush this item's lists: partial[item][s][te]
+      u64* dst = a.partial + (size_t)item * a.L * GT_BM;
+      for (int s = 0; s < a.L; ++s) dst[s * GT_BM + te] = list[s * GT_BM + te];
+    }
+  }
+  __syncthreads();
+  if (warp == 1) { tc::tc_fence_after(); tc::tmem_dealloc(tmem_base, 512); }
+}
+
+// ---- query preparation: qn = q / max(||q||, 1e-12) (F.normalize, hippocampal.py:273), optional bf16 copy ----
+__global__ void __launch_bounds__(256) normalize_queries_kernel(const float* __restrict__ q, int n, int d,
+                                                                float* __restrict__ qn, __nv_bfloat16* __restrict__ qb) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= n) return;
+  const float* x = q + (size_t)w * d;
+  float ss = 0.f;
+  for (int e = lane; e < d; e += 32) ss = fmaf(x[e], x[e], ss);
+  const float denom = fmaxf(sqrtf(warp_sum(ss)), 1e-12f);
+  for (int e = lane; e < d; e += 32) {
+    const float v = x[e] / denom;
+    qn[(size_t)w * d + e] = v;
+    if (qb) qb[(size_t)w * d + e] = __float2bfloat16_rn(v);
+  }
+}
+
+// ---- finish: merge the per-group lists of one A row; K6: exact re-score + certification ----
+struct FinishArgs {
+  const u64* partial; int n_atiles, n_groups, L, n2;   // n2 = pow2 >= n_groups*L
+  int k;
+  long long n_a_rows;
+  long long row_base;
+  // re-score (K6) - null rows => no re-score (K7)
+  const void* rows; int bf16; int d;
+  const float* qn; const float* scale; const float* bias; float eps;
+  const float* a_scale;      // K7: output score multiplier per A row (inv_norm of the row), may be null
+  long long* out_idx; float* out_score; int* uncertain;
+};
+
+__global__ void __launch_bounds__(128) gemm_topk_finish_kernel(const FinishArgs f) {
+  extern __shared__ __align__(16) unsigned char fsm[];
+  u64* keys = reinterpret_cast<u64*>(fsm);              // [n2]
+  u64* ex = keys + f.n2;                                // [GT_MAX_L] exact keys
+  const long long b = blockIdx.x;
+  const int atile = (int)(b / GT_BM), r = (int)(b % GT_BM);
+  const int n_in = f.n_groups * f.L;
+  for (int i = threadIdx.x; i < f.n2; i += blockDim.x) {
+    u64 key = 0ull;
+    if (i < n_in) {
+      const int g = i / f.L, s = i % f.L;
+      key = f.partial[((size_t)(g * f.n_atiles + atile) * f.L + s) * GT_BM + r];
+    }
+    keys[i] = key;
+  }
+  block_bitonic_sort_desc(keys, f.n2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (f.rows == nullptr) {
+    const float mul = f.a_scale ? f.a_scale[b] : 1.f;
+    for (int i = threadIdx.x; i < f.k; i += blockDim.x) {
+      const u64 key = i < f.n2 ? keys[i] : 0ull;
+      f.out_idx[b * f.k + i] = key ? f.row_base + (long long)key_row(key) : -1ll;
+      f.out_score[b * f.k + i] = key ? key_score(key) * mul : -INFINITY;
+    }
+    return;
+  }
+  // exact fp32 re-score of the L best candidates, one warp per candidate; same operation order as
+  // scan_topk.cu (lane-strided 128-bit chunks, fmaf nest, xor-tree warp sum) so both paths agree bit for bit
+  const int n_cand = min(f.L, f.n2);
+  const float* q = f.qn + (size_t)b * f.d;
+  for (int c = warp; c < GT_MAX_L; c += 4) {
+    u64 key = 0ull;
+    if (c < n_cand && keys[c] != 0ull) {
+      const unsigned row = key_row(keys[c]);
+      float acc = 0.f;
+      if (f.bf16) {
+        const uint4* x8 = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(f.rows) + (size_t)row * f.d);
+        const float4* q4 = reinterpret_cast<const float4*>(q);
+        for (int ch = lane; ch < (f.d >> 3); ch += 32) {
+          const uint4 x = x8[ch];
+          const float4 qa = q4[2 * ch], qb = q4[2 * ch + 1];
+          acc = fmaf(bf16_lo(x.x), qa.x, acc); acc = fmaf(bf16_hi(x.x), qa.y, acc);
+          acc = fmaf(bf16_lo(x.y), qa.z, acc); acc = fmaf(bf16_hi(x.y), qa.w, acc);
+          acc = fmaf(bf16_lo(x.z), qb.x, acc); acc = fmaf(bf16_hi(x.z), qb.y, acc);
+          acc = fmaf(bf16_lo(x.w), qb.z, acc); acc = fmaf(bf16_hi(x.w), qb.w, acc);
+        }
+      } else {
+        const float4* x4 = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(f.rows) + (size_t)row * f.d);
+        const float4* q4 = reinterpret_cast<const float4*>(q);
+        for (int ch = lane; ch < (f.d >> 2); ch += 32) {
+          const float4 x = x4[ch], qq = q4[ch];
+          acc = fmaf(x.x, qq.x, fmaf(x.y, qq.y, fmaf(x.z, qq.z, fmaf(x.w, qq.w, acc))));
+        }
+      }
+      const float dot = warp_sum(acc);
+      const float sc = f.scale ? f.scale[row] : 1.f, bi = f.bias ? f.bias[row] : 0.f;
+      key = make_key(fmaf(dot, sc, bi), row);
+    }
+    if (lane == 0) ex[c] = key;
+  }
+  block_bitonic_sort_desc(ex, GT_MAX_L);
+  for (int i = threadIdx.x; i < f.k; i += blockDim.x) {
+    const u64 key = i < GT_MAX_L ? ex[i] : 0ull;
+    f.out_idx[b * f.k + i] = key ? f.row_base + (long long)key_row(key) : -1ll;
+    f.out_score[b * f.k + i] = key ? key_score(key) : -INFINITY;
+  }
+  if (threadIdx.x == 0 && f.uncertain) {
+    // rows outside the shortlist have approximate score <= s_L (the L-th best approximate score)
+    int flag = 0;
+    if (f.L - 1 < f.n2 && keys[f.L - 1] != 0ull) {
+      const float bound = key_score(keys[f.L - 1]) + f.eps;
+      const u64 kth = ex[f.k - 1];
+      if (kth == 0ull || !(key_score(kth) > bound)) flag = 1;
+    }
+    f.uncertain[b] = flag;
+  }
+}
+
+// ---- host ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+int encode_tmap_2d(CUtensorMap* map, const void* base, int elem_bytes, bool bf16, long long n_rows, int d, int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  AURA_REQUIRE(fn != nullptr, AURA_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  const cuuint64_t gdim[2] = {(cuuint64_t)d, (cuuint64_t)n_rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)d * elem_bytes};
+  const cuuint32_t box[2] = {(cuuint32_t)(GT_SLAB / elem_bytes), (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = fn(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                        const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  AURA_REQUIRE(r == CUDA_SUCCESS, AURA_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return AURA_OK;
+}
+
+struct GemmPlan {
+  int n_atiles, n_ctiles, n_groups, grid, L, n_stages, k_blocks, n2;
+  size_t smem, partial_bytes;
+};
+
+static int list_len(int k, bool rescore) {
+  int L = rescore ? k + 14 : k;      // shortlist margin for the certified re-score
+  L = (L + 7) / 8 * 8;
+  return L > GT_MAX_L ? GT_MAX_L : L;
+}
+
+static bool make_gemm_plan(long long n_a_rows, long long n_b_rows, int d, int elem_bytes, int k, bool rescore, GemmPlan* p) {
+  p->L = list_len(k, rescore);
+  if (p->L < k) return false;
+  p->n_atiles = (int)((n_a_rows + GT_BM - 1) / GT_BM);
+  p->n_ctiles = (int)((n_b_rows + GT_BN - 1) / GT_BN);
+  const int sms = sm_count();
+  int groups = sms / p->n_atiles;
+  if (groups < 1) groups = 1;
+  if (groups > p->n_ctiles) groups = p->n_ctiles;
+  if (const char* e = getenv("AURA_GEMM_GROUPS")) { const int v = atoi(e); if (v >= 1 && v <= p->n_ctiles) groups = v; }
+  p->n_groups = groups;
+  const long long items = (long long)p->n_atiles * groups;
+  p->grid = (int)(items < sms ? items : sms);
+  const int elems = GT_SLAB / elem_bytes;
+  p->k_blocks = (d + elems - 1) / elems;
+  const size_t fixed = (size_t)p->L * GT_BM * 8 + 2 * GT_BN * 8 + GT_BM * 4 + (2 * GT_MAX_STAGES + 4) * 8 + 16;
+  const size_t cap = (size_t)max_smem_optin() - 1024 /* alignment slack */;
+  int stages = (int)((cap - fixed) / GT_STAGE_BYTES);
+  if (stages > GT_MAX_STAGES) stages = GT_MAX_STAGES;
+  if (const char* e = getenv("AURA_GEMM_STAGES")) { const int v = atoi(e); if (v >= 2 && v <= stages) stages = v; }
+  if (stages < 2) return false;
+  p->n_stages = stages;
+  p->smem = (size_t)stages * GT_STAGE_BYTES + fixed + 1024;
+  p->partial_bytes = (size_t)items * p->L * GT_BM * 8;
+  int n2 = 2;
+  while (n2 < groups * p->L) n2 <<= 1;
+  p->n2 = n2;
+  return ((size_t)n2 + GT_MAX_L) * 8 <= cap;
+}
+
+static size_t align256(size_t v) { return (v + 255) / 256 * 256; }
+
+static int run_gemm_topk(const void* a_mat, long long n_a_rows, long long a_row_first, const void* b_mat, long long n_b_rows,
+                         int d, bool bf16, const float* scale, const float* bias, bool exclude_self, const GemmPlan& p,
+                         u64* partial, cudaStream_t st) {
+  const int eb = bf16 ? 2 : 4;
+  CUtensorMap ta, tb;
+  int rc = encode_tmap_2d(&ta, a_mat, eb, bf16, n_a_rows, d, GT_BM);
+  if (rc != AURA_OK) return rc;
+  rc = encode_tmap_2d(&tb, b_mat, eb, bf16, n_b_rows, d, GT_BN);
+  if (rc != AURA_OK) return rc;
+  GemmTopkArgs a;
+  a.n_atiles = p.n_atiles; a.n_ctiles = p.n_ctiles; a.n_groups = p.n_groups;
+  a.n_a_rows = n_a_rows; a.n_b_rows = n_b_rows; a.a_row_first = a_row_first;
+  a.k_blocks = p.k_blocks; a.L = p.L; a.n_stages = p.n_stages; a.exclude_self = exclude_self ? 1 : 0;
+  a.scale = scale; a.bias = bias; a.partial = partial;
+  if (bf16) {
+    AURA_CUDA_OK(cudaFuncSetAttribute(gemm_topk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+    gemm_topk_kernel<false><<<p.grid, GT_THREADS, p.smem, st>>>(ta, tb, a);
+  } else {
+    AURA_CUDA_OK(cudaFuncSetAttribute(gemm_topk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+    gemm_topk_kernel<true><<<p.grid, GT_THREADS, p.smem, st>>>(ta, tb, a);
+  }
+  AURA_CUDA_OK(cudaGetLastError());
+  note_launches(1);
+  return AURA_OK;
+}
+
+static int check_shapes(const char* who, const void* rows, int dtype, long long n_rows, int d, int k) {
+  AURA_REQUIRE(dtype == AURA_F32 || dtype == AURA_BF16, AURA_ERR_INVALID_ARG, "%s: bad dtype %d", who, dtype);
+  AURA_REQUIRE(n_rows >= 1 && n_rows < 0xFFFFFFFFll && d >= 1, AURA_ERR_INVALID_ARG, "%s: n_rows=%lld d=%d", who, n_rows, d);
+  AURA_REQUIRE(k >= 1 && k <= GT_MAX_L, AURA_ERR_INVALID_ARG, "%s: k=%d not in [1,%d]", who, k, GT_MAX_L);
+  const int eb = dtype == AURA_BF16 ? 2 : 4;
+  AURA_REQUIRE(((size_t)d * eb) % 16 == 0 && (reinterpret_cast<uintptr_t>(rows) & 15) == 0, AURA_ERR_UNSUPPORTED,
+               "%s: rows must be 16-byte aligned with a 16-byte multiple row pitch (d=%d)", who, d);
+  return AURA_OK;
+}
+
+}  // namespace aura
+using namespace aura;
+
+extern "C" size_t aura_batch_topk_workspace_bytes(int64_t n_rows, int d, int dtype, int n_queries, int k) {
+  GemmPlan p;
+  if (n_queries < 1 || n_rows < 1 || d < 1 || k < 1) return 0;
+  if (!make_gemm_plan(n_queries, n_rows, d, dtype == AURA_BF16 ? 2 : 4, k, true, &p)) return 0;
+  return align256(p.partial_bytes) + align256((size_t)n_queries * d * 4) + align256((size_t)n_queries * d * 2) + 256;
+}
+
+extern "C" int aura_batch_topk(const void* rows, int dtype, int64_t n_rows, int d, const float* queries, int n_queries,
+                               const float* scale, const float* bias, int k, int64_t row_base, float eps,
+                               int64_t* out_idx, float* out_score, int32_t* out_uncertain, void* workspace,
+                               size_t workspace_bytes, void* stream) {
+  int rc = check_shapes("aura_batch_topk", rows, dtype, n_rows, d, k);
+  if (rc != AURA_OK) return rc;
+  AURA_REQUIRE(n_queries >= 1 && queries && out_idx && out_score && workspace, AURA_ERR_INVALID_ARG,
+               "aura_batch_topk: null pointer / n_queries=%d", n_queries);
+  AURA_REQUIRE(k + 1 <= GT_MAX_L, AURA_ERR_INVALID_ARG, "aura_batch_topk: k=%d too large for the certified shortlist", k);
+  const bool bf16 = dtype == AURA_BF16;
+  GemmPlan p;
+  AURA_REQUIRE(make_gemm_plan(n_queries, n_rows, d, bf16 ? 2 : 4, k, true, &p), AURA_ERR_UNSUPPORTED,
+               "aura_batch_topk: no plan for n_queries=%d k=%d", n_queries, k);
+  AURA_REQUIRE(workspace_bytes >= aura_batch_topk_workspace_bytes(n_rows, d, dtype, n_queries, k), AURA_ERR_WORKSPACE,
+               "aura_batch_topk: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned char* ws = reinterpret_cast<unsigned char*>(workspace);
+  u64* partial = reinterpret_cast<u64*>(ws);
+  float* qn = reinterpret_cast<float*>(ws + align256(p.partial_bytes));
+  __nv_bfloat16* qb = bf16 ? reinterpret_cast<__nv_bfloat16*>(ws + align256(p.partial_bytes) + align256((size_t)n_queries * d * 4))
+                           : nullptr;
+  normalize_queries_kernel<<<(n_queries + 7) / 8, 256, 0, st>>>(queries, n_queries, d, qn, qb);
+  note_launches(1);
+  rc = run_gemm_topk(bf16 ? (const void*)qb : (const void*)qn, n_queries, 0, rows, n_rows, d, bf16, scale, bias, false, p,
+                     partial, st);
+  if (rc != AURA_OK) return rc;
+  FinishArgs f;
+  f.partial = partial; f.n_atiles = p.n_atiles; f.n_groups = p.n_groups; f.L = p.L; f.n2 = p.n2; f.k = k;
+  f.n_a_rows = n_queries; f.row_base = row_base; f.rows = rows; f.bf16 = bf16 ? 1 : 0; f.d = d; f.qn = qn;
+  f.scale = scale; f.bias = bias; f.eps = eps; f.a_scale = nullptr;
+  f.out_idx = reinterpret_cast<long long*>(out_idx); f.out_score = out_score; f.uncertain = out_uncertain;
+  const size_t fsmem = ((size_t)p.n2 + GT_MAX_L) * 8;
+  AURA_CUDA_OK(cudaFuncSetAttribute(gemm_topk_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+  gemm_topk_finish_kernel<<<n_queries, 128, fsmem, st>>>(f);
+  AURA_CUDA_OK(cudaGetLastError());
+  note_launches(1);
+  return AURA_OK;
+}
+
+extern "C" size_t aura_allpairs_topk_workspace_bytes(int64_t n_a_rows, int64_t n_rows, int d, int dtype, int k) {
+  GemmPlan p;
+  if (n_a_rows < 1 || n_rows < 1 || d < 1 || k < 1) return 0;
+  if (!make_gemm_plan(n_a_rows, n_rows, d, dtype == AURA_BF16 ? 2 : 4, k, false, &p)) return 0;
+  return align256(p.partial_bytes) + 256;
+}
+
+extern "C" int aura_allpairs_topk(const void* rows, int dtype, int64_t n_rows, int d, int64_t a_row_first,
+                                  int64_t n_a_rows, const float* inv_norm, int k, int64_t* out_idx, float* out_score,
+                                  void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_shapes("aura_allpairs_topk", rows, dtype, n_rows, d, k);
+  if (rc != AURA_OK) return rc;
+  AURA_REQUIRE(a_row_first >= 0 && n_a_rows >= 1 && a_row_first + n_a_rows <= n_rows, AURA_ERR_INVALID_ARG,
+               "aura_allpairs_topk: A block [%lld,+%lld) outside the bank", (long long)a_row_first, (long long)n_a_rows);
+  AURA_REQUIRE(out_idx && out_score && workspace, AURA_ERR_INVALID_ARG, "aura_allpairs_topk: null pointer");
+  const bool bf16 = dtype == AURA_BF16;
+  GemmPlan p;
+  AURA_REQUIRE(make_gemm_plan(n_a_rows, n_rows, d, bf16 ? 2 : 4, k, false, &p), AURA_ERR_UNSUPPORTED,
+               "aura_allpairs_topk: no plan for k=%d", k);
+  AURA_REQUIRE(workspace_bytes >= aura_allpairs_topk_workspace_bytes(n_a_rows, n_rows, d, dtype, k), AURA_ERR_WORKSPACE,
+               "aura_allpairs_topk: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  u64* partial = reinterpret_cast<u64*>(workspace);
+  const unsigned char* a_mat = reinterpret_cast<const unsigned char*>(rows) + (size_t)a_row_first * d * (bf16 ? 2 : 4);
+  rc = run_gemm_topk(a_mat, n_a_rows, a_row_first, rows, n_rows, d, bf16, inv_norm, nullptr, true, p, partial, st);
+  if (rc != AURA_OK) return rc;
+  FinishArgs f;
+  f.partial = partial; f.n_atiles = p.n_atiles; f.n_groups = p.n_groups; f.L = p.L; f.n2 = p.n2; f.k = k;
+  f.n_a_rows = n_a_rows; f.row_base = 0; f.rows = nullptr; f.bf16 = 0; f.d = d; f.qn = nullptr;
+  f.scale = nullptr; f.bias = nullptr; f.eps = 0.f; f.a_scale = inv_norm ? inv_norm + a_row_first : nullptr;
+  f.out_idx = reinterpret_cast<long long*>(out_idx); f.out_score = out_score; f.uncertain = nullptr;
+  const size_t fsmem = ((size_t)p.n2 + GT_MAX_L) * 8;
+  AURA_CUDA_OK(cudaFuncSetAttribute(gemm_topk_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+  gemm_topk_finish_kernel<<<(unsigned)n_a_rows, 128, fsmem, st>>>(f);
+  AURA_CUDA_OK(cudaGetLastError());
+  note_launches(1);
+  return AURA_OK;
+}

@@ -261,3 +261,77 @@ def ivf_search(rows: torch.Tensor, n_rows: int, queries: torch.Tensor, centroids
                               _ptr(scale), _ptr(bias), k, row_base, out_idx.data_ptr(), out_score.data_ptr(),
                               _ptr(probes), ws.data_ptr(), ws.numel(), _stream()), "aura_ivf_search")
     return (out_idx, out_score, probes) if return_probes else (out_idx, out_score)
+
+
+# ---------------------------------------------------------------------------- tensor-core paths
+TC_EPS_COS = 2.0 ** -9 + 1e-4   # |tensor-core cosine - fp32 cosine| bound: both operands rounded to 11 bits + fp32 sums
+
+
+def batch_topk_supported(rows: torch.Tensor, k: int) -> bool:
+    return (rows.shape[1] * rows.element_size()) % 16 == 0 and rows.data_ptr() % 16 == 0 and 1 <= k <= 50
+
+
+def batch_topk(rows: torch.Tensor, queries: torch.Tensor, k: int, scale: Optional[torch.Tensor],
+               bias: Optional[torch.Tensor] = None, n_rows: Optional[int] = None, row_base: int = 0,
+               eps: float = TC_EPS_COS) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """Tensor-core shortlist + exact fp32 re-score.  Returns (idx[B,k], score[B,k], uncertain[B] int32)."""
+    rows = _dev(rows, "rows")
+    queries = _dev(queries, "queries")
+    if queries.dtype != torch.float32:
+        raise TypeError("queries must be float32")
+    b, d = queries.shape
+    n = rows.shape[0] if n_rows is None else int(n_rows)
+    dev = rows.device
+    out_idx = torch.empty(b, k, dtype=torch.int64, device=dev)
+    out_score = torch.empty(b, k, dtype=torch.float32, device=dev)
+    flags = torch.empty(b, dtype=torch.int32, device=dev)
+    lib = _lib.load()
+    code = _dtype_code(rows)
+    nbytes = lib.aura_batch_topk_workspace_bytes(n, d, code, b, k)
+    if nbytes == 0:
+        raise _lib.AuraLibraryError(f"aura_batch_topk: unsupported shape n={n} d={d} B={b} k={k}")
+    ws = _workspace(nbytes, dev, "batch")
+    check(lib.aura_batch_topk(rows.data_ptr(), code, n, d, queries.data_ptr(), b, _ptr(scale), _ptr(bias), k, row_base,
+                              float(eps), out_idx.data_ptr(), out_score.data_ptr(), flags.data_ptr(), ws.data_ptr(),
+                              ws.numel(), _stream()), "aura_batch_topk")
+    return out_idx, out_score, flags
+
+
+def exact_topk_batched(rows: torch.Tensor, queries: torch.Tensor, k: int, scale: Optional[torch.Tensor],
+                       bias: Optional[torch.Tensor] = None, n_rows: Optional[int] = None, row_base: int = 0,
+                       eps: float = TC_EPS_COS, stats: Optional[dict] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Exact top-k of a query block: tensor-core pass, then the exact streaming scan for the (rare) queries
+    whose result could not be certified.  One small D2H read (the flag count) per call."""
+    idx, score, flags = batch_topk(rows, queries, k, scale, bias, n_rows, row_base, eps)
+    bad = torch.nonzero(flags, as_tuple=False).squeeze(-1)
+    if stats is not None:
+        stats["uncertain"] = stats.get("uncertain", 0) + int(bad.numel())
+    if bad.numel() > 0:
+        i2, s2 = scan_topk(rows, queries[bad].contiguous(), k, scale, bias, n_rows=n_rows, row_base=row_base)
+        idx[bad] = i2
+        score[bad] = s2
+    return idx, score
+
+
+def allpairs_topk(rows: torch.Tensor, k: int = 32, inv_norm: Optional[torch.Tensor] = None,
+                  n_rows: Optional[int] = None, a_first: int = 0, n_a: Optional[int] = None
+                  ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Cognitive map: top-k cosine neighbours (self excluded) of rows[a_first:a_first+n_a] within rows[:n_rows]."""
+    rows = _dev(rows, "rows")
+    n = rows.shape[0] if n_rows is None else int(n_rows)
+    na = n - a_first if n_a is None else int(n_a)
+    d = rows.shape[1]
+    dev = rows.device
+    if inv_norm is None:
+        inv_norm = row_inv_norms(rows)
+    out_idx = torch.empty(na, k, dtype=torch.int64, device=dev)
+    out_score = torch.empty(na, k, dtype=torch.float32, device=dev)
+    lib = _lib.load()
+    code = _dtype_code(rows)
+    nbytes = lib.aura_allpairs_topk_workspace_bytes(na, n, d, code, k)
+    if nbytes == 0:
+        raise _lib.AuraLibraryError(f"aura_allpairs_topk: unsupported shape n={n} d={d} k={k}")
+    ws = _workspace(nbytes, dev, "allpairs")
+    check(lib.aura_allpairs_topk(rows.data_ptr(), code, n, d, a_first, na, inv_norm.data_ptr(), k, out_idx.data_ptr(),
+                                 out_score.data_ptr(), ws.data_ptr(), ws.numel(), _stream()), "aura_allpairs_topk")
+    return out_idx, out_score

@@ -142,6 +142,28 @@ int aura_ivf_search(const void* rows, int dtype, int64_t n_rows, int d, const fl
                     int64_t* out_idx, float* out_score, int64_t* out_probes, void* workspace, size_t workspace_bytes,
                     void* stream);
 
+/* ---- batched exact search on the tensor cores (the batch the reference loops over one query at a
+ * time, memory_augmented_layer.py:113-128; score of hippocampal.py:272-307) -------------------
+ * Same result contract as aura_scan_topk.  tcgen05 (tf32 from an fp32 bank, bf16 from a bf16 bank) scores
+ * every (query,row) pair and keeps a per-query shortlist; the shortlist is re-scored in exact fp32 and the
+ * result certified: out_uncertain[b] = 0 means the top-k of query b is provably the exact fp32 top-k given
+ * that tensor-core scores are within `eps` (score units) of the exact ones; 1 means the caller must re-run
+ * query b through aura_scan_topk.  Needs d*sizeof(elem) % 16 == 0 and k <= 63. */
+size_t aura_batch_topk_workspace_bytes(int64_t n_rows, int d, int dtype, int n_queries, int k);
+int aura_batch_topk(const void* rows, int dtype, int64_t n_rows, int d, const float* queries, int n_queries,
+                    const float* scale, const float* bias, int k, int64_t row_base, float eps, int64_t* out_idx,
+                    float* out_score, int32_t* out_uncertain, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- cognitive map: all-pairs cosine + top-k neighbours per row, self excluded ---------------------
+ * (training_recipes.md:292-308; README.md:39,64 - documented upstream, never implemented.)
+ * For the A block rows[a_row_first, a_row_first+n_a_rows): out_idx/out_score [n_a_rows, k] = the k rows of
+ * the whole bank with the largest cos(row_i, row_j) = dot * inv_norm[i] * inv_norm[j], j != i, best first.
+ * The A block argument is what a row-sharded build passes per GPU. k <= 64. */
+size_t aura_allpairs_topk_workspace_bytes(int64_t n_a_rows, int64_t n_rows, int d, int dtype, int k);
+int aura_allpairs_topk(const void* rows, int dtype, int64_t n_rows, int d, int64_t a_row_first, int64_t n_a_rows,
+                       const float* inv_norm, int k, int64_t* out_idx, float* out_score, void* workspace,
+                       size_t workspace_bytes, void* stream);
+
 /* ---- k-way merge of per-shard top-k blocks (after the NCCL all-gather) ----------
  * in_score/in_idx: [n_queries, n_lists * k_in] (any order inside a row); out: [n_queries, k_out]. */
 int aura_topk_merge(const float* in_score, const int64_t* in_idx, int n_queries, int n_lists, int k_in,

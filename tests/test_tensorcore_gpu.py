@@ -1,0 +1,102 @@
+"""GPU parity of the tcgen05 paths: aura_batch_topk (K6) and aura_allpairs_topk (K7) against the CPU oracle.
+
+K6 bar: identical to the exact scan - rows equal except at score ties, scores within 1e-4 relative (fp32 bank);
+queries the kernel cannot certify must be flagged (never silently wrong).
+K7 bar (bf16 bank, fp32 accumulate): scores within 1e-2 (north_star), neighbour sets equal except near-ties.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle.hippo_oracle import cognitive_map_topk, exact_cosine_topk
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _ops():
+    from aura_snn_rag_b200 import ops
+    return ops
+
+
+@pytest.mark.parametrize("n,d,b,k", [
+    (3000, 64, 5, 10), (5000, 768, 130, 10), (20000, 768, 64, 10), (1000, 32, 3, 5), (4097, 100, 17, 7),
+    (70000, 256, 300, 10), (300, 768, 200, 32),
+])
+def test_batch_topk_fp32_equals_oracle(n, d, b, k):
+    ops = _ops()
+    g = torch.Generator().manual_seed(n + d + b)
+    bank = torch.randn(n, d, generator=g)
+    q = bank[torch.randint(0, n, (b,), generator=g)] + 0.1 * torch.randn(b, d, generator=g)
+    ref_i, ref_s = exact_cosine_topk(bank, q, k)
+    rows = bank.to(DEV)
+    inv = ops.row_inv_norms(rows)
+    idx, sc, flags = ops.batch_topk(rows, q.to(DEV), k, inv)
+    torch.cuda.synchronize()
+    idx, sc, flags = idx.cpu(), sc.cpu(), flags.cpu()
+    sure = flags == 0
+    assert sure.float().mean() > 0.5          # certification must not be vacuous on Gaussian data
+    np.testing.assert_allclose(sc[sure].numpy(), ref_s[sure].numpy(), rtol=1e-4, atol=1e-6)
+    mism = (idx[sure] != ref_i[sure])
+    if mism.any():   # only swaps between (near-)equal scores
+        assert np.all(np.abs(sc[sure][mism].numpy() - ref_s[sure][mism].numpy()) <= 2e-6)
+    # the full path (fallback for flagged queries) equals the scan path exactly
+    i2, s2 = ops.exact_topk_batched(rows, q.to(DEV), k, inv)
+    i3, s3 = ops.scan_topk(rows, q.to(DEV), k, inv)
+    assert torch.equal(i2, i3) and torch.equal(s2, s3)
+
+
+def test_batch_topk_affine_terms_bf16_and_row_base():
+    ops = _ops()
+    g = torch.Generator().manual_seed(11)
+    n, d, b, k = 9000, 128, 40, 10
+    bank = torch.randn(n, d, generator=g)
+    q = torch.randn(b, d, generator=g)
+    strength = 0.5 + 0.5 * torch.rand(n, generator=g)
+    bias = (0.2 * torch.rand(n, generator=g) * strength).to(DEV)
+    for dt in (torch.float32, torch.bfloat16):
+        rows = bank.to(DEV).to(dt)
+        inv = ops.row_inv_norms(rows)
+        scale = 0.5 * strength.to(DEV) * inv
+        i1, s1 = ops.exact_topk_batched(rows, q.to(DEV), k, scale, bias, row_base=1 << 33, eps=0.5 * ops.TC_EPS_COS)
+        i2, s2 = ops.scan_topk(rows, q.to(DEV), k, scale, bias, row_base=1 << 33)
+        assert torch.equal(i1, i2) and torch.equal(s1, s2)
+
+
+def test_batch_topk_flags_uncertain_results():
+    """Near-duplicate rows make the shortlist margin collapse: the kernel must say so."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(2)
+    base = torch.randn(1, 64, generator=g)
+    bank = base + 1e-4 * torch.randn(5000, 64, generator=g)      # 5000 rows within 1e-4 of each other
+    rows = bank.to(DEV)
+    inv = ops.row_inv_norms(rows)
+    q = base.to(DEV).repeat(4, 1)
+    _, _, flags = ops.batch_topk(rows, q, 10, inv)
+    assert flags.cpu().sum() == 4
+    i1, s1 = ops.exact_topk_batched(rows, q, 10, inv)
+    i2, s2 = ops.scan_topk(rows, q, 10, inv)
+    assert torch.equal(i1, i2) and torch.equal(s1, s2)
+
+
+@pytest.mark.parametrize("n,d,k,dt", [(2000, 64, 8, torch.bfloat16), (5000, 768, 32, torch.bfloat16),
+                                      (3001, 128, 32, torch.float32), (40000, 256, 32, torch.bfloat16)])
+def test_allpairs_topk_matches_oracle(n, d, k, dt):
+    ops = _ops()
+    g = torch.Generator().manual_seed(n + k)
+    centres = torch.randn(64, d, generator=g)
+    bank = (centres[torch.randint(0, 64, (n,), generator=g)] + 0.7 * torch.randn(n, d, generator=g)).to(dt)
+    ref_i, ref_s = cognitive_map_topk(bank.float(), k)
+    rows = bank.to(DEV)
+    idx, sc = ops.allpairs_topk(rows, k)
+    torch.cuda.synchronize()
+    idx, sc = idx.cpu(), sc.cpu()
+    tol = 1e-2 if dt == torch.bfloat16 else 3e-3      # bf16 bar of the north star; tf32 from an fp32 bank
+    np.testing.assert_allclose(sc.numpy(), ref_s.numpy(), atol=tol, rtol=0)
+    assert (idx != torch.arange(n).unsqueeze(1)).all()          # self excluded
+    overlap = np.mean([len(set(a) & set(b)) / k for a, b in zip(idx.tolist(), ref_i.tolist())])
+    assert overlap > (0.99 if dt == torch.bfloat16 else 0.97), overlap
+    # sharded call: an A block in the middle of the bank gives the same rows of the result
+    a0, na = n // 3, 257
+    idx2, sc2 = ops.allpairs_topk(rows, k, a_first=a0, n_a=na)
+    assert torch.equal(idx2.cpu(), idx[a0:a0 + na]) and torch.equal(sc2.cpu(), sc[a0:a0 + na])
