@@ -36,6 +36,7 @@ static constexpr int GT_B_BYTES = GT_BN * GT_SLAB;   // 32 KB
 static constexpr int GT_STAGE_BYTES = GT_A_BYTES + GT_B_BYTES;
 static constexpr int GT_MAX_STAGES = 4;
 static constexpr int GT_THREADS = 192;       // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
+static constexpr int GT_L = 32;             // per-row list length kept by the epilogue (registers)
 static constexpr int GT_MAX_L = 64;
 
 struct GemmTopkArgs {
@@ -51,22 +52,28 @@ struct GemmTopkArgs {
   u64* partial;               // [n_atiles * n_groups][L][128]
 };
 
-// thread-private top-L list living in shared memory: list[s*128 + te], the slot of the minimum in min_pos[te]
-__device__ __noinline__ float list_insert(u64* list, int* min_pos, int te, int L, u64 key) {
-  int pos = min_pos[te];
-  const u64 cur = list[pos * GT_BM + te];
-  if (key > cur) {
-    list[pos * GT_BM + te] = key;
-    u64 m = ~0ull;
-#pragma unroll 4
-    for (int s = 0; s < L; ++s) {
-      const u64 v = list[s * GT_BM + te];
-      if (v < m) { m = v; pos = s; }
-    }
-    min_pos[te] = pos;
-    return m ? key_score(m) : -INFINITY;
+// v[j] for a run-time j without spilling v[] to local memory: 5-level select tree
+__device__ __forceinline__ float select32(const float (&v)[32], int j) {
+  float a[16], b[8], c[4];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) a[i] = (j & 16) ? v[i + 16] : v[i];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) b[i] = (j & 8) ? a[i + 8] : a[i];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) c[i] = (j & 4) ? b[i + 4] : b[i];
+  const float d0 = (j & 2) ? c[2] : c[0], d1 = (j & 2) ? c[3] : c[1];
+  return (j & 1) ? d1 : d0;
+}
+
+// thread-private top-GT_L list, sorted descending, entirely in registers.  All compares are independent
+// (key > e[i] is monotone in i), so an insertion is ~GT_L predicated moves with no dependent chain.
+__device__ __forceinline__ void list_insert_sorted(u64 (&e)[GT_L], u64 key) {
+#pragma unroll
+  for (int i = GT_L - 1; i >= 1; --i) {
+    const bool ci = key > e[i], cp = key > e[i - 1];
+    e[i] = ci ? (cp ? e[i - 1] : key) : e[i];
   }
-  return cur ? key_score(cur) : -INFINITY;
+  e[0] = key > e[0] ? key : e[0];
 }
 
 template <bool TF32>
@@ -78,10 +85,8 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int S = a.n_stages;
   unsigned char* ring = smem;
-  u64* list = reinterpret_cast<u64*>(ring + (size_t)S * GT_STAGE_BYTES);
-  float2* sbuf = reinterpret_cast<float2*>(list + (size_t)a.L * GT_BM);   // [2][GT_BN] (scale, bias)
-  int* min_pos = reinterpret_cast<int*>(sbuf + 2 * GT_BN);                // [128]
-  uint64_t* full = reinterpret_cast<uint64_t*>(min_pos + GT_BM);
+  float2* sbuf = reinterpret_cast<float2*>(ring + (size_t)S * GT_STAGE_BYTES);   // [2][GT_BN] (scale, bias)
+  uint64_t* full = reinterpret_cast<uint64_t*>(sbuf + 2 * GT_BN);
   uint64_t* empty = full + GT_MAX_STAGES;
   uint64_t* tfull = empty + GT_MAX_STAGES;
   uint64_t* tempty = tfull + 2;
@@ -168,10 +173,12 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const int atile = item % a.n_atiles, group = item / a.n_atiles;
       const int ct0 = (int)(((long long)a.n_ctiles * group) / a.n_groups);
       const int ct1 = (int)(((long long)a.n_ctiles * (group + 1)) / a.n_groups);
-      for (int s = 0; s < a.L; ++s) list[s * GT_BM + te] = 0ull;
-      min_pos[te] = 0;
-      float thr = -INFINITY;
+      u64 e[GT_L];
+#pragma unroll
+      for (int s = 0; s < GT_L; ++s) e[s] = 0ull;
       const long long my_row = a.a_row_first + (long long)atile * GT_BM + te;   // global id of this A row
+      const bool live = (long long)atile * GT_BM + te < a.n_a_rows;
+      float thr = live ? -INFINITY : INFINITY;        // rows past the end of A never select anything
       for (int ct = ct0; ct < ct1; ++ct, ++tile_n) {
         const unsigned acc = tile_n & 1u, acc_phase = (tile_n >> 1) & 1u;
         const long long col0 = (long long)ct * GT_BN;
@@ -195,13 +202,23 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         for (int c0 = 0; c0 < GT_BN; c0 += 32) {
           float v[32];
           tc::tmem_ld_32x32(taddr + c0, v);
+          unsigned mask = 0u;
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const float2 t = sb[c0 + j];
-            const float s = fmaf(v[j], t.x, t.y);
-            if (s >= thr) {
-              const long long gc = col0 + c0 + j;
-              if (!(diag && gc == my_row)) thr = list_insert(list, min_pos, te, a.L, make_key(s, (unsigned)gc));
+            mask |= (fmaf(v[j], t.x, t.y) >= thr) ? (1u << j) : 0u;
+          }
+          if (diag) { const long long dj = my_row - col0 - c0; if (dj >= 0 && dj < 32) mask &= ~(1u << (int)dj); }
+          // rare path; the loop runs max-over-lanes popcount(mask) times for the warp
+          while (mask) {
+            const int j = __ffs(mask) - 1;
+            mask &= mask - 1u;
+            const float2 t = sb[c0 + j];
+            const float sc = fmaf(select32(v, j), t.x, t.y);
+            const u64 key = make_key(sc, (unsigned)(col0 + c0 + j));
+            if (key > e[GT_L - 1]) {
+              list_insert_sorted(e, key);
+              if (e[GT_L - 1] != 0ull) thr = key_score(e[GT_L - 1]);
             }
           }
         }
@@ -209,9 +226,10 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty[acc]);
       }
-      // flush this item's lists: partial[item][s][te]
-      u64* dst = a.partial + (size_t)item * a.L * GT_BM;
-      for (int s = 0; s < a.L; ++s) dst[s * GT_BM + te] = list[s * GT_BM + te];
+      // flush this item's list: partial[item][s][te]
+      u64* dst = a.partial + (size_t)item * GT_L * GT_BM;
+#pragma unroll
+      for (int s = 0; s < GT_L; ++s) dst[s * GT_BM + te] = e[s];
     }
   }
   __syncthreads();
@@ -362,14 +380,13 @@ struct GemmPlan {
 };
 
 static int list_len(int k, bool rescore) {
-  int L = rescore ? k + 14 : k;      // shortlist margin for the certified re-score
-  L = (L + 7) / 8 * 8;
-  return L > GT_MAX_L ? GT_MAX_L : L;
+  // K6 keeps a margin of >= 14 candidates beyond k for the certified re-score; K7 needs exactly k
+  return (rescore ? k + 14 : k) <= GT_L ? GT_L : 0;
 }
 
 static bool make_gemm_plan(long long n_a_rows, long long n_b_rows, int d, int elem_bytes, int k, bool rescore, GemmPlan* p) {
   p->L = list_len(k, rescore);
-  if (p->L < k) return false;
+  if (p->L == 0) return false;
   p->n_atiles = (int)((n_a_rows + GT_BM - 1) / GT_BM);
   p->n_ctiles = (int)((n_b_rows + GT_BN - 1) / GT_BN);
   const int sms = sm_count();
@@ -382,7 +399,7 @@ static bool make_gemm_plan(long long n_a_rows, long long n_b_rows, int d, int el
   p->grid = (int)(items < sms ? items : sms);
   const int elems = GT_SLAB / elem_bytes;
   p->k_blocks = (d + elems - 1) / elems;
-  const size_t fixed = (size_t)p->L * GT_BM * 8 + 2 * GT_BN * 8 + GT_BM * 4 + (2 * GT_MAX_STAGES + 4) * 8 + 16;
+  const size_t fixed = 2 * GT_BN * 8 + (2 * GT_MAX_STAGES + 4) * 8 + 16;
   const size_t cap = (size_t)max_smem_optin() - 1024 /* alignment slack */;
   int stages = (int)((cap - fixed) / GT_STAGE_BYTES);
   if (stages > GT_MAX_STAGES) stages = GT_MAX_STAGES;
@@ -428,7 +445,7 @@ static int run_gemm_topk(const void* a_mat, long long n_a_rows, long long a_row_
 static int check_shapes(const char* who, const void* rows, int dtype, long long n_rows, int d, int k) {
   AURA_REQUIRE(dtype == AURA_F32 || dtype == AURA_BF16, AURA_ERR_INVALID_ARG, "%s: bad dtype %d", who, dtype);
   AURA_REQUIRE(n_rows >= 1 && n_rows < 0xFFFFFFFFll && d >= 1, AURA_ERR_INVALID_ARG, "%s: n_rows=%lld d=%d", who, n_rows, d);
-  AURA_REQUIRE(k >= 1 && k <= GT_MAX_L, AURA_ERR_INVALID_ARG, "%s: k=%d not in [1,%d]", who, k, GT_MAX_L);
+  AURA_REQUIRE(k >= 1 && k <= GT_L, AURA_ERR_INVALID_ARG, "%s: k=%d not in [1,%d]", who, k, GT_L);
   const int eb = dtype == AURA_BF16 ? 2 : 4;
   AURA_REQUIRE(((size_t)d * eb) % 16 == 0 && (reinterpret_cast<uintptr_t>(rows) & 15) == 0, AURA_ERR_UNSUPPORTED,
                "%s: rows must be 16-byte aligned with a 16-byte multiple row pitch (d=%d)", who, d);
@@ -453,7 +470,7 @@ extern "C" int aura_batch_topk(const void* rows, int dtype, int64_t n_rows, int 
   if (rc != AURA_OK) return rc;
   AURA_REQUIRE(n_queries >= 1 && queries && out_idx && out_score && workspace, AURA_ERR_INVALID_ARG,
                "aura_batch_topk: null pointer / n_queries=%d", n_queries);
-  AURA_REQUIRE(k + 1 <= GT_MAX_L, AURA_ERR_INVALID_ARG, "aura_batch_topk: k=%d too large for the certified shortlist", k);
+  AURA_REQUIRE(k + 14 <= GT_L, AURA_ERR_UNSUPPORTED, "aura_batch_topk: k=%d too large for the certified shortlist (max %d)", k, GT_L - 14);
   const bool bf16 = dtype == AURA_BF16;
   GemmPlan p;
   AURA_REQUIRE(make_gemm_plan(n_queries, n_rows, d, bf16 ? 2 : 4, k, true, &p), AURA_ERR_UNSUPPORTED,

@@ -335,10 +335,26 @@ class HippocampalFormation(nn.Module):
             idx, score = ops.ivf_search(self.memory_features, m, q, self.centroids, nprobe, self._list_offsets,
                                         self._list_rows, kk, scale, bias)
         else:
-            idx, score = ops.scan_topk(self.memory_features, q, kk, scale, bias, n_rows=m)
+            idx, score = self._exact(q, kk, scale, bias, 0.5 * self._max_strength())
         if gather:
             return idx, score, ops.gather_rows(self.memory_features, idx)
         return idx, score
+
+    def _max_strength(self) -> float:
+        """Upper bound of the live strengths (the tensor-core error bound scales with it); cached per version."""
+        if getattr(self, "_max_strength_key", None) != self._version:
+            self._max_strength_val = float(self.memory_metadata[:self.memory_count, 0].abs().max()) if self.memory_count else 1.0
+            self._max_strength_key = self._version
+        return self._max_strength_val
+
+    def _exact(self, q: torch.Tensor, k: int, scale, bias, score_per_cos: float):
+        """Exact top-k of a query block over all live rows: tcgen05 shortlist + exact fp32 re-score for blocks of
+        >= TC_MIN_BATCH queries (identical results to the scan, see ops.exact_topk_batched), else the streaming scan."""
+        m = self.memory_count
+        if q.shape[0] >= ops.TC_MIN_BATCH and ops.batch_topk_supported(self.memory_features, k) and m >= 1024:
+            return ops.exact_topk_batched(self.memory_features, q, k, scale, bias, n_rows=m,
+                                          eps=ops.TC_EPS_COS * score_per_cos)
+        return ops.scan_topk(self.memory_features, q, k, scale, bias, n_rows=m)
 
     def retrieve_similar_memories(self, query_features, location=None, k: int = 5) -> List[Tuple[Union[str, int], float]]:
         """List[(memory_id, combined score)], best first (hippocampal.py:245-319)."""
@@ -364,7 +380,44 @@ class HippocampalFormation(nn.Module):
         q = self._queries(queries)
         m = self.memory_count
         kk = min(int(k), m)
-        idx, score = ops.scan_topk(self.memory_features, q, kk, self._inv_norm, None, n_rows=m)
+        idx, score = self._exact(q, kk, self._inv_norm, None, 1.0)
         if gather:
             return ops.gather_rows(self.memory_features, idx), score, idx
         return idx, score
+
+    # ------------------------------------------------------------------ cognitive map
+    def build_cognitive_map(self, k: int = 32) -> Tuple[torch.Tensor, torch.Tensor]:
+        """All-pairs cosine similarity of the live memories, top-k neighbours per memory, self excluded
+        (the O(n^2) "cognitive map" of README.md:39,64 / training_recipes.md:292-308, which the reference
+        documents but never implements).  Returns (neighbour rows int64 [M,k'], similarities fp32 [M,k']),
+        best first, k' = min(k, M-1); one tcgen05 GEMM with the top-k fused into its epilogue."""
+        m = self.memory_count
+        kk = min(int(k), m - 1)
+        if kk < 1:
+            e = torch.empty(m, 0, device=self.device)
+            self._cmap = (e.long(), e)
+            return self._cmap
+        nbr, sim = ops.allpairs_topk(self.memory_features, kk, self._inv_norm, n_rows=m)
+        self._cmap = (nbr, sim)
+        self._cmap_version = self._version
+        return nbr, sim
+
+    @property
+    def cognitive_map(self) -> Dict[Tuple[Union[str, int], Union[str, int]], float]:
+        """{(memory_id_i, memory_id_j): distance}, distance = 1 - cosine, over the k-NN edges - the view
+        training_recipes.md:292-308 reads.  Host-side dict: meant for inspection-sized banks."""
+        if getattr(self, "_cmap", None) is None or getattr(self, "_cmap_version", None) != self._version:
+            self.build_cognitive_map()
+        nbr, sim = (t.cpu() for t in self._cmap)
+        out: Dict[Tuple[Union[str, int], Union[str, int]], float] = {}
+        for i in range(nbr.shape[0]):
+            a = self._ids.owner(i) if self.track_ids else i
+            if a is None:
+                continue
+            for j, s in zip(nbr[i].tolist(), sim[i].tolist()):
+                if j < 0:
+                    continue
+                b = self._ids.owner(j) if self.track_ids else j
+                if b is not None:
+                    out[(a, b)] = 1.0 - s
+        return out

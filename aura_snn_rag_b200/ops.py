@@ -264,11 +264,13 @@ def ivf_search(rows: torch.Tensor, n_rows: int, queries: torch.Tensor, centroids
 
 
 # ---------------------------------------------------------------------------- tensor-core paths
+TC_MAX_K = 18                  # aura_batch_topk keeps 32 candidates per query: k + 14 <= 32
+TC_MIN_BATCH = 8               # below this the CUDA-core streaming scan is faster (measured on B200)
 TC_EPS_COS = 2.0 ** -9 + 1e-4   # |tensor-core cosine - fp32 cosine| bound: both operands rounded to 11 bits + fp32 sums
 
 
 def batch_topk_supported(rows: torch.Tensor, k: int) -> bool:
-    return (rows.shape[1] * rows.element_size()) % 16 == 0 and rows.data_ptr() % 16 == 0 and 1 <= k <= 50
+    return (rows.shape[1] * rows.element_size()) % 16 == 0 and rows.data_ptr() % 16 == 0 and 1 <= k <= TC_MAX_K
 
 
 def batch_topk(rows: torch.Tensor, queries: torch.Tensor, k: int, scale: Optional[torch.Tensor],

@@ -226,7 +226,11 @@ def run_ours(args):
             hf.create_episodic_memories(blk[a - r0:b - r0])
     sync()
     bank = hf.memory_features
-    shard = ShardedBank(bank, lo, scale=hf._inv_norm)
+    def local_search(q, k):            # the product's exact path: tcgen05 shortlist + fp32 re-score (+ scan fallback)
+        return ops.exact_topk_batched(bank, q, k, hf._inv_norm, None, n_rows=hi - lo, row_base=lo, stats=stats)
+
+    stats = {}
+    shard = ShardedBank(bank, lo, scale=hf._inv_norm, local_search=local_search, merge=ops.topk_merge)
 
     # ---- queries: distinct batch per step, pinned host copies for the e2e leg
     gq = torch.Generator().manual_seed(SEED_QUERY)
@@ -309,22 +313,26 @@ def run_ours(args):
         step_ms = ms / K
         flops = 2.0 * B * N_ROWS * DIM
         alg_bytes = N_ROWS * DIM * 4
-        # batch kernel: CUDA-core streaming scan, QB queries per pass -> bank re-read B/QB times.  The bound that
-        # applies to the step is the tensor pipe (2*B*N*d flop); achieved is reported against it.
-        tf = flops / (step_ms / 1e3) / 1e12
+        # dominant kernel: gemm_topk_kernel<tf32> (one launch per step; > 95 % of the step, see profiles/).
+        # It reads the fp32 bank as TF32, whose dense peak is half the bf16 peak: `peak` is the measured
+        # sustained bf16 cuBLAS figure (the contract's denominator), frac_of_tf32_peak halves it.
+        tf = flops / world / (step_ms / 1e3) / 1e12
         roof = {"bound": "tensor", "achieved": tf, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                "frac": tf / peaks["bf16_tflops_sustained"], "traffic": None, "kernel": args.kernel_name,
-                "algorithmic_flops_per_launch": flops, "algorithmic_bytes_per_launch": alg_bytes,
-                "peak_source": peaks["source"] + " (bf16 sustained)"}
+                "frac": tf / peaks["bf16_tflops_sustained"],
+                "frac_of_tf32_peak": tf / (0.5 * peaks["bf16_tflops_sustained"]), "traffic": None,
+                "kernel": args.kernel_name, "algorithmic_flops_per_launch": flops / world,
+                "algorithmic_bytes_per_launch": alg_bytes / world, "timing": "whole step (kernel share in profiles/)",
+                "peak_source": peaks["source"] + " (bf16 sustained; tf32 dense peak = half)"}
         line = {"metric": METRIC, "value": qps, "unit": "queries/s", "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-                "dtype": "f32", "data": "synthetic",
+                "dtype": "f32 (tf32 tensor-core shortlist, exact fp32 re-score, certified)", "data": "synthetic",
                 "config": {"workload": "C2: 1M x 768 fp32 exact brute-force top-10, batch of B queries per step",
                            "rows": N_ROWS, "d": DIM, "k": TOPK, "batch": B, "sharding": f"rows/{world}",
                            "l2": "bank 3.07 GB >> 126 MB L2, distinct query batch per step; no flush needed"},
                 "e2e": {"value": B * K / (ms_e2e / 1e3), "unit": "queries/s", "ms_per_step": ms_e2e / K,
                         "h2d_bytes_per_step": B * DIM * 4, "d2h_bytes_per_step": B * TOPK * 12},
-                "gpu_launches": int(launches), "roofline": roof, "clocks": clocks, "top1_hit_rate": hit}
+                "gpu_launches": int(launches), "roofline": roof, "clocks": clocks, "top1_hit_rate": hit,
+                "uncertified_queries_rerun": int(stats.get("uncertain", 0))}
         line.update(extra)
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(bank, q_dev, args)
@@ -361,7 +369,7 @@ def main():
     ap.add_argument("--cpu-queries", type=int, default=24)
     ap.add_argument("--ref-queries-per-step", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--kernel-name", default="scan_topk_kernel<f32,QB=8> (CUDA-core streaming scan)")
+    ap.add_argument("--kernel-name", default="gemm_topk_kernel<tf32> (tcgen05 M128 N256, fused top-32) + exact fp32 re-score")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

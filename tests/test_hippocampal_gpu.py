@@ -203,3 +203,27 @@ def test_bulk_write_equals_sequential_writes(monkeypatch):
     assert torch.equal(a.memory_metadata[:700], b.memory_metadata[:700])
     q = rows[5] + 0.05
     assert a.retrieve_similar_memories(q, k=7) == b.retrieve_similar_memories(q, k=7)
+
+
+def test_cognitive_map_api_matches_oracle():
+    """cognitive_map (training_recipes.md:292-308): k-NN edges with distance = 1 - cosine."""
+    from aura_snn_rag_b200 import HippocampalFormation
+    from oracle.hippo_oracle import cognitive_map_dict, cognitive_map_topk
+    g = torch.Generator().manual_seed(21)
+    n, d, k = 300, 64, 8
+    rows = torch.randn(n, d, generator=g)
+    hf = HippocampalFormation(max_memories=512, feature_dim=d, n_place_cells=4, n_time_cells=2, n_grid_cells=2,
+                              use_centroid_index=False)
+    ids = [f"mem{i}" for i in range(n)]
+    hf.create_episodic_memories(rows, ids)
+    nbr, sim = hf.build_cognitive_map(k)
+    ref_i, ref_s = cognitive_map_topk(rows, k)
+    np.testing.assert_allclose(sim.cpu().numpy(), ref_s.numpy(), atol=3e-3)       # tf32 products, fp32 bank
+    assert np.mean([len(set(a) & set(b)) / k for a, b in zip(nbr.cpu().tolist(), ref_i.tolist())]) > 0.97
+    cmap = hf.cognitive_map
+    ref = cognitive_map_dict(ids, ref_i, ref_s)
+    common = set(cmap) & set(ref)
+    assert len(common) > 0.97 * len(ref)
+    assert max(abs(cmap[p] - ref[p]) for p in common) < 3e-3
+    closest = min(cmap.items(), key=lambda kv: kv[1])
+    assert closest[1] >= -1e-3 and closest[0][0] != closest[0][1]

@@ -21,7 +21,7 @@ def _ops():
 
 @pytest.mark.parametrize("n,d,b,k", [
     (3000, 64, 5, 10), (5000, 768, 130, 10), (20000, 768, 64, 10), (1000, 32, 3, 5), (4097, 100, 17, 7),
-    (70000, 256, 300, 10), (300, 768, 200, 32),
+    (70000, 256, 300, 10), (300, 768, 200, 18),
 ])
 def test_batch_topk_fp32_equals_oracle(n, d, b, k):
     ops = _ops()
@@ -44,6 +44,15 @@ def test_batch_topk_fp32_equals_oracle(n, d, b, k):
     i2, s2 = ops.exact_topk_batched(rows, q.to(DEV), k, inv)
     i3, s3 = ops.scan_topk(rows, q.to(DEV), k, inv)
     assert torch.equal(i2, i3) and torch.equal(s2, s3)
+
+
+def test_batch_topk_rejects_k_beyond_the_certified_shortlist():
+    ops = _ops()
+    rows = torch.randn(500, 64, device=DEV)
+    assert not ops.batch_topk_supported(rows, 19) and ops.batch_topk_supported(rows, 18)
+    from aura_snn_rag_b200._lib import AuraLibraryError
+    with pytest.raises(AuraLibraryError):
+        ops.batch_topk(rows, rows[:4].contiguous(), 19, None)
 
 
 def test_batch_topk_affine_terms_bf16_and_row_base():
