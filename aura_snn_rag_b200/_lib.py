@@ -34,8 +34,8 @@ SIGNATURES = {
     "aura_scan_topk": (_i, [_p, _i, _i64, _i, _p, _i, _p, _p, _i, _i64, _p, _p, _p, _sz, _p]),
     "aura_bank_write": (_i, [_p, _i, _i, _i64, _i, _p, _p, _i, _p, _p, _f, _p, _p]),
     "aura_kmeans_seed": (_i, [_p, _i, _i, _p, _i, _p, _p]),
-    "aura_kmeans_assign_workspace_bytes": (_sz, [_i]),
-    "aura_kmeans_assign": (_i, [_p, _i, _i64, _i, _p, _i, _p, _p, _i, _p, _p, _sz, _p]),
+    "aura_kmeans_assign_workspace_bytes": (_sz, [_i64, _i, _i, _i]),
+    "aura_kmeans_assign": (_i, [_p, _i, _i64, _i, _p, _i, _p, _p, _p, _i, _p, _p, _sz, _p]),
     "aura_ivf_build_lists_workspace_bytes": (_sz, [_i]),
     "aura_ivf_build_lists": (_i, [_p, _i64, _i, _p, _p, _p, _sz, _p]),
     "aura_kmeans_list_sums": (_i, [_p, _i, _i, _p, _p, _i, _p, _p, _p]),
@@ -43,9 +43,9 @@ SIGNATURES = {
     "aura_ivf_list_counts": (_i, [_p, _i, _p, _p]),
     "aura_online_assign_workspace_bytes": (_sz, []),
     "aura_online_assign": (_i, [_p, _i, _i, _i64, _i, _p, _i, _p, _p, _p, _i, _p, _sz, _p]),
-    "aura_ivf_coarse_workspace_bytes": (_sz, [_i, _i]),
+    "aura_ivf_coarse_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "aura_ivf_coarse": (_i, [_p, _i, _i, _p, _i, _i, _p, _p, _sz, _p]),
-    "aura_ivf_search_workspace_bytes": (_sz, [_i, _i, _i]),
+    "aura_ivf_search_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "aura_ivf_search": (_i, [_p, _i, _i64, _i, _p, _i, _p, _i, _i, _p, _p, _p, _p, _i, _i64, _p, _p, _p, _p, _sz, _p]),
     "aura_batch_topk_workspace_bytes": (_sz, [_i64, _i, _i, _i, _i]),
     "aura_batch_topk": (_i, [_p, _i, _i64, _i, _p, _i, _p, _p, _i, _i64, _f, _p, _p, _p, _p, _sz, _p]),

@@ -33,6 +33,9 @@ int launch_scan(const void* rows, int dtype, long long n_rows, int d, const floa
                 void* workspace, const long long* probes, int nprobe, int n_lists, const int* list_offsets,
                 const int* list_rows, long long expected_rows, cudaStream_t st);
 
+// kmeans.cu: out[i] = ||x_i||^2 for n fp32 rows
+void launch_row_sq_norms(const float* x, int n, int d, float* out, cudaStream_t st);
+
 #define AURA_CUDA_OK(expr)                                                        \
   do {                                                                            \
     cudaError_t _e = (expr);                                                      \

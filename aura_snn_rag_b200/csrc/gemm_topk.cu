@@ -37,6 +37,7 @@ static constexpr int GT_STAGE_BYTES = GT_A_BYTES + GT_B_BYTES;
 static constexpr int GT_MAX_STAGES = 4;
 static constexpr int GT_THREADS = 192;       // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
 static constexpr int GT_L = 32;             // per-row list length kept by the epilogue (registers)
+static constexpr int GT_L_ASSIGN = 4;       // list length of the nearest-centroid variant
 static constexpr int GT_MAX_L = 64;
 
 struct GemmTopkArgs {
@@ -67,16 +68,17 @@ __device__ __forceinline__ float select32(const float (&v)[32], int j) {
 
 // thread-private top-GT_L list, sorted descending, entirely in registers.  All compares are independent
 // (key > e[i] is monotone in i), so an insertion is ~GT_L predicated moves with no dependent chain.
-__device__ __forceinline__ void list_insert_sorted(u64 (&e)[GT_L], u64 key) {
+template <int L>
+__device__ __forceinline__ void list_insert_sorted(u64 (&e)[L], u64 key) {
 #pragma unroll
-  for (int i = GT_L - 1; i >= 1; --i) {
+  for (int i = L - 1; i >= 1; --i) {
     const bool ci = key > e[i], cp = key > e[i - 1];
     e[i] = ci ? (cp ? e[i - 1] : key) : e[i];
   }
   e[0] = key > e[0] ? key : e[0];
 }
 
-template <bool TF32>
+template <bool TF32, int L>
 __global__ void __launch_bounds__(GT_THREADS, 1)
 gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const GemmTopkArgs a) {
@@ -173,9 +175,9 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const int atile = item % a.n_atiles, group = item / a.n_atiles;
       const int ct0 = (int)(((long long)a.n_ctiles * group) / a.n_groups);
       const int ct1 = (int)(((long long)a.n_ctiles * (group + 1)) / a.n_groups);
-      u64 e[GT_L];
+      u64 e[L];
 #pragma unroll
-      for (int s = 0; s < GT_L; ++s) e[s] = 0ull;
+      for (int s = 0; s < L; ++s) e[s] = 0ull;
       const long long my_row = a.a_row_first + (long long)atile * GT_BM + te;   // global id of this A row
       const bool live = (long long)atile * GT_BM + te < a.n_a_rows;
       float thr = live ? -INFINITY : INFINITY;        // rows past the end of A never select anything
@@ -216,9 +218,9 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             const float2 t = sb[c0 + j];
             const float sc = fmaf(select32(v, j), t.x, t.y);
             const u64 key = make_key(sc, (unsigned)(col0 + c0 + j));
-            if (key > e[GT_L - 1]) {
-              list_insert_sorted(e, key);
-              if (e[GT_L - 1] != 0ull) thr = key_score(e[GT_L - 1]);
+            if (key > e[L - 1]) {
+              list_insert_sorted<L>(e, key);
+              if (e[L - 1] != 0ull) thr = key_score(e[L - 1]);
             }
           }
         }
@@ -227,9 +229,9 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         if (lane == 0) mbar_arrive(&tempty[acc]);
       }
       // flush this item's list: partial[item][s][te]
-      u64* dst = a.partial + (size_t)item * GT_L * GT_BM;
+      u64* dst = a.partial + (size_t)item * L * GT_BM;
 #pragma unroll
-      for (int s = 0; s < GT_L; ++s) dst[s * GT_BM + te] = e[s];
+      for (int s = 0; s < L; ++s) dst[s * GT_BM + te] = e[s];
     }
   }
   __syncthreads();
@@ -384,8 +386,9 @@ static int list_len(int k, bool rescore) {
   return (rescore ? k + 14 : k) <= GT_L ? GT_L : 0;
 }
 
-static bool make_gemm_plan(long long n_a_rows, long long n_b_rows, int d, int elem_bytes, int k, bool rescore, GemmPlan* p) {
-  p->L = list_len(k, rescore);
+static bool make_gemm_plan(long long n_a_rows, long long n_b_rows, int d, int elem_bytes, int k, bool rescore, GemmPlan* p,
+                           int force_L = 0, int force_groups = 0) {
+  p->L = force_L ? force_L : list_len(k, rescore);
   if (p->L == 0) return false;
   p->n_atiles = (int)((n_a_rows + GT_BM - 1) / GT_BM);
   p->n_ctiles = (int)((n_b_rows + GT_BN - 1) / GT_BN);
@@ -394,6 +397,7 @@ static bool make_gemm_plan(long long n_a_rows, long long n_b_rows, int d, int el
   if (groups < 1) groups = 1;
   if (groups > p->n_ctiles) groups = p->n_ctiles;
   if (const char* e = getenv("AURA_GEMM_GROUPS")) { const int v = atoi(e); if (v >= 1 && v <= p->n_ctiles) groups = v; }
+  if (force_groups) groups = force_groups;
   p->n_groups = groups;
   const long long items = (long long)p->n_atiles * groups;
   p->grid = (int)(items < sms ? items : sms);
@@ -430,13 +434,11 @@ static int run_gemm_topk(const void* a_mat, long long n_a_rows, long long a_row_
   a.n_a_rows = n_a_rows; a.n_b_rows = n_b_rows; a.a_row_first = a_row_first;
   a.k_blocks = p.k_blocks; a.L = p.L; a.n_stages = p.n_stages; a.exclude_self = exclude_self ? 1 : 0;
   a.scale = scale; a.bias = bias; a.partial = partial;
-  if (bf16) {
-    AURA_CUDA_OK(cudaFuncSetAttribute(gemm_topk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
-    gemm_topk_kernel<false><<<p.grid, GT_THREADS, p.smem, st>>>(ta, tb, a);
-  } else {
-    AURA_CUDA_OK(cudaFuncSetAttribute(gemm_topk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
-    gemm_topk_kernel<true><<<p.grid, GT_THREADS, p.smem, st>>>(ta, tb, a);
-  }
+  void (*kern)(const CUtensorMap, const CUtensorMap, const GemmTopkArgs) =
+      p.L == GT_L_ASSIGN ? (bf16 ? gemm_topk_kernel<false, GT_L_ASSIGN> : gemm_topk_kernel<true, GT_L_ASSIGN>)
+                         : (bf16 ? gemm_topk_kernel<false, GT_L> : gemm_topk_kernel<true, GT_L>);
+  AURA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+  kern<<<p.grid, GT_THREADS, p.smem, st>>>(ta, tb, a);
   AURA_CUDA_OK(cudaGetLastError());
   note_launches(1);
   return AURA_OK;
@@ -449,6 +451,170 @@ static int check_shapes(const char* who, const void* rows, int dtype, long long 
   const int eb = dtype == AURA_BF16 ? 2 : 4;
   AURA_REQUIRE(((size_t)d * eb) % 16 == 0 && (reinterpret_cast<uintptr_t>(rows) & 15) == 0, AURA_ERR_UNSUPPORTED,
                "%s: rows must be 16-byte aligned with a 16-byte multiple row pitch (d=%d)", who, d);
+  return AURA_OK;
+}
+
+
+// ================================================================================================
+// Nearest-centroid assignment and coarse probe selection on the same kernel
+//   score(x, c) = 2 x.c - ||c||^2  (argmax == argmin ||x - c||, the expansion torch.cdist uses, hippocampal.py:358)
+// ================================================================================================
+__global__ void __launch_bounds__(256) centroid_terms_kernel(const float* __restrict__ csq, int n, float* __restrict__ scale2,
+                                                             float* __restrict__ neg_csq, float* __restrict__ cmax) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    scale2[i] = 2.0f;
+    neg_csq[i] = -csq[i];
+    atomicMax(reinterpret_cast<int*>(cmax), __float_as_int(sqrtf(csq[i])));   // non-negative floats order as ints
+  }
+}
+__global__ void __launch_bounds__(256) f32_to_bf16_kernel(const float* __restrict__ x, size_t n, __nv_bfloat16* __restrict__ y) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    y[i] = __float2bfloat16_rn(x[i]);
+}
+
+// One warp per bank row: take the 4 tensor-core candidates, re-score in exact fp32 those within the rounding band
+// of the best, write the assignment.  band = 2^-7 * 1.05 * ||x|| * max||c||  (|error of 2 x.c| <= 2^-8 ||x|| ||c||).
+__global__ void __launch_bounds__(256) assign_finish_kernel(const u64* __restrict__ partial, const void* __restrict__ rows,
+                                                            int bf16, int d, const float* __restrict__ cent,
+                                                            const float* __restrict__ csq, const float* __restrict__ inv_norm,
+                                                            const float* __restrict__ cmax, long long n_rows,
+                                                            int* __restrict__ assign, float* __restrict__ cid_f32,
+                                                            int cid_stride, float* __restrict__ best_out) {
+  const long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (r >= n_rows) return;
+  const long long atile = r / GT_BM;
+  const int te = (int)(r % GT_BM);
+  u64 mine = lane < GT_L_ASSIGN ? partial[((size_t)atile * GT_L_ASSIGN + lane) * GT_BM + te] : 0ull;
+  const u64 k0 = __shfl_sync(FULL, mine, 0);
+  const float s0 = key_score(k0);
+  const float band = 0.0078125f * 1.05f * (*cmax) / inv_norm[r];
+  const bool amb = lane < GT_L_ASSIGN && mine != 0ull && key_score(mine) >= s0 - band;
+  const unsigned amb_mask = __ballot_sync(FULL, amb);
+  int best_c = (int)key_row(k0);
+  float best_v = -s0;
+  if (__popc(amb_mask) > 1) {
+    u64 best_key = 0ull;   // max of key(-(csq - 2 dot), c): smallest distance, lower c on ties
+    for (unsigned m = amb_mask; m; m &= m - 1) {
+      const int j = __ffs(m) - 1;
+      const int c = (int)key_row(__shfl_sync(FULL, mine, j));
+      const float* cr = cent + (size_t)c * d;
+      float acc = 0.f;
+      if (bf16) {
+        const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(rows) + (size_t)r * d;
+        for (int e = lane; e < d; e += 32) acc = fmaf(__bfloat162float(x[e]), cr[e], acc);
+      } else {
+        const float* x = reinterpret_cast<const float*>(rows) + (size_t)r * d;
+        if ((d & 3) == 0) {
+          const float4* x4 = reinterpret_cast<const float4*>(x);
+          const float4* c4 = reinterpret_cast<const float4*>(cr);
+          for (int e = lane; e < (d >> 2); e += 32) {
+            const float4 a = x4[e], b = c4[e];
+            acc = fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, fmaf(a.w, b.w, acc))));
+          }
+        } else {
+          for (int e = lane; e < d; e += 32) acc = fmaf(x[e], cr[e], acc);
+        }
+      }
+      const float v = fmaf(-2.f, warp_sum(acc), csq[c]);
+      const u64 key = make_key(-v, (unsigned)c);
+      if (key > best_key) { best_key = key; best_c = c; best_v = v; }
+    }
+  }
+  if (lane == 0) {
+    assign[r] = best_c;
+    if (cid_f32) cid_f32[(size_t)r * cid_stride] = (float)best_c;
+    if (best_out) best_out[r] = best_v;
+  }
+}
+
+bool tc_assign_supported(const void* rows, int dtype, long long n_rows, int d, int n_cent) {
+  const int eb = dtype == AURA_BF16 ? 2 : 4;
+  if (((size_t)d * eb) % 16 != 0 || (reinterpret_cast<uintptr_t>(rows) & 15) != 0 || (d % 4) != 0) return false;
+  if (const char* e = getenv("AURA_ASSIGN_TC")) return atoi(e) != 0;
+  return (double)n_rows * n_cent >= 1.0e8 && n_cent >= 64;    // below that the exact SIMT kernel is fast enough
+}
+
+size_t tc_assign_workspace_bytes(long long n_rows, int d, int dtype, int n_cent) {
+  GemmPlan p;
+  if (!make_gemm_plan(n_rows, n_cent, d, dtype == AURA_BF16 ? 2 : 4, 1, false, &p, GT_L_ASSIGN, 1)) return 0;
+  return align256(p.partial_bytes) + 3 * align256((size_t)n_cent * 4) + align256((size_t)n_cent * d * 2) + 512;
+}
+
+// csq: ||c||^2 per centroid (device).  inv_norm: 1/||row|| per bank row (device).
+int tc_assign(const void* rows, int dtype, long long n_rows, int d, const float* cent, int n_cent, const float* csq,
+              const float* inv_norm, int* assign, float* cid_f32, int cid_stride, float* best_out, void* workspace,
+              cudaStream_t st) {
+  const bool bf16 = dtype == AURA_BF16;
+  GemmPlan p;
+  AURA_REQUIRE(make_gemm_plan(n_rows, n_cent, d, bf16 ? 2 : 4, 1, false, &p, GT_L_ASSIGN, 1), AURA_ERR_UNSUPPORTED,
+               "tc_assign: no plan");
+  unsigned char* ws = reinterpret_cast<unsigned char*>(workspace);
+  u64* partial = reinterpret_cast<u64*>(ws);
+  float* scale2 = reinterpret_cast<float*>(ws + align256(p.partial_bytes));
+  float* neg_csq = scale2 + align256((size_t)n_cent * 4) / 4;
+  float* cmax = neg_csq + align256((size_t)n_cent * 4) / 4;
+  __nv_bfloat16* cent_bf = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<unsigned char*>(cmax) + align256((size_t)n_cent * 4));
+  AURA_CUDA_OK(cudaMemsetAsync(cmax, 0, 4, st));
+  centroid_terms_kernel<<<(n_cent + 255) / 256, 256, 0, st>>>(csq, n_cent, scale2, neg_csq, cmax);
+  const void* b_mat = cent;
+  if (bf16) {
+    f32_to_bf16_kernel<<<sm_count() * 4, 256, 0, st>>>(cent, (size_t)n_cent * d, cent_bf);
+    b_mat = cent_bf;
+    note_launches(1);
+  }
+  note_launches(1);
+  int rc = run_gemm_topk(rows, n_rows, 0, b_mat, n_cent, d, bf16, scale2, neg_csq, false, p, partial, st);
+  if (rc != AURA_OK) return rc;
+  const long long blocks = (n_rows + 7) / 8;
+  assign_finish_kernel<<<(unsigned)blocks, 256, 0, st>>>(partial, rows, bf16 ? 1 : 0, d, cent, csq, inv_norm, cmax, n_rows,
+                                                        assign, cid_f32, cid_stride, best_out);
+  AURA_CUDA_OK(cudaGetLastError());
+  note_launches(1);
+  return AURA_OK;
+}
+
+bool tc_coarse_supported(const float* queries, int n_queries, int d, const float* cent, int n_cent, int nprobe) {
+  if ((d % 4) != 0 || ((reinterpret_cast<uintptr_t>(queries) | reinterpret_cast<uintptr_t>(cent)) & 15) != 0) return false;
+  if (nprobe > GT_L) return false;
+  if (const char* e = getenv("AURA_COARSE_TC")) return atoi(e) != 0;
+  return n_queries >= 64 && (double)n_queries * n_cent >= 2.5e5;
+}
+
+size_t tc_coarse_workspace_bytes(int n_queries, int d, int n_cent, int nprobe) {
+  GemmPlan p;
+  if (!make_gemm_plan(n_queries, n_cent, d, 4, nprobe, false, &p)) return 0;
+  return align256(p.partial_bytes) + 3 * align256((size_t)n_cent * 4) + align256((size_t)n_queries * nprobe * 4) + 512;
+}
+
+// probes[b, 0..nprobe) = centroid rows nearest to query b, ranked by the TF32 score (no exact re-score: probe
+// selection is the approximate stage of the index by construction).
+int tc_coarse(const float* queries, int n_queries, int d, const float* cent, int n_cent, const float* csq, int nprobe,
+              long long* probes, void* workspace, cudaStream_t st) {
+  GemmPlan p;
+  AURA_REQUIRE(make_gemm_plan(n_queries, n_cent, d, 4, nprobe, false, &p), AURA_ERR_UNSUPPORTED, "tc_coarse: no plan");
+  unsigned char* ws = reinterpret_cast<unsigned char*>(workspace);
+  u64* partial = reinterpret_cast<u64*>(ws);
+  float* scale2 = reinterpret_cast<float*>(ws + align256(p.partial_bytes));
+  float* neg_csq = scale2 + align256((size_t)n_cent * 4) / 4;
+  float* cmax = neg_csq + align256((size_t)n_cent * 4) / 4;
+  float* dummy_score = cmax + align256((size_t)n_cent * 4) / 4;
+  AURA_CUDA_OK(cudaMemsetAsync(cmax, 0, 4, st));
+  centroid_terms_kernel<<<(n_cent + 255) / 256, 256, 0, st>>>(csq, n_cent, scale2, neg_csq, cmax);
+  note_launches(1);
+  int rc = run_gemm_topk(queries, n_queries, 0, cent, n_cent, d, false, scale2, neg_csq, false, p, partial, st);
+  if (rc != AURA_OK) return rc;
+  FinishArgs f;
+  f.partial = partial; f.n_atiles = p.n_atiles; f.n_groups = p.n_groups; f.L = p.L; f.n2 = p.n2; f.k = nprobe;
+  f.n_a_rows = n_queries; f.row_base = 0; f.rows = nullptr; f.bf16 = 0; f.d = d; f.qn = nullptr;
+  f.scale = nullptr; f.bias = nullptr; f.eps = 0.f; f.a_scale = nullptr;
+  f.out_idx = probes; f.out_score = dummy_score; f.uncertain = nullptr;
+  const size_t fsmem = ((size_t)p.n2 + GT_MAX_L) * 8;
+  AURA_CUDA_OK(cudaFuncSetAttribute(gemm_topk_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+  gemm_topk_finish_kernel<<<n_queries, 128, fsmem, st>>>(f);
+  AURA_CUDA_OK(cudaGetLastError());
+  note_launches(1);
   return AURA_OK;
 }
 

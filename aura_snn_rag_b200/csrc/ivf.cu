@@ -5,7 +5,7 @@
 //               CTA = 8 queries held in shared memory x all centroid rows, one warp per centroid row
 //               (each centroid row is read once per 8 queries, 128-bit loads when d % 4 == 0).
 //   fine      : scan_topk.cu in indirect mode (CSR lists replace the mask passes of :264-268).
-#include "aura_common.cuh"
+#include "tc_common.cuh"
 
 namespace aura {
 
@@ -87,9 +87,21 @@ __global__ void __launch_bounds__(128) coarse_select_kernel(const float* __restr
 }
 
 static size_t coarse_ws(int n_queries, int n_cent) { return ((size_t)n_queries * n_cent * 4 + 255) / 256 * 256; }
+// the tensor-core formulation needs csq[n_cent] + its own scratch; the workspace is sized for whichever is larger
+static size_t coarse_ws_any(int n_queries, int d, int n_cent, int nprobe) {
+  const size_t simt = coarse_ws(n_queries, n_cent);
+  const size_t tcw = ((size_t)n_cent * 4 + 255) / 256 * 256 + tc_coarse_workspace_bytes(n_queries, d, n_cent, nprobe);
+  return simt > tcw ? simt : tcw;
+}
 
 static int run_coarse(const float* queries, int n_queries, int d, const float* centroids, int n_cent, int nprobe,
                       long long* probes, void* workspace, cudaStream_t st) {
+  if (tc_coarse_supported(queries, n_queries, d, centroids, n_cent, nprobe)) {
+    float* csq = reinterpret_cast<float*>(workspace);
+    launch_row_sq_norms(centroids, n_cent, d, csq, st);
+    return tc_coarse(queries, n_queries, d, centroids, n_cent, csq, nprobe, probes,
+                     reinterpret_cast<unsigned char*>(workspace) + ((size_t)n_cent * 4 + 255) / 256 * 256, st);
+  }
   float* dist = reinterpret_cast<float*>(workspace);
   const size_t smem = (size_t)CO_QT * d * 4;
   AURA_REQUIRE(smem <= (size_t)max_smem_optin() - 1024, AURA_ERR_UNSUPPORTED, "aura_ivf_coarse: d=%d too large", d);
@@ -112,9 +124,9 @@ static int run_coarse(const float* queries, int n_queries, int d, const float* c
 }  // namespace aura
 using namespace aura;
 
-extern "C" size_t aura_ivf_coarse_workspace_bytes(int n_queries, int n_centroid_rows) {
-  if (n_queries < 1 || n_centroid_rows < 1) return 0;
-  return coarse_ws(n_queries, n_centroid_rows);
+extern "C" size_t aura_ivf_coarse_workspace_bytes(int n_queries, int d, int n_centroid_rows, int nprobe) {
+  if (n_queries < 1 || n_centroid_rows < 1 || d < 1 || nprobe < 1) return 0;
+  return coarse_ws_any(n_queries, d, n_centroid_rows, nprobe);
 }
 
 extern "C" int aura_ivf_coarse(const float* queries, int n_queries, int d, const float* centroids, int n_centroid_rows,
@@ -124,15 +136,15 @@ extern "C" int aura_ivf_coarse(const float* queries, int n_queries, int d, const
   AURA_REQUIRE(nprobe >= 1 && nprobe <= AURA_MAX_NPROBE && nprobe <= n_centroid_rows, AURA_ERR_INVALID_ARG,
                "aura_ivf_coarse: nprobe=%d not in [1,min(%d,%d)]", nprobe, AURA_MAX_NPROBE, n_centroid_rows);
   AURA_REQUIRE(queries && centroids && probes && workspace, AURA_ERR_INVALID_ARG, "aura_ivf_coarse: null pointer");
-  AURA_REQUIRE(workspace_bytes >= coarse_ws(n_queries, n_centroid_rows), AURA_ERR_WORKSPACE,
+  AURA_REQUIRE(workspace_bytes >= coarse_ws_any(n_queries, d, n_centroid_rows, nprobe), AURA_ERR_WORKSPACE,
                "aura_ivf_coarse: workspace too small");
   return run_coarse(queries, n_queries, d, centroids, n_centroid_rows, nprobe, reinterpret_cast<long long*>(probes),
                     workspace, (cudaStream_t)stream);
 }
 
-extern "C" size_t aura_ivf_search_workspace_bytes(int n_queries, int n_centroid_rows, int k) {
-  if (n_queries < 1 || n_centroid_rows < 1 || k < 1) return 0;
-  return coarse_ws(n_queries, n_centroid_rows) + ((size_t)n_queries * AURA_MAX_NPROBE * 8 + 255) / 256 * 256 +
+extern "C" size_t aura_ivf_search_workspace_bytes(int n_queries, int d, int n_centroid_rows, int nprobe, int k) {
+  if (n_queries < 1 || n_centroid_rows < 1 || k < 1 || d < 1 || nprobe < 1) return 0;
+  return coarse_ws_any(n_queries, d, n_centroid_rows, nprobe) + ((size_t)n_queries * AURA_MAX_NPROBE * 8 + 255) / 256 * 256 +
          scan_workspace_bytes(n_queries, k);
 }
 
@@ -150,15 +162,15 @@ extern "C" int aura_ivf_search(const void* rows, int dtype, int64_t n_rows, int 
   AURA_REQUIRE(k >= 1 && k <= AURA_MAX_K, AURA_ERR_INVALID_ARG, "aura_ivf_search: k=%d not in [1,%d]", k, AURA_MAX_K);
   AURA_REQUIRE(rows && queries && centroids && list_offsets && list_rows && out_idx && out_score && workspace,
                AURA_ERR_INVALID_ARG, "aura_ivf_search: null pointer");
-  AURA_REQUIRE(workspace_bytes >= aura_ivf_search_workspace_bytes(n_queries, n_centroid_rows, k), AURA_ERR_WORKSPACE,
+  AURA_REQUIRE(workspace_bytes >= aura_ivf_search_workspace_bytes(n_queries, d, n_centroid_rows, nprobe, k), AURA_ERR_WORKSPACE,
                "aura_ivf_search: workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
   unsigned char* ws = reinterpret_cast<unsigned char*>(workspace);
   long long* probes = out_probes ? reinterpret_cast<long long*>(out_probes)
-                                 : reinterpret_cast<long long*>(ws + coarse_ws(n_queries, n_centroid_rows));
+                                 : reinterpret_cast<long long*>(ws + coarse_ws_any(n_queries, d, n_centroid_rows, nprobe));
   const int rc = run_coarse(queries, n_queries, d, centroids, n_centroid_rows, nprobe, probes, ws, st);
   if (rc != AURA_OK) return rc;
-  void* scan_ws = ws + coarse_ws(n_queries, n_centroid_rows) + ((size_t)n_queries * AURA_MAX_NPROBE * 8 + 255) / 256 * 256;
+  void* scan_ws = ws + coarse_ws_any(n_queries, d, n_centroid_rows, nprobe) + ((size_t)n_queries * AURA_MAX_NPROBE * 8 + 255) / 256 * 256;
   // expected candidates per query: nprobe lists of average length (plan sizing only)
   long long expect = (long long)((double)n_rows * nprobe / n_centroid_rows) + 1;
   return launch_scan(rows, dtype, n_rows, d, queries, n_queries, scale, bias, k, row_base,

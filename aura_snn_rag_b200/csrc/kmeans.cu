@@ -7,7 +7,7 @@
 // The tcgen05 formulation of the assign GEMM lives in gemm_sm100.cu; this one stays as the
 // exact-fp32 path for small problems and for re-checking rows whose two best centroids are
 // closer than the tensor-core rounding.
-#include "aura_common.cuh"
+#include "tc_common.cuh"
 
 namespace aura {
 
@@ -281,6 +281,11 @@ __global__ void __launch_bounds__(256) online_assign_kernel(const void* __restri
   }
 }
 
+void launch_row_sq_norms(const float* x, int n, int d, float* out, cudaStream_t st) {
+  row_sq_norm_kernel<<<(n + 7) / 8, 256, 0, st>>>(x, n, d, out);
+  note_launches(1);
+}
+
 static int blocks_for(long long n, int per) {
   long long g = (n + per - 1) / per;
   const long long cap = (long long)sm_count() * 8;
@@ -290,21 +295,32 @@ static int blocks_for(long long n, int per) {
 }  // namespace aura
 using namespace aura;
 
-extern "C" size_t aura_kmeans_assign_workspace_bytes(int n_centroids) { return (size_t)n_centroids * 4 + 256; }
+extern "C" size_t aura_kmeans_assign_workspace_bytes(int64_t n_rows, int d, int dtype, int n_centroids) {
+  if (n_centroids < 1) return 0;
+  const size_t csq = ((size_t)n_centroids * 4 + 255) / 256 * 256;
+  return csq + tc_assign_workspace_bytes(n_rows, d, dtype, n_centroids) + 256;
+}
 
 extern "C" int aura_kmeans_assign(const void* rows, int dtype, int64_t n_rows, int d, const float* centroids,
-                                  int n_centroids, int32_t* assign, float* cid_f32, int cid_stride, float* best_score,
-                                  void* workspace, size_t workspace_bytes, void* stream) {
+                                  int n_centroids, const float* row_inv_norm, int32_t* assign, float* cid_f32,
+                                  int cid_stride, float* best_score, void* workspace, size_t workspace_bytes, void* stream) {
   AURA_REQUIRE(dtype == AURA_F32 || dtype == AURA_BF16, AURA_ERR_INVALID_ARG, "aura_kmeans_assign: bad dtype %d", dtype);
   AURA_REQUIRE(n_rows >= 0 && d >= 1 && n_centroids >= 1, AURA_ERR_INVALID_ARG,
                "aura_kmeans_assign: n_rows=%lld d=%d n_centroids=%d", (long long)n_rows, d, n_centroids);
   if (n_rows == 0) return AURA_OK;
   AURA_REQUIRE(rows && centroids && assign && workspace, AURA_ERR_INVALID_ARG, "aura_kmeans_assign: null pointer");
-  AURA_REQUIRE(workspace_bytes >= aura_kmeans_assign_workspace_bytes(n_centroids), AURA_ERR_WORKSPACE,
+  AURA_REQUIRE(workspace_bytes >= aura_kmeans_assign_workspace_bytes(n_rows, d, dtype, n_centroids), AURA_ERR_WORKSPACE,
                "aura_kmeans_assign: workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
   float* csq = reinterpret_cast<float*>(workspace);
-  row_sq_norm_kernel<<<(n_centroids + 7) / 8, 256, 0, st>>>(centroids, n_centroids, d, csq);
+  launch_row_sq_norms(centroids, n_centroids, d, csq, st);
+  // large problems: tcgen05 GEMM + exact fp32 re-score of the near-tied candidates (gemm_topk.cu);
+  // small ones (and callers without per-row norms): exact fp32 SIMT tiles
+  if (row_inv_norm != nullptr && tc_assign_supported(rows, dtype, n_rows, d, n_centroids)) {
+    void* tws = reinterpret_cast<unsigned char*>(workspace) + ((size_t)n_centroids * 4 + 255) / 256 * 256;
+    return tc_assign(rows, dtype, n_rows, d, centroids, n_centroids, csq, row_inv_norm, assign, cid_f32, cid_stride,
+                     best_score, tws, st);
+  }
   const long long g = (n_rows + AS_BM - 1) / AS_BM;
   AURA_REQUIRE(g < 0x7fffffffll, AURA_ERR_UNSUPPORTED, "aura_kmeans_assign: too many rows");
   if (dtype == AURA_BF16)
@@ -314,7 +330,7 @@ extern "C" int aura_kmeans_assign(const void* rows, int dtype, int64_t n_rows, i
     kmeans_assign_kernel<false><<<(int)g, AS_THREADS, 0, st>>>(rows, n_rows, d, centroids, n_centroids, csq, assign,
                                                                cid_f32, cid_stride, best_score);
   AURA_CUDA_OK(cudaGetLastError());
-  note_launches(2);
+  note_launches(1);
   return AURA_OK;
 }
 

@@ -107,4 +107,16 @@ __device__ __forceinline__ void named_bar_sync(int id, int n_threads) {
 // 2-D row-major matrix [n_rows, d] of `elem_bytes`-byte elements; box = [128 bytes of K, box_rows], SWIZZLE_128B.
 int encode_tmap_2d(CUtensorMap* map, const void* base, int elem_bytes, bool bf16, long long n_rows, int d, int box_rows);
 
+
+// gemm_topk.cu: nearest-centroid assignment / coarse probe selection on the tcgen05 kernel
+bool tc_assign_supported(const void* rows, int dtype, long long n_rows, int d, int n_cent);
+size_t tc_assign_workspace_bytes(long long n_rows, int d, int dtype, int n_cent);
+int tc_assign(const void* rows, int dtype, long long n_rows, int d, const float* cent, int n_cent, const float* csq,
+              const float* inv_norm, int* assign, float* cid_f32, int cid_stride, float* best_out, void* workspace,
+              cudaStream_t st);
+bool tc_coarse_supported(const float* queries, int n_queries, int d, const float* cent, int n_cent, int nprobe);
+size_t tc_coarse_workspace_bytes(int n_queries, int d, int n_cent, int nprobe);
+int tc_coarse(const float* queries, int n_queries, int d, const float* cent, int n_cent, const float* csq, int nprobe,
+              long long* probes, void* workspace, cudaStream_t st);
+
 }  // namespace aura

@@ -266,7 +266,7 @@ class HippocampalFormation(nn.Module):
         seeds = seed_rows.to(device=self.device, dtype=torch.int64)[:k].contiguous()
         bank = self.memory_features
         ops.kmeans_seed(bank, seeds, self.centroids)                          # :355
-        ops.kmeans_assign(bank, m, self.centroids, k, self._cid)              # :358-359
+        ops.kmeans_assign(bank, m, self.centroids, k, self._cid, inv_norm=self._inv_norm)   # :358-359
         ops.ivf_build_lists(self._cid, m, rows_c, self._list_offsets, self._list_rows)
         sums = torch.empty(rows_c, bank.shape[1], device=self.device, dtype=torch.float64)
         counts = torch.empty(rows_c, device=self.device, dtype=torch.int64)
@@ -274,7 +274,8 @@ class HippocampalFormation(nn.Module):
         ops.kmeans_finalize(sums, counts, k, self.centroids)                  # :360-363 (empty keeps its seed)
         if k < self.centroids_k and k < rows_c:
             self.centroids[k:].zero_()                                        # :366-367
-        ops.kmeans_assign(bank, m, self.centroids, k, self._cid, self.memory_metadata[:, 2], 4)   # :370-371,:376
+        ops.kmeans_assign(bank, m, self.centroids, k, self._cid, self.memory_metadata[:, 2], 4,
+                          inv_norm=self._inv_norm)                              # :370-371,:376
         ops.ivf_build_lists(self._cid, m, rows_c, self._list_offsets, self._list_rows)
         counts_f = torch.zeros(max(self.centroids_k, 1), device=self.device, dtype=torch.float32)
         full = torch.empty(rows_c, device=self.device, dtype=torch.float32)

@@ -171,13 +171,14 @@ def kmeans_seed(rows: torch.Tensor, seed_rows: torch.Tensor, centroids: torch.Te
 
 def kmeans_assign(rows: torch.Tensor, n_rows: int, centroids: torch.Tensor, n_centroids: int, assign: torch.Tensor,
                   cid_f32: Optional[torch.Tensor] = None, cid_stride: int = 1,
-                  best: Optional[torch.Tensor] = None) -> None:
+                  best: Optional[torch.Tensor] = None, inv_norm: Optional[torch.Tensor] = None) -> None:
     """assign[i] (int32) = nearest of centroids[:n_centroids]; optional float id written at cid_f32[i*cid_stride]."""
     rows = _dev(rows, "rows")
     lib = _lib.load()
-    ws = _workspace(lib.aura_kmeans_assign_workspace_bytes(n_centroids), rows.device, "assign")
-    check(lib.aura_kmeans_assign(rows.data_ptr(), _dtype_code(rows), n_rows, rows.shape[1], centroids.data_ptr(),
-                                 n_centroids, assign.data_ptr(), _ptr(cid_f32), cid_stride, _ptr(best), ws.data_ptr(),
+    code = _dtype_code(rows)
+    ws = _workspace(lib.aura_kmeans_assign_workspace_bytes(n_rows, rows.shape[1], code, n_centroids), rows.device, "assign")
+    check(lib.aura_kmeans_assign(rows.data_ptr(), code, n_rows, rows.shape[1], centroids.data_ptr(), n_centroids,
+                                 _ptr(inv_norm), assign.data_ptr(), _ptr(cid_f32), cid_stride, _ptr(best), ws.data_ptr(),
                                  ws.numel(), _stream()), "aura_kmeans_assign")
 
 
@@ -228,7 +229,7 @@ def ivf_coarse(queries: torch.Tensor, centroids: torch.Tensor, nprobe: int) -> t
     c = centroids.shape[0]
     probes = torch.empty(b, nprobe, dtype=torch.int64, device=queries.device)
     lib = _lib.load()
-    ws = _workspace(lib.aura_ivf_coarse_workspace_bytes(b, c), queries.device, "coarse")
+    ws = _workspace(lib.aura_ivf_coarse_workspace_bytes(b, d, c, nprobe), queries.device, "coarse")
     check(lib.aura_ivf_coarse(queries.data_ptr(), b, d, centroids.data_ptr(), c, nprobe, probes.data_ptr(),
                               ws.data_ptr(), ws.numel(), _stream()), "aura_ivf_coarse")
     return probes
@@ -255,7 +256,7 @@ def ivf_search(rows: torch.Tensor, n_rows: int, queries: torch.Tensor, centroids
     out_score = torch.empty(b, k, dtype=torch.float32, device=dev)
     probes = torch.empty(b, nprobe, dtype=torch.int64, device=dev) if return_probes else None
     lib = _lib.load()
-    ws = _workspace(lib.aura_ivf_search_workspace_bytes(b, c, k), dev)
+    ws = _workspace(lib.aura_ivf_search_workspace_bytes(b, d, c, nprobe, k), dev)
     check(lib.aura_ivf_search(rows.data_ptr(), _dtype_code(rows), n_rows, d, queries.data_ptr(), b,
                               centroids.data_ptr(), c, nprobe, list_offsets.data_ptr(), list_rows.data_ptr(),
                               _ptr(scale), _ptr(bias), k, row_base, out_idx.data_ptr(), out_score.data_ptr(),

@@ -92,7 +92,11 @@ int aura_bank_write(void* rows, int dtype, int d, int64_t first_row, int n_new, 
  *                      supplies randperm(M)[:k], CPU and CUDA generators differ)
  * aura_kmeans_assign   assign[i] = argmin_c ||rows[i] - centroid_c||  via ||c||^2 - 2 x.c, first
  *                      minimum on ties (:358-359,:370-371); optionally also writes the id as float
- *                      into cid_f32[i*cid_stride] (metadata[:,2], :376) and the best score.
+ *                      into cid_f32[i*cid_stride] (metadata[:,2], :376) and the best score.  Exact fp32 SIMT
+ *                      tiles for small problems; when row_inv_norm (1/||row||, may be NULL) is given and
+ *                      n_rows*n_centroids >= 1e8 the scores come from a tcgen05 GEMM (tf32 / bf16) and the
+ *                      4 best candidates per row that lie within the rounding band 2^-7*||x||*max||c|| of
+ *                      the best are re-scored in exact fp32 (exact whenever at most 4 centroids are that close).
  * aura_ivf_build_lists counting sort of the assignments into CSR inverted lists (replaces the
  *                      P float-equality mask passes + nonzero of :264-268).
  * aura_kmeans_list_sums / aura_kmeans_finalize   per-cluster mean, empty clusters keep their seed
@@ -100,10 +104,10 @@ int aura_bank_write(void* rows, int dtype, int d, int64_t first_row, int n_new, 
  * aura_ivf_list_counts counts[c] = |list c| as fp32 (:372-374). */
 int aura_kmeans_seed(const void* rows, int dtype, int d, const int64_t* seed_rows, int n_seeds, float* centroids,
                      void* stream);
-size_t aura_kmeans_assign_workspace_bytes(int n_centroids);
+size_t aura_kmeans_assign_workspace_bytes(int64_t n_rows, int d, int dtype, int n_centroids);
 int aura_kmeans_assign(const void* rows, int dtype, int64_t n_rows, int d, const float* centroids, int n_centroids,
-                       int32_t* assign, float* cid_f32, int cid_stride, float* best_score, void* workspace,
-                       size_t workspace_bytes, void* stream);
+                       const float* row_inv_norm, int32_t* assign, float* cid_f32, int cid_stride, float* best_score,
+                       void* workspace, size_t workspace_bytes, void* stream);
 size_t aura_ivf_build_lists_workspace_bytes(int n_lists);
 int aura_ivf_build_lists(const int32_t* cid, int64_t n_rows, int n_lists, int32_t* list_offsets, int32_t* list_rows,
                          void* workspace, size_t workspace_bytes, void* stream);
@@ -127,15 +131,16 @@ int aura_online_assign(const void* rows, int dtype, int d, int64_t first_row, in
 /* ---- centroid index: query (hippocampal.py:257-307) ------------------------------------------
  * aura_ivf_coarse: probes[b, 0..nprobe) = the nprobe centroid rows nearest to query b by
  *   ||centroid_c - q||_2 over ALL n_centroid_rows rows of the buffer (zeroed tail rows included,
- *   as :261 does), nearest first, ties to the lower row (:262).
+ *   as :261 does), nearest first, ties to the lower row (:262).  Blocks of >= 64 queries are scored as one
+ *   TF32 tcgen05 GEMM (2 q.c - ||c||^2, nprobe <= 32); smaller blocks in exact fp32 difference form.
  * aura_ivf_search: coarse + scan of the probed inverted lists with the same score/top-k as
  *   aura_scan_topk.  A query whose probed lists are all empty scans every row (:269-270).
  *   Returned indices are bank rows (the reference returns candidate-local positions, :307-317:
  *   a documented bug this library does not reproduce). */
-size_t aura_ivf_coarse_workspace_bytes(int n_queries, int n_centroid_rows);
+size_t aura_ivf_coarse_workspace_bytes(int n_queries, int d, int n_centroid_rows, int nprobe);
 int aura_ivf_coarse(const float* queries, int n_queries, int d, const float* centroids, int n_centroid_rows, int nprobe,
                     int64_t* probes, void* workspace, size_t workspace_bytes, void* stream);
-size_t aura_ivf_search_workspace_bytes(int n_queries, int n_centroid_rows, int k);
+size_t aura_ivf_search_workspace_bytes(int n_queries, int d, int n_centroid_rows, int nprobe, int k);
 int aura_ivf_search(const void* rows, int dtype, int64_t n_rows, int d, const float* queries, int n_queries,
                     const float* centroids, int n_centroid_rows, int nprobe, const int32_t* list_offsets,
                     const int32_t* list_rows, const float* scale, const float* bias, int k, int64_t row_base,

@@ -227,3 +227,48 @@ def test_cognitive_map_api_matches_oracle():
     assert max(abs(cmap[p] - ref[p]) for p in common) < 3e-3
     closest = min(cmap.items(), key=lambda kv: kv[1])
     assert closest[1] >= -1e-3 and closest[0][0] != closest[0][1]
+
+
+def test_ingestion_and_batched_retrieval_helpers(tmp_path):
+    """tests/test_ingestion_and_gating.py:30-79 of the reference (stubbed one_shot_memorize_text writing ones),
+    plus the batched MemoryAugmentedLayer.retrieve_memories body against the per-item reference loop."""
+    import json
+    from aura_snn_rag_b200 import HippocampalFormation, memory_api as api
+
+    def stub(text, tokenizer, model, hippocampus, device, memory_id=None):
+        vec = torch.ones(hippocampus.memory_features.shape[1], device=hippocampus.device) * (1 + hippocampus.memory_count)
+        hippocampus.create_episodic_memory(memory_id, memory_id, vec)
+        return memory_id
+
+    hf = HippocampalFormation(feature_dim=16, n_place_cells=10, n_time_cells=5, n_grid_cells=5, max_memories=50)
+    p = tmp_path / "a.jsonl"
+    p.write_text(json.dumps({"text": "hello world"}) + "\n" + json.dumps({"instruction": "do X", "output": "done"})
+                 + "\nnot json\n" + json.dumps({"unknown": 1}) + "\n" + json.dumps("bare string") + "\n")
+    assert api.ingest_jsonl_to_memory(str(p), object(), object(), hf, "cuda", max_items=10, memorize=stub) == 3
+    assert hf.memory_count == 3 and "jsonl-2" in hf.id_to_idx
+    c = tmp_path / "b.csv"
+    c.write_text("Q1,A1\nQ2,A2\nshort\n,\n")
+    assert api.ingest_csv_pairs_to_memory(str(c), object(), object(), hf, "cuda", max_items=1, memorize=stub) == 1
+    assert api.ingest_csv_pairs_to_memory(str(c), object(), object(), hf, "cuda", memorize=stub) == 2
+    assert hf.memory_count == 6
+    assert api.ingest_jsonl_to_memory(str(p), None, object(), hf, "cuda") == 0
+
+    g = torch.Generator().manual_seed(4)
+    bank = HippocampalFormation(feature_dim=32, n_place_cells=4, n_time_cells=2, n_grid_cells=2, max_memories=4096,
+                                use_centroid_index=False)
+    rows = torch.randn(2000, 32, generator=g)
+    assert api.ingest_features_to_memory(bank, rows, prefix="r") == 2000
+    mid = api.store_custom_memory(bank, torch.stack([rows[5], rows[5]]), memory_id="custom")
+    assert mid == "custom" and bank.memory_count == 2001
+    assert api.retrieve_custom_memories(bank, torch.stack([rows[5], rows[5]]), k=2)[0][0] in ("r-5", "custom")
+    q = (rows[:12] + 0.05 * torch.randn(12, 32, generator=g)).cuda()
+    feats, scores = api.retrieve_memories(bank, q, k=5)                 # one batched search (tensor-core path)
+    for b in range(12):                                                 # reference loop: one search per item
+        res = bank.retrieve_similar_memories(q[b], k=5)
+        assert [r for r, _ in res][0] == f"r-{b}" or res[0][0] == "custom"
+        np.testing.assert_allclose(scores[b].cpu().numpy(), [s for _, s in res], rtol=1e-5)
+        for i, (mem_id, _) in enumerate(res):
+            assert torch.equal(feats[b, i].cpu(), bank.memory_features[bank.id_to_idx[mem_id]].cpu())
+    empty = HippocampalFormation(feature_dim=8, n_place_cells=4, n_time_cells=2, n_grid_cells=2, max_memories=8)
+    f0, s0 = api.retrieve_memories(empty, torch.randn(3, 8).cuda(), k=4)
+    assert f0.shape == (3, 4, 8) and float(f0.abs().sum()) == 0 and float(s0.abs().sum()) == 0

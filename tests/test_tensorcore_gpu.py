@@ -109,3 +109,56 @@ def test_allpairs_topk_matches_oracle(n, d, k, dt):
     a0, na = n // 3, 257
     idx2, sc2 = ops.allpairs_topk(rows, k, a_first=a0, n_a=na)
     assert torch.equal(idx2.cpu(), idx[a0:a0 + na]) and torch.equal(sc2.cpu(), sc[a0:a0 + na])
+
+
+@pytest.mark.parametrize("n,d,c,dt", [(20000, 128, 300, torch.float32), (9000, 768, 256, torch.float32),
+                                      (30000, 256, 1000, torch.bfloat16)])
+def test_tensorcore_assign_matches_exact_assign(n, d, c, dt, monkeypatch):
+    """aura_kmeans_assign: tcgen05 formulation (forced) vs the exact fp32 SIMT formulation vs the oracle's cdist."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(n + c)
+    centres = torch.randn(c // 4, d, generator=g)
+    bank = (centres[torch.randint(0, c // 4, (n,), generator=g)] + 0.3 * torch.randn(n, d, generator=g)).to(dt)
+    cent = bank[torch.randperm(n, generator=g)[:c]].float().contiguous()
+    ref = torch.argmin(torch.cdist(bank.float(), cent), dim=1)
+    rows, cent_d = bank.to(DEV), cent.to(DEV)
+    inv = ops.row_inv_norms(rows)
+    out = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("AURA_ASSIGN_TC", mode)
+        a = torch.empty(n, dtype=torch.int32, device=DEV)
+        best = torch.empty(n, dtype=torch.float32, device=DEV)
+        ops.kmeans_assign(rows, n, cent_d, c, a, best=best, inv_norm=inv)
+        torch.cuda.synchronize()
+        out[mode] = (a.cpu().long(), best.cpu())
+    assert (out["0"][0] == ref).float().mean() > 0.999
+    agree = (out["1"][0] == out["0"][0]).float().mean()
+    assert agree > 0.999, agree
+    # where they differ the two centroids are equidistant within fp32 rounding of the distance
+    dist = torch.cdist(bank.float(), cent)
+    bad = torch.nonzero(out["1"][0] != out["0"][0]).squeeze(-1)
+    for r in bad.tolist():
+        a1, a0 = out["1"][0][r], out["0"][0][r]
+        assert abs(float(dist[r, a1] - dist[r, a0])) <= 1e-4 * float(dist[r, a0])
+
+
+def test_tensorcore_coarse_probes_match_exact_coarse(monkeypatch):
+    ops = _ops()
+    g = torch.Generator().manual_seed(8)
+    c, d, b, p = 1024, 256, 200, 16
+    cent = torch.randn(c, d, generator=g)
+    cent[900:] = 0                                   # zeroed tail rows take part (hippocampal.py:261)
+    q = cent[torch.randint(0, 900, (b,), generator=g)] + 0.5 * torch.randn(b, d, generator=g)
+    dist = torch.norm(cent.unsqueeze(0) - q.unsqueeze(1), dim=2)
+    ref = torch.topk(-dist, p, dim=1).indices
+    res = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("AURA_COARSE_TC", mode)
+        res[mode] = ops.ivf_coarse(q.to(DEV), cent.to(DEV), p).cpu()
+    # the zeroed rows tie exactly (torch.topk leaves their order open; this library takes the lower row first)
+    np.testing.assert_allclose(torch.gather(dist, 1, res["0"]).numpy(), torch.gather(dist, 1, ref).numpy(), rtol=1e-6)
+    assert torch.equal(res["0"][:, 1:], torch.arange(900, 900 + p - 1).expand(b, p - 1))
+    assert torch.equal(res["0"][:, 0], ref[:, 0])
+    # TF32 scores: same nearest centroid, same distance profile up to the rounding of 2 q.c
+    assert (res["1"][:, 0] == ref[:, 0]).float().mean() > 0.99
+    np.testing.assert_allclose(torch.gather(dist, 1, res["1"]).numpy(), torch.gather(dist, 1, ref).numpy(), rtol=2e-3)
