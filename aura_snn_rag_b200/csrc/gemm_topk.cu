@@ -28,18 +28,6 @@
 
 namespace aura {
 
-static constexpr int GT_BM = 128;            // A rows per tile (TMEM lanes)
-static constexpr int GT_BN = 256;            // B rows per tile (TMEM columns per accumulator stage)
-static constexpr int GT_SLAB = 128;          // bytes of K per pipeline stage (one swizzle atom row)
-static constexpr int GT_A_BYTES = GT_BM * GT_SLAB;   // 16 KB
-static constexpr int GT_B_BYTES = GT_BN * GT_SLAB;   // 32 KB
-static constexpr int GT_STAGE_BYTES = GT_A_BYTES + GT_B_BYTES;
-static constexpr int GT_MAX_STAGES = 4;
-static constexpr int GT_THREADS = 192;       // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
-static constexpr int GT_L = 32;             // per-row list length kept by the epilogue (registers)
-static constexpr int GT_L_ASSIGN = 4;       // list length of the nearest-centroid variant
-static constexpr int GT_MAX_L = 64;
-
 struct GemmTopkArgs {
   int n_atiles, n_ctiles, n_groups;
   long long n_a_rows, n_b_rows;
@@ -52,31 +40,6 @@ struct GemmTopkArgs {
   const float* bias;          // per B row, may be null (0)
   u64* partial;               // [n_atiles * n_groups][L][128]
 };
-
-// v[j] for a run-time j without spilling v[] to local memory: 5-level select tree
-__device__ __forceinline__ float select32(const float (&v)[32], int j) {
-  float a[16], b[8], c[4];
-#pragma unroll
-  for (int i = 0; i < 16; ++i) a[i] = (j & 16) ? v[i + 16] : v[i];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) b[i] = (j & 8) ? a[i + 8] : a[i];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) c[i] = (j & 4) ? b[i + 4] : b[i];
-  const float d0 = (j & 2) ? c[2] : c[0], d1 = (j & 2) ? c[3] : c[1];
-  return (j & 1) ? d1 : d0;
-}
-
-// thread-private top-GT_L list, sorted descending, entirely in registers.  All compares are independent
-// (key > e[i] is monotone in i), so an insertion is ~GT_L predicated moves with no dependent chain.
-template <int L>
-__device__ __forceinline__ void list_insert_sorted(u64 (&e)[L], u64 key) {
-#pragma unroll
-  for (int i = L - 1; i >= 1; --i) {
-    const bool ci = key > e[i], cp = key > e[i - 1];
-    e[i] = ci ? (cp ? e[i - 1] : key) : e[i];
-  }
-  e[0] = key > e[0] ? key : e[0];
-}
 
 template <bool TF32, int L>
 __global__ void __launch_bounds__(GT_THREADS, 1)
@@ -254,6 +217,11 @@ __global__ void __launch_bounds__(256) normalize_queries_kernel(const float* __r
   }
 }
 
+void launch_normalize_queries(const float* q, int n, int d, float* qn, __nv_bfloat16* qb, cudaStream_t st) {
+  normalize_queries_kernel<<<(n + 7) / 8, 256, 0, st>>>(q, n, d, qn, qb);
+  note_launches(1);
+}
+
 // ---- finish: merge the per-group lists of one A row; K6: exact re-score + certification ----
 struct FinishArgs {
   const u64* partial; int n_atiles, n_groups, L, n2;   // n2 = pow2 >= n_groups*L
@@ -293,56 +261,11 @@ __global__ void __launch_bounds__(128) gemm_topk_finish_kernel(const FinishArgs 
     }
     return;
   }
-  // exact fp32 re-score of the L best candidates, one warp per candidate; same operation order as
-  // scan_topk.cu (lane-strided 128-bit chunks, fmaf nest, xor-tree warp sum) so both paths agree bit for bit
-  const int n_cand = min(f.L, f.n2);
-  const float* q = f.qn + (size_t)b * f.d;
-  for (int c = warp; c < GT_MAX_L; c += 4) {
-    u64 key = 0ull;
-    if (c < n_cand && keys[c] != 0ull) {
-      const unsigned row = key_row(keys[c]);
-      float acc = 0.f;
-      if (f.bf16) {
-        const uint4* x8 = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(f.rows) + (size_t)row * f.d);
-        const float4* q4 = reinterpret_cast<const float4*>(q);
-        for (int ch = lane; ch < (f.d >> 3); ch += 32) {
-          const uint4 x = x8[ch];
-          const float4 qa = q4[2 * ch], qb = q4[2 * ch + 1];
-          acc = fmaf(bf16_lo(x.x), qa.x, acc); acc = fmaf(bf16_hi(x.x), qa.y, acc);
-          acc = fmaf(bf16_lo(x.y), qa.z, acc); acc = fmaf(bf16_hi(x.y), qa.w, acc);
-          acc = fmaf(bf16_lo(x.z), qb.x, acc); acc = fmaf(bf16_hi(x.z), qb.y, acc);
-          acc = fmaf(bf16_lo(x.w), qb.z, acc); acc = fmaf(bf16_hi(x.w), qb.w, acc);
-        }
-      } else {
-        const float4* x4 = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(f.rows) + (size_t)row * f.d);
-        const float4* q4 = reinterpret_cast<const float4*>(q);
-        for (int ch = lane; ch < (f.d >> 2); ch += 32) {
-          const float4 x = x4[ch], qq = q4[ch];
-          acc = fmaf(x.x, qq.x, fmaf(x.y, qq.y, fmaf(x.z, qq.z, fmaf(x.w, qq.w, acc))));
-        }
-      }
-      const float dot = warp_sum(acc);
-      const float sc = f.scale ? f.scale[row] : 1.f, bi = f.bias ? f.bias[row] : 0.f;
-      key = make_key(fmaf(dot, sc, bi), row);
-    }
-    if (lane == 0) ex[c] = key;
-  }
-  block_bitonic_sort_desc(ex, GT_MAX_L);
-  for (int i = threadIdx.x; i < f.k; i += blockDim.x) {
-    const u64 key = i < GT_MAX_L ? ex[i] : 0ull;
-    f.out_idx[b * f.k + i] = key ? f.row_base + (long long)key_row(key) : -1ll;
-    f.out_score[b * f.k + i] = key ? key_score(key) : -INFINITY;
-  }
-  if (threadIdx.x == 0 && f.uncertain) {
-    // rows outside the shortlist have approximate score <= s_L (the L-th best approximate score)
-    int flag = 0;
-    if (f.L - 1 < f.n2 && keys[f.L - 1] != 0ull) {
-      const float bound = key_score(keys[f.L - 1]) + f.eps;
-      const u64 kth = ex[f.k - 1];
-      if (kth == 0ull || !(key_score(kth) > bound)) flag = 1;
-    }
-    f.uncertain[b] = flag;
-  }
+  RescoreArgs ra;
+  ra.rows = f.rows; ra.bf16 = f.bf16; ra.d = f.d; ra.q = f.qn + (size_t)b * f.d; ra.scale = f.scale; ra.bias = f.bias;
+  ra.eps = f.eps; ra.k = f.k; ra.L = f.L; ra.row_base = f.row_base;
+  ra.out_idx = f.out_idx + b * f.k; ra.out_score = f.out_score + b * f.k; ra.uncertain = f.uncertain ? f.uncertain + b : nullptr;
+  rescore_and_write(keys, f.n2, ex, ra);
 }
 
 // ---- host ------------------------------------------------------------------------------------------

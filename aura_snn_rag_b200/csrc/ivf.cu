@@ -121,6 +121,13 @@ static int run_coarse(const float* queries, int n_queries, int d, const float* c
   return AURA_OK;
 }
 
+// used by ivf_batch.cu
+size_t ivf_coarse_ws_bytes(int n_queries, int d, int n_cent, int nprobe) { return coarse_ws_any(n_queries, d, n_cent, nprobe); }
+int ivf_run_coarse(const float* queries, int n_queries, int d, const float* centroids, int n_cent, int nprobe,
+                   long long* probes, void* workspace, cudaStream_t st) {
+  return run_coarse(queries, n_queries, d, centroids, n_cent, nprobe, probes, workspace, st);
+}
+
 }  // namespace aura
 using namespace aura;
 

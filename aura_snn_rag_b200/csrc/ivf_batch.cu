@@ -1,0 +1,425 @@
+// aura_ivf_search_batch - list-major fine stage of the centroid index for a block of queries
+// (hippocampal.py:257-307 for B queries at once).
+//
+// The per-query path (ivf.cu + scan_topk.cu) streams nprobe lists per query: B * nprobe * |list| * d bytes.  At
+// BASELINE config 4 (10M x 1024 fp32, 4096 lists, nprobe 32, B = 4096) that is 1.3 TB per batch, although every list is
+// wanted by ~32 queries.  Here the (query, probe) pairs are counting-sorted BY LIST and every list is scored once
+// against the group of queries that probe it - a ragged grouped GEMM on the tensor cores:
+//   item  = (list c, tile of <= 128 of its queries, chunk of <= 2048 of its rows)
+//   A     = the queries of the group, gathered by row id with TMA gather4 from the normalised query block
+//   B     = the rows of the list chunk, gathered by row id with TMA gather4 straight from the bank (CSR order),
+//           so the inverted lists stay an index (int32 row ids) and the bank keeps the reference's insertion order
+//   MMA / TMEM / epilogue as in gemm_topk.cu (tf32 from an fp32 bank, bf16 from a bf16 bank, per-row top-32 in
+//   registers), one partial list per (pair, chunk)
+// and a finish kernel merges a query's partial lists, re-scores the 32 best in exact fp32 and certifies the top-k
+// (same rule as aura_batch_topk).  Algorithmic bytes per batch = bytes of the probed lists, each read once.
+#include <stdlib.h>
+
+#include "tc_common.cuh"
+
+namespace aura {
+
+static constexpr int IB_CH_TILES = 8;                       // column tiles per item
+static constexpr int IB_CH_ROWS = IB_CH_TILES * GT_BN;      // 2048 list rows per item
+static constexpr int IB_MERGE_CAP = 2048;                   // keys the finish kernel sorts at a time
+
+struct IvfBatchArgs {
+  int n_lists, nprobe, k_blocks, n_stages, cap_items;
+  const int* list_offsets; const int* list_rows;   // CSR of the bank
+  const int* q_off;         // [n_lists + 1]  pairs per list, exclusive scan
+  const int* pair_of_pos;   // [B * nprobe]   pair id (b * nprobe + p) at list-sorted position
+  const int4* items;        // [cap_items]    {list, query tile, chunk, 0}
+  const int* n_items;       // device scalar
+  const float* scale; const float* bias;           // per bank row
+  u64* partial;             // [cap_items][GT_L][128]
+};
+
+template <bool TF32>
+__global__ void __launch_bounds__(GT_THREADS, 1)
+ivf_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_b, const IvfBatchArgs a) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int S = a.n_stages;
+  unsigned char* ring = smem;
+  float2* sbuf = reinterpret_cast<float2*>(ring + (size_t)S * GT_STAGE_BYTES);   // [2][GT_BN] (scale, bias)
+  int* rid_s = reinterpret_cast<int*>(sbuf + 2 * GT_BN);                         // [2][GT_BN] bank row of each column
+  uint64_t* full = reinterpret_cast<uint64_t*>(rid_s + 2 * GT_BN);
+  uint64_t* empty = full + GT_MAX_STAGES;
+  uint64_t* tfull = empty + GT_MAX_STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int ELEMS_PER_SLAB = TF32 ? 32 : 64;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4); }
+    fence_mbar_init();
+    tc::tma_prefetch_desc(&tmap_q);
+    tc::tma_prefetch_desc(&tmap_b);
+  }
+  if (warp == 1) { tc::tmem_alloc(tmem_slot, 512); tc::tmem_relinquish(); }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int n_items = min(*a.n_items, a.cap_items);
+
+  if (warp == 0) {
+    // ===================== producer warp: every lane issues gather4 copies =====================
+    const uint64_t pol_b = l2_policy_evict_first();
+    const uint64_t pol_a = l2_policy_evict_last();
+    int stage = 0; unsigned phase = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int4 it = a.items[item];
+      const int qb = a.q_off[it.x], nq = a.q_off[it.x + 1] - qb;
+      const int a0 = qb + it.y * GT_BM, n_a = min(GT_BM, nq - it.y * GT_BM);
+      const int lb = a.list_offsets[it.x], len = a.list_offsets[it.x + 1] - lb;
+      const int r0 = it.z * IB_CH_ROWS, r1 = min(len, r0 + IB_CH_ROWS);
+      int qa[4];   // query rows of A-tile rows 4*lane .. 4*lane+3 (rows past the group re-load a valid query, masked later)
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = min(4 * lane + u, n_a - 1);
+        qa[u] = a.pair_of_pos[a0 + i] / a.nprobe;
+      }
+      for (int cr = r0; cr < r1; cr += GT_BN) {
+        int rb[8];   // bank rows of B-tile rows 8*lane .. 8*lane+7
+#pragma unroll
+        for (int u = 0; u < 8; ++u) rb[u] = a.list_rows[lb + min(cr + 8 * lane + u, r1 - 1)];
+        for (int kb = 0; kb < a.k_blocks; ++kb) {
+          if (lane == 0) {
+            tc::mbar_wait_guarded(&empty[stage], phase ^ 1u);
+            mbar_arrive_expect_tx(&full[stage], GT_STAGE_BYTES);
+          }
+          __syncwarp();
+          unsigned char* sa = ring + (size_t)stage * GT_STAGE_BYTES;
+          const int c0 = kb * ELEMS_PER_SLAB;
+          tc::tma_gather4(sa + (size_t)(4 * lane) * GT_SLAB, &tmap_q, c0, qa[0], qa[1], qa[2], qa[3], &full[stage], pol_a);
+          unsigned char* sbm = sa + GT_A_BYTES + (size_t)(8 * lane) * GT_SLAB;
+          tc::tma_gather4(sbm, &tmap_b, c0, rb[0], rb[1], rb[2], rb[3], &full[stage], pol_b);
+          tc::tma_gather4(sbm + 4 * GT_SLAB, &tmap_b, c0, rb[4], rb[5], rb[6], rb[7], &full[stage], pol_b);
+          if (++stage == S) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = tc::make_idesc(TF32 ? 2 : 1, GT_BM, GT_BN);
+      int stage = 0; unsigned phase = 0;
+      unsigned tile_n = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int4 it = a.items[item];
+        const int len = a.list_offsets[it.x + 1] - a.list_offsets[it.x];
+        const int r0 = it.z * IB_CH_ROWS, r1 = min(len, r0 + IB_CH_ROWS);
+        for (int cr = r0; cr < r1; cr += GT_BN, ++tile_n) {
+          const unsigned acc = tile_n & 1u, acc_phase = (tile_n >> 1) & 1u;
+          tc::mbar_wait_guarded(&tempty[acc], acc_phase ^ 1u);
+          tc::tc_fence_after();
+          const uint32_t d_tmem = tmem_base + acc * GT_BN;
+          for (int kb = 0; kb < a.k_blocks; ++kb) {
+            tc::mbar_wait_guarded(&full[stage], phase);
+            tc::tc_fence_after();
+            const unsigned char* sa = ring + (size_t)stage * GT_STAGE_BYTES;
+            const uint64_t da = tc::make_smem_desc_sw128(sa);
+            const uint64_t db = tc::make_smem_desc_sw128(sa + GT_A_BYTES);
+#pragma unroll
+            for (int j = 0; j < GT_SLAB / 32; ++j)
+              tc::umma<TF32>(d_tmem, da + (uint64_t)(2 * j), db + (uint64_t)(2 * j), idesc, (kb | j) != 0 ? 1u : 0u);
+            tc::umma_commit(&empty[stage]);
+            if (++stage == S) { stage = 0; phase ^= 1u; }
+          }
+          tc::umma_commit(&tfull[acc]);
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue: thread = one query of the group =====================
+    const int quarter = warp & 3;
+    const int te = quarter * 32 + lane;
+    const int et = threadIdx.x - 64;
+    unsigned tile_n = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int4 it = a.items[item];
+      const int nq = a.q_off[it.x + 1] - a.q_off[it.x];
+      const int n_a = min(GT_BM, nq - it.y * GT_BM);
+      const int lb = a.list_offsets[it.x], len = a.list_offsets[it.x + 1] - lb;
+      const int r0 = it.z * IB_CH_ROWS, r1 = min(len, r0 + IB_CH_ROWS);
+      u64 e[GT_L];
+#pragma unroll
+      for (int s = 0; s < GT_L; ++s) e[s] = 0ull;
+      float thr = te < n_a ? -INFINITY : INFINITY;
+      for (int cr = r0; cr < r1; cr += GT_BN, ++tile_n) {
+        const unsigned acc = tile_n & 1u, acc_phase = (tile_n >> 1) & 1u;
+        float2* sb = sbuf + acc * GT_BN;
+        int* rs = rid_s + acc * GT_BN;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int c = et + h * 128;
+          float2 t;
+          int rid = 0;
+          if (cr + c < r1) {
+            rid = a.list_rows[lb + cr + c];
+            t.x = a.scale ? a.scale[rid] : 1.f;
+            t.y = a.bias ? a.bias[rid] : 0.f;
+          } else { t.x = 0.f; t.y = __int_as_float(0x7fc00000); }
+          sb[c] = t;
+          rs[c] = rid;
+        }
+        tc::named_bar_sync(1, 128);
+        tc::mbar_wait_guarded(&tfull[acc], acc_phase);
+        tc::tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * GT_BN;
+#pragma unroll 1
+        for (int c0 = 0; c0 < GT_BN; c0 += 32) {
+          float v[32];
+          tc::tmem_ld_32x32(taddr + c0, v);
+          unsigned mask = 0u;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float2 t = sb[c0 + j];
+            mask |= (fmaf(v[j], t.x, t.y) >= thr) ? (1u << j) : 0u;
+          }
+          while (mask) {
+            const int j = __ffs(mask) - 1;
+            mask &= mask - 1u;
+            const float2 t = sb[c0 + j];
+            const u64 key = make_key(fmaf(select32(v, j), t.x, t.y), (unsigned)rs[c0 + j]);
+            if (key > e[GT_L - 1]) {
+              list_insert_sorted<GT_L>(e, key);
+              if (e[GT_L - 1] != 0ull) thr = key_score(e[GT_L - 1]);
+            }
+          }
+        }
+        tc::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[acc]);
+      }
+      u64* dst = a.partial + (size_t)item * GT_L * GT_BM;
+#pragma unroll
+      for (int s = 0; s < GT_L; ++s) dst[s * GT_BM + te] = te < n_a ? e[s] : 0ull;
+    }
+  }
+  __syncthreads();
+  if (warp == 1) { tc::tc_fence_after(); tc::tmem_dealloc(tmem_base, 512); }
+}
+
+// ---- work-table construction (all on device, no host sync) ----------------------------------------------
+__global__ void __launch_bounds__(256) ib_pair_hist_kernel(const long long* __restrict__ probes, int n_pairs, int n_lists,
+                                                           int* __restrict__ counts) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_pairs) return;
+  const long long c = probes[i];
+  if (c >= 0 && c < n_lists) atomicAdd(&counts[c], 1);
+}
+__global__ void __launch_bounds__(256) ib_pair_scatter_kernel(const long long* __restrict__ probes, int n_pairs, int n_lists,
+                                                              int* __restrict__ cursor, int* __restrict__ pair_of_pos,
+                                                              int* __restrict__ pos_of_pair) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_pairs) return;
+  const long long c = probes[i];
+  int pos = -1;
+  if (c >= 0 && c < n_lists) { pos = atomicAdd(&cursor[c], 1); pair_of_pos[pos] = i; }
+  pos_of_pair[i] = pos;
+}
+__global__ void __launch_bounds__(256) ib_item_count_kernel(const int* __restrict__ q_off, const int* __restrict__ list_offsets,
+                                                            int n_lists, int* __restrict__ items_c) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_lists) return;
+  const int nq = q_off[c + 1] - q_off[c], len = list_offsets[c + 1] - list_offsets[c];
+  items_c[c] = ((nq + GT_BM - 1) / GT_BM) * ((len + IB_CH_ROWS - 1) / IB_CH_ROWS);
+}
+__global__ void __launch_bounds__(256) ib_item_fill_kernel(const int* __restrict__ item_base, const int* __restrict__ list_offsets,
+                                                           int n_lists, int cap, int4* __restrict__ items,
+                                                           int* __restrict__ n_items) {
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (c >= n_lists) return;
+  const int base = item_base[c], cnt = item_base[c + 1] - base;
+  const int n_ch = (list_offsets[c + 1] - list_offsets[c] + IB_CH_ROWS - 1) / IB_CH_ROWS;
+  for (int i = lane; i < cnt; i += 32)
+    if (base + i < cap) items[base + i] = make_int4(c, i / n_ch, i % n_ch, 0);
+  if (c == n_lists - 1 && lane == 0) *n_items = item_base[n_lists];
+}
+
+// ---- finish: merge the partial lists of one query, exact re-score, certify -----------------------------
+struct IvfFinishArgs {
+  const long long* probes; const int* pos_of_pair; const int* q_off; const int* item_base; const int* list_offsets;
+  const int* n_items; int cap_items, nprobe, n_lists;
+  const u64* partial;
+  const void* rows; int bf16; int d; const float* qn; const float* scale; const float* bias; float eps;
+  int k; long long row_base;
+  long long* out_idx; float* out_score; int* uncertain;
+};
+
+__global__ void __launch_bounds__(128) ivf_finish_kernel(const IvfFinishArgs f) {
+  __shared__ u64 keys[IB_MERGE_CAP];
+  __shared__ u64 ex[GT_MAX_L];
+  const int b = blockIdx.x;
+  const bool overflow = *f.n_items > f.cap_items;
+  int n = 0;   // keys buffered so far (uniform across the CTA)
+  for (int p = 0; p < f.nprobe && !overflow; ++p) {
+    const long long c = f.probes[(size_t)b * f.nprobe + p];
+    if (c < 0 || c >= f.n_lists) continue;
+    const int len = f.list_offsets[c + 1] - f.list_offsets[c];
+    if (len == 0) continue;
+    const int n_ch = (len + IB_CH_ROWS - 1) / IB_CH_ROWS;
+    const int rel = f.pos_of_pair[(size_t)b * f.nprobe + p] - f.q_off[c];
+    const int t = rel / GT_BM, te = rel % GT_BM;
+    for (int j = 0; j < n_ch; ++j) {
+      const int item = f.item_base[c] + t * n_ch + j;
+      if (n + GT_L > IB_MERGE_CAP) {        // buffer full: keep the best GT_L so far
+        __syncthreads();
+        for (int i = n + threadIdx.x; i < IB_MERGE_CAP; i += blockDim.x) keys[i] = 0ull;
+        block_bitonic_sort_desc(keys, IB_MERGE_CAP);
+        n = GT_L;
+      }
+      if (threadIdx.x < GT_L) keys[n + threadIdx.x] = f.partial[((size_t)item * GT_L + threadIdx.x) * GT_BM + te];
+      n += GT_L;
+    }
+  }
+  __syncthreads();
+  for (int i = n + threadIdx.x; i < IB_MERGE_CAP; i += blockDim.x) keys[i] = 0ull;
+  block_bitonic_sort_desc(keys, IB_MERGE_CAP);
+  RescoreArgs ra;
+  ra.rows = f.rows; ra.bf16 = f.bf16; ra.d = f.d; ra.q = f.qn + (size_t)b * f.d; ra.scale = f.scale; ra.bias = f.bias;
+  ra.eps = f.eps; ra.k = f.k; ra.L = GT_L; ra.row_base = f.row_base;
+  ra.out_idx = f.out_idx + (size_t)b * f.k; ra.out_score = f.out_score + (size_t)b * f.k;
+  ra.uncertain = f.uncertain + b;
+  rescore_and_write(keys, IB_MERGE_CAP, ex, ra);
+  // no candidate at all (every probed list empty -> the reference scans all rows, hippocampal.py:269-270) or a
+  // work table that did not fit: hand the query back to the per-query path
+  if (threadIdx.x == 0 && (overflow || keys[0] == 0ull)) f.uncertain[b] = 1;
+}
+
+static size_t a256(size_t v) { return (v + 255) / 256 * 256; }
+static int ib_cap_items(int n_queries, int nprobe, int n_lists) {
+  const long long pairs = (long long)n_queries * nprobe;
+  long long cap = 4ll * n_lists + pairs / 16 + 1024;
+  if (cap > 200000) cap = 200000;
+  return (int)cap;
+}
+
+struct IbLayout {
+  size_t probes, counts, q_off, cursor, pair_of_pos, pos_of_pair, items_c, item_base, n_items, items, qn, qb, partial, coarse, total;
+};
+static IbLayout ib_layout(int n_queries, int d, int n_lists, int nprobe, int cap, size_t coarse_bytes) {
+  IbLayout L;
+  size_t o = 0;
+  const size_t pairs = (size_t)n_queries * nprobe;
+  L.probes = o; o += a256(pairs * 8);
+  L.counts = o; o += a256((size_t)n_lists * 4);
+  L.q_off = o; o += a256((size_t)(n_lists + 1) * 4);
+  L.cursor = o; o += a256((size_t)n_lists * 4);
+  L.pair_of_pos = o; o += a256(pairs * 4);
+  L.pos_of_pair = o; o += a256(pairs * 4);
+  L.items_c = o; o += a256((size_t)n_lists * 4);
+  L.item_base = o; o += a256((size_t)(n_lists + 1) * 4);
+  L.n_items = o; o += 256;
+  L.items = o; o += a256((size_t)cap * 16);
+  L.qn = o; o += a256((size_t)n_queries * d * 4);
+  L.qb = o; o += a256((size_t)n_queries * d * 2);
+  L.partial = o; o += a256((size_t)cap * GT_L * GT_BM * 8);
+  L.coarse = o; o += a256(coarse_bytes);
+  L.total = o;
+  return L;
+}
+
+// ivf.cu
+size_t ivf_coarse_ws_bytes(int n_queries, int d, int n_cent, int nprobe);
+int ivf_run_coarse(const float* queries, int n_queries, int d, const float* centroids, int n_cent, int nprobe,
+                   long long* probes, void* workspace, cudaStream_t st);
+// gemm_topk.cu
+void launch_normalize_queries(const float* q, int n, int d, float* qn, __nv_bfloat16* qb, cudaStream_t st);
+
+}  // namespace aura
+using namespace aura;
+
+extern "C" size_t aura_ivf_search_batch_workspace_bytes(int n_queries, int d, int n_centroid_rows, int nprobe) {
+  if (n_queries < 1 || d < 1 || n_centroid_rows < 1 || nprobe < 1) return 0;
+  const int cap = ib_cap_items(n_queries, nprobe, n_centroid_rows);
+  return ib_layout(n_queries, d, n_centroid_rows, nprobe, cap, ivf_coarse_ws_bytes(n_queries, d, n_centroid_rows, nprobe)).total;
+}
+
+extern "C" int aura_ivf_search_batch(const void* rows, int dtype, int64_t n_rows, int d, const float* queries, int n_queries,
+                                     const float* centroids, int n_centroid_rows, int nprobe, const int32_t* list_offsets,
+                                     const int32_t* list_rows, const float* scale, const float* bias, int k, int64_t row_base,
+                                     float eps, int64_t* out_idx, float* out_score, int32_t* out_uncertain, void* workspace,
+                                     size_t workspace_bytes, void* stream) {
+  AURA_REQUIRE(dtype == AURA_F32 || dtype == AURA_BF16, AURA_ERR_INVALID_ARG, "aura_ivf_search_batch: bad dtype %d", dtype);
+  AURA_REQUIRE(n_rows >= 1 && n_rows < 0x7fffffffll && d >= 1 && n_queries >= 1 && n_centroid_rows >= 1, AURA_ERR_INVALID_ARG,
+               "aura_ivf_search_batch: n_rows=%lld d=%d n_queries=%d n_centroid_rows=%d", (long long)n_rows, d, n_queries,
+               n_centroid_rows);
+  AURA_REQUIRE(nprobe >= 1 && nprobe <= AURA_MAX_NPROBE && nprobe <= n_centroid_rows, AURA_ERR_INVALID_ARG,
+               "aura_ivf_search_batch: nprobe=%d", nprobe);
+  AURA_REQUIRE(k >= 1 && k + 14 <= GT_L, AURA_ERR_UNSUPPORTED, "aura_ivf_search_batch: k=%d too large (max %d)", k, GT_L - 14);
+  const bool bf16 = dtype == AURA_BF16;
+  const int eb = bf16 ? 2 : 4;
+  AURA_REQUIRE(((size_t)d * eb) % 16 == 0 && (d % 4) == 0 && (reinterpret_cast<uintptr_t>(rows) & 15) == 0, AURA_ERR_UNSUPPORTED,
+               "aura_ivf_search_batch: rows must be 16-byte aligned with a 16-byte multiple pitch (d=%d)", d);
+  AURA_REQUIRE(rows && queries && centroids && list_offsets && list_rows && out_idx && out_score && out_uncertain && workspace,
+               AURA_ERR_INVALID_ARG, "aura_ivf_search_batch: null pointer");
+  AURA_REQUIRE(workspace_bytes >= aura_ivf_search_batch_workspace_bytes(n_queries, d, n_centroid_rows, nprobe),
+               AURA_ERR_WORKSPACE, "aura_ivf_search_batch: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int cap = ib_cap_items(n_queries, nprobe, n_centroid_rows);
+  const IbLayout L = ib_layout(n_queries, d, n_centroid_rows, nprobe, cap, ivf_coarse_ws_bytes(n_queries, d, n_centroid_rows, nprobe));
+  unsigned char* ws = reinterpret_cast<unsigned char*>(workspace);
+  long long* probes = reinterpret_cast<long long*>(ws + L.probes);
+  int* counts = reinterpret_cast<int*>(ws + L.counts);
+  int* q_off = reinterpret_cast<int*>(ws + L.q_off);
+  int* cursor = reinterpret_cast<int*>(ws + L.cursor);
+  int* pair_of_pos = reinterpret_cast<int*>(ws + L.pair_of_pos);
+  int* pos_of_pair = reinterpret_cast<int*>(ws + L.pos_of_pair);
+  int* items_c = reinterpret_cast<int*>(ws + L.items_c);
+  int* item_base = reinterpret_cast<int*>(ws + L.item_base);
+  int* n_items = reinterpret_cast<int*>(ws + L.n_items);
+  int4* items = reinterpret_cast<int4*>(ws + L.items);
+  float* qn = reinterpret_cast<float*>(ws + L.qn);
+  __nv_bfloat16* qb = bf16 ? reinterpret_cast<__nv_bfloat16*>(ws + L.qb) : nullptr;
+  u64* partial = reinterpret_cast<u64*>(ws + L.partial);
+
+  int rc = ivf_run_coarse(queries, n_queries, d, centroids, n_centroid_rows, nprobe, probes, ws + L.coarse, st);
+  if (rc != AURA_OK) return rc;
+  launch_normalize_queries(queries, n_queries, d, qn, qb, st);
+  const int n_pairs = n_queries * nprobe;
+  AURA_CUDA_OK(cudaMemsetAsync(counts, 0, (size_t)n_centroid_rows * 4, st));
+  ib_pair_hist_kernel<<<(n_pairs + 255) / 256, 256, 0, st>>>(probes, n_pairs, n_centroid_rows, counts);
+  launch_scan_offsets(counts, n_centroid_rows, q_off, cursor, st);
+  ib_pair_scatter_kernel<<<(n_pairs + 255) / 256, 256, 0, st>>>(probes, n_pairs, n_centroid_rows, cursor, pair_of_pos, pos_of_pair);
+  ib_item_count_kernel<<<(n_centroid_rows + 255) / 256, 256, 0, st>>>(q_off, list_offsets, n_centroid_rows, items_c);
+  launch_scan_offsets(items_c, n_centroid_rows, item_base, cursor, st);
+  ib_item_fill_kernel<<<(n_centroid_rows * 32 + 255) / 256, 256, 0, st>>>(item_base, list_offsets, n_centroid_rows, cap, items, n_items);
+  note_launches(4);
+
+  CUtensorMap tq, tb;
+  rc = encode_tmap_2d(&tq, bf16 ? (const void*)qb : (const void*)qn, eb, bf16, n_queries, d, 1);
+  if (rc != AURA_OK) return rc;
+  rc = encode_tmap_2d(&tb, rows, eb, bf16, n_rows, d, 1);
+  if (rc != AURA_OK) return rc;
+  IvfBatchArgs a;
+  a.n_lists = n_centroid_rows; a.nprobe = nprobe; a.cap_items = cap;
+  const int elems = GT_SLAB / eb;
+  a.k_blocks = (d + elems - 1) / elems;
+  const size_t fixed = 2 * GT_BN * 8 + 2 * GT_BN * 4 + (2 * GT_MAX_STAGES + 4) * 8 + 16;
+  int stages = (int)(((size_t)max_smem_optin() - 1024 - fixed) / GT_STAGE_BYTES);
+  if (stages > GT_MAX_STAGES) stages = GT_MAX_STAGES;
+  a.n_stages = stages;
+  a.list_offsets = list_offsets; a.list_rows = list_rows; a.q_off = q_off; a.pair_of_pos = pair_of_pos;
+  a.items = items; a.n_items = n_items; a.scale = scale; a.bias = bias; a.partial = partial;
+  const size_t smem = (size_t)stages * GT_STAGE_BYTES + fixed + 1024;
+  void (*kern)(const CUtensorMap, const CUtensorMap, const IvfBatchArgs) = bf16 ? ivf_gemm_kernel<false> : ivf_gemm_kernel<true>;
+  AURA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<sm_count(), GT_THREADS, smem, st>>>(tq, tb, a);
+  AURA_CUDA_OK(cudaGetLastError());
+
+  IvfFinishArgs f;
+  f.probes = probes; f.pos_of_pair = pos_of_pair; f.q_off = q_off; f.item_base = item_base; f.list_offsets = list_offsets;
+  f.n_items = n_items; f.cap_items = cap; f.nprobe = nprobe; f.n_lists = n_centroid_rows; f.partial = partial;
+  f.rows = rows; f.bf16 = bf16 ? 1 : 0; f.d = d; f.qn = qn; f.scale = scale; f.bias = bias; f.eps = eps; f.k = k;
+  f.row_base = row_base; f.out_idx = reinterpret_cast<long long*>(out_idx); f.out_score = out_score; f.uncertain = out_uncertain;
+  ivf_finish_kernel<<<n_queries, 128, 0, st>>>(f);
+  AURA_CUDA_OK(cudaGetLastError());
+  note_launches(2);
+  return AURA_OK;
+}

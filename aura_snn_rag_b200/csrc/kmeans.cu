@@ -286,6 +286,11 @@ void launch_row_sq_norms(const float* x, int n, int d, float* out, cudaStream_t 
   note_launches(1);
 }
 
+void launch_scan_offsets(const int* counts, int n, int* offsets, int* cursor, cudaStream_t st) {
+  scan_offsets_kernel<<<1, 1024, 0, st>>>(counts, n, offsets, cursor);
+  note_launches(1);
+}
+
 static int blocks_for(long long n, int per) {
   long long g = (n + per - 1) / per;
   const long long cap = (long long)sm_count() * 8;

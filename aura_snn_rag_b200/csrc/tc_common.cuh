@@ -30,6 +30,17 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
 
+// ---- TMA gather4: 4 rows (box = [128 bytes of K, 1 row]) of a 2-D tensor land as 4 consecutive 128-byte smem
+// rows, swizzled by the destination row like a tiled SWIZZLE_128B box (verified on B200, scripts/exp/gather4_test.cu)
+__device__ __forceinline__ void tma_gather4(void* dst, const CUtensorMap* map, int c0, int r0, int r1, int r2, int r3,
+                                            uint64_t* bar, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2], %8;"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "l"(policy)
+      : "memory");
+}
+
 // ---- TMEM allocation (one warp, .sync.aligned) ----
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_result, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)), "r"(ncols)
@@ -103,10 +114,119 @@ __device__ __forceinline__ void named_bar_sync(int id, int n_threads) {
 
 }  // namespace tc
 
+// ---- tile geometry and epilogue helpers shared by gemm_topk.cu and ivf_batch.cu ----
+static constexpr int GT_BM = 128;            // A rows per tile (TMEM lanes)
+static constexpr int GT_BN = 256;            // B rows per tile (TMEM columns per accumulator stage)
+static constexpr int GT_SLAB = 128;          // bytes of K per pipeline stage (one swizzle atom row)
+static constexpr int GT_A_BYTES = GT_BM * GT_SLAB;   // 16 KB
+static constexpr int GT_B_BYTES = GT_BN * GT_SLAB;   // 32 KB
+static constexpr int GT_STAGE_BYTES = GT_A_BYTES + GT_B_BYTES;
+static constexpr int GT_MAX_STAGES = 4;
+static constexpr int GT_THREADS = 192;       // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
+static constexpr int GT_L = 32;             // per-row list length kept by the epilogue (registers)
+static constexpr int GT_L_ASSIGN = 4;       // list length of the nearest-centroid variant
+static constexpr int GT_MAX_L = 64;
+
+
+// v[j] for a run-time j without spilling v[] to local memory: 5-level select tree
+__device__ __forceinline__ float select32(const float (&v)[32], int j) {
+  float a[16], b[8], c[4];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) a[i] = (j & 16) ? v[i + 16] : v[i];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) b[i] = (j & 8) ? a[i + 8] : a[i];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) c[i] = (j & 4) ? b[i + 4] : b[i];
+  const float d0 = (j & 2) ? c[2] : c[0], d1 = (j & 2) ? c[3] : c[1];
+  return (j & 1) ? d1 : d0;
+}
+
+// thread-private top-GT_L list, sorted descending, entirely in registers.  All compares are independent
+// (key > e[i] is monotone in i), so an insertion is ~GT_L predicated moves with no dependent chain.
+template <int L>
+__device__ __forceinline__ void list_insert_sorted(u64 (&e)[L], u64 key) {
+#pragma unroll
+  for (int i = L - 1; i >= 1; --i) {
+    const bool ci = key > e[i], cp = key > e[i - 1];
+    e[i] = ci ? (cp ? e[i - 1] : key) : e[i];
+  }
+  e[0] = key > e[0] ? key : e[0];
+}
+
+// Per-lane partial of dot(bank row, fp32 query) in exactly the operation order of scan_topk.cu (lane-strided 128-bit
+// chunks, fmaf nest); warp_sum() of the result is bit-identical to the scan kernel's dot product.
+__device__ __forceinline__ float exact_dot_partial(const void* rows, int bf16, int d, unsigned row, const float* q, int lane) {
+  float acc = 0.f;
+  const float4* q4 = reinterpret_cast<const float4*>(q);
+  if (bf16) {
+    const uint4* x8 = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(rows) + (size_t)row * d);
+    for (int ch = lane; ch < (d >> 3); ch += 32) {
+      const uint4 x = x8[ch];
+      const float4 qa = q4[2 * ch], qb = q4[2 * ch + 1];
+      acc = fmaf(bf16_lo(x.x), qa.x, acc); acc = fmaf(bf16_hi(x.x), qa.y, acc);
+      acc = fmaf(bf16_lo(x.y), qa.z, acc); acc = fmaf(bf16_hi(x.y), qa.w, acc);
+      acc = fmaf(bf16_lo(x.z), qb.x, acc); acc = fmaf(bf16_hi(x.z), qb.y, acc);
+      acc = fmaf(bf16_lo(x.w), qb.z, acc); acc = fmaf(bf16_hi(x.w), qb.w, acc);
+    }
+  } else {
+    const float4* x4 = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(rows) + (size_t)row * d);
+    for (int ch = lane; ch < (d >> 2); ch += 32) {
+      const float4 x = x4[ch], qq = q4[ch];
+      acc = fmaf(x.x, qq.x, fmaf(x.y, qq.y, fmaf(x.z, qq.z, fmaf(x.w, qq.w, acc))));
+    }
+  }
+  return acc;
+}
+
+
+// ---- shared tail of the finish kernels: exact fp32 re-score of the L best tensor-core candidates + certification ----
+// keys[0..n2) sorted descending (approximate keys), ex = GT_MAX_L scratch keys in shared memory; 128 threads.
+struct RescoreArgs {
+  const void* rows; int bf16; int d;
+  const float* q;              // this query, normalised fp32
+  const float* scale; const float* bias; float eps;
+  int k, L; long long row_base;
+  long long* out_idx; float* out_score; int* uncertain;   // already offset to this query
+};
+__device__ __forceinline__ void rescore_and_write(const u64* keys, int n2, u64* ex, const RescoreArgs& f) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_cand = min(f.L, n2);
+  for (int c = warp; c < GT_MAX_L; c += 4) {
+    u64 key = 0ull;
+    if (c < n_cand && keys[c] != 0ull) {
+      const unsigned row = key_row(keys[c]);
+      const float dot = warp_sum(exact_dot_partial(f.rows, f.bf16, f.d, row, f.q, lane));
+      const float sc = f.scale ? f.scale[row] : 1.f, bi = f.bias ? f.bias[row] : 0.f;
+      key = make_key(fmaf(dot, sc, bi), row);
+    }
+    if (lane == 0) ex[c] = key;
+  }
+  block_bitonic_sort_desc(ex, GT_MAX_L);
+  for (int i = threadIdx.x; i < f.k; i += blockDim.x) {
+    const u64 key = i < GT_MAX_L ? ex[i] : 0ull;
+    f.out_idx[i] = key ? f.row_base + (long long)key_row(key) : -1ll;
+    f.out_score[i] = key ? key_score(key) : -INFINITY;
+  }
+  if (threadIdx.x == 0 && f.uncertain) {
+    // rows outside the shortlist have approximate score <= s_L (the L-th best approximate score), hence exact
+    // score <= s_L + eps: the result is certified when the exact k-th best beats that
+    int flag = 0;
+    if (f.L - 1 < n2 && keys[f.L - 1] != 0ull) {
+      const float bound = key_score(keys[f.L - 1]) + f.eps;
+      const u64 kth = ex[min(f.k, GT_MAX_L) - 1];
+      if (kth == 0ull || !(key_score(kth) > bound)) flag = 1;
+    }
+    *f.uncertain = flag;
+  }
+}
+
 // ---- host: tensor-map encode through the runtime's driver entry point (no -lcuda link dependency) ----
 // 2-D row-major matrix [n_rows, d] of `elem_bytes`-byte elements; box = [128 bytes of K, box_rows], SWIZZLE_128B.
 int encode_tmap_2d(CUtensorMap* map, const void* base, int elem_bytes, bool bf16, long long n_rows, int d, int box_rows);
 
+
+// kmeans.cu: exclusive scan of counts[0..n) -> offsets[0..n] (and cursor := offsets), single CTA
+void launch_scan_offsets(const int* counts, int n, int* offsets, int* cursor, cudaStream_t st);
 
 // gemm_topk.cu: nearest-centroid assignment / coarse probe selection on the tcgen05 kernel
 bool tc_assign_supported(const void* rows, int dtype, long long n_rows, int d, int n_cent);

@@ -333,8 +333,13 @@ class HippocampalFormation(nn.Module):
         if self._centroid_path() and not force_exact:
             self._ensure_lists()
             nprobe = min(self.nprobe, self.centroids_k, self._centroid_buffer_rows())   # :262
-            idx, score = ops.ivf_search(self.memory_features, m, q, self.centroids, nprobe, self._list_offsets,
-                                        self._list_rows, kk, scale, bias)
+            if q.shape[0] >= ops.TC_IVF_MIN_BATCH and ops.batch_topk_supported(self.memory_features, kk):
+                idx, score = ops.ivf_search_batched(self.memory_features, m, q, self.centroids, nprobe,
+                                                    self._list_offsets, self._list_rows, kk, scale, bias,
+                                                    eps=ops.TC_EPS_COS * 0.5 * self._max_strength())
+            else:
+                idx, score = ops.ivf_search(self.memory_features, m, q, self.centroids, nprobe, self._list_offsets,
+                                            self._list_rows, kk, scale, bias)
         else:
             idx, score = self._exact(q, kk, scale, bias, 0.5 * self._max_strength())
         if gather:

@@ -338,3 +338,40 @@ def allpairs_topk(rows: torch.Tensor, k: int = 32, inv_norm: Optional[torch.Tens
     check(lib.aura_allpairs_topk(rows.data_ptr(), code, n, d, a_first, na, inv_norm.data_ptr(), k, out_idx.data_ptr(),
                                  out_score.data_ptr(), ws.data_ptr(), ws.numel(), _stream()), "aura_allpairs_topk")
     return out_idx, out_score
+
+
+TC_IVF_MIN_BATCH = 64          # list-major grouped GEMM pays off once lists are shared by several queries
+
+
+def ivf_search_batched(rows: torch.Tensor, n_rows: int, queries: torch.Tensor, centroids: torch.Tensor, nprobe: int,
+                       list_offsets: torch.Tensor, list_rows: torch.Tensor, k: int, scale: Optional[torch.Tensor],
+                       bias: Optional[torch.Tensor] = None, row_base: int = 0, eps: float = TC_EPS_COS,
+                       stats: Optional[dict] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Centroid-path query for a block of queries: list-major tensor-core pass (aura_ivf_search_batch), then the
+    per-query path for the queries it hands back (uncertified / no candidates)."""
+    rows = _dev(rows, "rows")
+    queries = _dev(queries, "queries")
+    if queries.dtype != torch.float32:
+        raise TypeError("queries must be float32")
+    b, d = queries.shape
+    c = centroids.shape[0]
+    dev = rows.device
+    out_idx = torch.empty(b, k, dtype=torch.int64, device=dev)
+    out_score = torch.empty(b, k, dtype=torch.float32, device=dev)
+    flags = torch.empty(b, dtype=torch.int32, device=dev)
+    lib = _lib.load()
+    ws = _workspace(lib.aura_ivf_search_batch_workspace_bytes(b, d, c, nprobe), dev, "ivfbatch")
+    check(lib.aura_ivf_search_batch(rows.data_ptr(), _dtype_code(rows), n_rows, d, queries.data_ptr(), b,
+                                    centroids.data_ptr(), c, nprobe, list_offsets.data_ptr(), list_rows.data_ptr(),
+                                    _ptr(scale), _ptr(bias), k, row_base, float(eps), out_idx.data_ptr(),
+                                    out_score.data_ptr(), flags.data_ptr(), ws.data_ptr(), ws.numel(), _stream()),
+          "aura_ivf_search_batch")
+    bad = torch.nonzero(flags, as_tuple=False).squeeze(-1)
+    if stats is not None:
+        stats["uncertain"] = stats.get("uncertain", 0) + int(bad.numel())
+    if bad.numel() > 0:
+        i2, s2 = ivf_search(rows, n_rows, queries[bad].contiguous(), centroids, nprobe, list_offsets, list_rows, k, scale,
+                            bias, row_base)
+        out_idx[bad] = i2
+        out_score[bad] = s2
+    return out_idx, out_score

@@ -147,6 +147,18 @@ int aura_ivf_search(const void* rows, int dtype, int64_t n_rows, int d, const fl
                     int64_t* out_idx, float* out_score, int64_t* out_probes, void* workspace, size_t workspace_bytes,
                     void* stream);
 
+/* Block-of-queries form of aura_ivf_search: the (query, probe) pairs are sorted by list and every probed list is
+ * scored ONCE against the group of queries probing it (ragged grouped GEMM on tcgen05, operands gathered by row id with
+ * TMA gather4), so a batch reads each probed list once instead of once per query.  Results: exact fp32 scores of the
+ * best candidates (same re-score + certification as aura_batch_topk); out_uncertain[b] = 1 hands query b back to
+ * aura_ivf_search (uncertified result, no candidates, or work table overflow).  k <= 18, d*sizeof(elem) % 16 == 0. */
+size_t aura_ivf_search_batch_workspace_bytes(int n_queries, int d, int n_centroid_rows, int nprobe);
+int aura_ivf_search_batch(const void* rows, int dtype, int64_t n_rows, int d, const float* queries, int n_queries,
+                          const float* centroids, int n_centroid_rows, int nprobe, const int32_t* list_offsets,
+                          const int32_t* list_rows, const float* scale, const float* bias, int k, int64_t row_base,
+                          float eps, int64_t* out_idx, float* out_score, int32_t* out_uncertain, void* workspace,
+                          size_t workspace_bytes, void* stream);
+
 /* ---- batched exact search on the tensor cores (the batch the reference loops over one query at a
  * time, memory_augmented_layer.py:113-128; score of hippocampal.py:272-307) -------------------
  * Same result contract as aura_scan_topk.  tcgen05 (tf32 from an fp32 bank, bf16 from a bf16 bank) scores

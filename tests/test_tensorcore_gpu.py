@@ -162,3 +162,35 @@ def test_tensorcore_coarse_probes_match_exact_coarse(monkeypatch):
     # TF32 scores: same nearest centroid, same distance profile up to the rounding of 2 q.c
     assert (res["1"][:, 0] == ref[:, 0]).float().mean() > 0.99
     np.testing.assert_allclose(torch.gather(dist, 1, res["1"]).numpy(), torch.gather(dist, 1, ref).numpy(), rtol=2e-3)
+
+
+@pytest.mark.parametrize("n,d,c,p,b,k,dt", [(30000, 128, 64, 8, 200, 10, torch.float32),
+                                            (60000, 256, 300, 16, 333, 10, torch.float32),
+                                            (40000, 128, 100, 8, 128, 5, torch.bfloat16)])
+def test_ivf_search_batched_equals_per_query_path(n, d, c, p, b, k, dt):
+    """List-major grouped-GEMM IVF (aura_ivf_search_batch) vs the per-query scan of the same probed lists."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(n + c)
+    centres = torch.randn(c // 2, d, generator=g)
+    bank = (centres[torch.randint(0, c // 2, (n,), generator=g)] + 0.5 * torch.randn(n, d, generator=g)).to(dt)
+    rows = bank.to(DEV)
+    inv = ops.row_inv_norms(rows)
+    cent = torch.zeros(c + 5, d)                    # 5 zeroed tail rows, as in the reference's 256-row buffer
+    cent[:c] = bank[torch.randperm(n, generator=g)[:c]].float()
+    cent_d = cent.to(DEV)
+    assign = torch.empty(n, dtype=torch.int32, device=DEV)
+    ops.kmeans_assign(rows, n, cent_d, c, assign)
+    offsets = torch.zeros(c + 6, dtype=torch.int32, device=DEV)
+    lrows = torch.zeros(n, dtype=torch.int32, device=DEV)
+    ops.ivf_build_lists(assign, n, c + 5, offsets, lrows)
+    q = (bank[torch.randint(0, n, (b,), generator=g)].float() + 0.2 * torch.randn(b, d, generator=g)).to(DEV)
+    strength = (0.5 + 0.5 * torch.rand(n, generator=g)).to(DEV)
+    scale, bias = 0.5 * strength * inv, 0.1 * strength
+    stats = {}
+    i1, s1 = ops.ivf_search_batched(rows, n, q, cent_d, p, offsets, lrows, k, scale, bias, eps=0.5 * ops.TC_EPS_COS,
+                                    stats=stats)
+    i2, s2 = ops.ivf_search(rows, n, q, cent_d, p, offsets, lrows, k, scale, bias)
+    torch.cuda.synchronize()
+    assert stats["uncertain"] < b // 2              # the grouped pass itself must answer most queries
+    assert torch.equal(s1, s2)
+    assert torch.equal(i1, i2)
