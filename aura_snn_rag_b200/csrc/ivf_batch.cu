@@ -6,9 +6,14 @@
 // wanted by ~32 queries.  Here the (query, probe) pairs are counting-sorted BY LIST and every list is scored once
 // against the group of queries that probe it - a ragged grouped GEMM on the tensor cores:
 //   item  = (list c, tile of <= 128 of its queries, chunk of <= 2048 of its rows)
-//   A     = the queries of the group, gathered by row id with TMA gather4 from the normalised query block
-//   B     = the rows of the list chunk, gathered by row id with TMA gather4 straight from the bank (CSR order),
-//           so the inverted lists stay an index (int32 row ids) and the bank keeps the reference's insertion order
+//   A     = the queries of the group, gathered by row id from the normalised query block
+//   B     = the rows of the list chunk, gathered by row id straight from the bank (CSR order), so the inverted
+//           lists stay an index (int32 row ids) and the bank keeps the reference's insertion order.
+//           Gathers are 16-byte cp.async (LDGSTS) copies issued by 4 producer warps into the SWIZZLE_128B layout
+//           the UMMA descriptors expect (8 lanes cover one 128-byte row slab; chunk j of row r lands at
+//           r*128 + ((j ^ (r & 7)) << 4)), multi-stage via commit/wait groups, then fence.proxy.async + mbarrier
+//           arrive.  (TMA tile::gather4 gives the same layout - scripts/exp/gather4_test.cu - but measured only
+//           ~5 GB/s per SM on B200: 57 ms per C4 batch against 6 ms of list bytes at the HBM roofline.)
 //   MMA / TMEM / epilogue as in gemm_topk.cu (tf32 from an fp32 bank, bf16 from a bf16 bank, per-row top-32 in
 //   registers), one partial list per (pair, chunk)
 // and a finish kernel merges a query's partial lists, re-scores the 32 best in exact fp32 and certifies the top-k
@@ -22,6 +27,8 @@ namespace aura {
 static constexpr int IB_CH_TILES = 8;                       // column tiles per item
 static constexpr int IB_CH_ROWS = IB_CH_TILES * GT_BN;      // 2048 list rows per item
 static constexpr int IB_MERGE_CAP = 2048;                   // keys the finish kernel sorts at a time
+static constexpr int IB_THREADS = 288;                      // warp 0 MMA, warps 1-4 epilogue, warps 5-8 gather producers
+static constexpr int IB_LOOKAHEAD = 2;                      // stages a producer thread keeps in flight behind the newest
 
 struct IvfBatchArgs {
   int n_lists, nprobe, k_blocks, n_stages, cap_items;
@@ -34,9 +41,18 @@ struct IvfBatchArgs {
   u64* partial;             // [cap_items][GT_L][128]
 };
 
+// 16-byte global -> shared async copy; src_bytes = 0 writes zeros (K tail past the end of a row)
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, unsigned src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 template <bool TF32>
-__global__ void __launch_bounds__(GT_THREADS, 1)
-ivf_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_b, const IvfBatchArgs a) {
+__global__ void __launch_bounds__(IB_THREADS, 1)
+ivf_gemm_kernel(const unsigned char* __restrict__ qmat, const unsigned char* __restrict__ bank, const int row_pitch,
+                const IvfBatchArgs a) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int S = a.n_stages;
@@ -53,57 +69,70 @@ ivf_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   constexpr int ELEMS_PER_SLAB = TF32 ? 32 : 64;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < S; ++s) { mbar_init(&full[s], 128); mbar_init(&empty[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4); }
     fence_mbar_init();
-    tc::tma_prefetch_desc(&tmap_q);
-    tc::tma_prefetch_desc(&tmap_b);
   }
-  if (warp == 1) { tc::tmem_alloc(tmem_slot, 512); tc::tmem_relinquish(); }
+  if (warp == 0) { tc::tmem_alloc(tmem_slot, 512); tc::tmem_relinquish(); }
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int n_items = min(*a.n_items, a.cap_items);
 
-  if (warp == 0) {
-    // ===================== producer warp: every lane issues gather4 copies =====================
-    const uint64_t pol_b = l2_policy_evict_first();
-    const uint64_t pol_a = l2_policy_evict_last();
+  if (warp >= 5) {
+    // ===================== gather producers: 128 threads, 16-byte cp.async into the swizzled stage =====================
+    const int pt = threadIdx.x - 160;               // 0..127
+    const int prow = pt >> 3, pj = pt & 7;          // this thread copies chunk pj of rows prow + 16*i
+    const uint32_t dst_off = (uint32_t)(prow * GT_SLAB + ((pj ^ (prow & 7)) << 4));
+    const uint32_t ring_u32 = smem_u32(ring);
     int stage = 0; unsigned phase = 0;
+    int pend_stage[IB_LOOKAHEAD];                   // stages whose copies are committed but not yet published
+    int n_pend = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const int4 it = a.items[item];
       const int qb = a.q_off[it.x], nq = a.q_off[it.x + 1] - qb;
       const int a0 = qb + it.y * GT_BM, n_a = min(GT_BM, nq - it.y * GT_BM);
       const int lb = a.list_offsets[it.x], len = a.list_offsets[it.x + 1] - lb;
       const int r0 = it.z * IB_CH_ROWS, r1 = min(len, r0 + IB_CH_ROWS);
-      int qa[4];   // query rows of A-tile rows 4*lane .. 4*lane+3 (rows past the group re-load a valid query, masked later)
+      const unsigned char* qsrc[8];   // A-tile rows prow + 16*i (rows past the group re-load a valid query, masked later)
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int i = min(4 * lane + u, n_a - 1);
-        qa[u] = a.pair_of_pos[a0 + i] / a.nprobe;
-      }
+      for (int i = 0; i < 8; ++i)
+        qsrc[i] = qmat + (size_t)(a.pair_of_pos[a0 + min(prow + 16 * i, n_a - 1)] / a.nprobe) * row_pitch + pj * 16;
       for (int cr = r0; cr < r1; cr += GT_BN) {
-        int rb[8];   // bank rows of B-tile rows 8*lane .. 8*lane+7
+        int rb[16];                   // bank rows of B-tile rows prow + 16*i
 #pragma unroll
-        for (int u = 0; u < 8; ++u) rb[u] = a.list_rows[lb + min(cr + 8 * lane + u, r1 - 1)];
+        for (int i = 0; i < 16; ++i) rb[i] = a.list_rows[lb + min(cr + prow + 16 * i, r1 - 1)];
         for (int kb = 0; kb < a.k_blocks; ++kb) {
-          if (lane == 0) {
-            tc::mbar_wait_guarded(&empty[stage], phase ^ 1u);
-            mbar_arrive_expect_tx(&full[stage], GT_STAGE_BYTES);
+          tc::mbar_wait_guarded(&empty[stage], phase ^ 1u);
+          const uint32_t sa = ring_u32 + (uint32_t)stage * GT_STAGE_BYTES + dst_off;
+          const size_t koff = (size_t)kb * GT_SLAB;
+          const bool in_row = (int)koff + pj * 16 < row_pitch;     // pitch is a multiple of 16: a chunk is all in or all out
+          const unsigned nb = in_row ? 16u : 0u;
+          const size_t ko = in_row ? koff : 0;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) cp_async16(sa + i * 16 * GT_SLAB, qsrc[i] + ko, nb);
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            cp_async16(sa + GT_A_BYTES + i * 16 * GT_SLAB, bank + (size_t)rb[i] * row_pitch + ko + pj * 16, nb);
+          cp_async_commit();
+          if (n_pend == IB_LOOKAHEAD) {             // the oldest committed stage has landed: publish it
+            cp_async_wait<IB_LOOKAHEAD>();
+            fence_proxy_async();
+            mbar_arrive(&full[pend_stage[0]]);
+#pragma unroll
+            for (int u = 0; u + 1 < IB_LOOKAHEAD; ++u) pend_stage[u] = pend_stage[u + 1];
+            --n_pend;
           }
-          __syncwarp();
-          unsigned char* sa = ring + (size_t)stage * GT_STAGE_BYTES;
-          const int c0 = kb * ELEMS_PER_SLAB;
-          tc::tma_gather4(sa + (size_t)(4 * lane) * GT_SLAB, &tmap_q, c0, qa[0], qa[1], qa[2], qa[3], &full[stage], pol_a);
-          unsigned char* sbm = sa + GT_A_BYTES + (size_t)(8 * lane) * GT_SLAB;
-          tc::tma_gather4(sbm, &tmap_b, c0, rb[0], rb[1], rb[2], rb[3], &full[stage], pol_b);
-          tc::tma_gather4(sbm + 4 * GT_SLAB, &tmap_b, c0, rb[4], rb[5], rb[6], rb[7], &full[stage], pol_b);
+          pend_stage[n_pend++] = stage;
           if (++stage == S) { stage = 0; phase ^= 1u; }
         }
       }
     }
-  } else if (warp == 1) {
+    cp_async_wait<0>();
+    fence_proxy_async();
+    for (int u = 0; u < n_pend; ++u) mbar_arrive(&full[pend_stage[u]]);
+  } else if (warp == 0) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       const uint32_t idesc = tc::make_idesc(TF32 ? 2 : 1, GT_BM, GT_BN);
@@ -138,7 +167,7 @@ ivf_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     // ===================== epilogue: thread = one query of the group =====================
     const int quarter = warp & 3;
     const int te = quarter * 32 + lane;
-    const int et = threadIdx.x - 64;
+    const int et = threadIdx.x - 32;
     unsigned tile_n = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const int4 it = a.items[item];
@@ -202,7 +231,7 @@ ivf_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     }
   }
   __syncthreads();
-  if (warp == 1) { tc::tc_fence_after(); tc::tmem_dealloc(tmem_base, 512); }
+  if (warp == 0) { tc::tc_fence_after(); tc::tmem_dealloc(tmem_base, 512); }
 }
 
 // ---- work-table construction (all on device, no host sync) ----------------------------------------------
@@ -392,11 +421,6 @@ extern "C" int aura_ivf_search_batch(const void* rows, int dtype, int64_t n_rows
   ib_item_fill_kernel<<<(n_centroid_rows * 32 + 255) / 256, 256, 0, st>>>(item_base, list_offsets, n_centroid_rows, cap, items, n_items);
   note_launches(4);
 
-  CUtensorMap tq, tb;
-  rc = encode_tmap_2d(&tq, bf16 ? (const void*)qb : (const void*)qn, eb, bf16, n_queries, d, 1);
-  if (rc != AURA_OK) return rc;
-  rc = encode_tmap_2d(&tb, rows, eb, bf16, n_rows, d, 1);
-  if (rc != AURA_OK) return rc;
   IvfBatchArgs a;
   a.n_lists = n_centroid_rows; a.nprobe = nprobe; a.cap_items = cap;
   const int elems = GT_SLAB / eb;
@@ -408,9 +432,11 @@ extern "C" int aura_ivf_search_batch(const void* rows, int dtype, int64_t n_rows
   a.list_offsets = list_offsets; a.list_rows = list_rows; a.q_off = q_off; a.pair_of_pos = pair_of_pos;
   a.items = items; a.n_items = n_items; a.scale = scale; a.bias = bias; a.partial = partial;
   const size_t smem = (size_t)stages * GT_STAGE_BYTES + fixed + 1024;
-  void (*kern)(const CUtensorMap, const CUtensorMap, const IvfBatchArgs) = bf16 ? ivf_gemm_kernel<false> : ivf_gemm_kernel<true>;
+  void (*kern)(const unsigned char*, const unsigned char*, int, const IvfBatchArgs) =
+      bf16 ? ivf_gemm_kernel<false> : ivf_gemm_kernel<true>;
   AURA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<sm_count(), GT_THREADS, smem, st>>>(tq, tb, a);
+  kern<<<sm_count(), IB_THREADS, smem, st>>>(reinterpret_cast<const unsigned char*>(bf16 ? (const void*)qb : (const void*)qn),
+                                             reinterpret_cast<const unsigned char*>(rows), d * eb, a);
   AURA_CUDA_OK(cudaGetLastError());
 
   IvfFinishArgs f;

@@ -49,6 +49,14 @@ q = hf.memory_features[pick] + 0.1 * 0.05 * torch.randn(B, D, device=dev, genera
 ms, (iv_idx, iv_sc) = timed(lambda: hf.retrieve_batch(q, K), iters=2, warm=1)
 res["ivf_batch_ms"] = ms
 res["ivf_qps"] = B / ms * 1e3
+st = {}
+hf._ensure_lists(); sc_, bi_ = hf._row_terms(None)
+ops.ivf_search_batched(hf.memory_features, hf.memory_count, q, hf.centroids, P, hf._list_offsets, hf._list_rows, K, sc_, bi_,
+                       eps=ops.TC_EPS_COS * 0.5, stats=st)
+res["ivf_uncertified_queries"] = st["uncertain"]
+probed = hf.centroid_counts[ops.ivf_coarse(q, hf.centroids, P).unique()].sum()
+res["probed_list_bytes_GB"] = float(probed) * D * 4 / 1e9
+res["ivf_list_bytes_per_s_TB"] = res["probed_list_bytes_GB"] / ms
 ms, (ex_idx, ex_sc) = timed(lambda: hf.retrieve_batch(q, K, force_exact=True), iters=2, warm=1)
 res["exact_batch_ms"] = ms
 res["exact_qps"] = B / ms * 1e3
