@@ -39,7 +39,14 @@ struct IvfBatchArgs {
   const int* n_items;       // device scalar
   const float* scale; const float* bias;           // per bank row
   u64* partial;             // [cap_items][GT_L][128]
+  int use_gthr, spread;     // tuning switches (experiments)
+  unsigned* gthr;           // [B] orderable lower bound of every query's final L-th best score (atomicMax)
 };
+
+// group position i (0..127) <-> A-tile row / TMEM lane: consecutive positions go to different epilogue warps, so a
+// group of ~32 queries keeps all four warps busy instead of filling warp 0 only
+__device__ __forceinline__ int ib_row_of_pos(int i, int spread) { return spread ? (i & 3) * 32 + (i >> 2) : i; }
+__device__ __forceinline__ int ib_pos_of_row(int r, int spread) { return spread ? (r & 31) * 4 + (r >> 5) : r; }
 
 // 16-byte global -> shared async copy; src_bytes = 0 writes zeros (K tail past the end of a row)
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, unsigned src_bytes) {
@@ -98,40 +105,64 @@ ivf_gemm_kernel(const unsigned char* __restrict__ qmat, const unsigned char* __r
       const unsigned char* qsrc[8];   // A-tile rows prow + 16*i (rows past the group re-load a valid query, masked later)
 #pragma unroll
       for (int i = 0; i < 8; ++i)
-        qsrc[i] = qmat + (size_t)(a.pair_of_pos[a0 + min(prow + 16 * i, n_a - 1)] / a.nprobe) * row_pitch + pj * 16;
+        qsrc[i] = qmat + (size_t)(a.pair_of_pos[a0 + min(ib_pos_of_row(prow + 16 * i, a.spread), n_a - 1)] / a.nprobe) * row_pitch + pj * 16;
       for (int cr = r0; cr < r1; cr += GT_BN) {
         int rb[16];                   // bank rows of B-tile rows prow + 16*i
 #pragma unroll
         for (int i = 0; i < 16; ++i) rb[i] = a.list_rows[lb + min(cr + prow + 16 * i, r1 - 1)];
-        for (int kb = 0; kb < a.k_blocks; ++kb) {
-          tc::mbar_wait_guarded(&empty[stage], phase ^ 1u);
-          const uint32_t sa = ring_u32 + (uint32_t)stage * GT_STAGE_BYTES + dst_off;
-          const size_t koff = (size_t)kb * GT_SLAB;
-          const bool in_row = (int)koff + pj * 16 < row_pitch;     // pitch is a multiple of 16: a chunk is all in or all out
-          const unsigned nb = in_row ? 16u : 0u;
-          const size_t ko = in_row ? koff : 0;
+        // k-blocks go in PAIRS into two consecutive stages: the two 128-byte pieces of a row are adjacent in memory
+        // and are requested back to back, so DRAM serves them from one open page (256 B per row visit, not 128 B)
+        for (int kb = 0; kb < a.k_blocks; kb += 2) {
+          const int nkb = min(2, a.k_blocks - kb);
+          int st[2]; unsigned sa[2];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) cp_async16(sa + i * 16 * GT_SLAB, qsrc[i] + ko, nb);
+          for (int h = 0; h < 2; ++h) {
+            st[h] = stage;
+            if (h < nkb) {
+              tc::mbar_wait_guarded(&empty[stage], phase ^ 1u);
+              sa[h] = ring_u32 + (uint32_t)stage * GT_STAGE_BYTES + dst_off;
+              if (++stage == S) { stage = 0; phase ^= 1u; }
+            }
+          }
+          const size_t koff0 = (size_t)kb * GT_SLAB;
+          bool in_row[2]; size_t ko[2];
 #pragma unroll
-          for (int i = 0; i < 16; ++i)
-            cp_async16(sa + GT_A_BYTES + i * 16 * GT_SLAB, bank + (size_t)rb[i] * row_pitch + ko + pj * 16, nb);
+          for (int h = 0; h < 2; ++h) {
+            in_row[h] = h < nkb && (int)(koff0 + h * GT_SLAB) + pj * 16 < row_pitch;
+            ko[h] = in_row[h] ? koff0 + h * GT_SLAB : 0;
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+              if (h < nkb) cp_async16(sa[h] + i * 16 * GT_SLAB, qsrc[i] + ko[h], in_row[h] ? 16u : 0u);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const unsigned char* src = bank + (size_t)rb[i] * row_pitch + pj * 16;
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+              if (h < nkb) cp_async16(sa[h] + GT_A_BYTES + i * 16 * GT_SLAB, src + ko[h], in_row[h] ? 16u : 0u);
+          }
           cp_async_commit();
-          if (n_pend == IB_LOOKAHEAD) {             // the oldest committed stage has landed: publish it
-            cp_async_wait<IB_LOOKAHEAD>();
+          if (n_pend == 1) {                        // the previous pair has landed: publish its stages
+            cp_async_wait<1>();
             fence_proxy_async();
             mbar_arrive(&full[pend_stage[0]]);
-#pragma unroll
-            for (int u = 0; u + 1 < IB_LOOKAHEAD; ++u) pend_stage[u] = pend_stage[u + 1];
-            --n_pend;
+            if (pend_stage[1] >= 0) mbar_arrive(&full[pend_stage[1]]);
+            n_pend = 0;
           }
-          pend_stage[n_pend++] = stage;
-          if (++stage == S) { stage = 0; phase ^= 1u; }
+          pend_stage[0] = st[0];
+          pend_stage[1] = nkb == 2 ? st[1] : -1;
+          n_pend = 1;
         }
       }
     }
     cp_async_wait<0>();
     fence_proxy_async();
-    for (int u = 0; u < n_pend; ++u) mbar_arrive(&full[pend_stage[u]]);
+    if (n_pend) {
+      mbar_arrive(&full[pend_stage[0]]);
+      if (pend_stage[1] >= 0) mbar_arrive(&full[pend_stage[1]]);
+    }
   } else if (warp == 0) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
@@ -178,9 +209,17 @@ ivf_gemm_kernel(const unsigned char* __restrict__ qmat, const unsigned char* __r
       u64 e[GT_L];
 #pragma unroll
       for (int s = 0; s < GT_L; ++s) e[s] = 0ull;
-      float thr = te < n_a ? -INFINITY : INFINITY;
+      const int my_pos = ib_pos_of_row(te, a.spread);
+      const bool live = my_pos < n_a;
+      float thr = live ? -INFINITY : INFINITY;
+      unsigned* my_gthr = a.gthr + (live ? a.pair_of_pos[a.q_off[it.x] + it.y * GT_BM + my_pos] / a.nprobe : 0);
+      unsigned published = 0u;
       for (int cr = r0; cr < r1; cr += GT_BN, ++tile_n) {
         const unsigned acc = tile_n & 1u, acc_phase = (tile_n >> 1) & 1u;
+        if (live && a.use_gthr) {   // other CTAs scoring other lists of this query may already have raised the bar
+          const unsigned g = *reinterpret_cast<volatile unsigned*>(my_gthr);
+          if (g != 0u) thr = fmaxf(thr, f32_from_orderable(g));
+        }
         float2* sb = sbuf + acc * GT_BN;
         int* rs = rid_s + acc * GT_BN;
 #pragma unroll
@@ -217,17 +256,21 @@ ivf_gemm_kernel(const unsigned char* __restrict__ qmat, const unsigned char* __r
             const u64 key = make_key(fmaf(select32(v, j), t.x, t.y), (unsigned)rs[c0 + j]);
             if (key > e[GT_L - 1]) {
               list_insert_sorted<GT_L>(e, key);
-              if (e[GT_L - 1] != 0ull) thr = key_score(e[GT_L - 1]);
+              if (e[GT_L - 1] != 0ull) thr = fmaxf(thr, key_score(e[GT_L - 1]));
             }
           }
         }
         tc::tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty[acc]);
+        if (live && a.use_gthr && e[GT_L - 1] != 0ull) {   // a full list: its L-th best bounds the query's final L-th best from below
+          const unsigned o = (unsigned)(e[GT_L - 1] >> 32);
+          if (o > published) { atomicMax(my_gthr, o); published = o; }
+        }
       }
       u64* dst = a.partial + (size_t)item * GT_L * GT_BM;
 #pragma unroll
-      for (int s = 0; s < GT_L; ++s) dst[s * GT_BM + te] = te < n_a ? e[s] : 0ull;
+      for (int s = 0; s < GT_L; ++s) dst[s * GT_BM + te] = live ? e[s] : 0ull;
     }
   }
   __syncthreads();
@@ -277,7 +320,7 @@ struct IvfFinishArgs {
   const int* n_items; int cap_items, nprobe, n_lists;
   const u64* partial;
   const void* rows; int bf16; int d; const float* qn; const float* scale; const float* bias; float eps;
-  int k; long long row_base;
+  int k; long long row_base; int spread;
   long long* out_idx; float* out_score; int* uncertain;
 };
 
@@ -294,7 +337,7 @@ __global__ void __launch_bounds__(128) ivf_finish_kernel(const IvfFinishArgs f) 
     if (len == 0) continue;
     const int n_ch = (len + IB_CH_ROWS - 1) / IB_CH_ROWS;
     const int rel = f.pos_of_pair[(size_t)b * f.nprobe + p] - f.q_off[c];
-    const int t = rel / GT_BM, te = rel % GT_BM;
+    const int t = rel / GT_BM, te = ib_row_of_pos(rel % GT_BM, f.spread);
     for (int j = 0; j < n_ch; ++j) {
       const int item = f.item_base[c] + t * n_ch + j;
       if (n + GT_L > IB_MERGE_CAP) {        // buffer full: keep the best GT_L so far
@@ -330,7 +373,7 @@ static int ib_cap_items(int n_queries, int nprobe, int n_lists) {
 }
 
 struct IbLayout {
-  size_t probes, counts, q_off, cursor, pair_of_pos, pos_of_pair, items_c, item_base, n_items, items, qn, qb, partial, coarse, total;
+  size_t probes, counts, q_off, cursor, pair_of_pos, pos_of_pair, items_c, item_base, n_items, items, qn, qb, partial, coarse, gthr, total;
 };
 static IbLayout ib_layout(int n_queries, int d, int n_lists, int nprobe, int cap, size_t coarse_bytes) {
   IbLayout L;
@@ -350,6 +393,7 @@ static IbLayout ib_layout(int n_queries, int d, int n_lists, int nprobe, int cap
   L.qb = o; o += a256((size_t)n_queries * d * 2);
   L.partial = o; o += a256((size_t)cap * GT_L * GT_BM * 8);
   L.coarse = o; o += a256(coarse_bytes);
+  L.gthr = o; o += a256((size_t)n_queries * 4);
   L.total = o;
   return L;
 }
@@ -407,6 +451,8 @@ extern "C" int aura_ivf_search_batch(const void* rows, int dtype, int64_t n_rows
   float* qn = reinterpret_cast<float*>(ws + L.qn);
   __nv_bfloat16* qb = bf16 ? reinterpret_cast<__nv_bfloat16*>(ws + L.qb) : nullptr;
   u64* partial = reinterpret_cast<u64*>(ws + L.partial);
+  unsigned* gthr = reinterpret_cast<unsigned*>(ws + L.gthr);
+  AURA_CUDA_OK(cudaMemsetAsync(gthr, 0, (size_t)n_queries * 4, st));
 
   int rc = ivf_run_coarse(queries, n_queries, d, centroids, n_centroid_rows, nprobe, probes, ws + L.coarse, st);
   if (rc != AURA_OK) return rc;
@@ -428,9 +474,12 @@ extern "C" int aura_ivf_search_batch(const void* rows, int dtype, int64_t n_rows
   const size_t fixed = 2 * GT_BN * 8 + 2 * GT_BN * 4 + (2 * GT_MAX_STAGES + 4) * 8 + 16;
   int stages = (int)(((size_t)max_smem_optin() - 1024 - fixed) / GT_STAGE_BYTES);
   if (stages > GT_MAX_STAGES) stages = GT_MAX_STAGES;
+  AURA_REQUIRE(stages >= 4, AURA_ERR_UNSUPPORTED, "aura_ivf_search_batch: needs 4 pipeline stages of shared memory");
   a.n_stages = stages;
   a.list_offsets = list_offsets; a.list_rows = list_rows; a.q_off = q_off; a.pair_of_pos = pair_of_pos;
-  a.items = items; a.n_items = n_items; a.scale = scale; a.bias = bias; a.partial = partial;
+  a.items = items; a.n_items = n_items; a.scale = scale; a.bias = bias; a.partial = partial; a.gthr = gthr;
+  { const char* e = getenv("AURA_IVF_GTHR"); a.use_gthr = e ? atoi(e) : 1; }
+  { const char* e = getenv("AURA_IVF_SPREAD"); a.spread = e ? atoi(e) : 1; }
   const size_t smem = (size_t)stages * GT_STAGE_BYTES + fixed + 1024;
   void (*kern)(const unsigned char*, const unsigned char*, int, const IvfBatchArgs) =
       bf16 ? ivf_gemm_kernel<false> : ivf_gemm_kernel<true>;
@@ -443,7 +492,7 @@ extern "C" int aura_ivf_search_batch(const void* rows, int dtype, int64_t n_rows
   f.probes = probes; f.pos_of_pair = pos_of_pair; f.q_off = q_off; f.item_base = item_base; f.list_offsets = list_offsets;
   f.n_items = n_items; f.cap_items = cap; f.nprobe = nprobe; f.n_lists = n_centroid_rows; f.partial = partial;
   f.rows = rows; f.bf16 = bf16 ? 1 : 0; f.d = d; f.qn = qn; f.scale = scale; f.bias = bias; f.eps = eps; f.k = k;
-  f.row_base = row_base; f.out_idx = reinterpret_cast<long long*>(out_idx); f.out_score = out_score; f.uncertain = out_uncertain;
+  f.row_base = row_base; f.spread = a.spread; f.out_idx = reinterpret_cast<long long*>(out_idx); f.out_score = out_score; f.uncertain = out_uncertain;
   ivf_finish_kernel<<<n_queries, 128, 0, st>>>(f);
   AURA_CUDA_OK(cudaGetLastError());
   note_launches(2);
