@@ -183,10 +183,8 @@ __global__ void __launch_bounds__(32 * (NW + 1), 1) scan_topk_kernel(const ScanA
     // ===== producer warp =====
     const uint64_t pol = l2_policy_evict_first();
     const unsigned char* base = reinterpret_cast<const unsigned char*>(a.rows);
-    long long it = 0;
-    for (long long g = s_begin; g < s_end; g += s_step, ++it) {
-      const int slot = (int)(it % S);
-      const unsigned ph = (unsigned)((it / S) & 1);
+    int slot = 0; unsigned ph = 0;
+    for (long long g = s_begin; g < s_end; g += s_step, slot = (slot + 1 == S ? 0 : slot + 1), ph ^= (slot == 0)) {
       unsigned char* st = ring + (size_t)slot * slot_bytes;
       float* st_scale = reinterpret_cast<float*>(st + a.stage_bytes);
       float* st_bias = st_scale + R;
@@ -232,10 +230,8 @@ __global__ void __launch_bounds__(32 * (NW + 1), 1) scan_topk_kernel(const ScanA
   } else {
     // ===== consumers: one warp per row, RU rows per step =====
     const int rpw = R / NW;  // <= 32
-    long long it = 0;
-    for (long long g = s_begin; g < s_end; g += s_step, ++it) {
-      const int slot = (int)(it % S);
-      const unsigned ph = (unsigned)((it / S) & 1);
+    int slot = 0; unsigned ph = 0;
+    for (long long g = s_begin; g < s_end; g += s_step, slot = (slot + 1 == S ? 0 : slot + 1), ph ^= (slot == 0)) {
       const unsigned char* st = ring + (size_t)slot * slot_bytes;
       const float* st_scale = reinterpret_cast<const float*>(st + a.stage_bytes);
       const float* st_bias = st_scale + R;
@@ -282,17 +278,21 @@ __global__ void __launch_bounds__(32 * (NW + 1), 1) scan_topk_kernel(const ScanA
           for (int u = 0; u < RU; ++u) rp[u] = reinterpret_cast<const float4*>(st + (size_t)min(r + u, w_hi - 1) * row_bytes);
           dot_rows_f32<QB, RU>(rp, reinterpret_cast<const float4*>(qs), d >> 2, lane, acc);
         }
+        // all RU*QB warp reductions first (independent shuffle chains overlap), then the rare insert path
+        float dots[RU][QB];
+#pragma unroll
+        for (int u = 0; u < RU; ++u)
+#pragma unroll
+          for (int qi = 0; qi < QB; ++qi) dots[u][qi] = warp_sum(acc[u][qi]);
 #pragma unroll
         for (int u = 0; u < RU; ++u) {
           const int src = min(r + u, w_hi - 1) - w_lo;
           const float s_u = __shfl_sync(FULL, sc, src), b_u = __shfl_sync(FULL, bi, src);
           const unsigned rid_u = __shfl_sync(FULL, rid, src);
-          const bool valid = (r + u) < w_hi;  // warp-uniform
+          if ((r + u) < w_hi) {  // warp-uniform
 #pragma unroll
-          for (int qi = 0; qi < QB; ++qi) {
-            const float dot = warp_sum(acc[u][qi]);
-            if (valid) {
-              const u64 key = make_key(fmaf(dot, s_u, b_u), rid_u);
+            for (int qi = 0; qi < QB; ++qi) {
+              const u64 key = make_key(fmaf(dots[u][qi], s_u, b_u), rid_u);
               if (key > tk[qi].thr) tk[qi].insert(key, lane);
             }
           }
@@ -425,7 +425,12 @@ static void make_plan(long long expected_rows, int d, int dtype, int n_queries, 
   if (p->pipelined) {
     p->q_bytes = (unsigned)(((size_t)p->qb * d * 4 + 127) / 128 * 128);
     const size_t extra = indirect ? ((size_t)(2 * nprobe + 1) * 4 + 127) / 128 * 128 : 0;
-    int rpw = (int)(49152 / (SCAN_NW * row_bytes));
+    // rows per warp per stage: a power of two, ~48 KB stages, but at least 2 (one-row stages starve the
+    // consumers: measured 4.1 TB/s against 6.5 on B200)
+    int rpw = 1;
+    const size_t stage_budget = dtype == AURA_BF16 ? 65536 : 49152;   // bf16 rows: 4 rows per warp step want rpw % 4 == 0
+    while (rpw * 2 <= 32 && (size_t)(rpw * 2) * SCAN_NW * row_bytes <= stage_budget) rpw *= 2;
+    if (rpw < 2 && (size_t)2 * SCAN_NW * row_bytes * 2 + 8192 <= (size_t)smem_cap) rpw = 2;
     if (const char* e = getenv("AURA_SCAN_RPW")) rpw = atoi(e);   // tuning knob (experiments only)
     if (rpw < 1) rpw = 1;
     if (rpw > 32) rpw = 32;
@@ -437,6 +442,9 @@ static void make_plan(long long expected_rows, int d, int dtype, int n_queries, 
     else {
       int s = (int)(((size_t)smem_cap - fixed) / slot);
       p->n_stage_bufs = s > SCAN_MAX_STAGES ? SCAN_MAX_STAGES : s;
+      // ~150 KB in flight per SM saturates HBM; a deeper ring only took L1 away and measured slower (6.48 vs 6.75 TB/s)
+      while (p->n_stage_bufs > 3 && (size_t)p->n_stage_bufs * slot > 163840) --p->n_stage_bufs;
+      if (const char* e = getenv("AURA_SCAN_STAGES")) { const int v = atoi(e); if (v >= 2 && v <= s && v <= SCAN_MAX_STAGES) p->n_stage_bufs = v; }
       if (const char* e = getenv("AURA_SCAN_STAGES")) { const int v = atoi(e); if (v >= 2 && v <= p->n_stage_bufs) p->n_stage_bufs = v; }
       const size_t ring = (size_t)p->n_stage_bufs * slot;
       size_t mk = 1;  // largest power of two of keys that fits the ring, capped
@@ -466,8 +474,11 @@ static void make_plan(long long expected_rows, int d, int dtype, int n_queries, 
 template <bool BF16, int QB, bool INDIRECT>
 static cudaError_t launch_pipelined(const ScanPlan& p, const ScanArgs& a, cudaStream_t st) {
   void (*kern)(ScanArgs) = nullptr;
+  // bf16 rows carry half the bytes per element: 4 rows per step keep enough loads / FMAs in flight per warp
+  const bool ru4 = BF16 && QB <= 2 && (p.rows_per_stage / SCAN_NW) % 4 == 0 && getenv("AURA_SCAN_RU2") == nullptr;
   switch (p.kpl) {
-    case 1: kern = scan_topk_kernel<BF16, QB, 1, SCAN_NW, SCAN_RU, INDIRECT>; break;
+    case 1: kern = ru4 ? scan_topk_kernel<BF16, QB, 1, SCAN_NW, (BF16 && QB <= 2 ? 4 : SCAN_RU), INDIRECT>
+                       : scan_topk_kernel<BF16, QB, 1, SCAN_NW, SCAN_RU, INDIRECT>; break;
     case 2: kern = scan_topk_kernel<BF16, (QB > 4 ? 4 : QB), 2, SCAN_NW, SCAN_RU, INDIRECT>; break;
     default: kern = scan_topk_kernel<BF16, (QB > 2 ? 2 : QB), 4, SCAN_NW, SCAN_RU, INDIRECT>; break;
   }
