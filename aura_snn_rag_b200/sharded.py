@@ -64,3 +64,95 @@ class ShardedBank:
         cat_score = all_score.permute(1, 0, 2).reshape(b, self.world * k).contiguous()
         out_score, out_idx = self._merge(cat_score, cat_idx, self.world, k, k)
         return out_idx, out_score
+
+
+class ShardedIndex:
+    """Row-sharded centroid index: every rank holds a `HippocampalFormation` over its own rows
+    (global rows [row_base, row_base + memory_count)), the centroids are replicated and kept bit-identical on all
+    ranks, every rank keeps its own CSR slice of every inverted list.
+
+    rebuild : seed rows are fetched from their owners (sum all-reduce of a [k,d] block that only the owner fills),
+              local assign -> local per-list fp64 sums + counts -> all-reduce -> identical new centroids everywhere
+              -> local re-assign + local lists (hippocampal.py:345-377 distributed over ranks).
+    search  : replicated queries, local coarse + fine search with global row ids, all-gather, k-way merge
+              (`ShardedBank.search` plumbing).  nprobe means the same as in the single index, so recall is comparable.
+
+    `all_reduce` / `all_gather` default to torch.distributed (NCCL on GPUs); they are injectable so that the
+    arithmetic can be checked against a single index inside one process (tests/test_sharded_gpu.py).
+    """
+
+    def __init__(self, local, row_base: int, n_total: int, all_reduce: Optional[Callable] = None,
+                 all_gather: Optional[Callable] = None, world: Optional[int] = None):
+        self.local = local
+        self.row_base = int(row_base)
+        self.n_total = int(n_total)
+        self.world = world if world is not None else (dist.get_world_size() if dist.is_initialized() else 1)
+        if all_reduce is None:
+            def all_reduce(t):
+                if self.world > 1:
+                    dist.all_reduce(t)
+                return t
+        if all_gather is None:
+            def all_gather(t):
+                if self.world == 1:
+                    return t.unsqueeze(0)
+                out = torch.empty(self.world * t.shape[0], *t.shape[1:], dtype=t.dtype, device=t.device)
+                dist.all_gather_into_tensor(out, t.contiguous())
+                return out.view(self.world, *t.shape)
+        self._all_reduce, self._all_gather = all_reduce, all_gather
+
+    def rebuild_centroids(self, seed_rows_global: torch.Tensor) -> None:
+        from . import ops
+        hf = self.local
+        m, dev = hf.memory_count, hf.device
+        k = min(hf.centroids_k, self.n_total)
+        rows_c = hf.centroids.shape[0]
+        seeds = seed_rows_global.to(device=dev, dtype=torch.int64)[:k]
+        mine = (seeds >= self.row_base) & (seeds < self.row_base + m)
+        block = torch.zeros(k, hf.memory_features.shape[1], device=dev, dtype=torch.float32)
+        if bool(mine.any()):
+            tmp = torch.empty(int(mine.sum()), block.shape[1], device=dev, dtype=torch.float32)
+            ops.kmeans_seed(hf.memory_features, (seeds[mine] - self.row_base).contiguous(), tmp)
+            block[mine] = tmp
+        self._all_reduce(block)                                   # every seed row has exactly one owner
+        hf.centroids[:k] = block
+        if k < rows_c:
+            hf.centroids[k:].zero_()
+        ops.kmeans_assign(hf.memory_features, m, hf.centroids, k, hf._cid, inv_norm=hf._inv_norm)
+        ops.ivf_build_lists(hf._cid, m, rows_c, hf._list_offsets, hf._list_rows)
+        sums = torch.empty(rows_c, block.shape[1], device=dev, dtype=torch.float64)
+        counts = torch.empty(rows_c, device=dev, dtype=torch.int64)
+        ops.kmeans_list_sums(hf.memory_features, hf._list_offsets, hf._list_rows, rows_c, sums, counts)
+        self._all_reduce(sums)
+        self._all_reduce(counts)
+        ops.kmeans_finalize(sums, counts, k, hf.centroids)        # identical inputs -> identical centroids on all ranks
+        ops.kmeans_assign(hf.memory_features, m, hf.centroids, k, hf._cid, hf.memory_metadata[:, 2], 4,
+                          inv_norm=hf._inv_norm)
+        ops.ivf_build_lists(hf._cid, m, rows_c, hf._list_offsets, hf._list_rows)
+        local_counts = torch.empty(rows_c, device=dev, dtype=torch.float32)
+        ops.ivf_list_counts(hf._list_offsets, rows_c, local_counts)
+        self._all_reduce(local_counts)
+        hf.centroid_counts = local_counts[:max(hf.centroids_k, 1)].clone()
+        hf._lists_dirty = False
+        hf._index_ready = True
+
+    def search(self, queries: torch.Tensor, k: int, exact: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
+        """(global rows int64 [B,k], scores [B,k]) on every rank; centroid path unless `exact`."""
+        from . import ops
+        hf = self.local
+        idx, score = hf.retrieve_batch(queries, k=k, force_exact=exact)
+        idx = torch.where(idx >= 0, idx + self.row_base, idx)
+        if idx.shape[1] < k:                                       # a shard with fewer than k rows
+            pad = k - idx.shape[1]
+            idx = torch.cat([idx, idx.new_full((idx.shape[0], pad), -1)], dim=1)
+            score = torch.cat([score, score.new_full((score.shape[0], pad), float("-inf"))], dim=1)
+        if self.world == 1:
+            return idx, score
+        b = idx.shape[0]
+        all_idx = self._all_gather(idx)                            # [G,B,k]
+        all_score = self._all_gather(score)
+        g = all_idx.shape[0]
+        cat_idx = all_idx.permute(1, 0, 2).reshape(b, g * k).contiguous()
+        cat_score = all_score.permute(1, 0, 2).reshape(b, g * k).contiguous()
+        out_score, out_idx = ops.topk_merge(cat_score, cat_idx, g, k, k)
+        return out_idx, out_score

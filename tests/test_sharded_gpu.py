@@ -1,0 +1,95 @@
+"""Sharded centroid index on one GPU: 3 shards in one process with emulated collectives must reproduce the
+single-index build (centroids, assignments, counts) and its query results; the NCCL plumbing itself is
+exercised by `bench.py --gpus N` and the gloo test."""
+import types
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def test_sharded_index_equals_single_index(monkeypatch):
+    import aura_snn_rag_b200.hippocampal as hmod
+    from aura_snn_rag_b200.sharded import ShardedIndex, shard_range
+    monkeypatch.setattr(hmod, "time", types.SimpleNamespace(time=lambda: 1.79e9))
+    g = torch.Generator().manual_seed(17)
+    n, d, c, p, k, world = 9000, 64, 48, 6, 10, 3
+    centres = torch.randn(24, d, generator=g)
+    rows = centres[torch.randint(0, 24, (n,), generator=g)] + 0.4 * torch.randn(n, d, generator=g)
+    seeds = torch.randperm(n, generator=g)[:c]
+    q = rows[torch.randint(0, n, (40,), generator=g)] + 0.1 * torch.randn(40, d, generator=g)
+
+    def make(m):
+        hf = hmod.HippocampalFormation(n_place_cells=4, n_time_cells=2, n_grid_cells=2, max_memories=m, feature_dim=d,
+                                       centroids_k=c, centroid_rows=c + 8, nprobe=p, track_ids=False)
+        hf.centroids_update_interval = 1 << 40
+        return hf
+
+    single = make(n)
+    single.create_episodic_memories(rows)
+    single.rebuild_centroids(seed_rows=seeds)
+    ref_idx, ref_sc = single.retrieve_batch(q, k)
+
+    shards = []
+    for r in range(world):
+        lo, hi = shard_range(n, r, world)
+        hf = make(hi - lo)
+        hf.create_episodic_memories(rows[lo:hi])
+        shards.append((hf, lo))
+
+    # emulate the collectives: run every rank up to the collective, reduce, continue (lock-step driver)
+    import threading
+    barrier = threading.Barrier(world)
+    slots = {}
+    lock = threading.Lock()
+
+    def make_collectives(rank):
+        state = {"n": 0}
+
+        def all_reduce(t):
+            key = ("r", state["n"]); state["n"] += 1
+            with lock:
+                slots.setdefault(key, []).append(t)
+            barrier.wait()
+            if rank == 0:
+                total = torch.stack([x.double() if x.is_floating_point() else x for x in slots[key]]).sum(0)
+                for x in slots[key]:
+                    x.copy_(total.to(x.dtype))
+            barrier.wait()
+            return t
+
+        def all_gather(t):
+            key = ("g", state["n"]); state["n"] += 1
+            with lock:
+                slots.setdefault(key, {})[rank] = t
+            barrier.wait()
+            out = torch.stack([slots[key][r] for r in range(world)])
+            barrier.wait()
+            return out
+        return all_reduce, all_gather
+
+    results = [None] * world
+
+    def run(rank):
+        torch.cuda.set_device(0)
+        hf, lo = shards[rank]
+        ar, ag = make_collectives(rank)
+        si = ShardedIndex(hf, lo, n, all_reduce=ar, all_gather=ag, world=world)
+        si.rebuild_centroids(seeds)
+        results[rank] = si.search(q.cuda(), k)
+
+    threads = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    [t.start() for t in threads]
+    [t.join() for t in threads]
+    torch.cuda.synchronize()
+    for hf, lo in shards:
+        np.testing.assert_allclose(hf.centroids.cpu().numpy(), single.centroids.cpu().numpy(), rtol=1e-5, atol=1e-6)
+        m = hf.memory_count
+        assert torch.equal(hf._cid[:m].cpu(), single._cid[lo:lo + m].cpu())
+        assert torch.equal(hf.centroid_counts.cpu(), single.centroid_counts.cpu())
+    for r in range(world):
+        idx, sc = results[r]
+        assert torch.equal(idx.cpu(), ref_idx.cpu())
+        np.testing.assert_allclose(sc.cpu().numpy(), ref_sc.cpu().numpy(), rtol=1e-6)
