@@ -302,10 +302,24 @@ def batch_topk(rows: torch.Tensor, queries: torch.Tensor, k: int, scale: Optiona
 
 def exact_topk_batched(rows: torch.Tensor, queries: torch.Tensor, k: int, scale: Optional[torch.Tensor],
                        bias: Optional[torch.Tensor] = None, n_rows: Optional[int] = None, row_base: int = 0,
-                       eps: float = TC_EPS_COS, stats: Optional[dict] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+                       eps: float = TC_EPS_COS, stats: Optional[dict] = None, defer: bool = False):
     """Exact top-k of a query block: tensor-core pass, then the exact streaming scan for the (rare) queries
-    whose result could not be certified.  One small D2H read (the flag count) per call."""
+    whose result could not be certified.  One small D2H read (the flag count) per call.
+
+    defer=True returns (idx, score, flags) WITHOUT reading the flags: the caller must later call
+    `exact_topk_fixup` with the same arguments for the flagged queries (ShardedBank does this after it has
+    enqueued its collectives, so that the only host sync of a step comes after all of its work is queued)."""
     idx, score, flags = batch_topk(rows, queries, k, scale, bias, n_rows, row_base, eps)
+    if defer:
+        return idx, score, flags
+    exact_topk_fixup(flags, idx, score, rows, queries, k, scale, bias, n_rows, row_base, stats)
+    return idx, score
+
+
+def exact_topk_fixup(flags: torch.Tensor, idx: torch.Tensor, score: torch.Tensor, rows: torch.Tensor,
+                     queries: torch.Tensor, k: int, scale: Optional[torch.Tensor], bias: Optional[torch.Tensor] = None,
+                     n_rows: Optional[int] = None, row_base: int = 0, stats: Optional[dict] = None) -> int:
+    """Re-run the flagged queries through the exact scan, in place.  Returns how many were flagged (host sync)."""
     bad = torch.nonzero(flags, as_tuple=False).squeeze(-1)
     if stats is not None:
         stats["uncertain"] = stats.get("uncertain", 0) + int(bad.numel())
@@ -313,7 +327,7 @@ def exact_topk_batched(rows: torch.Tensor, queries: torch.Tensor, k: int, scale:
         i2, s2 = scan_topk(rows, queries[bad].contiguous(), k, scale, bias, n_rows=n_rows, row_base=row_base)
         idx[bad] = i2
         score[bad] = s2
-    return idx, score
+    return int(bad.numel())
 
 
 def allpairs_topk(rows: torch.Tensor, k: int = 32, inv_norm: Optional[torch.Tensor] = None,

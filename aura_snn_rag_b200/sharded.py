@@ -29,40 +29,81 @@ def shard_range(n_rows: int, rank: int, world: int) -> Tuple[int, int]:
 class ShardedBank:
     def __init__(self, local_rows: torch.Tensor, row_base: int, group=None,
                  scale: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None,
-                 local_search: Optional[Callable] = None, merge: Optional[Callable] = None):
+                 local_search: Optional[Callable] = None, merge: Optional[Callable] = None,
+                 stats: Optional[dict] = None):
         self.rows = local_rows
         self.row_base = int(row_base)
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.stats = stats if stats is not None else {}
+        self._fixup = None
         if local_search is None or merge is None:
             from . import ops      # CUDA only; raises without the library
             if scale is None:
                 scale = ops.row_inv_norms(local_rows)
-            local_search = local_search or (lambda q, k: ops.scan_topk(self.rows, q, k, self.scale, self.bias,
-                                                                       row_base=self.row_base))
+            if local_search is None:
+                local_search, self._fixup = self._default_search(ops)
             merge = merge or ops.topk_merge
         self.scale, self.bias = scale, bias
         self._local_search = local_search
         self._merge = merge
 
+    def _default_search(self, ops):
+        """Exact local search: the tensor-core path for query blocks (flags deferred), the streaming scan otherwise."""
+        def search(q, k):
+            n = self.rows.shape[0]
+            if q.shape[0] >= ops.TC_MIN_BATCH and ops.batch_topk_supported(self.rows, k) and n >= 1024:
+                return ops.exact_topk_batched(self.rows, q, k, self.scale, self.bias, row_base=self.row_base, defer=True)
+            return ops.scan_topk(self.rows, q, k, self.scale, self.bias, row_base=self.row_base)
+
+        def fixup(flags, idx, score, q, k):
+            return ops.exact_topk_fixup(flags, idx, score, self.rows, q, k, self.scale, self.bias,
+                                        row_base=self.row_base, stats=self.stats)
+        return search, fixup
+
+    def _gather_merge(self, idx: torch.Tensor, score: torch.Tensor, k: int, flags: Optional[torch.Tensor]):
+        b = idx.shape[0]
+        # one collective: [idx | score bits | flag] per query, rank-major concatenation
+        payload = torch.empty(b, 2 * k + 1, dtype=torch.int64, device=idx.device)
+        payload[:, :k] = idx
+        payload[:, k:2 * k] = score.contiguous().view(torch.int32)
+        payload[:, 2 * k] = flags if flags is not None else 0
+        gathered = torch.empty(self.world * b, 2 * k + 1, dtype=torch.int64, device=idx.device)
+        dist.all_gather_into_tensor(gathered, payload, group=self.group)
+        gathered = gathered.view(self.world, b, 2 * k + 1)
+        cat_idx = gathered[:, :, :k].permute(1, 0, 2).reshape(b, self.world * k).contiguous()
+        cat_score = gathered[:, :, k:2 * k].to(torch.int32).view(torch.float32).permute(1, 0, 2) \
+            .reshape(b, self.world * k).contiguous()
+        out_score, out_idx = self._merge(cat_score, cat_idx, self.world, k, k)
+        any_flag = gathered[:, :, 2 * k].sum(dim=0)               # identical on every rank
+        return out_idx, out_score, any_flag
+
     def search(self, queries: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
         """queries [B,d] identical on all ranks -> (global rows int64 [B,k], scores fp32 [B,k]) on all ranks."""
         if queries.device != self.rows.device:
             queries = queries.to(self.rows.device, non_blocking=True)
-        idx, score = self._local_search(queries, k)
+        res = self._local_search(queries, k)
+        idx, score = res[0], res[1]
+        flags = res[2] if len(res) > 2 else None
         if self.world == 1:
+            if flags is not None:
+                self._fixup(flags, idx, score, queries, k)
             return idx, score
-        b = idx.shape[0]
-        all_idx = torch.empty(self.world * b, k, dtype=idx.dtype, device=idx.device)
-        all_score = torch.empty(self.world * b, k, dtype=score.dtype, device=score.device)
-        dist.all_gather_into_tensor(all_idx, idx.contiguous(), group=self.group)      # rank-major concatenation
-        dist.all_gather_into_tensor(all_score, score.contiguous(), group=self.group)
-        all_idx, all_score = all_idx.view(self.world, b, k), all_score.view(self.world, b, k)
-        # [G,B,k] -> [B,G*k] (the layout aura_topk_merge takes)
-        cat_idx = all_idx.permute(1, 0, 2).reshape(b, self.world * k).contiguous()
-        cat_score = all_score.permute(1, 0, 2).reshape(b, self.world * k).contiguous()
-        out_score, out_idx = self._merge(cat_score, cat_idx, self.world, k, k)
+        out_idx, out_score, any_flag = self._gather_merge(idx, score, k, flags)
+        if flags is not None:
+            # the only host sync of the step, after everything above has been enqueued; every rank sees the same
+            # flags, so the (rare) re-run below is entered by all ranks together
+            bad = torch.nonzero(any_flag, as_tuple=False).squeeze(-1)
+            if bad.numel() > 0:
+                qb = queries[bad].contiguous()
+                fl = torch.ones(bad.numel(), dtype=torch.int32, device=idx.device)
+                i2 = torch.empty(bad.numel(), k, dtype=idx.dtype, device=idx.device)
+                s2 = torch.empty(bad.numel(), k, dtype=score.dtype, device=idx.device)
+                self._fixup(fl, i2, s2, qb, k)
+                i3, s3, _ = self._gather_merge(i2, s2, k, None)
+                out_idx[bad] = i3
+                out_score[bad] = s3
         return out_idx, out_score
 
 

@@ -226,11 +226,9 @@ def run_ours(args):
             hf.create_episodic_memories(blk[a - r0:b - r0])
     sync()
     bank = hf.memory_features
-    def local_search(q, k):            # the product's exact path: tcgen05 shortlist + fp32 re-score (+ scan fallback)
-        return ops.exact_topk_batched(bank, q, k, hf._inv_norm, None, n_rows=hi - lo, row_base=lo, stats=stats)
-
     stats = {}
-    shard = ShardedBank(bank, lo, scale=hf._inv_norm, local_search=local_search, merge=ops.topk_merge)
+    # the product's sharded exact path: tcgen05 shortlist + fp32 re-score per shard, NCCL all-gather, k-way merge
+    shard = ShardedBank(bank, lo, scale=hf._inv_norm, stats=stats)
 
     # ---- queries: distinct batch per step, pinned host copies for the e2e leg
     gq = torch.Generator().manual_seed(SEED_QUERY)
