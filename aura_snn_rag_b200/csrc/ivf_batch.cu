@@ -304,13 +304,15 @@ __global__ void __launch_bounds__(256) ib_item_count_kernel(const int* __restric
 }
 __global__ void __launch_bounds__(256) ib_item_fill_kernel(const int* __restrict__ item_base, const int* __restrict__ list_offsets,
                                                            int n_lists, int cap, int4* __restrict__ items,
-                                                           int* __restrict__ n_items) {
+                                                           int* __restrict__ n_items, int chunk_major) {
   const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (c >= n_lists) return;
   const int base = item_base[c], cnt = item_base[c + 1] - base;
   const int n_ch = (list_offsets[c + 1] - list_offsets[c] + IB_CH_ROWS - 1) / IB_CH_ROWS;
+  const int n_qt = n_ch > 0 ? cnt / n_ch : 1;
   for (int i = lane; i < cnt; i += 32)
-    if (base + i < cap) items[base + i] = make_int4(c, i / n_ch, i % n_ch, 0);
+    if (base + i < cap)   // chunk-major: the query tiles of one chunk are adjacent and share it through L2
+      items[base + i] = chunk_major ? make_int4(c, i % n_qt, i / n_qt, 0) : make_int4(c, i / n_ch, i % n_ch, 0);
   if (c == n_lists - 1 && lane == 0) *n_items = item_base[n_lists];
 }
 
@@ -320,7 +322,7 @@ struct IvfFinishArgs {
   const int* n_items; int cap_items, nprobe, n_lists;
   const u64* partial;
   const void* rows; int bf16; int d; const float* qn; const float* scale; const float* bias; float eps;
-  int k; long long row_base; int spread;
+  int k; long long row_base; int spread, chunk_major;
   long long* out_idx; float* out_score; int* uncertain;
 };
 
@@ -338,8 +340,9 @@ __global__ void __launch_bounds__(128) ivf_finish_kernel(const IvfFinishArgs f) 
     const int n_ch = (len + IB_CH_ROWS - 1) / IB_CH_ROWS;
     const int rel = f.pos_of_pair[(size_t)b * f.nprobe + p] - f.q_off[c];
     const int t = rel / GT_BM, te = ib_row_of_pos(rel % GT_BM, f.spread);
+    const int n_qt = (f.q_off[c + 1] - f.q_off[c] + GT_BM - 1) / GT_BM;
     for (int j = 0; j < n_ch; ++j) {
-      const int item = f.item_base[c] + t * n_ch + j;
+      const int item = f.item_base[c] + (f.chunk_major ? j * n_qt + t : t * n_ch + j);
       if (n + GT_L > IB_MERGE_CAP) {        // buffer full: keep the best GT_L so far
         __syncthreads();
         for (int i = n + threadIdx.x; i < IB_MERGE_CAP; i += blockDim.x) keys[i] = 0ull;
@@ -457,6 +460,8 @@ extern "C" int aura_ivf_search_batch(const void* rows, int dtype, int64_t n_rows
   int rc = ivf_run_coarse(queries, n_queries, d, centroids, n_centroid_rows, nprobe, probes, ws + L.coarse, st);
   if (rc != AURA_OK) return rc;
   launch_normalize_queries(queries, n_queries, d, qn, qb, st);
+  int chunk_major = 1;
+  if (const char* e = getenv("AURA_IVF_ORDER")) chunk_major = atoi(e);
   const int n_pairs = n_queries * nprobe;
   AURA_CUDA_OK(cudaMemsetAsync(counts, 0, (size_t)n_centroid_rows * 4, st));
   ib_pair_hist_kernel<<<(n_pairs + 255) / 256, 256, 0, st>>>(probes, n_pairs, n_centroid_rows, counts);
@@ -464,7 +469,7 @@ extern "C" int aura_ivf_search_batch(const void* rows, int dtype, int64_t n_rows
   ib_pair_scatter_kernel<<<(n_pairs + 255) / 256, 256, 0, st>>>(probes, n_pairs, n_centroid_rows, cursor, pair_of_pos, pos_of_pair);
   ib_item_count_kernel<<<(n_centroid_rows + 255) / 256, 256, 0, st>>>(q_off, list_offsets, n_centroid_rows, items_c);
   launch_scan_offsets(items_c, n_centroid_rows, item_base, cursor, st);
-  ib_item_fill_kernel<<<(n_centroid_rows * 32 + 255) / 256, 256, 0, st>>>(item_base, list_offsets, n_centroid_rows, cap, items, n_items);
+  ib_item_fill_kernel<<<(n_centroid_rows * 32 + 255) / 256, 256, 0, st>>>(item_base, list_offsets, n_centroid_rows, cap, items, n_items, chunk_major);
   note_launches(4);
 
   IvfBatchArgs a;
@@ -492,7 +497,7 @@ extern "C" int aura_ivf_search_batch(const void* rows, int dtype, int64_t n_rows
   f.probes = probes; f.pos_of_pair = pos_of_pair; f.q_off = q_off; f.item_base = item_base; f.list_offsets = list_offsets;
   f.n_items = n_items; f.cap_items = cap; f.nprobe = nprobe; f.n_lists = n_centroid_rows; f.partial = partial;
   f.rows = rows; f.bf16 = bf16 ? 1 : 0; f.d = d; f.qn = qn; f.scale = scale; f.bias = bias; f.eps = eps; f.k = k;
-  f.row_base = row_base; f.spread = a.spread; f.out_idx = reinterpret_cast<long long*>(out_idx); f.out_score = out_score; f.uncertain = out_uncertain;
+  f.row_base = row_base; f.spread = a.spread; f.chunk_major = chunk_major; f.out_idx = reinterpret_cast<long long*>(out_idx); f.out_score = out_score; f.uncertain = out_uncertain;
   ivf_finish_kernel<<<n_queries, 128, 0, st>>>(f);
   AURA_CUDA_OK(cudaGetLastError());
   note_launches(2);

@@ -16,8 +16,7 @@ for r0 in range(0, M, 1 << 18):
 hf.rebuild_centroids(seed_rows=torch.randperm(M, device=dev, generator=g)[:C])
 pick = torch.randint(0, M, (B,), device=dev, generator=g)
 q = hf.memory_features[pick] + 0.005 * torch.randn(B, D, device=dev, generator=g)
-for env in ({"AURA_IVF_GTHR": 0, "AURA_IVF_SPREAD": 0}, {"AURA_IVF_GTHR": 0, "AURA_IVF_SPREAD": 1},
-            {"AURA_IVF_GTHR": 1, "AURA_IVF_SPREAD": 0}, {"AURA_IVF_GTHR": 1, "AURA_IVF_SPREAD": 1}):
+for env in ({"AURA_IVF_ORDER": 0}, {"AURA_IVF_ORDER": 1}, {"AURA_IVF_ORDER": 0}, {"AURA_IVF_ORDER": 1}):
     os.environ.update({k: str(v) for k, v in env.items()})
     ts = []
     for i in range(6):
