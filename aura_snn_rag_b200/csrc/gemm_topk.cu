@@ -268,6 +268,159 @@ __global__ void __launch_bounds__(128) gemm_topk_finish_kernel(const FinishArgs 
   rescore_and_write(keys, f.n2, ex, ra);
 }
 
+// ================================================================================================
+// Small query blocks (B <= 32): roles swapped - the BANK tile is the M operand (128 rows -> TMEM lanes), the whole
+// normalised query block is the N operand and stays resident in shared memory for the kernel's lifetime, so the only
+// stream is the bank (HBM-bound, like the single-query scan, for any B <= 32 - the production block size of
+// MemoryAugmentedLayer, colab_l4_training.py:91).  Epilogue thread = bank row; per (warp, query) a register-distributed
+// WarpTopK behind a warp-uniform threshold, exactly the structure of the scan kernel; CTA merge -> partial lists in the
+// layout gemm_topk_finish_kernel reads -> exact fp32 re-score + certification.
+// ================================================================================================
+static constexpr int SB_NQ = 32;                          // query columns (UMMA N)
+static constexpr int SB_STAGE_BYTES = GT_BM * GT_SLAB;    // one 128-row K-slab of the bank: 16 KB
+static constexpr int SB_MAX_STAGES = 8;
+static constexpr int SB_QBLOCK_BYTES = SB_NQ * GT_SLAB;   // one K-slab of the query block: 4 KB
+
+struct SmallBatchArgs {
+  long long n_rows;
+  int n_queries, k_blocks, n_stages, n_tiles;
+  const float* scale; const float* bias;
+  const unsigned* floor_ord;   // per query: orderable score no top-32 row can be below (0 = none), from a sample pre-pass
+  u64* partial;            // [grid][GT_L][128]
+};
+
+template <bool TF32>
+__global__ void __launch_bounds__(GT_THREADS, 1)
+smallbatch_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_b,
+                       const SmallBatchArgs a) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int S = a.n_stages;
+  unsigned char* qblk = smem;                                           // [k_blocks][SB_NQ rows][128 B]
+  unsigned char* ring = qblk + (size_t)a.k_blocks * SB_QBLOCK_BYTES;    // [S][128 rows][128 B]
+  uint64_t* full = reinterpret_cast<uint64_t*>(ring + (size_t)S * SB_STAGE_BYTES);
+  uint64_t* empty = full + SB_MAX_STAGES;
+  uint64_t* tfull = empty + SB_MAX_STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint64_t* qfull = tempty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(qfull + 1);
+  u64* merge = reinterpret_cast<u64*>(ring);                            // CTA merge scratch once the ring has drained
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int ELEMS_PER_SLAB = TF32 ? 32 : 64;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4); }
+    mbar_init(qfull, 1);
+    fence_mbar_init();
+    tc::tma_prefetch_desc(&tmap_q);
+    tc::tma_prefetch_desc(&tmap_b);
+  }
+  if (warp == 1) { tc::tmem_alloc(tmem_slot, 2 * SB_NQ); tc::tmem_relinquish(); }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int t_begin = (int)(((long long)a.n_tiles * blockIdx.x) / gridDim.x);
+  const int t_end = (int)(((long long)a.n_tiles * (blockIdx.x + 1)) / gridDim.x);
+
+  // lists start filled with a sentinel at the sample floor (row field 0 = invalid row 0xFFFFFFFF): anything scoring
+  // below the floor is rejected by the ordinary threshold test from the first tile on; sentinels are dropped at the merge
+  WarpTopK<1> tk[SB_NQ];
+#pragma unroll
+  for (int c = 0; c < SB_NQ; ++c) {
+    const u64 f = (a.floor_ord != nullptr && c < a.n_queries) ? ((u64)a.floor_ord[c] << 32) : 0ull;
+    tk[c].e[0] = f;
+    tk[c].thr = f;
+  }
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint64_t pol_b = l2_policy_evict_first(), pol_q = l2_policy_evict_last();
+      mbar_arrive_expect_tx(qfull, (unsigned)(a.k_blocks * SB_QBLOCK_BYTES));
+      for (int kb = 0; kb < a.k_blocks; ++kb)
+        tc::tma_load_2d(qblk + (size_t)kb * SB_QBLOCK_BYTES, &tmap_q, kb * ELEMS_PER_SLAB, 0, qfull, pol_q);
+      int stage = 0; unsigned phase = 0;
+      for (int t = t_begin; t < t_end; ++t)
+        for (int kb = 0; kb < a.k_blocks; ++kb) {
+          tc::mbar_wait_guarded(&empty[stage], phase ^ 1u);
+          mbar_arrive_expect_tx(&full[stage], SB_STAGE_BYTES);
+          tc::tma_load_2d(ring + (size_t)stage * SB_STAGE_BYTES, &tmap_b, kb * ELEMS_PER_SLAB, t * GT_BM, &full[stage], pol_b);
+          if (++stage == S) { stage = 0; phase ^= 1u; }
+        }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = tc::make_idesc(TF32 ? 2 : 1, GT_BM, SB_NQ);
+      tc::mbar_wait_guarded(qfull, 0u);
+      int stage = 0; unsigned phase = 0, tile_n = 0;
+      for (int t = t_begin; t < t_end; ++t, ++tile_n) {
+        const unsigned acc = tile_n & 1u, acc_phase = (tile_n >> 1) & 1u;
+        tc::mbar_wait_guarded(&tempty[acc], acc_phase ^ 1u);
+        tc::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * SB_NQ;
+        for (int kb = 0; kb < a.k_blocks; ++kb) {
+          tc::mbar_wait_guarded(&full[stage], phase);
+          tc::tc_fence_after();
+          const uint64_t da = tc::make_smem_desc_sw128(ring + (size_t)stage * SB_STAGE_BYTES);
+          const uint64_t db = tc::make_smem_desc_sw128(qblk + (size_t)kb * SB_QBLOCK_BYTES);
+#pragma unroll
+          for (int j = 0; j < GT_SLAB / 32; ++j)
+            tc::umma<TF32>(d_tmem, da + (uint64_t)(2 * j), db + (uint64_t)(2 * j), idesc, (kb | j) != 0 ? 1u : 0u);
+          tc::umma_commit(&empty[stage]);
+          if (++stage == S) { stage = 0; phase ^= 1u; }
+        }
+        tc::umma_commit(&tfull[acc]);
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int te = quarter * 32 + lane;
+    unsigned tile_n = 0;
+    for (int t = t_begin; t < t_end; ++t, ++tile_n) {
+      const unsigned acc = tile_n & 1u, acc_phase = (tile_n >> 1) & 1u;
+      const long long row = (long long)t * GT_BM + te;
+      const bool valid = row < a.n_rows;
+      const float sc = valid ? (a.scale ? a.scale[row] : 1.f) : 0.f;
+      const float bi = valid ? (a.bias ? a.bias[row] : 0.f) : 0.f;
+      tc::mbar_wait_guarded(&tfull[acc], acc_phase);
+      tc::tc_fence_after();
+      float v[32];
+      tc::tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * SB_NQ, v);
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);        // the accumulator is in registers: release it early
+#pragma unroll
+      for (int c = 0; c < SB_NQ; ++c) {
+        if (c < a.n_queries) {                         // uniform
+          const u64 key = valid ? make_key(fmaf(v[c], sc, bi), (unsigned)row) : 0ull;
+          unsigned pend = __ballot_sync(FULL, key > tk[c].thr);
+          while (pend) {
+            const int src = __ffs(pend) - 1;
+            pend &= pend - 1u;
+            const u64 kx = __shfl_sync(FULL, key, src);
+            if (kx > tk[c].thr) tk[c].insert(kx, lane);
+          }
+        }
+      }
+    }
+  }
+  // ---- CTA merge per query: 4 warps x 32 keys -> best 32 -> partial[blockIdx.x][s][query] ----
+  __syncthreads();
+#pragma unroll 1
+  for (int c = 0; c < a.n_queries; ++c) {
+    u64 mine = 0ull;
+#pragma unroll
+    for (int cc = 0; cc < SB_NQ; ++cc) if (cc == c) mine = tk[cc].e[0];
+    if ((mine & 0xFFFFFFFFull) == 0ull) mine = 0ull;       // floor sentinel / empty slot
+    if (warp >= 2) merge[(warp - 2) * 32 + lane] = mine;
+    block_bitonic_sort_desc(merge, 128);
+    if (threadIdx.x < GT_L) a.partial[((size_t)blockIdx.x * GT_L + threadIdx.x) * GT_BM + c] = merge[threadIdx.x];
+    __syncthreads();
+  }
+  if (warp == 1) { tc::tc_fence_after(); tc::tmem_dealloc(tmem_base, 2 * SB_NQ); }
+}
+
 // ---- host ------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -365,6 +518,96 @@ static int run_gemm_topk(const void* a_mat, long long n_a_rows, long long a_row_
   AURA_CUDA_OK(cudaGetLastError());
   note_launches(1);
   return AURA_OK;
+}
+
+// floor[q] = orderable score of the GT_L-th best key of query q in a sample pass's partial lists (0 when fewer exist)
+__global__ void __launch_bounds__(128) sample_floor_kernel(const u64* __restrict__ partial, int n_groups, int n2,
+                                                           unsigned* __restrict__ floor_ord) {
+  extern __shared__ __align__(16) unsigned char fsm[];
+  u64* keys = reinterpret_cast<u64*>(fsm);
+  const int q = blockIdx.x;
+  for (int i = threadIdx.x; i < n2; i += blockDim.x)
+    keys[i] = i < n_groups * GT_L ? partial[((size_t)(i / GT_L) * GT_L + (i % GT_L)) * GT_BM + q] : 0ull;
+  block_bitonic_sort_desc(keys, n2);
+  if (threadIdx.x == 0) floor_ord[q] = (unsigned)(keys[GT_L - 1] >> 32);
+}
+
+struct SmallPlan { int grid, n_stages, k_blocks, n_tiles, n2; size_t smem; };
+
+static bool make_small_plan(long long n_rows, int d, int elem_bytes, int n_queries, SmallPlan* p) {
+  // measured on B200 (1M x 768 fp32): 693 / 804 us at B = 8 / 16 against 764 / 869 us for the 128-row-tile kernel;
+  // at B = 32 the 32 per-query list updates per tile make it slower (1064 vs 838 us), so it serves B <= 16
+  int max_b = 16;
+  if (const char* e = getenv("AURA_SMALLBATCH")) max_b = atoi(e) == 0 ? 0 : SB_NQ;
+  if (n_queries > max_b) return false;
+  const int elems = GT_SLAB / elem_bytes;
+  p->k_blocks = (d + elems - 1) / elems;
+  const size_t qbytes = (size_t)p->k_blocks * SB_QBLOCK_BYTES;
+  const size_t fixed = (2 * SB_MAX_STAGES + 5) * 8 + 16;
+  const size_t cap = (size_t)max_smem_optin() - 1024;
+  if (qbytes + fixed + 3 * (size_t)SB_STAGE_BYTES > cap) return false;
+  int stages = (int)((cap - qbytes - fixed) / SB_STAGE_BYTES);
+  if (stages > SB_MAX_STAGES) stages = SB_MAX_STAGES;
+  p->n_stages = stages;
+  p->smem = qbytes + (size_t)stages * SB_STAGE_BYTES + fixed + 1024;
+  p->n_tiles = (int)((n_rows + GT_BM - 1) / GT_BM);
+  const int sms = sm_count();
+  p->grid = p->n_tiles < sms ? p->n_tiles : sms;
+  int n2 = 2;
+  while (n2 < p->grid * GT_L) n2 <<= 1;
+  p->n2 = n2;
+  return true;
+}
+
+static int launch_smallbatch(const CUtensorMap& tq, const CUtensorMap& tb, long long n_rows, int n_queries, const float* scale,
+                             const float* bias, const unsigned* floor_ord, const SmallPlan& p, int grid, u64* partial,
+                             bool bf16, cudaStream_t st) {
+  SmallBatchArgs a;
+  a.n_rows = n_rows; a.n_queries = n_queries; a.k_blocks = p.k_blocks; a.n_stages = p.n_stages;
+  a.n_tiles = (int)((n_rows + GT_BM - 1) / GT_BM);
+  a.scale = scale; a.bias = bias; a.floor_ord = floor_ord; a.partial = partial;
+  void (*kern)(const CUtensorMap, const CUtensorMap, const SmallBatchArgs) =
+      bf16 ? smallbatch_topk_kernel<false> : smallbatch_topk_kernel<true>;
+  AURA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+  kern<<<grid, GT_THREADS, p.smem, st>>>(tq, tb, a);
+  AURA_CUDA_OK(cudaGetLastError());
+  note_launches(1);
+  return AURA_OK;
+}
+
+// floor_ord: SB_NQ unsigned of caller scratch
+static int run_smallbatch(const void* q_mat, int n_queries, const void* rows, long long n_rows, int d, bool bf16,
+                          const float* scale, const float* bias, const SmallPlan& p, u64* partial, unsigned* floor_ord,
+                          cudaStream_t st) {
+  const int eb = bf16 ? 2 : 4;
+  CUtensorMap tq, tb;
+  int rc = encode_tmap_2d(&tq, q_mat, eb, bf16, n_queries, d, SB_NQ);
+  if (rc != AURA_OK) return rc;
+  rc = encode_tmap_2d(&tb, rows, eb, bf16, n_rows, d, GT_BM);
+  if (rc != AURA_OK) return rc;
+  // sample pre-pass: one tile per CTA over the first rows gives every query a floor under its final 32nd-best score, so
+  // the per-warp lists of the main pass start selective instead of each paying its own warm-up
+  const long long sample = (long long)p.grid * GT_BM;
+  const unsigned* fl = nullptr;
+  // off by default: measured slower (the pre-pass + floor kernel cost ~200 us, list warm-up was not the bottleneck)
+  const bool use_floor = n_rows >= 16 * sample && getenv("AURA_SMALLBATCH_FLOOR") != nullptr;
+  if (use_floor) {
+    rc = launch_smallbatch(tq, tb, sample, n_queries, scale, bias, nullptr, p, p.grid, partial, bf16, st);
+    if (rc != AURA_OK) return rc;
+    const size_t fsmem = (size_t)p.n2 * 8;
+    AURA_CUDA_OK(cudaFuncSetAttribute(sample_floor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+    sample_floor_kernel<<<n_queries, 128, fsmem, st>>>(partial, p.grid, p.n2, floor_ord);
+    AURA_CUDA_OK(cudaGetLastError());
+    note_launches(1);
+    fl = floor_ord;
+  }
+  return launch_smallbatch(tq, tb, n_rows, n_queries, scale, bias, fl, p, p.grid, partial, bf16, st);
+}
+
+// partial-list region of aura_batch_topk: large enough for either kernel (the small-batch kernel writes one list block per CTA)
+static size_t batch_partial_bytes(const GemmPlan& p) {
+  const size_t small = (size_t)sm_count() * GT_L * GT_BM * 8;
+  return p.partial_bytes > small ? p.partial_bytes : small;
 }
 
 static int check_shapes(const char* who, const void* rows, int dtype, long long n_rows, int d, int k) {
@@ -548,7 +791,7 @@ extern "C" size_t aura_batch_topk_workspace_bytes(int64_t n_rows, int d, int dty
   GemmPlan p;
   if (n_queries < 1 || n_rows < 1 || d < 1 || k < 1) return 0;
   if (!make_gemm_plan(n_queries, n_rows, d, dtype == AURA_BF16 ? 2 : 4, k, true, &p)) return 0;
-  return align256(p.partial_bytes) + align256((size_t)n_queries * d * 4) + align256((size_t)n_queries * d * 2) + 256;
+  return align256(batch_partial_bytes(p)) + align256((size_t)n_queries * d * 4) + align256((size_t)n_queries * d * 2) + 512;
 }
 
 extern "C" int aura_batch_topk(const void* rows, int dtype, int64_t n_rows, int d, const float* queries, int n_queries,
@@ -569,14 +812,25 @@ extern "C" int aura_batch_topk(const void* rows, int dtype, int64_t n_rows, int 
   cudaStream_t st = (cudaStream_t)stream;
   unsigned char* ws = reinterpret_cast<unsigned char*>(workspace);
   u64* partial = reinterpret_cast<u64*>(ws);
-  float* qn = reinterpret_cast<float*>(ws + align256(p.partial_bytes));
-  __nv_bfloat16* qb = bf16 ? reinterpret_cast<__nv_bfloat16*>(ws + align256(p.partial_bytes) + align256((size_t)n_queries * d * 4))
+  float* qn = reinterpret_cast<float*>(ws + align256(batch_partial_bytes(p)));
+  __nv_bfloat16* qb = bf16 ? reinterpret_cast<__nv_bfloat16*>(ws + align256(batch_partial_bytes(p)) + align256((size_t)n_queries * d * 4))
                            : nullptr;
   normalize_queries_kernel<<<(n_queries + 7) / 8, 256, 0, st>>>(queries, n_queries, d, qn, qb);
   note_launches(1);
-  rc = run_gemm_topk(bf16 ? (const void*)qb : (const void*)qn, n_queries, 0, rows, n_rows, d, bf16, scale, bias, false, p,
-                     partial, st);
-  if (rc != AURA_OK) return rc;
+  SmallPlan sp;
+  if (make_small_plan(n_rows, d, bf16 ? 2 : 4, n_queries, &sp)) {
+    // B <= 32: bank tile as the M operand, query block resident in shared memory (HBM-bound for the whole block)
+    unsigned* floor_ord = reinterpret_cast<unsigned*>(ws + align256(batch_partial_bytes(p)) + align256((size_t)n_queries * d * 4) +
+                                                      align256((size_t)n_queries * d * 2));
+    rc = run_smallbatch(bf16 ? (const void*)qb : (const void*)qn, n_queries, rows, n_rows, d, bf16, scale, bias, sp, partial,
+                        floor_ord, st);
+    if (rc != AURA_OK) return rc;
+    p.n_atiles = 1; p.n_groups = sp.grid; p.L = GT_L; p.n2 = sp.n2;
+  } else {
+    rc = run_gemm_topk(bf16 ? (const void*)qb : (const void*)qn, n_queries, 0, rows, n_rows, d, bf16, scale, bias, false, p,
+                       partial, st);
+    if (rc != AURA_OK) return rc;
+  }
   FinishArgs f;
   f.partial = partial; f.n_atiles = p.n_atiles; f.n_groups = p.n_groups; f.L = p.L; f.n2 = p.n2; f.k = k;
   f.n_a_rows = n_queries; f.row_base = row_base; f.rows = rows; f.bf16 = bf16 ? 1 : 0; f.d = d; f.qn = qn;

@@ -50,6 +50,27 @@ if what in ("all", "k6", "k6one"):
             print(f"K6 bf16 B={b:5d}: median {med*1e3:8.1f} us  {2.0*b*n*d/med/1e9:7.1f} TFLOP/s  {n*d*2/med/1e6:6.0f} GB/s  qps {b/med*1e3:9.0f} uncertain {int(fl.sum())}", flush=True)
         del rows16
     del rows32
+if what == "small":
+    rows32 = torch.randn(n, d, device=dev)
+    inv = ops.row_inv_norms(rows32)
+    pick = torch.randint(0, n, (128,), device=dev)
+    qall = rows32[pick] + 0.1 * torch.randn(128, d, device=dev)
+    for dt, rows, iv in (("fp32", rows32, inv),):
+        for b in (1, 2, 4, 8, 16, 32, 33, 64, 128):
+            q = qall[:b].contiguous()
+            for env in ({"AURA_SMALLBATCH": 1}, {"AURA_SMALLBATCH": 0}):
+                os.environ.update({a: str(v) for a, v in env.items()})
+                med, mn = timeit(lambda: ops.batch_topk(rows, q, 10, iv), iters=10)
+                _, _, fl = ops.batch_topk(rows, q, 10, iv)
+                print(f"{dt} B={b:4d} {env}: {med*1e3:8.1f} us  qps {b/med*1e3:9.0f}  GB/s {n*d*4/med/1e6:6.0f} uncertain {int(fl.sum())}", flush=True)
+            med, mn = timeit(lambda: ops.scan_topk(rows, q, 10, iv), iters=5)
+            print(f"{dt} B={b:4d} scan: {med*1e3:8.1f} us  qps {b/med*1e3:9.0f}", flush=True)
+    rows16 = rows32.to(torch.bfloat16); inv16 = ops.row_inv_norms(rows16)
+    os.environ["AURA_SMALLBATCH"] = "1"
+    for b in (8, 32):
+        q = qall[:b].contiguous()
+        med, mn = timeit(lambda: ops.batch_topk(rows16, q, 10, inv16), iters=10)
+        print(f"bf16 B={b:4d}: {med*1e3:8.1f} us  qps {b/med*1e3:9.0f} GB/s {n*d*2/med/1e6:6.0f}", flush=True)
 if what in ("all", "k7", "k7one"):
     for nn in ((262144,) if what == "k7one" else (65536, 262144)):
         bank = torch.randn(nn, d, device=dev).to(torch.bfloat16)
