@@ -5,39 +5,46 @@
 
 namespace aura {
 
+// sum of squares of bank row r, one warp, fixed lane-strided order: the ONLY arithmetic that produces inv_norm, so the
+// value written at insert time (aura_bank_write) and a later recomputation (aura_row_inv_norms) agree bit for bit
+template <bool BF16>
+__device__ __forceinline__ float row_sumsq_warp(const void* rows, long long r, int d, int lane) {
+  float ss = 0.f;
+  if (BF16) {
+    const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(rows) + (size_t)r * d;
+    if ((d & 7) == 0) {
+      const uint4* x8 = reinterpret_cast<const uint4*>(x);
+      for (int c = lane; c < (d >> 3); c += 32) {
+        const uint4 v = x8[c];
+        const unsigned u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { const float a = bf16_lo(u[i]), b = bf16_hi(u[i]); ss = fmaf(a, a, fmaf(b, b, ss)); }
+      }
+    } else {
+      for (int e = lane; e < d; e += 32) { const float v = __bfloat162float(x[e]); ss = fmaf(v, v, ss); }
+    }
+  } else {
+    const float* x = reinterpret_cast<const float*>(rows) + (size_t)r * d;
+    if ((d & 3) == 0) {
+      const float4* x4 = reinterpret_cast<const float4*>(x);
+      for (int c = lane; c < (d >> 2); c += 32) {
+        const float4 v = x4[c];
+        ss = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, ss))));
+      }
+    } else {
+      for (int e = lane; e < d; e += 32) ss = fmaf(x[e], x[e], ss);
+    }
+  }
+  return warp_sum(ss);
+}
+
 template <bool BF16>
 __global__ void __launch_bounds__(256) inv_norm_kernel(const void* rows, long long n_rows, int d, float* inv_norm) {
   const int lane = threadIdx.x & 31;
   const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
   for (long long r = w; r < n_rows; r += nw) {
-    float ss = 0.f;
-    if (BF16) {
-      const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(rows) + (size_t)r * d;
-      if ((d & 7) == 0) {
-        const uint4* x8 = reinterpret_cast<const uint4*>(x);
-        for (int c = lane; c < (d >> 3); c += 32) {
-          const uint4 v = x8[c];
-          const unsigned u[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-          for (int i = 0; i < 4; ++i) { const float a = bf16_lo(u[i]), b = bf16_hi(u[i]); ss = fmaf(a, a, fmaf(b, b, ss)); }
-        }
-      } else {
-        for (int e = lane; e < d; e += 32) { const float v = __bfloat162float(x[e]); ss = fmaf(v, v, ss); }
-      }
-    } else {
-      const float* x = reinterpret_cast<const float*>(rows) + (size_t)r * d;
-      if ((d & 3) == 0) {
-        const float4* x4 = reinterpret_cast<const float4*>(x);
-        for (int c = lane; c < (d >> 2); c += 32) {
-          const float4 v = x4[c];
-          ss = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, ss))));
-        }
-      } else {
-        for (int e = lane; e < d; e += 32) ss = fmaf(x[e], x[e], ss);
-      }
-    }
-    ss = warp_sum(ss);
+    const float ss = row_sumsq_warp<BF16>(rows, r, d, lane);
     if (lane == 0) inv_norm[r] = 1.0f / fmaxf(sqrtf(ss), 1e-12f);  // F.normalize eps, hippocampal.py:278
   }
 }
@@ -92,29 +99,19 @@ __global__ void __launch_bounds__(256) bank_write_kernel(void* rows, int d, long
                                                          const float* __restrict__ feats, float* locations, int sd,
                                                          const float* __restrict__ location, float* metadata,
                                                          float timestamp, float* inv_norm) {
-  __shared__ float warp_ss[8];
   const long long r = first_row + blockIdx.x;
   const float* f = feats + (size_t)blockIdx.x * d;
-  float ss = 0.f;
   for (int e = threadIdx.x; e < d; e += blockDim.x) {
-    float v = f[e];
-    if (BF16) {
-      const __nv_bfloat16 b = __float2bfloat16_rn(v);
-      reinterpret_cast<__nv_bfloat16*>(rows)[(size_t)r * d + e] = b;
-      v = __bfloat162float(b);
-    } else {
-      reinterpret_cast<float*>(rows)[(size_t)r * d + e] = v;
-    }
-    ss = fmaf(v, v, ss);
+    if (BF16) reinterpret_cast<__nv_bfloat16*>(rows)[(size_t)r * d + e] = __float2bfloat16_rn(f[e]);
+    else reinterpret_cast<float*>(rows)[(size_t)r * d + e] = f[e];
   }
-  ss = warp_sum(ss);
-  if ((threadIdx.x & 31) == 0) warp_ss[threadIdx.x >> 5] = ss;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    float t = 0.f;
-    for (int w = 0; w < 8; ++w) t += warp_ss[w];
-    inv_norm[r] = 1.0f / fmaxf(sqrtf(t), 1e-12f);
-    reinterpret_cast<float4*>(metadata)[r] = make_float4(1.0f, timestamp, -1.0f, 0.0f);  // :215,:232
+  __syncthreads();                                   // the stored row is visible to the whole CTA
+  if (threadIdx.x < 32) {                            // norm of the values AS STORED (bf16 banks normalise their rounded rows)
+    const float ss = row_sumsq_warp<BF16>(rows, r, d, threadIdx.x);
+    if (threadIdx.x == 0) {
+      inv_norm[r] = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+      reinterpret_cast<float4*>(metadata)[r] = make_float4(1.0f, timestamp, -1.0f, 0.0f);  // :215,:232
+    }
   }
   if (locations != nullptr && threadIdx.x < sd)
     locations[(size_t)r * sd + threadIdx.x] = location ? location[threadIdx.x] : 0.f;  // :212

@@ -427,3 +427,53 @@ class HippocampalFormation(nn.Module):
                 if b is not None:
                     out[(a, b)] = 1.0 - s
         return out
+
+    # ------------------------------------------------------------------ persistence / resume
+    def refresh_derived(self) -> None:
+        """Recompute everything derived from the registered buffers (inverse norms, int32 centroid ids, inverted
+        lists) - call after `load_state_dict` or after writing `memory_features` / `memory_metadata` directly."""
+        m = self.memory_count
+        if m > 0:
+            ops.row_inv_norms(self.memory_features[:m], out=self._inv_norm[:m])
+            self._cid[:m] = self.memory_metadata[:m, 2].to(torch.int32)
+        self._lists_dirty = True
+        self._terms_key = None
+        self._version += 1
+
+    def index_state(self) -> Dict[str, Any]:
+        """The Python-side state the reference never persists (`memory_count`, `_index_ready`, knobs, id table;
+        TODO.md:11, colab_l4_training.py:712-734 save only the buffers): after a resume the reference's bank is
+        logically empty.  Save this dict next to `state_dict()`; `load_index_state` restores it."""
+        return {
+            "memory_count": int(self.memory_count), "index_ready": bool(self._index_ready),
+            "centroids_k": int(self.centroids_k), "centroids_update_interval": int(self.centroids_update_interval),
+            "nprobe": int(self.nprobe), "use_centroid_index": bool(self.use_centroid_index),
+            "centroid_counts_len": int(self.centroid_counts.numel()),
+            "id_to_idx": dict(self._ids.id_to_idx) if self.track_ids else None,
+            "timestamps": {k: v.timestamp for k, v in self.episodic_memories.items()} if self.track_ids else None,
+        }
+
+    def load_index_state(self, state: Dict[str, Any]) -> None:
+        """Restore `index_state()` after `load_state_dict` (buffer names are the reference's, so old checkpoints load)."""
+        self.memory_count = int(state["memory_count"])
+        self._index_ready = bool(state["index_ready"])
+        self.centroids_k = int(state["centroids_k"])
+        self.centroids_update_interval = int(state["centroids_update_interval"])
+        self.nprobe = int(state["nprobe"])
+        self.use_centroid_index = bool(state["use_centroid_index"])
+        self._ids = IdTable()
+        self.episodic_memories = {}
+        if state.get("id_to_idx") is not None:
+            ts = state.get("timestamps") or {}
+            for mid, row in state["id_to_idx"].items():          # dict order = first-insertion order, as the reference's
+                self._ids.set(mid, int(row))
+                self.episodic_memories[mid] = EpisodicMemory(memory_id=mid, feature_idx=int(row),
+                                                             timestamp=float(ts.get(mid, 0.0)))
+        self.refresh_derived()
+
+    def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs):
+        # the reference rebinds `centroid_counts` to a centroids_k-long tensor on every rebuild (:374): accept either length
+        key = prefix + "centroid_counts"
+        if key in state_dict and state_dict[key].shape != self.centroid_counts.shape:
+            self.centroid_counts = torch.zeros_like(state_dict[key], device=self.device)
+        super()._load_from_state_dict(state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs)

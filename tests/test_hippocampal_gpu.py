@@ -272,3 +272,41 @@ def test_ingestion_and_batched_retrieval_helpers(tmp_path):
     empty = HippocampalFormation(feature_dim=8, n_place_cells=4, n_time_cells=2, n_grid_cells=2, max_memories=8)
     f0, s0 = api.retrieve_memories(empty, torch.randn(3, 8).cuda(), k=4)
     assert f0.shape == (3, 4, 8) and float(f0.abs().sum()) == 0 and float(s0.abs().sum()) == 0
+
+
+def test_checkpoint_resume_restores_the_index(monkeypatch):
+    """state_dict (the reference's 13 buffers) + index_state(): a resumed module answers queries exactly like the
+    original; a state_dict produced by the REFERENCE layout (no derived buffers) loads with strict=True."""
+    import aura_snn_rag_b200.hippocampal as hmod
+    clock = _Clock()
+    monkeypatch.setattr(hmod, "time", types.SimpleNamespace(time=clock.time))
+    g = torch.Generator().manual_seed(31)
+    rows = torch.randn(1500, 48, generator=g)
+
+    def make():
+        hf = hmod.HippocampalFormation(n_place_cells=4, n_time_cells=2, n_grid_cells=2, max_memories=2048, feature_dim=48,
+                                       centroids_k=12, nprobe=3)
+        hf.centroids_update_interval = 500
+        return hf
+
+    a = make()
+    for i in range(1500):
+        clock.now = C.T0 + i
+        a.create_episodic_memory(f"m{i}", "e", rows[i])
+    a.decay_memories(0.1)
+    assert a._index_ready and a.centroid_counts.numel() == 12
+    sd = {k: v.clone() for k, v in a.state_dict().items()}
+    assert len(sd) == 13
+    st = a.index_state()
+    b = make()
+    b.load_state_dict(sd, strict=True)
+    assert b.memory_count == 0 and b.retrieve_similar_memories(rows[0]) == []     # the reference's behaviour after resume
+    b.load_index_state(st)
+    clock.now = C.T0 + 5000
+    for q in (rows[3], rows[700] + 0.1, rows[1499]):
+        assert a.retrieve_similar_memories(q, k=6) == b.retrieve_similar_memories(q, k=6)
+    ia, sa = a.retrieve_batch(rows[:70] + 0.05, k=5)
+    ib, sb = b.retrieve_batch(rows[:70] + 0.05, k=5)
+    assert torch.equal(ia, ib) and torch.equal(sa, sb)
+    b.create_episodic_memory("new", "e", rows[0] * 2)
+    assert b.memory_count == 1501 and b.id_to_idx["new"] == 1500 and list(b.id_to_idx)[:2] == ["m0", "m1"]
