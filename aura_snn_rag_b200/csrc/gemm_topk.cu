@@ -39,6 +39,7 @@ struct GemmTopkArgs {
   const float* scale;         // per B row, may be null (1)
   const float* bias;          // per B row, may be null (0)
   u64* partial;               // [n_atiles * n_groups][L][128]
+  const u64* ceil_keys;       // per A row: only keys strictly below this one are eligible (multi-round top-k), may be null
 };
 
 template <bool TF32, int L>
@@ -144,6 +145,10 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const long long my_row = a.a_row_first + (long long)atile * GT_BM + te;   // global id of this A row
       const bool live = (long long)atile * GT_BM + te < a.n_a_rows;
       float thr = live ? -INFINITY : INFINITY;        // rows past the end of A never select anything
+      // multi-round selection (k > 18): round r only admits keys strictly below the 32nd key of round r-1
+      const u64 ceil_key = (a.ceil_keys != nullptr && live) ? a.ceil_keys[(long long)atile * GT_BM + te] : ~0ull;
+      const float ceil_score = ceil_key == ~0ull ? INFINITY : key_score(ceil_key);
+      if (ceil_key == 0ull) thr = INFINITY;           // previous round already exhausted this row's candidates
       for (int ct = ct0; ct < ct1; ++ct, ++tile_n) {
         const unsigned acc = tile_n & 1u, acc_phase = (tile_n >> 1) & 1u;
         const long long col0 = (long long)ct * GT_BN;
@@ -171,7 +176,8 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const float2 t = sb[c0 + j];
-            mask |= (fmaf(v[j], t.x, t.y) >= thr) ? (1u << j) : 0u;
+            const float sj = fmaf(v[j], t.x, t.y);
+            mask |= (sj >= thr && sj <= ceil_score) ? (1u << j) : 0u;
           }
           if (diag) { const long long dj = my_row - col0 - c0; if (dj >= 0 && dj < 32) mask &= ~(1u << (int)dj); }
           // rare path; the loop runs max-over-lanes popcount(mask) times for the warp
@@ -181,7 +187,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             const float2 t = sb[c0 + j];
             const float sc = fmaf(select32(v, j), t.x, t.y);
             const u64 key = make_key(sc, (unsigned)(col0 + c0 + j));
-            if (key > e[L - 1]) {
+            if (key > e[L - 1] && key < ceil_key) {
               list_insert_sorted<L>(e, key);
               if (e[L - 1] != 0ull) thr = key_score(e[L - 1]);
             }
@@ -233,6 +239,8 @@ struct FinishArgs {
   const float* qn; const float* scale; const float* bias; float eps;
   const float* a_scale;      // K7: output score multiplier per A row (inv_norm of the row), may be null
   long long* out_idx; float* out_score; int* uncertain;
+  // multi-round mode: append this round's 32 best approximate keys to cand[b][round*32..] and publish the new ceiling
+  u64* cand; u64* ceil_out; int round;
 };
 
 __global__ void __launch_bounds__(128) gemm_topk_finish_kernel(const FinishArgs f) {
@@ -259,6 +267,11 @@ __global__ void __launch_bounds__(128) gemm_topk_finish_kernel(const FinishArgs 
       f.out_idx[b * f.k + i] = key ? f.row_base + (long long)key_row(key) : -1ll;
       f.out_score[b * f.k + i] = key ? key_score(key) * mul : -INFINITY;
     }
+    return;
+  }
+  if (f.cand != nullptr) {
+    for (int i = threadIdx.x; i < GT_L; i += blockDim.x) f.cand[(size_t)b * GT_MAX_L + f.round * GT_L + i] = keys[i];
+    if (threadIdx.x == 0) f.ceil_out[b] = keys[GT_L - 1];     // 0 = fewer than 32 were left: nothing below
     return;
   }
   RescoreArgs ra;
@@ -421,6 +434,36 @@ smallbatch_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
   if (warp == 1) { tc::tc_fence_after(); tc::tmem_dealloc(tmem_base, 2 * SB_NQ); }
 }
 
+// multi-round tail: the candidates of all rounds (already in descending approximate order) -> exact re-score + certify
+struct CandRescoreArgs {
+  const u64* cand; int n_cand;      // n_cand = rounds * 32
+  const void* rows; int bf16; int d; const float* qn; const float* scale; const float* bias; float eps;
+  int k; long long row_base; long long* out_idx; float* out_score; int* uncertain;
+};
+__global__ void __launch_bounds__(128) cand_rescore_kernel(const CandRescoreArgs f) {
+  __shared__ u64 keys[GT_MAX_L];
+  __shared__ u64 ex[GT_MAX_L];
+  const long long b = blockIdx.x;
+  for (int i = threadIdx.x; i < GT_MAX_L; i += blockDim.x) keys[i] = i < f.n_cand ? f.cand[(size_t)b * GT_MAX_L + i] : 0ull;
+  __syncthreads();
+  RescoreArgs ra;
+  ra.rows = f.rows; ra.bf16 = f.bf16; ra.d = f.d; ra.q = f.qn + (size_t)b * f.d; ra.scale = f.scale; ra.bias = f.bias;
+  ra.eps = f.eps; ra.k = f.k; ra.L = f.n_cand; ra.row_base = f.row_base;
+  ra.out_idx = f.out_idx + b * f.k; ra.out_score = f.out_score + b * f.k; ra.uncertain = f.uncertain ? f.uncertain + b : nullptr;
+  rescore_and_write(keys, GT_MAX_L, ex, ra);
+}
+int launch_cand_rescore(const u64* cand, int n_cand, const void* rows, int bf16, int d, const float* qn, const float* scale,
+                        const float* bias, float eps, int k, long long row_base, long long* out_idx, float* out_score,
+                        int* uncertain, int n_queries, cudaStream_t st) {
+  CandRescoreArgs f;
+  f.cand = cand; f.n_cand = n_cand; f.rows = rows; f.bf16 = bf16; f.d = d; f.qn = qn; f.scale = scale; f.bias = bias;
+  f.eps = eps; f.k = k; f.row_base = row_base; f.out_idx = out_idx; f.out_score = out_score; f.uncertain = uncertain;
+  cand_rescore_kernel<<<n_queries, 128, 0, st>>>(f);
+  AURA_CUDA_OK(cudaGetLastError());
+  note_launches(1);
+  return AURA_OK;
+}
+
 // ---- host ------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -459,7 +502,9 @@ struct GemmPlan {
 
 static int list_len(int k, bool rescore) {
   // K6 keeps a margin of >= 14 candidates beyond k for the certified re-score; K7 needs exactly k
-  return (rescore ? k + 14 : k) <= GT_L ? GT_L : 0;
+  // K6 keeps a margin of >= 14 candidates beyond k for the certified re-score, in up to GT_MAX_ROUNDS rounds of 32
+  if (rescore) return k + 14 <= GT_MAX_L ? GT_L : 0;
+  return k <= GT_L ? GT_L : 0;
 }
 
 static bool make_gemm_plan(long long n_a_rows, long long n_b_rows, int d, int elem_bytes, int k, bool rescore, GemmPlan* p,
@@ -498,7 +543,7 @@ static size_t align256(size_t v) { return (v + 255) / 256 * 256; }
 
 static int run_gemm_topk(const void* a_mat, long long n_a_rows, long long a_row_first, const void* b_mat, long long n_b_rows,
                          int d, bool bf16, const float* scale, const float* bias, bool exclude_self, const GemmPlan& p,
-                         u64* partial, cudaStream_t st) {
+                         u64* partial, cudaStream_t st, const u64* ceil_keys = nullptr) {
   const int eb = bf16 ? 2 : 4;
   CUtensorMap ta, tb;
   int rc = encode_tmap_2d(&ta, a_mat, eb, bf16, n_a_rows, d, GT_BM);
@@ -509,7 +554,7 @@ static int run_gemm_topk(const void* a_mat, long long n_a_rows, long long a_row_
   a.n_atiles = p.n_atiles; a.n_ctiles = p.n_ctiles; a.n_groups = p.n_groups;
   a.n_a_rows = n_a_rows; a.n_b_rows = n_b_rows; a.a_row_first = a_row_first;
   a.k_blocks = p.k_blocks; a.L = p.L; a.n_stages = p.n_stages; a.exclude_self = exclude_self ? 1 : 0;
-  a.scale = scale; a.bias = bias; a.partial = partial;
+  a.scale = scale; a.bias = bias; a.partial = partial; a.ceil_keys = ceil_keys;
   void (*kern)(const CUtensorMap, const CUtensorMap, const GemmTopkArgs) =
       p.L == GT_L_ASSIGN ? (bf16 ? gemm_topk_kernel<false, GT_L_ASSIGN> : gemm_topk_kernel<true, GT_L_ASSIGN>)
                          : (bf16 ? gemm_topk_kernel<false, GT_L> : gemm_topk_kernel<true, GT_L>);
@@ -610,10 +655,10 @@ static size_t batch_partial_bytes(const GemmPlan& p) {
   return p.partial_bytes > small ? p.partial_bytes : small;
 }
 
-static int check_shapes(const char* who, const void* rows, int dtype, long long n_rows, int d, int k) {
+static int check_shapes(const char* who, const void* rows, int dtype, long long n_rows, int d, int k, int k_max = GT_L) {
   AURA_REQUIRE(dtype == AURA_F32 || dtype == AURA_BF16, AURA_ERR_INVALID_ARG, "%s: bad dtype %d", who, dtype);
   AURA_REQUIRE(n_rows >= 1 && n_rows < 0xFFFFFFFFll && d >= 1, AURA_ERR_INVALID_ARG, "%s: n_rows=%lld d=%d", who, n_rows, d);
-  AURA_REQUIRE(k >= 1 && k <= GT_L, AURA_ERR_INVALID_ARG, "%s: k=%d not in [1,%d]", who, k, GT_L);
+  AURA_REQUIRE(k >= 1 && k <= k_max, AURA_ERR_INVALID_ARG, "%s: k=%d not in [1,%d]", who, k, k_max);
   const int eb = dtype == AURA_BF16 ? 2 : 4;
   AURA_REQUIRE(((size_t)d * eb) % 16 == 0 && (reinterpret_cast<uintptr_t>(rows) & 15) == 0, AURA_ERR_UNSUPPORTED,
                "%s: rows must be 16-byte aligned with a 16-byte multiple row pitch (d=%d)", who, d);
@@ -775,7 +820,7 @@ int tc_coarse(const float* queries, int n_queries, int d, const float* cent, int
   f.partial = partial; f.n_atiles = p.n_atiles; f.n_groups = p.n_groups; f.L = p.L; f.n2 = p.n2; f.k = nprobe;
   f.n_a_rows = n_queries; f.row_base = 0; f.rows = nullptr; f.bf16 = 0; f.d = d; f.qn = nullptr;
   f.scale = nullptr; f.bias = nullptr; f.eps = 0.f; f.a_scale = nullptr;
-  f.out_idx = probes; f.out_score = dummy_score; f.uncertain = nullptr;
+  f.out_idx = probes; f.out_score = dummy_score; f.uncertain = nullptr; f.cand = nullptr; f.ceil_out = nullptr; f.round = 0;
   const size_t fsmem = ((size_t)p.n2 + GT_MAX_L) * 8;
   AURA_CUDA_OK(cudaFuncSetAttribute(gemm_topk_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
   gemm_topk_finish_kernel<<<n_queries, 128, fsmem, st>>>(f);
@@ -791,18 +836,18 @@ extern "C" size_t aura_batch_topk_workspace_bytes(int64_t n_rows, int d, int dty
   GemmPlan p;
   if (n_queries < 1 || n_rows < 1 || d < 1 || k < 1) return 0;
   if (!make_gemm_plan(n_queries, n_rows, d, dtype == AURA_BF16 ? 2 : 4, k, true, &p)) return 0;
-  return align256(batch_partial_bytes(p)) + align256((size_t)n_queries * d * 4) + align256((size_t)n_queries * d * 2) + 512;
+  return align256(batch_partial_bytes(p)) + align256((size_t)n_queries * d * 4) + align256((size_t)n_queries * d * 2) + 512 +
+         align256((size_t)n_queries * GT_MAX_L * 8) + align256((size_t)n_queries * 8);
 }
 
 extern "C" int aura_batch_topk(const void* rows, int dtype, int64_t n_rows, int d, const float* queries, int n_queries,
                                const float* scale, const float* bias, int k, int64_t row_base, float eps,
                                int64_t* out_idx, float* out_score, int32_t* out_uncertain, void* workspace,
                                size_t workspace_bytes, void* stream) {
-  int rc = check_shapes("aura_batch_topk", rows, dtype, n_rows, d, k);
+  int rc = check_shapes("aura_batch_topk", rows, dtype, n_rows, d, k, GT_MAX_L - 14);
   if (rc != AURA_OK) return rc;
   AURA_REQUIRE(n_queries >= 1 && queries && out_idx && out_score && workspace, AURA_ERR_INVALID_ARG,
                "aura_batch_topk: null pointer / n_queries=%d", n_queries);
-  AURA_REQUIRE(k + 14 <= GT_L, AURA_ERR_UNSUPPORTED, "aura_batch_topk: k=%d too large for the certified shortlist (max %d)", k, GT_L - 14);
   const bool bf16 = dtype == AURA_BF16;
   GemmPlan p;
   AURA_REQUIRE(make_gemm_plan(n_queries, n_rows, d, bf16 ? 2 : 4, k, true, &p), AURA_ERR_UNSUPPORTED,
@@ -817,31 +862,53 @@ extern "C" int aura_batch_topk(const void* rows, int dtype, int64_t n_rows, int 
                            : nullptr;
   normalize_queries_kernel<<<(n_queries + 7) / 8, 256, 0, st>>>(queries, n_queries, d, qn, qb);
   note_launches(1);
-  SmallPlan sp;
-  if (make_small_plan(n_rows, d, bf16 ? 2 : 4, n_queries, &sp)) {
-    // B <= 32: bank tile as the M operand, query block resident in shared memory (HBM-bound for the whole block)
-    unsigned* floor_ord = reinterpret_cast<unsigned*>(ws + align256(batch_partial_bytes(p)) + align256((size_t)n_queries * d * 4) +
-                                                      align256((size_t)n_queries * d * 2));
-    rc = run_smallbatch(bf16 ? (const void*)qb : (const void*)qn, n_queries, rows, n_rows, d, bf16, scale, bias, sp, partial,
-                        floor_ord, st);
-    if (rc != AURA_OK) return rc;
-    p.n_atiles = 1; p.n_groups = sp.grid; p.L = GT_L; p.n2 = sp.n2;
-  } else {
-    rc = run_gemm_topk(bf16 ? (const void*)qb : (const void*)qn, n_queries, 0, rows, n_rows, d, bf16, scale, bias, false, p,
-                       partial, st);
-    if (rc != AURA_OK) return rc;
-  }
+  const size_t off_floor = align256(batch_partial_bytes(p)) + align256((size_t)n_queries * d * 4) + align256((size_t)n_queries * d * 2);
+  unsigned* floor_ord = reinterpret_cast<unsigned*>(ws + off_floor);
+  u64* cand = reinterpret_cast<u64*>(ws + off_floor + 512);
+  u64* ceil_buf = cand + align256((size_t)n_queries * GT_MAX_L * 8) / 8;
+  const int rounds = (k + 14 + GT_L - 1) / GT_L;          // 32 candidates per round; k <= 18 needs one
+  const void* a_mat = bf16 ? (const void*)qb : (const void*)qn;
   FinishArgs f;
-  f.partial = partial; f.n_atiles = p.n_atiles; f.n_groups = p.n_groups; f.L = p.L; f.n2 = p.n2; f.k = k;
-  f.n_a_rows = n_queries; f.row_base = row_base; f.rows = rows; f.bf16 = bf16 ? 1 : 0; f.d = d; f.qn = qn;
+  f.k = k; f.n_a_rows = n_queries; f.row_base = row_base; f.rows = rows; f.bf16 = bf16 ? 1 : 0; f.d = d; f.qn = qn;
   f.scale = scale; f.bias = bias; f.eps = eps; f.a_scale = nullptr;
   f.out_idx = reinterpret_cast<long long*>(out_idx); f.out_score = out_score; f.uncertain = out_uncertain;
+  f.cand = nullptr; f.ceil_out = nullptr; f.round = 0;
+  SmallPlan sp;
+  bool used_small = false;
+  if (rounds == 1 && make_small_plan(n_rows, d, bf16 ? 2 : 4, n_queries, &sp)) {
+    used_small = true;
+    // 5 <= B <= 16: bank tile as the M operand, query block resident in shared memory
+    rc = run_smallbatch(a_mat, n_queries, rows, n_rows, d, bf16, scale, bias, sp, partial, floor_ord, st);
+    if (rc != AURA_OK) return rc;
+    p.n_atiles = 1; p.n_groups = sp.grid; p.L = GT_L; p.n2 = sp.n2;
+  }
+  f.partial = partial; f.n_atiles = p.n_atiles; f.n_groups = p.n_groups; f.L = p.L; f.n2 = p.n2;
   const size_t fsmem = ((size_t)p.n2 + GT_MAX_L) * 8;
   AURA_CUDA_OK(cudaFuncSetAttribute(gemm_topk_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
-  gemm_topk_finish_kernel<<<n_queries, 128, fsmem, st>>>(f);
-  AURA_CUDA_OK(cudaGetLastError());
-  note_launches(1);
-  return AURA_OK;
+  if (rounds == 1) {
+    if (!used_small) {
+      rc = run_gemm_topk(a_mat, n_queries, 0, rows, n_rows, d, bf16, scale, bias, false, p, partial, st);
+      if (rc != AURA_OK) return rc;
+    }
+    gemm_topk_finish_kernel<<<n_queries, 128, fsmem, st>>>(f);
+    AURA_CUDA_OK(cudaGetLastError());
+    note_launches(1);
+    return AURA_OK;
+  }
+  // k > 18: rounds of 32.  Round r admits only keys strictly below the 32nd key of round r-1 (total order on
+  // (score, row), identical tensor-core scores in every round), so the rounds enumerate the approximate ranking
+  // without gaps or repeats; all candidates are then re-scored exactly and certified like the one-round case.
+  f.cand = cand; f.ceil_out = ceil_buf;
+  for (int r = 0; r < rounds; ++r) {
+    rc = run_gemm_topk(a_mat, n_queries, 0, rows, n_rows, d, bf16, scale, bias, false, p, partial, st, r ? ceil_buf : nullptr);
+    if (rc != AURA_OK) return rc;
+    f.round = r;
+    gemm_topk_finish_kernel<<<n_queries, 128, fsmem, st>>>(f);
+    AURA_CUDA_OK(cudaGetLastError());
+    note_launches(1);
+  }
+  return launch_cand_rescore(cand, rounds * GT_L, rows, bf16 ? 1 : 0, d, qn, scale, bias, eps, k, row_base,
+                             reinterpret_cast<long long*>(out_idx), out_score, out_uncertain, n_queries, st);
 }
 
 extern "C" size_t aura_allpairs_topk_workspace_bytes(int64_t n_a_rows, int64_t n_rows, int d, int dtype, int k) {
@@ -874,7 +941,7 @@ extern "C" int aura_allpairs_topk(const void* rows, int dtype, int64_t n_rows, i
   f.partial = partial; f.n_atiles = p.n_atiles; f.n_groups = p.n_groups; f.L = p.L; f.n2 = p.n2; f.k = k;
   f.n_a_rows = n_a_rows; f.row_base = 0; f.rows = nullptr; f.bf16 = 0; f.d = d; f.qn = nullptr;
   f.scale = nullptr; f.bias = nullptr; f.eps = 0.f; f.a_scale = inv_norm ? inv_norm + a_row_first : nullptr;
-  f.out_idx = reinterpret_cast<long long*>(out_idx); f.out_score = out_score; f.uncertain = nullptr;
+  f.out_idx = reinterpret_cast<long long*>(out_idx); f.out_score = out_score; f.uncertain = nullptr; f.cand = nullptr; f.ceil_out = nullptr; f.round = 0;
   const size_t fsmem = ((size_t)p.n2 + GT_MAX_L) * 8;
   AURA_CUDA_OK(cudaFuncSetAttribute(gemm_topk_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
   gemm_topk_finish_kernel<<<(unsigned)n_a_rows, 128, fsmem, st>>>(f);

@@ -265,7 +265,7 @@ def ivf_search(rows: torch.Tensor, n_rows: int, queries: torch.Tensor, centroids
 
 
 # ---------------------------------------------------------------------------- tensor-core paths
-TC_MAX_K = 18                  # aura_batch_topk keeps 32 candidates per query: k + 14 <= 32
+TC_MAX_K = 114                 # tensor-core paths: 32 candidates per round, up to 4 rounds, margin 14 (k <= 18: one round)
 TC_MIN_BATCH = 5               # below this the CUDA-core streaming scan is faster (measured on B200: B=4 scan 690 us)
 TC_EPS_COS = 2.0 ** -9 + 1e-4   # |tensor-core cosine - fp32 cosine| bound: both operands rounded to 11 bits + fp32 sums
 

@@ -49,10 +49,31 @@ def test_batch_topk_fp32_equals_oracle(n, d, b, k):
 def test_batch_topk_rejects_k_beyond_the_certified_shortlist():
     ops = _ops()
     rows = torch.randn(500, 64, device=DEV)
-    assert not ops.batch_topk_supported(rows, 19) and ops.batch_topk_supported(rows, 18)
+    assert not ops.batch_topk_supported(rows, 115) and ops.batch_topk_supported(rows, 114)
     from aura_snn_rag_b200._lib import AuraLibraryError
     with pytest.raises(AuraLibraryError):
-        ops.batch_topk(rows, rows[:4].contiguous(), 19, None)
+        ops.batch_topk(rows, rows[:4].contiguous(), 115, None)
+
+
+@pytest.mark.parametrize("n,d,b,k,dt", [(30000, 128, 40, 19, torch.float32), (50000, 256, 150, 50, torch.float32),
+                                        (40000, 768, 20, 100, torch.float32), (30000, 128, 33, 100, torch.bfloat16),
+                                        (90, 64, 9, 64, torch.float32)])
+def test_batch_topk_multi_round_large_k(n, d, b, k, dt):
+    """k > 18: rounds of 32 candidates under a moving ceiling; the result must equal the exact scan."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(n + k)
+    bank = torch.randn(n, d, generator=g).to(dt)
+    q = bank[torch.randint(0, n, (b,), generator=g)].float() + 0.3 * torch.randn(b, d, generator=g)
+    rows = bank.to(DEV)
+    inv = ops.row_inv_norms(rows)
+    kk = min(k, n)
+    i1, s1, flags = ops.batch_topk(rows, q.to(DEV), kk, inv)
+    i2, s2 = ops.scan_topk(rows, q.to(DEV), kk, inv)
+    sure = (flags == 0)
+    assert float(sure.float().mean()) > 0.5
+    assert torch.equal(i1[sure], i2[sure]) and torch.equal(s1[sure], s2[sure])
+    i3, s3 = ops.exact_topk_batched(rows, q.to(DEV), kk, inv)
+    assert torch.equal(i3, i2) and torch.equal(s3, s2)
 
 
 def test_batch_topk_affine_terms_bf16_and_row_base():
