@@ -439,6 +439,7 @@ struct CandRescoreArgs {
   const u64* cand; int n_cand;      // n_cand = rounds * 32
   const void* rows; int bf16; int d; const float* qn; const float* scale; const float* bias; float eps;
   int k; long long row_base; long long* out_idx; float* out_score; int* uncertain;
+  const int* force_flag;            // optional: queries that must be handed back regardless of certification
 };
 __global__ void __launch_bounds__(128) cand_rescore_kernel(const CandRescoreArgs f) {
   __shared__ u64 keys[GT_MAX_L];
@@ -451,11 +452,13 @@ __global__ void __launch_bounds__(128) cand_rescore_kernel(const CandRescoreArgs
   ra.eps = f.eps; ra.k = f.k; ra.L = f.n_cand; ra.row_base = f.row_base;
   ra.out_idx = f.out_idx + b * f.k; ra.out_score = f.out_score + b * f.k; ra.uncertain = f.uncertain ? f.uncertain + b : nullptr;
   rescore_and_write(keys, GT_MAX_L, ex, ra);
+  if (threadIdx.x == 0 && f.force_flag && f.uncertain && f.force_flag[b]) f.uncertain[b] = 1;
 }
 int launch_cand_rescore(const u64* cand, int n_cand, const void* rows, int bf16, int d, const float* qn, const float* scale,
                         const float* bias, float eps, int k, long long row_base, long long* out_idx, float* out_score,
-                        int* uncertain, int n_queries, cudaStream_t st) {
+                        int* uncertain, int n_queries, cudaStream_t st, const int* force_flag) {
   CandRescoreArgs f;
+  f.force_flag = force_flag;
   f.cand = cand; f.n_cand = n_cand; f.rows = rows; f.bf16 = bf16; f.d = d; f.qn = qn; f.scale = scale; f.bias = bias;
   f.eps = eps; f.k = k; f.row_base = row_base; f.out_idx = out_idx; f.out_score = out_score; f.uncertain = uncertain;
   cand_rescore_kernel<<<n_queries, 128, 0, st>>>(f);
@@ -908,7 +911,7 @@ extern "C" int aura_batch_topk(const void* rows, int dtype, int64_t n_rows, int 
     note_launches(1);
   }
   return launch_cand_rescore(cand, rounds * GT_L, rows, bf16 ? 1 : 0, d, qn, scale, bias, eps, k, row_base,
-                             reinterpret_cast<long long*>(out_idx), out_score, out_uncertain, n_queries, st);
+                             reinterpret_cast<long long*>(out_idx), out_score, out_uncertain, n_queries, st, nullptr);
 }
 
 extern "C" size_t aura_allpairs_topk_workspace_bytes(int64_t n_a_rows, int64_t n_rows, int d, int dtype, int k) {

@@ -40,6 +40,7 @@ struct IvfBatchArgs {
   const float* scale; const float* bias;           // per bank row
   u64* partial;             // [cap_items][GT_L][128]
   int use_gthr, spread;     // tuning switches (experiments)
+  const u64* ceil_keys;     // per query: only keys strictly below are eligible (multi-round top-k), may be null
   unsigned* gthr;           // [B] orderable lower bound of every query's final L-th best score (atomicMax)
 };
 
@@ -212,8 +213,12 @@ ivf_gemm_kernel(const unsigned char* __restrict__ qmat, const unsigned char* __r
       const int my_pos = ib_pos_of_row(te, a.spread);
       const bool live = my_pos < n_a;
       float thr = live ? -INFINITY : INFINITY;
-      unsigned* my_gthr = a.gthr + (live ? a.pair_of_pos[a.q_off[it.x] + it.y * GT_BM + my_pos] / a.nprobe : 0);
+      const int my_query = live ? a.pair_of_pos[a.q_off[it.x] + it.y * GT_BM + my_pos] / a.nprobe : 0;
+      unsigned* my_gthr = a.gthr + my_query;
       unsigned published = 0u;
+      const u64 ceil_key = (a.ceil_keys != nullptr && live) ? a.ceil_keys[my_query] : ~0ull;
+      const float ceil_score = ceil_key == ~0ull ? INFINITY : key_score(ceil_key);
+      if (ceil_key == 0ull) thr = INFINITY;
       for (int cr = r0; cr < r1; cr += GT_BN, ++tile_n) {
         const unsigned acc = tile_n & 1u, acc_phase = (tile_n >> 1) & 1u;
         if (live && a.use_gthr) {   // other CTAs scoring other lists of this query may already have raised the bar
@@ -247,14 +252,15 @@ ivf_gemm_kernel(const unsigned char* __restrict__ qmat, const unsigned char* __r
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const float2 t = sb[c0 + j];
-            mask |= (fmaf(v[j], t.x, t.y) >= thr) ? (1u << j) : 0u;
+            const float sj = fmaf(v[j], t.x, t.y);
+            mask |= (sj >= thr && sj <= ceil_score) ? (1u << j) : 0u;
           }
           while (mask) {
             const int j = __ffs(mask) - 1;
             mask &= mask - 1u;
             const float2 t = sb[c0 + j];
             const u64 key = make_key(fmaf(select32(v, j), t.x, t.y), (unsigned)rs[c0 + j]);
-            if (key > e[GT_L - 1]) {
+            if (key > e[GT_L - 1] && key < ceil_key) {
               list_insert_sorted<GT_L>(e, key);
               if (e[GT_L - 1] != 0ull) thr = fmaxf(thr, key_score(e[GT_L - 1]));
             }
@@ -323,6 +329,7 @@ struct IvfFinishArgs {
   const u64* partial;
   const void* rows; int bf16; int d; const float* qn; const float* scale; const float* bias; float eps;
   int k; long long row_base; int spread, chunk_major;
+  u64* cand; u64* ceil_out; int round; int* force_flag;   // multi-round mode (see gemm_topk.cu)
   long long* out_idx; float* out_score; int* uncertain;
 };
 
@@ -356,6 +363,14 @@ __global__ void __launch_bounds__(128) ivf_finish_kernel(const IvfFinishArgs f) 
   __syncthreads();
   for (int i = n + threadIdx.x; i < IB_MERGE_CAP; i += blockDim.x) keys[i] = 0ull;
   block_bitonic_sort_desc(keys, IB_MERGE_CAP);
+  if (f.cand != nullptr) {
+    for (int i = threadIdx.x; i < GT_L; i += blockDim.x) f.cand[(size_t)b * GT_MAX_L + f.round * GT_L + i] = keys[i];
+    if (threadIdx.x == 0) {
+      f.ceil_out[b] = keys[GT_L - 1];
+      if (f.round == 0) f.force_flag[b] = (overflow || keys[0] == 0ull) ? 1 : 0;
+    }
+    return;
+  }
   RescoreArgs ra;
   ra.rows = f.rows; ra.bf16 = f.bf16; ra.d = f.d; ra.q = f.qn + (size_t)b * f.d; ra.scale = f.scale; ra.bias = f.bias;
   ra.eps = f.eps; ra.k = f.k; ra.L = GT_L; ra.row_base = f.row_base;
@@ -376,7 +391,7 @@ static int ib_cap_items(int n_queries, int nprobe, int n_lists) {
 }
 
 struct IbLayout {
-  size_t probes, counts, q_off, cursor, pair_of_pos, pos_of_pair, items_c, item_base, n_items, items, qn, qb, partial, coarse, gthr, total;
+  size_t probes, counts, q_off, cursor, pair_of_pos, pos_of_pair, items_c, item_base, n_items, items, qn, qb, partial, coarse, gthr, cand, ceil, force, total;
 };
 static IbLayout ib_layout(int n_queries, int d, int n_lists, int nprobe, int cap, size_t coarse_bytes) {
   IbLayout L;
@@ -397,6 +412,9 @@ static IbLayout ib_layout(int n_queries, int d, int n_lists, int nprobe, int cap
   L.partial = o; o += a256((size_t)cap * GT_L * GT_BM * 8);
   L.coarse = o; o += a256(coarse_bytes);
   L.gthr = o; o += a256((size_t)n_queries * 4);
+  L.cand = o; o += a256((size_t)n_queries * GT_MAX_L * 8);
+  L.ceil = o; o += a256((size_t)n_queries * 8);
+  L.force = o; o += a256((size_t)n_queries * 4);
   L.total = o;
   return L;
 }
@@ -406,6 +424,9 @@ size_t ivf_coarse_ws_bytes(int n_queries, int d, int n_cent, int nprobe);
 int ivf_run_coarse(const float* queries, int n_queries, int d, const float* centroids, int n_cent, int nprobe,
                    long long* probes, void* workspace, cudaStream_t st);
 // gemm_topk.cu
+int launch_cand_rescore(const u64* cand, int n_cand, const void* rows, int bf16, int d, const float* qn, const float* scale,
+                        const float* bias, float eps, int k, long long row_base, long long* out_idx, float* out_score,
+                        int* uncertain, int n_queries, cudaStream_t st, const int* force_flag);
 void launch_normalize_queries(const float* q, int n, int d, float* qn, __nv_bfloat16* qb, cudaStream_t st);
 
 }  // namespace aura
@@ -428,7 +449,7 @@ extern "C" int aura_ivf_search_batch(const void* rows, int dtype, int64_t n_rows
                n_centroid_rows);
   AURA_REQUIRE(nprobe >= 1 && nprobe <= AURA_MAX_NPROBE && nprobe <= n_centroid_rows, AURA_ERR_INVALID_ARG,
                "aura_ivf_search_batch: nprobe=%d", nprobe);
-  AURA_REQUIRE(k >= 1 && k + 14 <= GT_L, AURA_ERR_UNSUPPORTED, "aura_ivf_search_batch: k=%d too large (max %d)", k, GT_L - 14);
+  AURA_REQUIRE(k >= 1 && k + 14 <= GT_MAX_L, AURA_ERR_UNSUPPORTED, "aura_ivf_search_batch: k=%d too large (max %d)", k, GT_MAX_L - 14);
   const bool bf16 = dtype == AURA_BF16;
   const int eb = bf16 ? 2 : 4;
   AURA_REQUIRE(((size_t)d * eb) % 16 == 0 && (d % 4) == 0 && (reinterpret_cast<uintptr_t>(rows) & 15) == 0, AURA_ERR_UNSUPPORTED,
@@ -489,17 +510,31 @@ extern "C" int aura_ivf_search_batch(const void* rows, int dtype, int64_t n_rows
   void (*kern)(const unsigned char*, const unsigned char*, int, const IvfBatchArgs) =
       bf16 ? ivf_gemm_kernel<false> : ivf_gemm_kernel<true>;
   AURA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<sm_count(), IB_THREADS, smem, st>>>(reinterpret_cast<const unsigned char*>(bf16 ? (const void*)qb : (const void*)qn),
-                                             reinterpret_cast<const unsigned char*>(rows), d * eb, a);
-  AURA_CUDA_OK(cudaGetLastError());
+  u64* cand = reinterpret_cast<u64*>(ws + L.cand);
+  u64* ceil_buf = reinterpret_cast<u64*>(ws + L.ceil);
+  int* force = reinterpret_cast<int*>(ws + L.force);
+  const int rounds = (k + 14 + GT_L - 1) / GT_L;      // rounds of 32 candidates (see aura_batch_topk)
 
   IvfFinishArgs f;
   f.probes = probes; f.pos_of_pair = pos_of_pair; f.q_off = q_off; f.item_base = item_base; f.list_offsets = list_offsets;
   f.n_items = n_items; f.cap_items = cap; f.nprobe = nprobe; f.n_lists = n_centroid_rows; f.partial = partial;
   f.rows = rows; f.bf16 = bf16 ? 1 : 0; f.d = d; f.qn = qn; f.scale = scale; f.bias = bias; f.eps = eps; f.k = k;
   f.row_base = row_base; f.spread = a.spread; f.chunk_major = chunk_major; f.out_idx = reinterpret_cast<long long*>(out_idx); f.out_score = out_score; f.uncertain = out_uncertain;
-  ivf_finish_kernel<<<n_queries, 128, 0, st>>>(f);
-  AURA_CUDA_OK(cudaGetLastError());
-  note_launches(2);
+  f.cand = rounds > 1 ? cand : nullptr; f.ceil_out = ceil_buf; f.round = 0; f.force_flag = force;
+  for (int r = 0; r < rounds; ++r) {
+    if (r > 0) AURA_CUDA_OK(cudaMemsetAsync(gthr, 0, (size_t)n_queries * 4, st));
+    a.ceil_keys = r ? ceil_buf : nullptr;
+    kern<<<sm_count(), IB_THREADS, smem, st>>>(reinterpret_cast<const unsigned char*>(bf16 ? (const void*)qb : (const void*)qn),
+                                               reinterpret_cast<const unsigned char*>(rows), d * eb, a);
+    AURA_CUDA_OK(cudaGetLastError());
+    f.round = r;
+    ivf_finish_kernel<<<n_queries, 128, 0, st>>>(f);
+    AURA_CUDA_OK(cudaGetLastError());
+    note_launches(2);
+  }
+  if (rounds > 1)
+    return launch_cand_rescore(cand, rounds * GT_L, rows, bf16 ? 1 : 0, d, qn, scale, bias, eps, k, row_base,
+                               reinterpret_cast<long long*>(out_idx), out_score, out_uncertain, n_queries, st, force);
   return AURA_OK;
 }
+

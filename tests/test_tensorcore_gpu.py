@@ -188,7 +188,9 @@ def test_tensorcore_coarse_probes_match_exact_coarse(monkeypatch):
 @pytest.mark.parametrize("n,d,c,p,b,k,dt", [(30000, 128, 64, 8, 200, 10, torch.float32),
                                             (60000, 256, 300, 16, 333, 10, torch.float32),
                                             (40000, 128, 100, 8, 128, 5, torch.bfloat16),
-                                            (20000, 100, 50, 8, 100, 10, torch.float32)])
+                                            (20000, 100, 50, 8, 100, 10, torch.float32),
+                                            (50000, 128, 64, 8, 90, 100, torch.float32),
+                                            (30000, 256, 40, 6, 70, 40, torch.bfloat16)])
 def test_ivf_search_batched_equals_per_query_path(n, d, c, p, b, k, dt):
     """List-major grouped-GEMM IVF (aura_ivf_search_batch) vs the per-query scan of the same probed lists."""
     ops = _ops()
