@@ -259,6 +259,11 @@ __global__ void __launch_bounds__(128) gemm_topk_finish_kernel(const FinishArgs 
     keys[i] = key;
   }
   block_bitonic_sort_desc(keys, f.n2);
+  if (f.cand != nullptr) {
+    for (int i = threadIdx.x; i < GT_L; i += blockDim.x) f.cand[(size_t)b * GT_MAX_L + f.round * GT_L + i] = keys[i];
+    if (threadIdx.x == 0) f.ceil_out[b] = keys[GT_L - 1];     // 0 = fewer than 32 were left: nothing below
+    return;
+  }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (f.rows == nullptr) {
     const float mul = f.a_scale ? f.a_scale[b] : 1.f;
@@ -267,11 +272,6 @@ __global__ void __launch_bounds__(128) gemm_topk_finish_kernel(const FinishArgs 
       f.out_idx[b * f.k + i] = key ? f.row_base + (long long)key_row(key) : -1ll;
       f.out_score[b * f.k + i] = key ? key_score(key) * mul : -INFINITY;
     }
-    return;
-  }
-  if (f.cand != nullptr) {
-    for (int i = threadIdx.x; i < GT_L; i += blockDim.x) f.cand[(size_t)b * GT_MAX_L + f.round * GT_L + i] = keys[i];
-    if (threadIdx.x == 0) f.ceil_out[b] = keys[GT_L - 1];     // 0 = fewer than 32 were left: nothing below
     return;
   }
   RescoreArgs ra;
@@ -791,15 +791,24 @@ int tc_assign(const void* rows, int dtype, long long n_rows, int d, const float*
 
 bool tc_coarse_supported(const float* queries, int n_queries, int d, const float* cent, int n_cent, int nprobe) {
   if ((d % 4) != 0 || ((reinterpret_cast<uintptr_t>(queries) | reinterpret_cast<uintptr_t>(cent)) & 15) != 0) return false;
-  if (nprobe > GT_L) return false;
+  if (nprobe > GT_MAX_L) return false;
   if (const char* e = getenv("AURA_COARSE_TC")) return atoi(e) != 0;
   return n_queries >= 64 && (double)n_queries * n_cent >= 2.5e5;
 }
 
 size_t tc_coarse_workspace_bytes(int n_queries, int d, int n_cent, int nprobe) {
   GemmPlan p;
-  if (!make_gemm_plan(n_queries, n_cent, d, 4, nprobe, false, &p)) return 0;
-  return align256(p.partial_bytes) + 3 * align256((size_t)n_cent * 4) + align256((size_t)n_queries * nprobe * 4) + 512;
+  if (!make_gemm_plan(n_queries, n_cent, d, 4, nprobe < GT_L ? nprobe : GT_L, false, &p)) return 0;
+  return align256(p.partial_bytes) + 3 * align256((size_t)n_cent * 4) + align256((size_t)n_queries * nprobe * 4) + 512 +
+         align256((size_t)n_queries * GT_MAX_L * 8) + align256((size_t)n_queries * 8);
+}
+
+__global__ void __launch_bounds__(128) cand_to_probes_kernel(const u64* __restrict__ cand, int nprobe, long long* __restrict__ probes) {
+  const int b = blockIdx.x;
+  for (int i = threadIdx.x; i < nprobe; i += blockDim.x) {
+    const u64 key = cand[(size_t)b * GT_MAX_L + i];
+    probes[(size_t)b * nprobe + i] = key ? (long long)key_row(key) : -1ll;
+  }
 }
 
 // probes[b, 0..nprobe) = centroid rows nearest to query b, ranked by the TF32 score (no exact re-score: probe
@@ -807,28 +816,42 @@ size_t tc_coarse_workspace_bytes(int n_queries, int d, int n_cent, int nprobe) {
 int tc_coarse(const float* queries, int n_queries, int d, const float* cent, int n_cent, const float* csq, int nprobe,
               long long* probes, void* workspace, cudaStream_t st) {
   GemmPlan p;
-  AURA_REQUIRE(make_gemm_plan(n_queries, n_cent, d, 4, nprobe, false, &p), AURA_ERR_UNSUPPORTED, "tc_coarse: no plan");
+  const int k1 = nprobe < GT_L ? nprobe : GT_L;
+  AURA_REQUIRE(make_gemm_plan(n_queries, n_cent, d, 4, k1, false, &p), AURA_ERR_UNSUPPORTED, "tc_coarse: no plan");
   unsigned char* ws = reinterpret_cast<unsigned char*>(workspace);
   u64* partial = reinterpret_cast<u64*>(ws);
   float* scale2 = reinterpret_cast<float*>(ws + align256(p.partial_bytes));
   float* neg_csq = scale2 + align256((size_t)n_cent * 4) / 4;
   float* cmax = neg_csq + align256((size_t)n_cent * 4) / 4;
   float* dummy_score = cmax + align256((size_t)n_cent * 4) / 4;
+  u64* cand = reinterpret_cast<u64*>(reinterpret_cast<unsigned char*>(dummy_score) + align256((size_t)n_queries * nprobe * 4) + 512);
+  u64* ceil_buf = cand + align256((size_t)n_queries * GT_MAX_L * 8) / 8;
   AURA_CUDA_OK(cudaMemsetAsync(cmax, 0, 4, st));
   centroid_terms_kernel<<<(n_cent + 255) / 256, 256, 0, st>>>(csq, n_cent, scale2, neg_csq, cmax);
   note_launches(1);
-  int rc = run_gemm_topk(queries, n_queries, 0, cent, n_cent, d, false, scale2, neg_csq, false, p, partial, st);
-  if (rc != AURA_OK) return rc;
   FinishArgs f;
-  f.partial = partial; f.n_atiles = p.n_atiles; f.n_groups = p.n_groups; f.L = p.L; f.n2 = p.n2; f.k = nprobe;
+  f.partial = partial; f.n_atiles = p.n_atiles; f.n_groups = p.n_groups; f.L = p.L; f.n2 = p.n2; f.k = k1;
   f.n_a_rows = n_queries; f.row_base = 0; f.rows = nullptr; f.bf16 = 0; f.d = d; f.qn = nullptr;
   f.scale = nullptr; f.bias = nullptr; f.eps = 0.f; f.a_scale = nullptr;
   f.out_idx = probes; f.out_score = dummy_score; f.uncertain = nullptr; f.cand = nullptr; f.ceil_out = nullptr; f.round = 0;
   const size_t fsmem = ((size_t)p.n2 + GT_MAX_L) * 8;
   AURA_CUDA_OK(cudaFuncSetAttribute(gemm_topk_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
-  gemm_topk_finish_kernel<<<n_queries, 128, fsmem, st>>>(f);
-  AURA_CUDA_OK(cudaGetLastError());
-  note_launches(1);
+  const int rounds = (nprobe + GT_L - 1) / GT_L;
+  if (rounds > 1) { f.cand = cand; f.ceil_out = ceil_buf; }
+  for (int r = 0; r < rounds; ++r) {
+    int rc = run_gemm_topk(queries, n_queries, 0, cent, n_cent, d, false, scale2, neg_csq, false, p, partial, st,
+                           r ? ceil_buf : nullptr);
+    if (rc != AURA_OK) return rc;
+    f.round = r;
+    gemm_topk_finish_kernel<<<n_queries, 128, fsmem, st>>>(f);
+    AURA_CUDA_OK(cudaGetLastError());
+    note_launches(1);
+  }
+  if (rounds > 1) {
+    cand_to_probes_kernel<<<n_queries, 128, 0, st>>>(cand, nprobe, probes);
+    AURA_CUDA_OK(cudaGetLastError());
+    note_launches(1);
+  }
   return AURA_OK;
 }
 

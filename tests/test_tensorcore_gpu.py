@@ -183,6 +183,13 @@ def test_tensorcore_coarse_probes_match_exact_coarse(monkeypatch):
     # TF32 scores: same nearest centroid, same distance profile up to the rounding of 2 q.c
     assert (res["1"][:, 0] == ref[:, 0]).float().mean() > 0.99
     np.testing.assert_allclose(torch.gather(dist, 1, res["1"]).numpy(), torch.gather(dist, 1, ref).numpy(), rtol=2e-3)
+    # nprobe > 32: two rounds of 32 on the tensor path
+    p2 = 64
+    ref2 = torch.topk(-dist, p2, dim=1).indices
+    monkeypatch.setenv("AURA_COARSE_TC", "1")
+    got = ops.ivf_coarse(q.to(DEV), cent.to(DEV), p2).cpu()
+    assert all(len(set(r)) == p2 for r in got.tolist())                       # no repeats across rounds
+    np.testing.assert_allclose(torch.gather(dist, 1, got).numpy(), torch.gather(dist, 1, ref2).numpy(), rtol=2e-3)
 
 
 @pytest.mark.parametrize("n,d,c,p,b,k,dt", [(30000, 128, 64, 8, 200, 10, torch.float32),
