@@ -106,6 +106,7 @@ class HippocampalFormation(nn.Module):
         self.centroids_k = int(centroids_k)
         self.centroids_update_interval = 512
         self.nprobe = int(nprobe)                       # reference literal 8 (:262)
+        self.ivf_strict = True                          # batched centroid path: re-run uncertified queries exactly (ops.ivf_search_batched)
         rows = int(centroid_rows) if centroid_rows is not None else max(256, self.centroids_k)
         self.register_buffer('centroids', torch.zeros(rows, feature_dim, **f32))
         self.register_buffer('centroid_counts', torch.zeros(rows, **f32))
@@ -336,7 +337,8 @@ class HippocampalFormation(nn.Module):
             if q.shape[0] >= ops.TC_IVF_MIN_BATCH and ops.batch_topk_supported(self.memory_features, kk):
                 idx, score = ops.ivf_search_batched(self.memory_features, m, q, self.centroids, nprobe,
                                                     self._list_offsets, self._list_rows, kk, scale, bias,
-                                                    eps=ops.TC_EPS_COS * 0.5 * self._max_strength())
+                                                    eps=ops.TC_EPS_COS * 0.5 * self._max_strength(),
+                                                    strict=self.ivf_strict)
             else:
                 idx, score = ops.ivf_search(self.memory_features, m, q, self.centroids, nprobe, self._list_offsets,
                                             self._list_rows, kk, scale, bias)

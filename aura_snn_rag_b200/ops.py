@@ -360,9 +360,17 @@ TC_IVF_MIN_BATCH = 64          # list-major grouped GEMM pays off once lists are
 def ivf_search_batched(rows: torch.Tensor, n_rows: int, queries: torch.Tensor, centroids: torch.Tensor, nprobe: int,
                        list_offsets: torch.Tensor, list_rows: torch.Tensor, k: int, scale: Optional[torch.Tensor],
                        bias: Optional[torch.Tensor] = None, row_base: int = 0, eps: float = TC_EPS_COS,
-                       stats: Optional[dict] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+                       stats: Optional[dict] = None, strict: bool = True) -> Tuple[torch.Tensor, torch.Tensor]:
     """Centroid-path query for a block of queries: list-major tensor-core pass (aura_ivf_search_batch), then the
-    per-query path for the queries it hands back (uncertified / no candidates)."""
+    per-query path for the queries it hands back.
+
+    strict=True  : every flagged query (result not certified exact among its candidates, or no candidates) is re-run
+                   through the per-query path - results equal `ivf_search` bit for bit.
+    strict=False : only queries WITHOUT candidates are re-run (the reference then scans all rows, hippocampal.py:
+                   269-270); uncertified ones keep the exact-re-scored tensor-core shortlist.  The scores returned are
+                   still exact fp32; a candidate can only be missed if its TF32/bf16 score fell more than the shortlist
+                   margin (>= 14 places) below its exact rank - near-tie heavy data (thousands of near-duplicates per
+                   query) is where this mode saves the per-query re-runs."""
     rows = _dev(rows, "rows")
     queries = _dev(queries, "queries")
     if queries.dtype != torch.float32:
@@ -380,6 +388,8 @@ def ivf_search_batched(rows: torch.Tensor, n_rows: int, queries: torch.Tensor, c
                                     _ptr(scale), _ptr(bias), k, row_base, float(eps), out_idx.data_ptr(),
                                     out_score.data_ptr(), flags.data_ptr(), ws.data_ptr(), ws.numel(), _stream()),
           "aura_ivf_search_batch")
+    if not strict:
+        flags = flags * (out_idx[:, 0] < 0).to(flags.dtype)        # keep only "no candidate at all"
     bad = torch.nonzero(flags, as_tuple=False).squeeze(-1)
     if stats is not None:
         stats["uncertain"] = stats.get("uncertain", 0) + int(bad.numel())
