@@ -30,6 +30,17 @@ static constexpr int IB_MERGE_CAP = 2048;                   // keys the finish k
 static constexpr int IB_THREADS = 288;                      // warp 0 MMA, warps 1-4 epilogue, warps 5-8 gather producers
 static constexpr int IB_LOOKAHEAD = 2;                      // stages a producer thread keeps in flight behind the newest
 
+static constexpr int IB_MAX_CHUNKS = 16;                    // chunks per list: long lists get longer chunks, not more of them
+
+// chunk geometry of a list of `len` rows: n_ch chunks of ch_rows rows (a multiple of the 256-row tile)
+__host__ __device__ __forceinline__ void ib_chunks(int len, int& n_ch, int& ch_rows) {
+  n_ch = (len + IB_CH_ROWS - 1) / IB_CH_ROWS;
+  if (n_ch > IB_MAX_CHUNKS) n_ch = IB_MAX_CHUNKS;
+  if (n_ch < 1) { n_ch = 0; ch_rows = IB_CH_ROWS; return; }
+  ch_rows = ((len + n_ch - 1) / n_ch + GT_BN - 1) / GT_BN * GT_BN;
+  n_ch = (len + ch_rows - 1) / ch_rows;
+}
+
 struct IvfBatchArgs {
   int n_lists, nprobe, k_blocks, n_stages, cap_items;
   const int* list_offsets; const int* list_rows;   // CSR of the bank
@@ -38,7 +49,9 @@ struct IvfBatchArgs {
   const int4* items;        // [cap_items]    {list, query tile, chunk, 0}
   const int* n_items;       // device scalar
   const float* scale; const float* bias;           // per bank row
-  u64* partial;             // [cap_items][GT_L][128]
+  const int* pbase;         // [n_lists + 1]  first partial list of every list (exclusive scan of queries x chunks)
+  int cap_plists;
+  u64* partial;             // [cap_plists][GT_L]: one sorted list per (pair, chunk), at pbase[c] + chunk * nq_c + rel
   int use_gthr, spread;     // tuning switches (experiments)
   const u64* ceil_keys;     // per query: only keys strictly below are eligible (multi-round top-k), may be null
   unsigned* gthr;           // [B] orderable lower bound of every query's final L-th best score (atomicMax)
@@ -86,7 +99,8 @@ ivf_gemm_kernel(const unsigned char* __restrict__ qmat, const unsigned char* __r
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int n_items = min(*a.n_items, a.cap_items);
+  // a work table or partial-list area that does not fit processes nothing (the finish kernel hands every query back)
+  const int n_items = (*a.n_items <= a.cap_items && a.pbase[a.n_lists] <= a.cap_plists) ? *a.n_items : 0;
 
   if (warp >= 5) {
     // ===================== gather producers: 128 threads, 16-byte cp.async into the swizzled stage =====================
@@ -102,7 +116,9 @@ ivf_gemm_kernel(const unsigned char* __restrict__ qmat, const unsigned char* __r
       const int qb = a.q_off[it.x], nq = a.q_off[it.x + 1] - qb;
       const int a0 = qb + it.y * GT_BM, n_a = min(GT_BM, nq - it.y * GT_BM);
       const int lb = a.list_offsets[it.x], len = a.list_offsets[it.x + 1] - lb;
-      const int r0 = it.z * IB_CH_ROWS, r1 = min(len, r0 + IB_CH_ROWS);
+      int n_ch_, ch_rows_;
+      ib_chunks(len, n_ch_, ch_rows_);
+      const int r0 = it.z * ch_rows_, r1 = min(len, r0 + ch_rows_);
       const unsigned char* qsrc[8];   // A-tile rows prow + 16*i (rows past the group re-load a valid query, masked later)
 #pragma unroll
       for (int i = 0; i < 8; ++i)
@@ -173,7 +189,9 @@ ivf_gemm_kernel(const unsigned char* __restrict__ qmat, const unsigned char* __r
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int4 it = a.items[item];
         const int len = a.list_offsets[it.x + 1] - a.list_offsets[it.x];
-        const int r0 = it.z * IB_CH_ROWS, r1 = min(len, r0 + IB_CH_ROWS);
+        int n_ch_, ch_rows_;
+      ib_chunks(len, n_ch_, ch_rows_);
+      const int r0 = it.z * ch_rows_, r1 = min(len, r0 + ch_rows_);
         for (int cr = r0; cr < r1; cr += GT_BN, ++tile_n) {
           const unsigned acc = tile_n & 1u, acc_phase = (tile_n >> 1) & 1u;
           tc::mbar_wait_guarded(&tempty[acc], acc_phase ^ 1u);
@@ -206,7 +224,9 @@ ivf_gemm_kernel(const unsigned char* __restrict__ qmat, const unsigned char* __r
       const int nq = a.q_off[it.x + 1] - a.q_off[it.x];
       const int n_a = min(GT_BM, nq - it.y * GT_BM);
       const int lb = a.list_offsets[it.x], len = a.list_offsets[it.x + 1] - lb;
-      const int r0 = it.z * IB_CH_ROWS, r1 = min(len, r0 + IB_CH_ROWS);
+      int n_ch_, ch_rows_;
+      ib_chunks(len, n_ch_, ch_rows_);
+      const int r0 = it.z * ch_rows_, r1 = min(len, r0 + ch_rows_);
       u64 e[GT_L];
 #pragma unroll
       for (int s = 0; s < GT_L; ++s) e[s] = 0ull;
@@ -274,9 +294,11 @@ ivf_gemm_kernel(const unsigned char* __restrict__ qmat, const unsigned char* __r
           if (o > published) { atomicMax(my_gthr, o); published = o; }
         }
       }
-      u64* dst = a.partial + (size_t)item * GT_L * GT_BM;
+      if (live) {
+        u64* dst = a.partial + ((size_t)a.pbase[it.x] + (size_t)it.z * nq + it.y * GT_BM + my_pos) * GT_L;
 #pragma unroll
-      for (int s = 0; s < GT_L; ++s) dst[s * GT_BM + te] = live ? e[s] : 0ull;
+        for (int s = 0; s < GT_L; ++s) dst[s] = e[s];
+      }
     }
   }
   __syncthreads();
@@ -302,11 +324,14 @@ __global__ void __launch_bounds__(256) ib_pair_scatter_kernel(const long long* _
   pos_of_pair[i] = pos;
 }
 __global__ void __launch_bounds__(256) ib_item_count_kernel(const int* __restrict__ q_off, const int* __restrict__ list_offsets,
-                                                            int n_lists, int* __restrict__ items_c) {
+                                                            int n_lists, int* __restrict__ items_c, int* __restrict__ plists_c) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= n_lists) return;
   const int nq = q_off[c + 1] - q_off[c], len = list_offsets[c + 1] - list_offsets[c];
-  items_c[c] = ((nq + GT_BM - 1) / GT_BM) * ((len + IB_CH_ROWS - 1) / IB_CH_ROWS);
+  int n_ch, ch_rows;
+  ib_chunks(len, n_ch, ch_rows);
+  items_c[c] = ((nq + GT_BM - 1) / GT_BM) * n_ch;
+  plists_c[c] = nq * n_ch;
 }
 __global__ void __launch_bounds__(256) ib_item_fill_kernel(const int* __restrict__ item_base, const int* __restrict__ list_offsets,
                                                            int n_lists, int cap, int4* __restrict__ items,
@@ -314,7 +339,8 @@ __global__ void __launch_bounds__(256) ib_item_fill_kernel(const int* __restrict
   const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (c >= n_lists) return;
   const int base = item_base[c], cnt = item_base[c + 1] - base;
-  const int n_ch = (list_offsets[c + 1] - list_offsets[c] + IB_CH_ROWS - 1) / IB_CH_ROWS;
+  int n_ch, ch_rows;
+  ib_chunks(list_offsets[c + 1] - list_offsets[c], n_ch, ch_rows);
   const int n_qt = n_ch > 0 ? cnt / n_ch : 1;
   for (int i = lane; i < cnt; i += 32)
     if (base + i < cap)   // chunk-major: the query tiles of one chunk are adjacent and share it through L2
@@ -326,6 +352,7 @@ __global__ void __launch_bounds__(256) ib_item_fill_kernel(const int* __restrict
 struct IvfFinishArgs {
   const long long* probes; const int* pos_of_pair; const int* q_off; const int* item_base; const int* list_offsets;
   const int* n_items; int cap_items, nprobe, n_lists;
+  const int* pbase; int cap_plists;
   const u64* partial;
   const void* rows; int bf16; int d; const float* qn; const float* scale; const float* bias; float eps;
   int k; long long row_base; int spread, chunk_major;
@@ -337,26 +364,25 @@ __global__ void __launch_bounds__(128) ivf_finish_kernel(const IvfFinishArgs f) 
   __shared__ u64 keys[IB_MERGE_CAP];
   __shared__ u64 ex[GT_MAX_L];
   const int b = blockIdx.x;
-  const bool overflow = *f.n_items > f.cap_items;
+  const bool overflow = *f.n_items > f.cap_items || f.pbase[f.n_lists] > f.cap_plists;
   int n = 0;   // keys buffered so far (uniform across the CTA)
   for (int p = 0; p < f.nprobe && !overflow; ++p) {
     const long long c = f.probes[(size_t)b * f.nprobe + p];
     if (c < 0 || c >= f.n_lists) continue;
     const int len = f.list_offsets[c + 1] - f.list_offsets[c];
     if (len == 0) continue;
-    const int n_ch = (len + IB_CH_ROWS - 1) / IB_CH_ROWS;
+    int n_ch, ch_rows;
+    ib_chunks(len, n_ch, ch_rows);
     const int rel = f.pos_of_pair[(size_t)b * f.nprobe + p] - f.q_off[c];
-    const int t = rel / GT_BM, te = ib_row_of_pos(rel % GT_BM, f.spread);
-    const int n_qt = (f.q_off[c + 1] - f.q_off[c] + GT_BM - 1) / GT_BM;
+    const int nq = f.q_off[c + 1] - f.q_off[c];
     for (int j = 0; j < n_ch; ++j) {
-      const int item = f.item_base[c] + (f.chunk_major ? j * n_qt + t : t * n_ch + j);
       if (n + GT_L > IB_MERGE_CAP) {        // buffer full: keep the best GT_L so far
         __syncthreads();
         for (int i = n + threadIdx.x; i < IB_MERGE_CAP; i += blockDim.x) keys[i] = 0ull;
         block_bitonic_sort_desc(keys, IB_MERGE_CAP);
         n = GT_L;
       }
-      if (threadIdx.x < GT_L) keys[n + threadIdx.x] = f.partial[((size_t)item * GT_L + threadIdx.x) * GT_BM + te];
+      if (threadIdx.x < GT_L) keys[n + threadIdx.x] = f.partial[((size_t)f.pbase[c] + (size_t)j * nq + rel) * GT_L + threadIdx.x];
       n += GT_L;
     }
   }
@@ -385,13 +411,18 @@ __global__ void __launch_bounds__(128) ivf_finish_kernel(const IvfFinishArgs f) 
 static size_t a256(size_t v) { return (v + 255) / 256 * 256; }
 static int ib_cap_items(int n_queries, int nprobe, int n_lists) {
   const long long pairs = (long long)n_queries * nprobe;
-  long long cap = 4ll * n_lists + pairs / 16 + 1024;
-  if (cap > 200000) cap = 200000;
+  long long cap = 16ll * n_lists + pairs / 8 + 4096;       // 16 B per item
+  if (cap > 1000000) cap = 1000000;
   return (int)cap;
+}
+// partial lists (256 B each): one per (pair, chunk of its list)
+static int ib_cap_plists(int n_queries, int nprobe) {
+  const long long cap = (long long)IB_MAX_CHUNKS * n_queries * nprobe + 4096;   // cannot overflow: <= IB_MAX_CHUNKS per pair
+  return (int)(cap > 64000000 ? 64000000 : cap);
 }
 
 struct IbLayout {
-  size_t probes, counts, q_off, cursor, pair_of_pos, pos_of_pair, items_c, item_base, n_items, items, qn, qb, partial, coarse, gthr, cand, ceil, force, total;
+  size_t probes, counts, q_off, cursor, pair_of_pos, pos_of_pair, items_c, item_base, n_items, items, qn, qb, partial, coarse, gthr, cand, ceil, force, plists_c, pbase, total;
 };
 static IbLayout ib_layout(int n_queries, int d, int n_lists, int nprobe, int cap, size_t coarse_bytes) {
   IbLayout L;
@@ -409,7 +440,9 @@ static IbLayout ib_layout(int n_queries, int d, int n_lists, int nprobe, int cap
   L.items = o; o += a256((size_t)cap * 16);
   L.qn = o; o += a256((size_t)n_queries * d * 4);
   L.qb = o; o += a256((size_t)n_queries * d * 2);
-  L.partial = o; o += a256((size_t)cap * GT_L * GT_BM * 8);
+  L.partial = o; o += a256((size_t)ib_cap_plists(n_queries, nprobe) * GT_L * 8);
+  L.plists_c = o; o += a256((size_t)n_lists * 4);
+  L.pbase = o; o += a256((size_t)(n_lists + 1) * 4);
   L.coarse = o; o += a256(coarse_bytes);
   L.gthr = o; o += a256((size_t)n_queries * 4);
   L.cand = o; o += a256((size_t)n_queries * GT_MAX_L * 8);
@@ -488,8 +521,11 @@ extern "C" int aura_ivf_search_batch(const void* rows, int dtype, int64_t n_rows
   ib_pair_hist_kernel<<<(n_pairs + 255) / 256, 256, 0, st>>>(probes, n_pairs, n_centroid_rows, counts);
   launch_scan_offsets(counts, n_centroid_rows, q_off, cursor, st);
   ib_pair_scatter_kernel<<<(n_pairs + 255) / 256, 256, 0, st>>>(probes, n_pairs, n_centroid_rows, cursor, pair_of_pos, pos_of_pair);
-  ib_item_count_kernel<<<(n_centroid_rows + 255) / 256, 256, 0, st>>>(q_off, list_offsets, n_centroid_rows, items_c);
+  int* plists_c = reinterpret_cast<int*>(ws + L.plists_c);
+  int* pbase = reinterpret_cast<int*>(ws + L.pbase);
+  ib_item_count_kernel<<<(n_centroid_rows + 255) / 256, 256, 0, st>>>(q_off, list_offsets, n_centroid_rows, items_c, plists_c);
   launch_scan_offsets(items_c, n_centroid_rows, item_base, cursor, st);
+  launch_scan_offsets(plists_c, n_centroid_rows, pbase, cursor, st);
   ib_item_fill_kernel<<<(n_centroid_rows * 32 + 255) / 256, 256, 0, st>>>(item_base, list_offsets, n_centroid_rows, cap, items, n_items, chunk_major);
   note_launches(4);
 
@@ -503,7 +539,7 @@ extern "C" int aura_ivf_search_batch(const void* rows, int dtype, int64_t n_rows
   AURA_REQUIRE(stages >= 4, AURA_ERR_UNSUPPORTED, "aura_ivf_search_batch: needs 4 pipeline stages of shared memory");
   a.n_stages = stages;
   a.list_offsets = list_offsets; a.list_rows = list_rows; a.q_off = q_off; a.pair_of_pos = pair_of_pos;
-  a.items = items; a.n_items = n_items; a.scale = scale; a.bias = bias; a.partial = partial; a.gthr = gthr;
+  a.items = items; a.n_items = n_items; a.scale = scale; a.bias = bias; a.partial = partial; a.gthr = gthr; a.pbase = pbase; a.cap_plists = ib_cap_plists(n_queries, nprobe);
   { const char* e = getenv("AURA_IVF_GTHR"); a.use_gthr = e ? atoi(e) : 1; }
   { const char* e = getenv("AURA_IVF_SPREAD"); a.spread = e ? atoi(e) : 1; }
   const size_t smem = (size_t)stages * GT_STAGE_BYTES + fixed + 1024;
@@ -518,6 +554,7 @@ extern "C" int aura_ivf_search_batch(const void* rows, int dtype, int64_t n_rows
   IvfFinishArgs f;
   f.probes = probes; f.pos_of_pair = pos_of_pair; f.q_off = q_off; f.item_base = item_base; f.list_offsets = list_offsets;
   f.n_items = n_items; f.cap_items = cap; f.nprobe = nprobe; f.n_lists = n_centroid_rows; f.partial = partial;
+  f.pbase = pbase; f.cap_plists = a.cap_plists;
   f.rows = rows; f.bf16 = bf16 ? 1 : 0; f.d = d; f.qn = qn; f.scale = scale; f.bias = bias; f.eps = eps; f.k = k;
   f.row_base = row_base; f.spread = a.spread; f.chunk_major = chunk_major; f.out_idx = reinterpret_cast<long long*>(out_idx); f.out_score = out_score; f.uncertain = out_uncertain;
   f.cand = rounds > 1 ? cand : nullptr; f.ceil_out = ceil_buf; f.round = 0; f.force_flag = force;
@@ -538,3 +575,17 @@ extern "C" int aura_ivf_search_batch(const void* rows, int dtype, int64_t n_rows
   return AURA_OK;
 }
 
+
+/* Diagnostics: number of work items the last aura_ivf_search_batch call on this workspace generated, and the capacity
+ * of its work table (a call whose items exceed the capacity hands every query back to the per-query path). */
+extern "C" int aura_ivf_search_batch_items(const void* workspace, int n_queries, int d, int n_centroid_rows, int nprobe,
+                                           int32_t* host_items, int32_t* host_cap, void* stream) {
+  AURA_REQUIRE(workspace && host_items && host_cap, AURA_ERR_INVALID_ARG, "aura_ivf_search_batch_items: null pointer");
+  const int cap = ib_cap_items(n_queries, nprobe, n_centroid_rows);
+  const IbLayout L = ib_layout(n_queries, d, n_centroid_rows, nprobe, cap, ivf_coarse_ws_bytes(n_queries, d, n_centroid_rows, nprobe));
+  AURA_CUDA_OK(cudaMemcpyAsync(host_items, reinterpret_cast<const unsigned char*>(workspace) + L.n_items, 4,
+                               cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  AURA_CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));
+  *host_cap = cap;
+  return AURA_OK;
+}

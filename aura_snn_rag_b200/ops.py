@@ -388,6 +388,12 @@ def ivf_search_batched(rows: torch.Tensor, n_rows: int, queries: torch.Tensor, c
                                     _ptr(scale), _ptr(bias), k, row_base, float(eps), out_idx.data_ptr(),
                                     out_score.data_ptr(), flags.data_ptr(), ws.data_ptr(), ws.numel(), _stream()),
           "aura_ivf_search_batch")
+    if stats is not None:
+        import ctypes as _C
+        items, cap = _C.c_int32(0), _C.c_int32(0)
+        check(lib.aura_ivf_search_batch_items(ws.data_ptr(), b, d, c, nprobe, _C.addressof(items), _C.addressof(cap), _stream()),
+              "aura_ivf_search_batch_items")
+        stats["items"], stats["items_cap"] = items.value, cap.value
     if not strict:
         flags = flags * (out_idx[:, 0] < 0).to(flags.dtype)        # keep only "no candidate at all"
     bad = torch.nonzero(flags, as_tuple=False).squeeze(-1)

@@ -159,6 +159,11 @@ int aura_ivf_search_batch(const void* rows, int dtype, int64_t n_rows, int d, co
                           float eps, int64_t* out_idx, float* out_score, int32_t* out_uncertain, void* workspace,
                           size_t workspace_bytes, void* stream);
 
+/* diagnostics: work items generated by the last aura_ivf_search_batch call on `workspace` and the table capacity
+ * (synchronises `stream`; not for hot paths) */
+int aura_ivf_search_batch_items(const void* workspace, int n_queries, int d, int n_centroid_rows, int nprobe,
+                                int32_t* host_items, int32_t* host_cap, void* stream);
+
 /* ---- batched exact search on the tensor cores (the batch the reference loops over one query at a
  * time, memory_augmented_layer.py:113-128; score of hippocampal.py:272-307) -------------------
  * Same result contract as aura_scan_topk.  tcgen05 (tf32 from an fp32 bank, bf16 from a bf16 bank) scores

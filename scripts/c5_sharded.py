@@ -88,7 +88,7 @@ st = {}
 sc_, bi_ = hf._row_terms(None)
 ops.ivf_search_batched(hf.memory_features, hf.memory_count, q, hf.centroids, P, hf._list_offsets, hf._list_rows, K, sc_, bi_,
                        eps=ops.TC_EPS_COS * 0.5, stats=st)
-res["uncertified_on_rank0"] = st["uncertain"]
+res["uncertified_on_rank0"] = st["uncertain"]; res["items"] = st.get("items"); res["items_cap"] = st.get("items_cap")
 cnt = (hf._list_offsets[1:] - hf._list_offsets[:-1]).float()
 res["local_list_len_min_mean_max"] = [float(cnt.min()), float(cnt.mean()), float(cnt.max())]
 if rank == 0:
