@@ -192,15 +192,30 @@ struct RescoreArgs {
 __device__ __forceinline__ void rescore_and_write(const u64* keys, int n2, u64* ex, const RescoreArgs& f) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_cand = min(f.L, n2);
-  for (int c = warp; c < GT_MAX_L; c += 4) {
-    u64 key = 0ull;
-    if (c < n_cand && keys[c] != 0ull) {
-      const unsigned row = key_row(keys[c]);
-      const float dot = warp_sum(exact_dot_partial(f.rows, f.bf16, f.d, row, f.q, lane));
-      const float sc = f.scale ? f.scale[row] : 1.f, bi = f.bias ? f.bias[row] : 0.f;
-      key = make_key(fmaf(dot, sc, bi), row);
+  // each warp re-scores candidates warp, warp+4, ...; four at a time so that their row loads overlap
+  for (int c0 = warp; c0 < GT_MAX_L; c0 += 16) {
+    float part[4];
+    unsigned rowv[4];
+    bool live[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int c = c0 + 4 * u;
+      live[u] = c < n_cand && keys[c] != 0ull;
+      rowv[u] = live[u] ? key_row(keys[c]) : 0u;
     }
-    if (lane == 0) ex[c] = key;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) part[u] = live[u] ? exact_dot_partial(f.rows, f.bf16, f.d, rowv[u], f.q, lane) : 0.f;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int c = c0 + 4 * u;
+      u64 key = 0ull;
+      if (live[u]) {
+        const float dot = warp_sum(part[u]);
+        const float sc = f.scale ? f.scale[rowv[u]] : 1.f, bi = f.bias ? f.bias[rowv[u]] : 0.f;
+        key = make_key(fmaf(dot, sc, bi), rowv[u]);
+      }
+      if (lane == 0 && c < GT_MAX_L) ex[c] = key;
+    }
   }
   block_bitonic_sort_desc(ex, GT_MAX_L);
   for (int i = threadIdx.x; i < f.k; i += blockDim.x) {

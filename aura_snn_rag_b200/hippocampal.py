@@ -383,15 +383,33 @@ class HippocampalFormation(nn.Module):
                 out.append((owner, s))
         return out
 
-    def exact_topk(self, queries, k: int = 10, gather: bool = False):
-        """Pure cosine exact top-k, no temporal / strength terms (.tmp_infer_old.py:40-49)."""
+    def exact_topk(self, queries, k: int = 10, gather: bool = False, defer: bool = False):
+        """Pure cosine exact top-k, no temporal / strength terms (.tmp_infer_old.py:40-49).
+
+        defer=True (query blocks on the tensor-core path only) returns (idx, score, flags, q_dev) without any host
+        sync: flags[b] != 0 marks the rare query whose result is not yet certified; pass everything to
+        `exact_topk_fixup` once the flags have been read.  This lets a serving loop keep several batches in flight
+        (bench.py's e2e leg); defer=False does the check itself."""
         q = self._queries(queries)
         m = self.memory_count
         kk = min(int(k), m)
+        if defer:
+            if not (q.shape[0] >= ops.TC_MIN_BATCH and ops.batch_topk_supported(self.memory_features, kk) and m >= 1024):
+                idx, score = ops.scan_topk(self.memory_features, q, kk, self._inv_norm, None, n_rows=m)
+                return idx, score, torch.zeros(q.shape[0], dtype=torch.int32, device=self.device), q
+            idx, score, flags = ops.exact_topk_batched(self.memory_features, q, kk, self._inv_norm, None, n_rows=m,
+                                                       eps=ops.TC_EPS_COS, defer=True)
+            return idx, score, flags, q
         idx, score = self._exact(q, kk, self._inv_norm, None, 1.0)
         if gather:
             return ops.gather_rows(self.memory_features, idx), score, idx
         return idx, score
+
+    def exact_topk_fixup(self, flags: torch.Tensor, idx: torch.Tensor, score: torch.Tensor, q_dev: torch.Tensor,
+                         k: int = 10) -> int:
+        """Second half of `exact_topk(..., defer=True)`: re-run the flagged queries through the exact scan, in place."""
+        return ops.exact_topk_fixup(flags, idx, score, self.memory_features, q_dev, idx.shape[1], self._inv_norm, None,
+                                    n_rows=self.memory_count)
 
     # ------------------------------------------------------------------ cognitive map
     def build_cognitive_map(self, k: int = 32) -> Tuple[torch.Tensor, torch.Tensor]:

@@ -310,3 +310,40 @@ def test_checkpoint_resume_restores_the_index(monkeypatch):
     assert torch.equal(ia, ib) and torch.equal(sa, sb)
     b.create_episodic_memory("new", "e", rows[0] * 2)
     assert b.memory_count == 1501 and b.id_to_idx["new"] == 1500 and list(b.id_to_idx)[:2] == ["m0", "m1"]
+
+
+@pytest.mark.parametrize("name", ["ivf_d64_n3000", "c1k_d768_n6000"])
+def test_bf16_bank_tracks_the_fp32_reference(name, monkeypatch):
+    """bank_dtype=bfloat16: same write sequence, rows rounded to bf16 on insert; scores stay within the north star's
+    1e-2 bf16 bar of the fp32 reference and the exact-path top-k overlaps it almost everywhere."""
+    import aura_snn_rag_b200.hippocampal as hmod
+    case = C.CASE_BY_NAME[name]
+    gold = load(name)
+    clock = _Clock()
+    monkeypatch.setattr(hmod, "time", types.SimpleNamespace(time=clock.time))
+    hf = hmod.HippocampalFormation(n_place_cells=8, n_time_cells=4, n_grid_cells=4, max_memories=case.max_memories,
+                                   feature_dim=case.d, bank_dtype=torch.bfloat16)
+    hf.centroids_k = case.centroids_k
+    hf.centroids_update_interval = case.interval
+
+    def create(i, row, next_seeds):
+        after = hf.memory_count + 1
+        trig = (after % hf.centroids_update_interval == 0) and after > hf.centroids_k
+        hf.create_episodic_memory(f"m{i}", f"e{i}", row, seed_rows=next_seeds(after) if trig else None)
+
+    def set_time(t):
+        clock.now = t
+
+    rows, queries, _ = replay_writes(case, gold, hf, set_time, create, lambda s: hf.rebuild_centroids(seed_rows=s),
+                                     hf.decay_memories, hf.update_spatial_state)
+    assert hf.memory_features.dtype == torch.bfloat16 and hf._index_ready
+    hf._index_ready = False                                   # exact path, compared with the reference's exact output
+    overlap = []
+    for qi, q in enumerate(queries):
+        res = hf.retrieve_similar_memories(torch.from_numpy(q), k=case.k)
+        g_ids, g_sc = gold["exact_idnum"][qi], gold["exact_scores"][qi]
+        n_ret = int((g_ids >= 0).sum())
+        assert len(res) == n_ret
+        np.testing.assert_allclose([s for _, s in res], g_sc[:n_ret], atol=1e-2)
+        overlap.append(len({int(i[1:]) for i, _ in res} & set(g_ids[:n_ret].tolist())) / n_ret)
+    assert np.mean(overlap) > 0.9
