@@ -207,6 +207,181 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   if (warp == 1) { tc::tc_fence_after(); tc::tmem_dealloc(tmem_base, 512); }
 }
 
+// ================================================================================================
+// CTA-pair variant (cta_group::2): one tcgen05.mma spans two SMs - M = 256 (each CTA holds its own 128 A rows and their
+// accumulators in its own TMEM), N = 256 with each CTA loading HALF of the B tile.  Same math and epilogue as above; what
+// changes is operand traffic: 32 KB per k-block per CTA instead of 48 KB, so the ring is 6-7 stages deep instead of 4.
+//   full[s]   lives in the leader: 1 arrival (leader's expect_tx of both CTAs' bytes) + the TMA bytes of BOTH CTAs
+//   empty[s]  / tfull[a] in each CTA: arrived by the leader's tcgen05.commit multicast
+//   tempty[a] lives in the leader: 8 arrivals (4 epilogue warps of each CTA; the peer arrives through mapa)
+// ================================================================================================
+static constexpr int G2_STAGE_BYTES = GT_A_BYTES + GT_BM * GT_SLAB;   // A 16 KB + half of B 16 KB
+static constexpr int G2_MAX_STAGES = 7;
+
+template <bool TF32, int L>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GT_THREADS, 1)
+gemm_topk2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                  const GemmTopkArgs a) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int S = a.n_stages;
+  unsigned char* ring = smem;
+  float2* sbuf = reinterpret_cast<float2*>(ring + (size_t)S * G2_STAGE_BYTES);
+  uint64_t* full = reinterpret_cast<uint64_t*>(sbuf + 2 * GT_BN);
+  uint64_t* empty = full + G2_MAX_STAGES;
+  uint64_t* tfull = empty + G2_MAX_STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = tc::cluster_ctarank();          // 0 = leader (issues the MMAs)
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  constexpr int ELEMS_PER_SLAB = TF32 ? 32 : 64;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 8); }
+    fence_mbar_init();
+    tc::tma_prefetch_desc(&tmap_a);
+    tc::tma_prefetch_desc(&tmap_b);
+  }
+  if (warp == 1) { tc::tmem_alloc_2sm(tmem_slot, 512); tc::tmem_relinquish_2sm(); }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::cluster_sync_all();                                // barriers of both CTAs are initialised before any remote use
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // items: (pair A tile of 256 rows, column group); n_atiles counts 128-row tiles and is even
+  const int n_patiles = a.n_atiles >> 1;
+  const int n_items = n_patiles * a.n_groups;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint64_t pol_b = l2_policy_evict_first(), pol_a = l2_policy_evict_last();
+      int stage = 0; unsigned phase = 0;
+      for (int item = pair; item < n_items; item += n_pairs) {
+        const int patile = item % n_patiles, group = item / n_patiles;
+        const int ct0 = (int)(((long long)a.n_ctiles * group) / a.n_groups);
+        const int ct1 = (int)(((long long)a.n_ctiles * (group + 1)) / a.n_groups);
+        const int a_row = (patile * 2 + (int)rank) * GT_BM;
+        for (int ct = ct0; ct < ct1; ++ct) {
+          const int b_row = ct * GT_BN + (int)rank * GT_BM;
+          for (int kb = 0; kb < a.k_blocks; ++kb) {
+            tc::mbar_wait_guarded(&empty[stage], phase ^ 1u);
+            unsigned char* sa = ring + (size_t)stage * G2_STAGE_BYTES;
+            if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * G2_STAGE_BYTES);
+            tc::tma_load_2d_2sm(sa, &tmap_a, kb * ELEMS_PER_SLAB, a_row, &full[stage], pol_a);
+            tc::tma_load_2d_2sm(sa + GT_A_BYTES, &tmap_b, kb * ELEMS_PER_SLAB, b_row, &full[stage], pol_b);
+            if (++stage == S) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      const uint32_t idesc = tc::make_idesc(TF32 ? 2 : 1, 2 * GT_BM, GT_BN);
+      int stage = 0; unsigned phase = 0, tile_n = 0;
+      for (int item = pair; item < n_items; item += n_pairs) {
+        const int group = item / n_patiles;
+        const int ct0 = (int)(((long long)a.n_ctiles * group) / a.n_groups);
+        const int ct1 = (int)(((long long)a.n_ctiles * (group + 1)) / a.n_groups);
+        for (int ct = ct0; ct < ct1; ++ct, ++tile_n) {
+          const unsigned acc = tile_n & 1u, acc_phase = (tile_n >> 1) & 1u;
+          tc::mbar_wait_guarded(&tempty[acc], acc_phase ^ 1u);
+          tc::tc_fence_after();
+          const uint32_t d_tmem = tmem_base + acc * GT_BN;
+          for (int kb = 0; kb < a.k_blocks; ++kb) {
+            tc::mbar_wait_guarded(&full[stage], phase);
+            tc::tc_fence_after();
+            const unsigned char* sa = ring + (size_t)stage * G2_STAGE_BYTES;
+            const uint64_t da = tc::make_smem_desc_sw128(sa);
+            const uint64_t db = tc::make_smem_desc_sw128(sa + GT_A_BYTES);
+#pragma unroll
+            for (int j = 0; j < GT_SLAB / 32; ++j)
+              tc::umma_2sm<TF32>(d_tmem, da + (uint64_t)(2 * j), db + (uint64_t)(2 * j), idesc, (kb | j) != 0 ? 1u : 0u);
+            tc::umma_commit_2sm(&empty[stage]);
+            if (++stage == S) { stage = 0; phase ^= 1u; }
+          }
+          tc::umma_commit_2sm(&tfull[acc]);
+        }
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int te = quarter * 32 + lane;
+    const int et = threadIdx.x - 64;
+    unsigned tile_n = 0;
+    for (int item = pair; item < n_items; item += n_pairs) {
+      const int patile = item % n_patiles, group = item / n_patiles;
+      const int atile = patile * 2 + (int)rank;
+      const int ct0 = (int)(((long long)a.n_ctiles * group) / a.n_groups);
+      const int ct1 = (int)(((long long)a.n_ctiles * (group + 1)) / a.n_groups);
+      u64 e[L];
+#pragma unroll
+      for (int s = 0; s < L; ++s) e[s] = 0ull;
+      const long long my_row = a.a_row_first + (long long)atile * GT_BM + te;
+      const bool live = (long long)atile * GT_BM + te < a.n_a_rows;
+      float thr = live ? -INFINITY : INFINITY;
+      const u64 ceil_key = (a.ceil_keys != nullptr && live) ? a.ceil_keys[(long long)atile * GT_BM + te] : ~0ull;
+      const float ceil_score = ceil_key == ~0ull ? INFINITY : key_score(ceil_key);
+      if (ceil_key == 0ull) thr = INFINITY;
+      for (int ct = ct0; ct < ct1; ++ct, ++tile_n) {
+        const unsigned acc = tile_n & 1u, acc_phase = (tile_n >> 1) & 1u;
+        const long long col0 = (long long)ct * GT_BN;
+        float2* sb = sbuf + acc * GT_BN;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int c = et + h * 128;
+          const long long gc = col0 + c;
+          float2 t;
+          if (gc < a.n_b_rows) { t.x = a.scale ? a.scale[gc] : 1.f; t.y = a.bias ? a.bias[gc] : 0.f; }
+          else { t.x = 0.f; t.y = __int_as_float(0x7fc00000); }
+          sb[c] = t;
+        }
+        tc::named_bar_sync(1, 128);
+        tc::mbar_wait_guarded(&tfull[acc], acc_phase);
+        tc::tc_fence_after();
+        const bool diag = a.exclude_self && my_row >= col0 && my_row < col0 + GT_BN;
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * GT_BN;
+#pragma unroll 1
+        for (int c0 = 0; c0 < GT_BN; c0 += 32) {
+          float v[32];
+          tc::tmem_ld_32x32(taddr + c0, v);
+          unsigned mask = 0u;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float2 t = sb[c0 + j];
+            const float sj = fmaf(v[j], t.x, t.y);
+            mask |= (sj >= thr && sj <= ceil_score) ? (1u << j) : 0u;
+          }
+          if (diag) { const long long dj = my_row - col0 - c0; if (dj >= 0 && dj < 32) mask &= ~(1u << (int)dj); }
+          while (mask) {
+            const int j = __ffs(mask) - 1;
+            mask &= mask - 1u;
+            const float2 t = sb[c0 + j];
+            const u64 key = make_key(fmaf(select32(v, j), t.x, t.y), (unsigned)(col0 + c0 + j));
+            if (key > e[L - 1] && key < ceil_key) {
+              list_insert_sorted<L>(e, key);
+              if (e[L - 1] != 0ull) thr = key_score(e[L - 1]);
+            }
+          }
+        }
+        tc::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive_leader(&tempty[acc]);
+      }
+      const int item1 = group * a.n_atiles + atile;            // layout gemm_topk_finish_kernel reads
+      u64* dst = a.partial + (size_t)item1 * L * GT_BM;
+#pragma unroll
+      for (int s = 0; s < L; ++s) dst[s * GT_BM + te] = e[s];
+    }
+  }
+  __syncthreads();
+  tc::cluster_sync_all();                                // the peer's smem / TMEM stay valid until the leader is done
+  if (warp == 1) { tc::tc_fence_after(); tc::tmem_dealloc_2sm(tmem_base, 512); }
+}
+
 // ---- query preparation: qn = q / max(||q||, 1e-12) (F.normalize, hippocampal.py:273), optional bf16 copy ----
 __global__ void __launch_bounds__(256) normalize_queries_kernel(const float* __restrict__ q, int n, int d,
                                                                 float* __restrict__ qn, __nv_bfloat16* __restrict__ qb) {
@@ -499,6 +674,7 @@ int encode_tmap_2d(CUtensorMap* map, const void* base, int elem_bytes, bool bf16
 }
 
 struct GemmPlan {
+  int two_cta;     // CTA-pair kernel: n_atiles is even, grid is a multiple of 2
   int n_atiles, n_ctiles, n_groups, grid, L, n_stages, k_blocks, n2;
   size_t smem, partial_bytes;
 };
@@ -517,25 +693,40 @@ static bool make_gemm_plan(long long n_a_rows, long long n_b_rows, int d, int el
   p->n_atiles = (int)((n_a_rows + GT_BM - 1) / GT_BM);
   p->n_ctiles = (int)((n_b_rows + GT_BN - 1) / GT_BN);
   const int sms = sm_count();
-  int groups = sms / p->n_atiles;
+  // CTA pairs (cta_group::2) when there are at least two A tiles of real work; AURA_GEMM_2CTA=0/1 overrides
+  p->two_cta = 0;
+  if (const char* e = getenv("AURA_GEMM_2CTA")) p->two_cta = (atoi(e) != 0 && (sms % 2) == 0 && force_L == 0 && p->n_atiles >= 2) ? 1 : 0;
+  if (p->two_cta) p->n_atiles = (p->n_atiles + 1) / 2 * 2;
+  const int units = p->two_cta ? sms / 2 : sms;                 // schedulable units (pairs or CTAs)
+  const int work_rows = p->two_cta ? p->n_atiles / 2 : p->n_atiles;
+  int groups = units / work_rows;
   if (groups < 1) groups = 1;
   if (groups > p->n_ctiles) groups = p->n_ctiles;
   if (const char* e = getenv("AURA_GEMM_GROUPS")) { const int v = atoi(e); if (v >= 1 && v <= p->n_ctiles) groups = v; }
   if (force_groups) groups = force_groups;
   p->n_groups = groups;
-  const long long items = (long long)p->n_atiles * groups;
-  p->grid = (int)(items < sms ? items : sms);
+  const long long items = (long long)work_rows * groups;
+  const long long want = items < units ? items : units;
+  p->grid = (int)(p->two_cta ? 2 * want : want);
   const int elems = GT_SLAB / elem_bytes;
   p->k_blocks = (d + elems - 1) / elems;
-  const size_t fixed = 2 * GT_BN * 8 + (2 * GT_MAX_STAGES + 4) * 8 + 16;
   const size_t cap = (size_t)max_smem_optin() - 1024 /* alignment slack */;
-  int stages = (int)((cap - fixed) / GT_STAGE_BYTES);
-  if (stages > GT_MAX_STAGES) stages = GT_MAX_STAGES;
-  if (const char* e = getenv("AURA_GEMM_STAGES")) { const int v = atoi(e); if (v >= 2 && v <= stages) stages = v; }
+  int stages;
+  if (p->two_cta) {
+    const size_t fixed = 2 * GT_BN * 8 + (2 * G2_MAX_STAGES + 4) * 8 + 16;
+    stages = (int)((cap - fixed) / G2_STAGE_BYTES);
+    if (stages > G2_MAX_STAGES) stages = G2_MAX_STAGES;
+    p->smem = (size_t)stages * G2_STAGE_BYTES + fixed + 1024;
+  } else {
+    const size_t fixed = 2 * GT_BN * 8 + (2 * GT_MAX_STAGES + 4) * 8 + 16;
+    stages = (int)((cap - fixed) / GT_STAGE_BYTES);
+    if (stages > GT_MAX_STAGES) stages = GT_MAX_STAGES;
+    if (const char* e = getenv("AURA_GEMM_STAGES")) { const int v = atoi(e); if (v >= 2 && v <= stages) stages = v; }
+    p->smem = (size_t)stages * GT_STAGE_BYTES + fixed + 1024;
+  }
   if (stages < 2) return false;
   p->n_stages = stages;
-  p->smem = (size_t)stages * GT_STAGE_BYTES + fixed + 1024;
-  p->partial_bytes = (size_t)items * p->L * GT_BM * 8;
+  p->partial_bytes = (size_t)p->n_atiles * groups * p->L * GT_BM * 8;
   int n2 = 2;
   while (n2 < groups * p->L) n2 <<= 1;
   p->n2 = n2;
@@ -551,7 +742,7 @@ static int run_gemm_topk(const void* a_mat, long long n_a_rows, long long a_row_
   CUtensorMap ta, tb;
   int rc = encode_tmap_2d(&ta, a_mat, eb, bf16, n_a_rows, d, GT_BM);
   if (rc != AURA_OK) return rc;
-  rc = encode_tmap_2d(&tb, b_mat, eb, bf16, n_b_rows, d, GT_BN);
+  rc = encode_tmap_2d(&tb, b_mat, eb, bf16, n_b_rows, d, p.two_cta ? GT_BM : GT_BN);   // a CTA pair loads half of B each
   if (rc != AURA_OK) return rc;
   GemmTopkArgs a;
   a.n_atiles = p.n_atiles; a.n_ctiles = p.n_ctiles; a.n_groups = p.n_groups;
@@ -561,8 +752,9 @@ static int run_gemm_topk(const void* a_mat, long long n_a_rows, long long a_row_
   void (*kern)(const CUtensorMap, const CUtensorMap, const GemmTopkArgs) =
       p.L == GT_L_ASSIGN ? (bf16 ? gemm_topk_kernel<false, GT_L_ASSIGN> : gemm_topk_kernel<true, GT_L_ASSIGN>)
                          : (bf16 ? gemm_topk_kernel<false, GT_L> : gemm_topk_kernel<true, GT_L>);
+  if (p.two_cta) kern = bf16 ? gemm_topk2_kernel<false, GT_L> : gemm_topk2_kernel<true, GT_L>;
   AURA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
-  kern<<<p.grid, GT_THREADS, p.smem, st>>>(ta, tb, a);
+  kern<<<p.grid, GT_THREADS, p.smem, st>>>(ta, tb, a);     // the pair kernel carries __cluster_dims__(2,1,1)
   AURA_CUDA_OK(cudaGetLastError());
   note_launches(1);
   return AURA_OK;
