@@ -42,7 +42,7 @@ struct GemmTopkArgs {
   const u64* ceil_keys;       // per A row: only keys strictly below this one are eligible (multi-round top-k), may be null
 };
 
-template <bool TF32, int L>
+template <bool TF32, int L, bool CEIL>
 __global__ void __launch_bounds__(GT_THREADS, 1)
 gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const GemmTopkArgs a) {
@@ -146,7 +146,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const bool live = (long long)atile * GT_BM + te < a.n_a_rows;
       float thr = live ? -INFINITY : INFINITY;        // rows past the end of A never select anything
       // multi-round selection (k > 18): round r only admits keys strictly below the 32nd key of round r-1
-      const u64 ceil_key = (a.ceil_keys != nullptr && live) ? a.ceil_keys[(long long)atile * GT_BM + te] : ~0ull;
+      const u64 ceil_key = (CEIL && live) ? a.ceil_keys[(long long)atile * GT_BM + te] : ~0ull;
       const float ceil_score = ceil_key == ~0ull ? INFINITY : key_score(ceil_key);
       if (ceil_key == 0ull) thr = INFINITY;           // previous round already exhausted this row's candidates
       for (int ct = ct0; ct < ct1; ++ct, ++tile_n) {
@@ -177,7 +177,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           for (int j = 0; j < 32; ++j) {
             const float2 t = sb[c0 + j];
             const float sj = fmaf(v[j], t.x, t.y);
-            mask |= (sj >= thr && sj <= ceil_score) ? (1u << j) : 0u;
+            mask |= (sj >= thr && (!CEIL || sj <= ceil_score)) ? (1u << j) : 0u;
           }
           if (diag) { const long long dj = my_row - col0 - c0; if (dj >= 0 && dj < 32) mask &= ~(1u << (int)dj); }
           // rare path; the loop runs max-over-lanes popcount(mask) times for the warp
@@ -187,7 +187,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             const float2 t = sb[c0 + j];
             const float sc = fmaf(select32(v, j), t.x, t.y);
             const u64 key = make_key(sc, (unsigned)(col0 + c0 + j));
-            if (key > e[L - 1] && key < ceil_key) {
+            if (key > e[L - 1] && (!CEIL || key < ceil_key)) {
               list_insert_sorted<L>(e, key);
               if (e[L - 1] != 0ull) thr = key_score(e[L - 1]);
             }
@@ -218,7 +218,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 static constexpr int G2_STAGE_BYTES = GT_A_BYTES + GT_BM * GT_SLAB;   // A 16 KB + half of B 16 KB
 static constexpr int G2_MAX_STAGES = 7;
 
-template <bool TF32, int L>
+template <bool TF32, int L, bool CEIL>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GT_THREADS, 1)
 gemm_topk2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                   const GemmTopkArgs a) {
@@ -323,7 +323,7 @@ gemm_topk2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       const long long my_row = a.a_row_first + (long long)atile * GT_BM + te;
       const bool live = (long long)atile * GT_BM + te < a.n_a_rows;
       float thr = live ? -INFINITY : INFINITY;
-      const u64 ceil_key = (a.ceil_keys != nullptr && live) ? a.ceil_keys[(long long)atile * GT_BM + te] : ~0ull;
+      const u64 ceil_key = (CEIL && live) ? a.ceil_keys[(long long)atile * GT_BM + te] : ~0ull;
       const float ceil_score = ceil_key == ~0ull ? INFINITY : key_score(ceil_key);
       if (ceil_key == 0ull) thr = INFINITY;
       for (int ct = ct0; ct < ct1; ++ct, ++tile_n) {
@@ -353,7 +353,7 @@ gemm_topk2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           for (int j = 0; j < 32; ++j) {
             const float2 t = sb[c0 + j];
             const float sj = fmaf(v[j], t.x, t.y);
-            mask |= (sj >= thr && sj <= ceil_score) ? (1u << j) : 0u;
+            mask |= (sj >= thr && (!CEIL || sj <= ceil_score)) ? (1u << j) : 0u;
           }
           if (diag) { const long long dj = my_row - col0 - c0; if (dj >= 0 && dj < 32) mask &= ~(1u << (int)dj); }
           while (mask) {
@@ -361,7 +361,7 @@ gemm_topk2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             mask &= mask - 1u;
             const float2 t = sb[c0 + j];
             const u64 key = make_key(fmaf(select32(v, j), t.x, t.y), (unsigned)(col0 + c0 + j));
-            if (key > e[L - 1] && key < ceil_key) {
+            if (key > e[L - 1] && (!CEIL || key < ceil_key)) {
               list_insert_sorted<L>(e, key);
               if (e[L - 1] != 0ull) thr = key_score(e[L - 1]);
             }
@@ -749,10 +749,13 @@ static int run_gemm_topk(const void* a_mat, long long n_a_rows, long long a_row_
   a.n_a_rows = n_a_rows; a.n_b_rows = n_b_rows; a.a_row_first = a_row_first;
   a.k_blocks = p.k_blocks; a.L = p.L; a.n_stages = p.n_stages; a.exclude_self = exclude_self ? 1 : 0;
   a.scale = scale; a.bias = bias; a.partial = partial; a.ceil_keys = ceil_keys;
-  void (*kern)(const CUtensorMap, const CUtensorMap, const GemmTopkArgs) =
-      p.L == GT_L_ASSIGN ? (bf16 ? gemm_topk_kernel<false, GT_L_ASSIGN> : gemm_topk_kernel<true, GT_L_ASSIGN>)
-                         : (bf16 ? gemm_topk_kernel<false, GT_L> : gemm_topk_kernel<true, GT_L>);
-  if (p.two_cta) kern = bf16 ? gemm_topk2_kernel<false, GT_L> : gemm_topk2_kernel<true, GT_L>;
+  void (*kern)(const CUtensorMap, const CUtensorMap, const GemmTopkArgs);
+  const bool ceil = ceil_keys != nullptr;
+  if (p.L == GT_L_ASSIGN) kern = bf16 ? gemm_topk_kernel<false, GT_L_ASSIGN, false> : gemm_topk_kernel<true, GT_L_ASSIGN, false>;
+  else if (p.two_cta) kern = ceil ? (bf16 ? gemm_topk2_kernel<false, GT_L, true> : gemm_topk2_kernel<true, GT_L, true>)
+                                  : (bf16 ? gemm_topk2_kernel<false, GT_L, false> : gemm_topk2_kernel<true, GT_L, false>);
+  else kern = ceil ? (bf16 ? gemm_topk_kernel<false, GT_L, true> : gemm_topk_kernel<true, GT_L, true>)
+                   : (bf16 ? gemm_topk_kernel<false, GT_L, false> : gemm_topk_kernel<true, GT_L, false>);
   AURA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
   kern<<<p.grid, GT_THREADS, p.smem, st>>>(ta, tb, a);     // the pair kernel carries __cluster_dims__(2,1,1)
   AURA_CUDA_OK(cudaGetLastError());

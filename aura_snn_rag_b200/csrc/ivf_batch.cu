@@ -70,7 +70,7 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-template <bool TF32>
+template <bool TF32, bool CEIL>
 __global__ void __launch_bounds__(IB_THREADS, 1)
 ivf_gemm_kernel(const unsigned char* __restrict__ qmat, const unsigned char* __restrict__ bank, const int row_pitch,
                 const IvfBatchArgs a) {
@@ -236,7 +236,7 @@ ivf_gemm_kernel(const unsigned char* __restrict__ qmat, const unsigned char* __r
       const int my_query = live ? a.pair_of_pos[a.q_off[it.x] + it.y * GT_BM + my_pos] / a.nprobe : 0;
       unsigned* my_gthr = a.gthr + my_query;
       unsigned published = 0u;
-      const u64 ceil_key = (a.ceil_keys != nullptr && live) ? a.ceil_keys[my_query] : ~0ull;
+      const u64 ceil_key = (CEIL && live) ? a.ceil_keys[my_query] : ~0ull;
       const float ceil_score = ceil_key == ~0ull ? INFINITY : key_score(ceil_key);
       if (ceil_key == 0ull) thr = INFINITY;
       for (int cr = r0; cr < r1; cr += GT_BN, ++tile_n) {
@@ -273,14 +273,14 @@ ivf_gemm_kernel(const unsigned char* __restrict__ qmat, const unsigned char* __r
           for (int j = 0; j < 32; ++j) {
             const float2 t = sb[c0 + j];
             const float sj = fmaf(v[j], t.x, t.y);
-            mask |= (sj >= thr && sj <= ceil_score) ? (1u << j) : 0u;
+            mask |= (sj >= thr && (!CEIL || sj <= ceil_score)) ? (1u << j) : 0u;
           }
           while (mask) {
             const int j = __ffs(mask) - 1;
             mask &= mask - 1u;
             const float2 t = sb[c0 + j];
             const u64 key = make_key(fmaf(select32(v, j), t.x, t.y), (unsigned)rs[c0 + j]);
-            if (key > e[GT_L - 1] && key < ceil_key) {
+            if (key > e[GT_L - 1] && (!CEIL || key < ceil_key)) {
               list_insert_sorted<GT_L>(e, key);
               if (e[GT_L - 1] != 0ull) thr = fmaxf(thr, key_score(e[GT_L - 1]));
             }
@@ -543,9 +543,11 @@ extern "C" int aura_ivf_search_batch(const void* rows, int dtype, int64_t n_rows
   { const char* e = getenv("AURA_IVF_GTHR"); a.use_gthr = e ? atoi(e) : 1; }
   { const char* e = getenv("AURA_IVF_SPREAD"); a.spread = e ? atoi(e) : 1; }
   const size_t smem = (size_t)stages * GT_STAGE_BYTES + fixed + 1024;
-  void (*kern)(const unsigned char*, const unsigned char*, int, const IvfBatchArgs) =
-      bf16 ? ivf_gemm_kernel<false> : ivf_gemm_kernel<true>;
-  AURA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  typedef void (*IvfKern)(const unsigned char*, const unsigned char*, int, const IvfBatchArgs);
+  IvfKern kern0 = bf16 ? ivf_gemm_kernel<false, false> : ivf_gemm_kernel<true, false>;    // first round: no ceiling
+  IvfKern kern1 = bf16 ? ivf_gemm_kernel<false, true> : ivf_gemm_kernel<true, true>;
+  AURA_CUDA_OK(cudaFuncSetAttribute(kern0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  AURA_CUDA_OK(cudaFuncSetAttribute(kern1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   u64* cand = reinterpret_cast<u64*>(ws + L.cand);
   u64* ceil_buf = reinterpret_cast<u64*>(ws + L.ceil);
   int* force = reinterpret_cast<int*>(ws + L.force);
@@ -561,7 +563,7 @@ extern "C" int aura_ivf_search_batch(const void* rows, int dtype, int64_t n_rows
   for (int r = 0; r < rounds; ++r) {
     if (r > 0) AURA_CUDA_OK(cudaMemsetAsync(gthr, 0, (size_t)n_queries * 4, st));
     a.ceil_keys = r ? ceil_buf : nullptr;
-    kern<<<sm_count(), IB_THREADS, smem, st>>>(reinterpret_cast<const unsigned char*>(bf16 ? (const void*)qb : (const void*)qn),
+    (r ? kern1 : kern0)<<<sm_count(), IB_THREADS, smem, st>>>(reinterpret_cast<const unsigned char*>(bf16 ? (const void*)qb : (const void*)qn),
                                                reinterpret_cast<const unsigned char*>(rows), d * eb, a);
     AURA_CUDA_OK(cudaGetLastError());
     f.round = r;
