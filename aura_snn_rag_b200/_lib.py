@@ -55,6 +55,8 @@ SIGNATURES = {
     "aura_allpairs_topk_workspace_bytes": (_sz, [_i64, _i64, _i, _i, _i]),
     "aura_allpairs_topk": (_i, [_p, _i, _i64, _i, _i64, _i64, _p, _i, _p, _p, _p, _sz, _p]),
     "aura_topk_merge": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _p]),
+    "aura_pack_topk": (_i, [_p, _p, _p, _i, _i, _p, _p]),
+    "aura_topk_merge_packed": (_i, [_p, _i, _i, _i, _p, _p, _p, _p]),
     "aura_gather_rows": (_i, [_p, _i, _i, _p, _i64, _p, _p]),
 }
 

@@ -70,3 +70,95 @@ extern "C" int aura_topk_merge(const float* in_score, const int64_t* in_idx, int
   note_launches(1);
   return AURA_OK;
 }
+
+// ---- sharded search plumbing: one payload per rank, one merge kernel -------------------------------------------------
+// payload[b] = { idx[b][0..k) , score bits[b][0..k) , flag[b] } as int64: what a rank contributes to the all-gather
+namespace aura {
+__global__ void __launch_bounds__(256) pack_topk_kernel(const long long* __restrict__ idx, const float* __restrict__ score,
+                                                        const int* __restrict__ flags, int n_queries, int k,
+                                                        long long* __restrict__ payload) {
+  const int w = 2 * k + 1;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (long long)n_queries * w; i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / w), j = (int)(i % w);
+    long long v;
+    if (j < k) v = idx[(size_t)b * k + j];
+    else if (j < 2 * k) v = (long long)__float_as_int(score[(size_t)b * k + (j - k)]);
+    else v = flags ? (long long)flags[b] : 0ll;
+    payload[i] = v;
+  }
+}
+
+// gathered: [n_ranks][n_queries][2k+1]; one CTA per query merges the n_ranks*k pairs (score desc, lower global row on ties)
+__global__ void __launch_bounds__(256) merge_packed_kernel(const long long* __restrict__ gathered, int n_ranks, int n_queries, int k,
+                                                           float* __restrict__ out_score, long long* __restrict__ out_idx,
+                                                           int* __restrict__ any_flag, int n2) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  u64* keys = reinterpret_cast<u64*>(smem);
+  const int b = blockIdx.x, w = 2 * k + 1, n_in = n_ranks * k;
+  auto idx_at = [&](int i) { return gathered[((size_t)(i / k) * n_queries + b) * w + (i % k)]; };
+  auto score_at = [&](int i) { return __int_as_float((int)gathered[((size_t)(i / k) * n_queries + b) * w + k + (i % k)]); };
+  for (int i = threadIdx.x; i < n2; i += blockDim.x) {
+    u64 key = 0ull;
+    if (i < n_in && idx_at(i) >= 0) key = ((u64)f32_orderable(score_at(i)) << 32) | (u64)(0xFFFFFFFFu - (unsigned)i);
+    keys[i] = key;
+  }
+  for (int size = 2; size <= n2; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      __syncthreads();
+      for (int t = threadIdx.x; t < (n2 >> 1); t += blockDim.x) {
+        const int lo = 2 * t - (t & (stride - 1)), hi = lo + stride;
+        const bool desc = ((lo & size) == 0);
+        const u64 x = keys[lo], y = keys[hi];
+        bool x_first;
+        const unsigned sx = (unsigned)(x >> 32), sy = (unsigned)(y >> 32);
+        if (sx != sy) x_first = sx > sy;
+        else if (x == 0ull || y == 0ull) x_first = x > y;
+        else x_first = idx_at((int)key_row(x)) < idx_at((int)key_row(y));
+        if (x_first != desc) { keys[lo] = y; keys[hi] = x; }
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < k; i += blockDim.x) {
+    const u64 key = i < n2 ? keys[i] : 0ull;
+    out_score[(size_t)b * k + i] = key ? score_at((int)key_row(key)) : -INFINITY;
+    out_idx[(size_t)b * k + i] = key ? idx_at((int)key_row(key)) : -1ll;
+  }
+  if (threadIdx.x == 0 && any_flag) {
+    int f = 0;
+    for (int r = 0; r < n_ranks; ++r) f |= (int)gathered[((size_t)r * n_queries + b) * w + 2 * k] != 0;
+    any_flag[b] = f;
+  }
+}
+}  // namespace aura
+
+extern "C" int aura_pack_topk(const int64_t* idx, const float* score, const int32_t* flags, int n_queries, int k,
+                              int64_t* payload, void* stream) {
+  AURA_REQUIRE(n_queries >= 1 && k >= 1 && idx && score && payload, AURA_ERR_INVALID_ARG, "aura_pack_topk: bad argument");
+  const long long n = (long long)n_queries * (2 * k + 1);
+  int g = (int)((n + 255) / 256);
+  if (g > sm_count() * 8) g = sm_count() * 8;
+  pack_topk_kernel<<<g, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const long long*>(idx), score, flags, n_queries, k,
+                                                        reinterpret_cast<long long*>(payload));
+  AURA_CUDA_OK(cudaGetLastError());
+  note_launches(1);
+  return AURA_OK;
+}
+
+extern "C" int aura_topk_merge_packed(const int64_t* gathered, int n_ranks, int n_queries, int k, float* out_score,
+                                      int64_t* out_idx, int32_t* any_flag, void* stream) {
+  AURA_REQUIRE(n_ranks >= 1 && n_queries >= 1 && k >= 1 && gathered && out_score && out_idx, AURA_ERR_INVALID_ARG,
+               "aura_topk_merge_packed: bad argument");
+  int n2 = 2;
+  while (n2 < n_ranks * k) n2 <<= 1;
+  AURA_REQUIRE((size_t)n2 * 8 <= (size_t)max_smem_optin() - 1024, AURA_ERR_UNSUPPORTED,
+               "aura_topk_merge_packed: n_ranks*k=%d does not fit shared memory", n_ranks * k);
+  const size_t smem = (size_t)n2 * 8;
+  AURA_CUDA_OK(cudaFuncSetAttribute(merge_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  merge_packed_kernel<<<n_queries, 256, smem, (cudaStream_t)stream>>>(reinterpret_cast<const long long*>(gathered), n_ranks,
+                                                                      n_queries, k, out_score,
+                                                                      reinterpret_cast<long long*>(out_idx), any_flag, n2);
+  AURA_CUDA_OK(cudaGetLastError());
+  note_launches(1);
+  return AURA_OK;
+}

@@ -127,6 +127,27 @@ def topk_merge(scores: torch.Tensor, idx: torch.Tensor, n_lists: int, k_in: int,
     return out_s, out_i
 
 
+def pack_topk(idx: torch.Tensor, score: torch.Tensor, flags: Optional[torch.Tensor], out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """[B, 2k+1] int64 payload of one rank for the sharded all-gather (ids, score bits, certification flag)."""
+    b, k = idx.shape
+    if out is None:
+        out = torch.empty(b, 2 * k + 1, dtype=torch.int64, device=idx.device)
+    check(_lib.load().aura_pack_topk(idx.data_ptr(), score.data_ptr(), _ptr(flags), b, k, out.data_ptr(), _stream()),
+          "aura_pack_topk")
+    return out
+
+
+def topk_merge_packed(gathered: torch.Tensor, n_ranks: int, b: int, k: int):
+    """Merge the rank-major gathered payloads [n_ranks*B, 2k+1] -> (idx [B,k], score [B,k], any_flag [B] int32)."""
+    dev = gathered.device
+    out_s = torch.empty(b, k, dtype=torch.float32, device=dev)
+    out_i = torch.empty(b, k, dtype=torch.int64, device=dev)
+    flag = torch.empty(b, dtype=torch.int32, device=dev)
+    check(_lib.load().aura_topk_merge_packed(gathered.data_ptr(), n_ranks, b, k, out_s.data_ptr(), out_i.data_ptr(),
+                                             flag.data_ptr(), _stream()), "aura_topk_merge_packed")
+    return out_i, out_s, flag
+
+
 def gather_rows(rows: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
     rows = _dev(rows, "rows")
     idx = _dev(idx, "idx")

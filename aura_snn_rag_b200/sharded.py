@@ -38,8 +38,11 @@ class ShardedBank:
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.stats = stats if stats is not None else {}
         self._fixup = None
+        self._packed = local_search is None and merge is None
+        self._ops = None
         if local_search is None or merge is None:
             from . import ops      # CUDA only; raises without the library
+            self._ops = ops
             if scale is None:
                 scale = ops.row_inv_norms(local_rows)
             if local_search is None:
@@ -64,7 +67,13 @@ class ShardedBank:
 
     def _gather_merge(self, idx: torch.Tensor, score: torch.Tensor, k: int, flags: Optional[torch.Tensor]):
         b = idx.shape[0]
-        # one collective: [idx | score bits | flag] per query, rank-major concatenation
+        if self._packed:
+            # product path: pack kernel -> ONE collective -> merge kernel (3 launches, no torch elementwise ops)
+            payload = self._ops.pack_topk(idx.contiguous(), score.contiguous(), flags)
+            gathered = torch.empty(self.world * b, 2 * k + 1, dtype=torch.int64, device=idx.device)
+            dist.all_gather_into_tensor(gathered, payload, group=self.group)
+            return self._ops.topk_merge_packed(gathered, self.world, b, k)
+        # injected local_search / merge (CPU plumbing tests): same payload layout, torch ops
         payload = torch.empty(b, 2 * k + 1, dtype=torch.int64, device=idx.device)
         payload[:, :k] = idx
         payload[:, k:2 * k] = score.contiguous().view(torch.int32)
@@ -190,10 +199,8 @@ class ShardedIndex:
         if self.world == 1:
             return idx, score
         b = idx.shape[0]
-        all_idx = self._all_gather(idx)                            # [G,B,k]
-        all_score = self._all_gather(score)
-        g = all_idx.shape[0]
-        cat_idx = all_idx.permute(1, 0, 2).reshape(b, g * k).contiguous()
-        cat_score = all_score.permute(1, 0, 2).reshape(b, g * k).contiguous()
-        out_score, out_idx = ops.topk_merge(cat_score, cat_idx, g, k, k)
+        payload = ops.pack_topk(idx.contiguous(), score.contiguous(), None)       # [B, 2k+1]
+        gathered = self._all_gather(payload)                                       # [G, B, 2k+1], one collective
+        g = gathered.shape[0]
+        out_idx, out_score, _ = ops.topk_merge_packed(gathered.reshape(g * b, 2 * k + 1).contiguous(), g, b, k)
         return out_idx, out_score

@@ -191,6 +191,14 @@ int aura_allpairs_topk(const void* rows, int dtype, int64_t n_rows, int d, int64
 int aura_topk_merge(const float* in_score, const int64_t* in_idx, int n_queries, int n_lists, int k_in,
                     int k_out, float* out_score, int64_t* out_idx, void* stream);
 
+/* Sharded search, one collective per step: aura_pack_topk writes what a rank contributes to the all-gather,
+ * payload[b] = { idx[b][0..k), score bits[b][0..k), flag[b] } as int64 [n_queries, 2k+1]; aura_topk_merge_packed merges the
+ * rank-major gathered block [n_ranks, n_queries, 2k+1] (same order rule as aura_topk_merge) and ORs the flags. */
+int aura_pack_topk(const int64_t* idx, const float* score, const int32_t* flags, int n_queries, int k, int64_t* payload,
+                   void* stream);
+int aura_topk_merge_packed(const int64_t* gathered, int n_ranks, int n_queries, int k, float* out_score, int64_t* out_idx,
+                           int32_t* any_flag, void* stream);
+
 /* Gather bank rows of a result block: out[b, j, :] = rows[idx[b, j]] (zeros when idx < 0), as fp32.
  * Replaces the per-result id_to_idx lookup + row copy of memory_augmented_layer.py:124-128. */
 int aura_gather_rows(const void* rows, int dtype, int d, const int64_t* idx, int64_t n_idx, float* out, void* stream);

@@ -93,3 +93,22 @@ def test_sharded_index_equals_single_index(monkeypatch):
         idx, sc = results[r]
         assert torch.equal(idx.cpu(), ref_idx.cpu())
         np.testing.assert_allclose(sc.cpu().numpy(), ref_sc.cpu().numpy(), rtol=1e-6)
+
+
+def test_pack_and_merge_packed_equal_the_reference_merge():
+    from aura_snn_rag_b200 import ops
+    from oracle.hippo_oracle import merge_topk
+    g = torch.Generator().manual_seed(3)
+    G, B, k = 5, 37, 10
+    scores = torch.randn(G, B, k, generator=g)
+    scores[1, :, 3] = scores[3, :, 7]                      # cross-rank score ties
+    ids = torch.randperm(10 ** 7, generator=g)[: G * B * k].reshape(G, B, k) + 3 * 10 ** 9
+    ids[2, 5, 4:] = -1                                     # a rank with fewer than k results
+    flags = torch.zeros(G, B, dtype=torch.int32); flags[4, 11] = 1
+    payloads = [ops.pack_topk(ids[r].cuda(), scores[r].cuda(), flags[r].cuda()) for r in range(G)]
+    gathered = torch.cat(payloads, 0)
+    oi, os_, fl = ops.topk_merge_packed(gathered, G, B, k)
+    s2 = scores.clone(); s2[ids < 0] = -float("inf")
+    ref_s, ref_i = merge_topk(s2.permute(1, 0, 2).reshape(B, G * k), ids.permute(1, 0, 2).reshape(B, G * k), k)
+    assert torch.equal(oi.cpu(), ref_i) and torch.equal(os_.cpu(), ref_s)
+    assert fl.cpu().tolist() == [1 if b == 11 else 0 for b in range(B)]
