@@ -120,6 +120,7 @@ class HippocampalFormation(nn.Module):
         self.register_buffer('_scale', torch.zeros(max_memories, **f32), persistent=False)
         self.register_buffer('_bias', torch.zeros(max_memories, **f32), persistent=False)
         self._lists_dirty = True
+        self._host_stage: Dict[int, Tuple[torch.Tensor, torch.Tensor]] = {}   # pinned result staging per k
         self._terms_key = None        # (fp32 now, location key, version) the cached _scale/_bias belong to
         self._version = 0             # bumped by every write / decay
 
@@ -369,8 +370,17 @@ class HippocampalFormation(nn.Module):
         if self.memory_count == 0:
             return []                                                           # :251-252
         idx, score = self.retrieve_batch(query_features, k=k, location=location)
-        rows = idx[0].tolist()
-        scores = score[0].tolist()
+        # one host sync for both results: pinned staging buffers, two async copies, one stream synchronise
+        kk = idx.shape[1]
+        stage = self._host_stage.get(kk)
+        if stage is None:
+            stage = (torch.empty(kk, dtype=torch.int64).pin_memory(), torch.empty(kk, dtype=torch.float32).pin_memory())
+            self._host_stage[kk] = stage
+        stage[0].copy_(idx[0], non_blocking=True)
+        stage[1].copy_(score[0], non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        rows = stage[0].tolist()
+        scores = stage[1].tolist()
         out: List[Tuple[Union[str, int], float]] = []
         for r, s in zip(rows, scores):
             if r < 0:
