@@ -90,30 +90,55 @@ class ShardedBank:
 
     def search(self, queries: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
         """queries [B,d] identical on all ranks -> (global rows int64 [B,k], scores fp32 [B,k]) on all ranks."""
+        return self.finalize(self.search_deferred(queries, k))
+
+    def search_deferred(self, queries: torch.Tensor, k: int):
+        """Enqueue one search (local top-k, pack, all-gather, merge, flag reduction + async copy of the flag count to
+        pinned memory) and return a handle WITHOUT synchronising; `finalize(handle)` waits for exactly this search and
+        runs the (rare) exact re-run.  A serving loop that finalises search i after enqueuing search i+1 keeps the GPU
+        busy while the host prepares the next launches (bench.py does this)."""
         if queries.device != self.rows.device:
             queries = queries.to(self.rows.device, non_blocking=True)
         res = self._local_search(queries, k)
         idx, score = res[0], res[1]
         flags = res[2] if len(res) > 2 else None
         if self.world == 1:
-            if flags is not None:
-                self._fixup(flags, idx, score, queries, k)
-            return idx, score
+            return {"idx": idx, "score": score, "flags": flags, "queries": queries, "k": k, "local": True}
         out_idx, out_score, any_flag = self._gather_merge(idx, score, k, flags)
-        if flags is not None:
-            # the only host sync of the step, after everything above has been enqueued; every rank sees the same
-            # flags, so the (rare) re-run below is entered by all ranks together
-            bad = torch.nonzero(any_flag, as_tuple=False).squeeze(-1)
-            if bad.numel() > 0:
-                qb = queries[bad].contiguous()
-                fl = torch.ones(bad.numel(), dtype=torch.int32, device=idx.device)
-                i2 = torch.empty(bad.numel(), k, dtype=idx.dtype, device=idx.device)
-                s2 = torch.empty(bad.numel(), k, dtype=score.dtype, device=idx.device)
-                self._fixup(fl, i2, s2, qb, k)
-                i3, s3, _ = self._gather_merge(i2, s2, k, None)
-                out_idx[bad] = i3
-                out_score[bad] = s3
-        return out_idx, out_score
+        h = {"idx": out_idx, "score": out_score, "any_flag": any_flag, "queries": queries, "k": k, "local": False,
+             "checked": flags is None}
+        if flags is not None and queries.is_cuda:
+            n_bad = torch.empty(1, dtype=torch.int64).pin_memory()
+            n_bad.copy_((any_flag != 0).sum().reshape(1), non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(queries.device))
+            h["n_bad"], h["event"] = n_bad, ev
+        return h
+
+    def finalize(self, h) -> Tuple[torch.Tensor, torch.Tensor]:
+        idx, score, queries, k = h["idx"], h["score"], h["queries"], h["k"]
+        if h["local"]:
+            if h["flags"] is not None:
+                self._fixup(h["flags"], idx, score, queries, k)
+            return idx, score
+        if h["checked"]:
+            return idx, score
+        if "event" in h:
+            h["event"].synchronize()                      # waits for this search only
+            if int(h["n_bad"][0]) == 0:
+                return idx, score
+        # every rank sees the same flags, so the (rare) re-run below is entered by all ranks together
+        bad = torch.nonzero(h["any_flag"], as_tuple=False).squeeze(-1)
+        if bad.numel() > 0:
+            qb = queries[bad].contiguous()
+            fl = torch.ones(bad.numel(), dtype=torch.int32, device=idx.device)
+            i2 = torch.empty(bad.numel(), k, dtype=idx.dtype, device=idx.device)
+            s2 = torch.empty(bad.numel(), k, dtype=score.dtype, device=idx.device)
+            self._fixup(fl, i2, s2, qb, k)
+            i3, s3, _ = self._gather_merge(i2, s2, k, None)
+            idx[bad] = i3
+            score[bad] = s3
+        return idx, score
 
 
 class ShardedIndex:
