@@ -67,6 +67,9 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, unsign
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
@@ -109,8 +112,6 @@ ivf_gemm_kernel(const unsigned char* __restrict__ qmat, const unsigned char* __r
     const uint32_t dst_off = (uint32_t)(prow * GT_SLAB + ((pj ^ (prow & 7)) << 4));
     const uint32_t ring_u32 = smem_u32(ring);
     int stage = 0; unsigned phase = 0;
-    int pend_stage[IB_LOOKAHEAD];                   // stages whose copies are committed but not yet published
-    int n_pend = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const int4 it = a.items[item];
       const int qb = a.q_off[it.x], nq = a.q_off[it.x + 1] - qb;
@@ -160,26 +161,16 @@ ivf_gemm_kernel(const unsigned char* __restrict__ qmat, const unsigned char* __r
             for (int h = 0; h < 2; ++h)
               if (h < nkb) cp_async16(sa[h] + GT_A_BYTES + i * 16 * GT_SLAB, src + ko[h], in_row[h] ? 16u : 0u);
           }
-          cp_async_commit();
-          if (n_pend == 1) {                        // the previous pair has landed: publish its stages
-            cp_async_wait<1>();
-            fence_proxy_async();
-            mbar_arrive(&full[pend_stage[0]]);
-            if (pend_stage[1] >= 0) mbar_arrive(&full[pend_stage[1]]);
-            n_pend = 0;
-          }
-          pend_stage[0] = st[0];
-          pend_stage[1] = nkb == 2 ? st[1] : -1;
-          n_pend = 1;
+          // completion is signalled asynchronously: the mbarrier of each stage receives this thread's arrival when all
+          // of its copies issued so far have landed (cp.async.mbarrier.arrive.noinc), so the thread never blocks on its
+          // own loads and up to a full ring of stages stays in flight
+#pragma unroll
+          for (int h = 0; h < 2; ++h)
+            if (h < nkb) cp_async_arrive_noinc(&full[st[h]]);
         }
       }
     }
     cp_async_wait<0>();
-    fence_proxy_async();
-    if (n_pend) {
-      mbar_arrive(&full[pend_stage[0]]);
-      if (pend_stage[1] >= 0) mbar_arrive(&full[pend_stage[1]]);
-    }
   } else if (warp == 0) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
@@ -199,6 +190,7 @@ ivf_gemm_kernel(const unsigned char* __restrict__ qmat, const unsigned char* __r
           const uint32_t d_tmem = tmem_base + acc * GT_BN;
           for (int kb = 0; kb < a.k_blocks; ++kb) {
             tc::mbar_wait_guarded(&full[stage], phase);
+            fence_proxy_async();                      // cp.async wrote the stage through the generic proxy; the MMA reads it through the async proxy
             tc::tc_fence_after();
             const unsigned char* sa = ring + (size_t)stage * GT_STAGE_BYTES;
             const uint64_t da = tc::make_smem_desc_sw128(sa);
