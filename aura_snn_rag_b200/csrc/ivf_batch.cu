@@ -53,6 +53,8 @@ struct IvfBatchArgs {
   int cap_plists;
   u64* partial;             // [cap_plists][GT_L]: one sorted list per (pair, chunk), at pbase[c] + chunk * nq_c + rel
   int use_gthr, spread;     // tuning switches (experiments)
+  int l2_hint;              // bit 0: single-tile lists evict-first, bit 1: multi-tile lists evict-last, bit 2: query rows evict-last
+  int sync_polls;           // sibling CTAs of a cluster wait at most this many polls for each other per tile (0: never)
   const u64* ceil_keys;     // per query: only keys strictly below are eligible (multi-round top-k), may be null
   unsigned* gthr;           // [B] orderable lower bound of every query's final L-th best score (atomicMax)
 };
@@ -65,6 +67,15 @@ __device__ __forceinline__ int ib_pos_of_row(int r, int spread) { return spread 
 // 16-byte global -> shared async copy; src_bytes = 0 writes zeros (K tail past the end of a row)
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, unsigned src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+// same with an L2 eviction policy
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, unsigned src_bytes, uint64_t policy) {
+  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2, %3;" ::"r"(dst), "l"(src), "r"(src_bytes), "l"(policy) : "memory");
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_normal() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+  return p;
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
@@ -88,18 +99,23 @@ ivf_gemm_kernel(const unsigned char* __restrict__ qmat, const unsigned char* __r
   uint64_t* tfull = empty + GT_MAX_STAGES;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint32_t* sync_ctr = tmem_slot + 1;      // tiles announced by the sibling CTAs of this cluster (monotonic)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cs = (int)tc::cluster_nctarank(), crank = (int)tc::cluster_ctarank();
+  const int cid = blockIdx.x / cs, ncl = gridDim.x / cs;
   constexpr int ELEMS_PER_SLAB = TF32 ? 32 : 64;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) { mbar_init(&full[s], 128); mbar_init(&empty[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4); }
+    *sync_ctr = 0u;
     fence_mbar_init();
   }
   if (warp == 0) { tc::tmem_alloc(tmem_slot, 512); tc::tmem_relinquish(); }
   tc::tc_fence_before();
   __syncthreads();
+  tc::cluster_sync_all();     // sibling counters are written remotely: every CTA of the cluster has initialised its own
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   // a work table or partial-list area that does not fit processes nothing (the finish kernel hands every query back)
@@ -111,9 +127,17 @@ ivf_gemm_kernel(const unsigned char* __restrict__ qmat, const unsigned char* __r
     const int prow = pt >> 3, pj = pt & 7;          // this thread copies chunk pj of rows prow + 16*i
     const uint32_t dst_off = (uint32_t)(prow * GT_SLAB + ((pj ^ (prow & 7)) << 4));
     const uint32_t ring_u32 = smem_u32(ring);
-    int stage = 0; unsigned phase = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    int stage = 0; unsigned phase = 0, sib_expected = 0u;
+    // L2 residency: rows of a list probed by a single query tile are never needed again (evict first); rows of a list
+    // with several query tiles are re-read by the sibling items and query rows by every tile (evict last)
+    const uint64_t pol_stream = (a.l2_hint & 1) ? l2_policy_evict_first() : l2_policy_evict_normal();
+    const uint64_t pol_keep = (a.l2_hint & 2) ? l2_policy_evict_last() : l2_policy_evict_normal();
+    const uint64_t pol_a = (a.l2_hint & 4) ? l2_policy_evict_last() : l2_policy_evict_normal();
+    for (int grp = cid; grp * cs < n_items; grp += ncl) {
+      const int item = grp * cs + crank;
+      if (item >= n_items) continue;
       const int4 it = a.items[item];
+      if (it.x < 0) continue;          // padding slot
       const int qb = a.q_off[it.x], nq = a.q_off[it.x + 1] - qb;
       const int a0 = qb + it.y * GT_BM, n_a = min(GT_BM, nq - it.y * GT_BM);
       const int lb = a.list_offsets[it.x], len = a.list_offsets[it.x + 1] - lb;
@@ -124,7 +148,31 @@ ivf_gemm_kernel(const unsigned char* __restrict__ qmat, const unsigned char* __r
 #pragma unroll
       for (int i = 0; i < 8; ++i)
         qsrc[i] = qmat + (size_t)(a.pair_of_pos[a0 + min(ib_pos_of_row(prow + 16 * i, a.spread), n_a - 1)] / a.nprobe) * row_pitch + pj * 16;
+      // siblings: the other CTAs of this cluster whose item is another query tile of the same list chunk.  Each announces
+      // every tile it starts to the others and waits (bounded - this is pacing, not correctness) until they have started
+      // it too, so the chunk is fetched from HBM once and the other copies hit L2 while the lines are still resident.
+      unsigned sib_mask = 0u; int n_sib = 0;
+      for (int j = 0; j < cs; ++j)
+        if (j != crank && grp * cs + j < n_items) {
+          const int4 o = a.items[grp * cs + j];
+          if (o.x == it.x && o.z == it.z) { sib_mask |= 1u << j; ++n_sib; }
+        }
+      bool in_step = n_sib > 0 && a.sync_polls > 0;
+      const uint64_t pol_b = nq > GT_BM ? pol_keep : pol_stream;
       for (int cr = r0; cr < r1; cr += GT_BN) {
+        if (n_sib > 0) {
+          if (pt == 0)
+            for (int j = 0; j < cs; ++j)
+              if ((sib_mask >> j) & 1u) tc::cluster_red_inc(sync_ctr, j);
+          sib_expected += (unsigned)n_sib;
+          if (in_step) {
+            int polls = 0;
+            while ((int)(*reinterpret_cast<volatile uint32_t*>(sync_ctr) - sib_expected) < 0) {
+              if (++polls > a.sync_polls) { in_step = false; break; }     // the sibling is far behind: stop waiting for it
+              __nanosleep(64);
+            }
+          }
+        }
         int rb[16];                   // bank rows of B-tile rows prow + 16*i
 #pragma unroll
         for (int i = 0; i < 16; ++i) rb[i] = a.list_rows[lb + min(cr + prow + 16 * i, r1 - 1)];
@@ -153,13 +201,13 @@ ivf_gemm_kernel(const unsigned char* __restrict__ qmat, const unsigned char* __r
           for (int i = 0; i < 8; ++i)
 #pragma unroll
             for (int h = 0; h < 2; ++h)
-              if (h < nkb) cp_async16(sa[h] + i * 16 * GT_SLAB, qsrc[i] + ko[h], in_row[h] ? 16u : 0u);
+              if (h < nkb) cp_async16(sa[h] + i * 16 * GT_SLAB, qsrc[i] + ko[h], in_row[h] ? 16u : 0u, pol_a);
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const unsigned char* src = bank + (size_t)rb[i] * row_pitch + pj * 16;
 #pragma unroll
             for (int h = 0; h < 2; ++h)
-              if (h < nkb) cp_async16(sa[h] + GT_A_BYTES + i * 16 * GT_SLAB, src + ko[h], in_row[h] ? 16u : 0u);
+              if (h < nkb) cp_async16(sa[h] + GT_A_BYTES + i * 16 * GT_SLAB, src + ko[h], in_row[h] ? 16u : 0u, pol_b);
           }
           // completion is signalled asynchronously: the mbarrier of each stage receives this thread's arrival when all
           // of its copies issued so far have landed (cp.async.mbarrier.arrive.noinc), so the thread never blocks on its
@@ -177,8 +225,11 @@ ivf_gemm_kernel(const unsigned char* __restrict__ qmat, const unsigned char* __r
       const uint32_t idesc = tc::make_idesc(TF32 ? 2 : 1, GT_BM, GT_BN);
       int stage = 0; unsigned phase = 0;
       unsigned tile_n = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      for (int grp = cid; grp * cs < n_items; grp += ncl) {
+        const int item = grp * cs + crank;
+        if (item >= n_items) continue;
         const int4 it = a.items[item];
+        if (it.x < 0) continue;        // padding slot
         const int len = a.list_offsets[it.x + 1] - a.list_offsets[it.x];
         int n_ch_, ch_rows_;
       ib_chunks(len, n_ch_, ch_rows_);
@@ -211,8 +262,11 @@ ivf_gemm_kernel(const unsigned char* __restrict__ qmat, const unsigned char* __r
     const int te = quarter * 32 + lane;
     const int et = threadIdx.x - 32;
     unsigned tile_n = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    for (int grp = cid; grp * cs < n_items; grp += ncl) {
+      const int item = grp * cs + crank;
+      if (item >= n_items) continue;
       const int4 it = a.items[item];
+      if (it.x < 0) continue;          // padding slot
       const int nq = a.q_off[it.x + 1] - a.q_off[it.x];
       const int n_a = min(GT_BM, nq - it.y * GT_BM);
       const int lb = a.list_offsets[it.x], len = a.list_offsets[it.x + 1] - lb;
@@ -294,6 +348,7 @@ ivf_gemm_kernel(const unsigned char* __restrict__ qmat, const unsigned char* __r
     }
   }
   __syncthreads();
+  tc::cluster_sync_all();     // no CTA leaves while a sibling may still write its counter
   if (warp == 0) { tc::tc_fence_after(); tc::tmem_dealloc(tmem_base, 512); }
 }
 
@@ -316,28 +371,37 @@ __global__ void __launch_bounds__(256) ib_pair_scatter_kernel(const long long* _
   pos_of_pair[i] = pos;
 }
 __global__ void __launch_bounds__(256) ib_item_count_kernel(const int* __restrict__ q_off, const int* __restrict__ list_offsets,
-                                                            int n_lists, int* __restrict__ items_c, int* __restrict__ plists_c) {
+                                                            int n_lists, int cs, int* __restrict__ items_c, int* __restrict__ plists_c) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= n_lists) return;
   const int nq = q_off[c + 1] - q_off[c], len = list_offsets[c + 1] - list_offsets[c];
   int n_ch, ch_rows;
   ib_chunks(len, n_ch, ch_rows);
-  items_c[c] = ((nq + GT_BM - 1) / GT_BM) * n_ch;
+  // two sections: lists probed by more than one query tile first, their tile count padded to the cluster size so
+  // that the tiles of one chunk ("siblings") fall into one aligned group of cs items; single-tile lists after them
+  const int n_qt = (nq + GT_BM - 1) / GT_BM;
+  const bool heavy = n_qt > 1;
+  items_c[c] = heavy ? (n_qt + cs - 1) / cs * cs * n_ch : 0;
+  items_c[n_lists + c] = heavy ? 0 : n_qt * n_ch;
   plists_c[c] = nq * n_ch;
 }
-__global__ void __launch_bounds__(256) ib_item_fill_kernel(const int* __restrict__ item_base, const int* __restrict__ list_offsets,
-                                                           int n_lists, int cap, int4* __restrict__ items,
-                                                           int* __restrict__ n_items, int chunk_major) {
+__global__ void __launch_bounds__(256) ib_item_fill_kernel(const int* __restrict__ item_base, const int* __restrict__ q_off,
+                                                           const int* __restrict__ list_offsets, int n_lists, int cap,
+                                                           int4* __restrict__ items, int* __restrict__ n_items, int chunk_major) {
   const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (c >= n_lists) return;
-  const int base = item_base[c], cnt = item_base[c + 1] - base;
+  int base = item_base[c], cnt = item_base[c + 1] - base;
+  if (cnt == 0) { base = item_base[n_lists + c]; cnt = item_base[n_lists + c + 1] - base; }
   int n_ch, ch_rows;
   ib_chunks(list_offsets[c + 1] - list_offsets[c], n_ch, ch_rows);
-  const int n_qt = n_ch > 0 ? cnt / n_ch : 1;
+  const int n_qt = (q_off[c + 1] - q_off[c] + GT_BM - 1) / GT_BM;
+  const int n_qt_pad = n_ch > 0 ? cnt / n_ch : 1;     // > n_qt in the padded section: the extra slots are skipped (x = -1)
   for (int i = lane; i < cnt; i += 32)
-    if (base + i < cap)   // chunk-major: the query tiles of one chunk are adjacent and share it through L2
-      items[base + i] = chunk_major ? make_int4(c, i % n_qt, i / n_qt, 0) : make_int4(c, i / n_ch, i % n_ch, 0);
-  if (c == n_lists - 1 && lane == 0) *n_items = item_base[n_lists];
+    if (base + i < cap) {  // chunk-major: the query tiles of one chunk are adjacent and run at the same time
+      const int qt = chunk_major ? i % n_qt_pad : i / n_ch, ch = chunk_major ? i / n_qt_pad : i % n_ch;
+      items[base + i] = make_int4(qt < n_qt ? c : -1, qt, ch, 0);
+    }
+  if (c == n_lists - 1 && lane == 0) *n_items = item_base[2 * n_lists];
 }
 
 // ---- finish: merge the partial lists of one query, exact re-score, certify -----------------------------
@@ -403,8 +467,9 @@ __global__ void __launch_bounds__(128) ivf_finish_kernel(const IvfFinishArgs f) 
 static size_t a256(size_t v) { return (v + 255) / 256 * 256; }
 static int ib_cap_items(int n_queries, int nprobe, int n_lists) {
   const long long pairs = (long long)n_queries * nprobe;
-  long long cap = 16ll * n_lists + pairs / 8 + 4096;       // 16 B per item
-  if (cap > 1000000) cap = 1000000;
+  const long long heavy = pairs / 128 < n_lists ? pairs / 128 : n_lists;       // lists that can hold more than one query tile
+  long long cap = 16ll * n_lists + pairs / 8 + 48 * heavy + 4096;               // 16 B per item; 48 = padding to a cluster of 4
+  if (cap > 2000000) cap = 2000000;
   return (int)cap;
 }
 // partial lists (256 B each): one per (pair, chunk of its list)
@@ -423,11 +488,11 @@ static IbLayout ib_layout(int n_queries, int d, int n_lists, int nprobe, int cap
   L.probes = o; o += a256(pairs * 8);
   L.counts = o; o += a256((size_t)n_lists * 4);
   L.q_off = o; o += a256((size_t)(n_lists + 1) * 4);
-  L.cursor = o; o += a256((size_t)n_lists * 4);
+  L.cursor = o; o += a256((size_t)n_lists * 8);
   L.pair_of_pos = o; o += a256(pairs * 4);
   L.pos_of_pair = o; o += a256(pairs * 4);
-  L.items_c = o; o += a256((size_t)n_lists * 4);
-  L.item_base = o; o += a256((size_t)(n_lists + 1) * 4);
+  L.items_c = o; o += a256((size_t)n_lists * 8);
+  L.item_base = o; o += a256((size_t)(2 * n_lists + 1) * 4);
   L.n_items = o; o += 256;
   L.items = o; o += a256((size_t)cap * 16);
   L.qn = o; o += a256((size_t)n_queries * d * 4);
@@ -507,6 +572,12 @@ extern "C" int aura_ivf_search_batch(const void* rows, int dtype, int64_t n_rows
   if (rc != AURA_OK) return rc;
   launch_normalize_queries(queries, n_queries, d, qn, qb, st);
   int chunk_major = 1;
+  // AURA_IVF_CLUSTER=2|4 launches the CTAs in clusters: the query tiles of one list chunk go to the CTAs of one cluster,
+  // which pace each other tile by tile so the chunk is fetched from HBM once.  Measured at BASELINE config 4: within 2 %
+  // of the plain launch (the few lists probed by thousands of queries have 32 sibling tiles, not 2-4), so it is off.
+  int cs = 1;
+  if (const char* e = getenv("AURA_IVF_CLUSTER")) cs = atoi(e);
+  if (cs != 1 && cs != 2 && cs != 4) cs = 1;
   if (const char* e = getenv("AURA_IVF_ORDER")) chunk_major = atoi(e);
   const int n_pairs = n_queries * nprobe;
   AURA_CUDA_OK(cudaMemsetAsync(counts, 0, (size_t)n_centroid_rows * 4, st));
@@ -515,10 +586,10 @@ extern "C" int aura_ivf_search_batch(const void* rows, int dtype, int64_t n_rows
   ib_pair_scatter_kernel<<<(n_pairs + 255) / 256, 256, 0, st>>>(probes, n_pairs, n_centroid_rows, cursor, pair_of_pos, pos_of_pair);
   int* plists_c = reinterpret_cast<int*>(ws + L.plists_c);
   int* pbase = reinterpret_cast<int*>(ws + L.pbase);
-  ib_item_count_kernel<<<(n_centroid_rows + 255) / 256, 256, 0, st>>>(q_off, list_offsets, n_centroid_rows, items_c, plists_c);
-  launch_scan_offsets(items_c, n_centroid_rows, item_base, cursor, st);
+  ib_item_count_kernel<<<(n_centroid_rows + 255) / 256, 256, 0, st>>>(q_off, list_offsets, n_centroid_rows, cs, items_c, plists_c);
+  launch_scan_offsets(items_c, 2 * n_centroid_rows, item_base, cursor, st);
   launch_scan_offsets(plists_c, n_centroid_rows, pbase, cursor, st);
-  ib_item_fill_kernel<<<(n_centroid_rows * 32 + 255) / 256, 256, 0, st>>>(item_base, list_offsets, n_centroid_rows, cap, items, n_items, chunk_major);
+  ib_item_fill_kernel<<<(n_centroid_rows * 32 + 255) / 256, 256, 0, st>>>(item_base, q_off, list_offsets, n_centroid_rows, cap, items, n_items, chunk_major);
   note_launches(4);
 
   IvfBatchArgs a;
@@ -534,6 +605,8 @@ extern "C" int aura_ivf_search_batch(const void* rows, int dtype, int64_t n_rows
   a.items = items; a.n_items = n_items; a.scale = scale; a.bias = bias; a.partial = partial; a.gthr = gthr; a.pbase = pbase; a.cap_plists = ib_cap_plists(n_queries, nprobe);
   { const char* e = getenv("AURA_IVF_GTHR"); a.use_gthr = e ? atoi(e) : 1; }
   { const char* e = getenv("AURA_IVF_SPREAD"); a.spread = e ? atoi(e) : 1; }
+  { const char* e = getenv("AURA_IVF_L2HINT"); a.l2_hint = e ? atoi(e) : 3; }
+  { const char* e = getenv("AURA_IVF_SYNC_POLLS"); a.sync_polls = e ? atoi(e) : 512; }
   const size_t smem = (size_t)stages * GT_STAGE_BYTES + fixed + 1024;
   typedef void (*IvfKern)(const unsigned char*, const unsigned char*, int, const IvfBatchArgs);
   IvfKern kern0 = bf16 ? ivf_gemm_kernel<false, false> : ivf_gemm_kernel<true, false>;    // first round: no ceiling
@@ -552,12 +625,24 @@ extern "C" int aura_ivf_search_batch(const void* rows, int dtype, int64_t n_rows
   f.rows = rows; f.bf16 = bf16 ? 1 : 0; f.d = d; f.qn = qn; f.scale = scale; f.bias = bias; f.eps = eps; f.k = k;
   f.row_base = row_base; f.spread = a.spread; f.chunk_major = chunk_major; f.out_idx = reinterpret_cast<long long*>(out_idx); f.out_score = out_score; f.uncertain = out_uncertain;
   f.cand = rounds > 1 ? cand : nullptr; f.ceil_out = ceil_buf; f.round = 0; f.force_flag = force;
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute cattr[1];
+  cattr[0].id = cudaLaunchAttributeClusterDimension;
+  cattr[0].val.clusterDim.x = cs; cattr[0].val.clusterDim.y = 1; cattr[0].val.clusterDim.z = 1;
+  cfg.gridDim = dim3(sm_count() / cs * cs); cfg.blockDim = dim3(IB_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cfg.attrs = cattr; cfg.numAttrs = 1;
+  if (cs > 1) {            // some GPCs cannot seat every cluster: size the persistent grid to what is co-resident
+    int n_cl = 0;
+    if (cudaOccupancyMaxActiveClusters(&n_cl, kern0, &cfg) == cudaSuccess && n_cl > 0 && n_cl * cs < (int)cfg.gridDim.x)
+      cfg.gridDim = dim3(n_cl * cs);
+    (void)cudaGetLastError();
+  }
+  { const char* e = getenv("AURA_IVF_GRID"); if (e && atoi(e) >= cs) cfg.gridDim = dim3(atoi(e) / cs * cs); }
   for (int r = 0; r < rounds; ++r) {
     if (r > 0) AURA_CUDA_OK(cudaMemsetAsync(gthr, 0, (size_t)n_queries * 4, st));
     a.ceil_keys = r ? ceil_buf : nullptr;
-    (r ? kern1 : kern0)<<<sm_count(), IB_THREADS, smem, st>>>(reinterpret_cast<const unsigned char*>(bf16 ? (const void*)qb : (const void*)qn),
-                                               reinterpret_cast<const unsigned char*>(rows), d * eb, a);
-    AURA_CUDA_OK(cudaGetLastError());
+    AURA_CUDA_OK(cudaLaunchKernelEx(&cfg, r ? kern1 : kern0, reinterpret_cast<const unsigned char*>(bf16 ? (const void*)qb : (const void*)qn),
+                                    reinterpret_cast<const unsigned char*>(rows), d * eb, a));
     f.round = r;
     ivf_finish_kernel<<<n_queries, 128, 0, st>>>(f);
     AURA_CUDA_OK(cudaGetLastError());

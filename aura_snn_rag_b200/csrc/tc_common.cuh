@@ -97,6 +97,17 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
   return r;
 }
+__device__ __forceinline__ uint32_t cluster_nctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+  return r;
+}
+// add 1 to the same-offset shared-memory word of CTA `rank` of this cluster
+__device__ __forceinline__ void cluster_red_inc(uint32_t* local_word, int rank) {
+  uint32_t raddr;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(smem_u32(local_word)), "r"(rank));
+  asm volatile("red.relaxed.cluster.shared::cluster.add.u32 [%0], 1;" ::"r"(raddr) : "memory");
+}
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");

@@ -16,7 +16,21 @@ for r0 in range(0, M, 1 << 18):
 hf.rebuild_centroids(seed_rows=torch.randperm(M, device=dev, generator=g)[:C])
 pick = torch.randint(0, M, (B,), device=dev, generator=g)
 q = hf.memory_features[pick] + 0.005 * torch.randn(B, D, device=dev, generator=g)
-for env in ({"AURA_IVF_ORDER": 0}, {"AURA_IVF_ORDER": 1}, {"AURA_IVF_ORDER": 0}, {"AURA_IVF_ORDER": 1}):
+ref = None
+for i in range(3):   # box sanity: exact search of 1024 queries (known: ~33 ms at 10M x 1024)
+    torch.cuda.synchronize(); e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); hf.exact_topk(q[:1024], K); e1.record(); torch.cuda.synchronize()
+    print("exact 1024 queries ms", round(e0.elapsed_time(e1), 2), flush=True)
+# list statistics: how many query tiles re-read each list
+probes = ops.ivf_coarse(q, hf.centroids, P) if hasattr(ops, "ivf_coarse") else None
+if probes is not None:
+    pr = probes[0] if isinstance(probes, tuple) else probes
+    nq = torch.bincount(pr.flatten().long(), minlength=C).float()
+    ln = (hf._list_offsets[1:] - hf._list_offsets[:-1]).float() if hasattr(hf, "_list_offsets") else None
+    if ln is not None:
+        once = (ln * (nq > 0)).sum().item(); t128 = (ln * torch.ceil(nq / 128)).sum().item()
+        print(f"list rows probed once {once:.3e}, x query tiles {t128:.3e} ({t128/once:.2f}x), lists with >128 queries {(nq > 128).sum().item()}, max nq {nq.max().item():.0f}, max len {ln.max().item():.0f}", flush=True)
+for env in [dict(AURA_IVF_CLUSTER=c, AURA_IVF_SYNC_POLLS=p, AURA_IVF_L2HINT=h) for (c, p, h) in ((1,0,0),(1,0,1),(1,0,3),(1,0,7),(1,0,0),(1,0,1),(1,0,3),(1,0,7),(2,512,3),(2,512,0),(1,0,0),(2,512,3),(2,512,0),(2,0,0))]:
     os.environ.update({k: str(v) for k, v in env.items()})
     ts = []
     for i in range(6):
@@ -24,4 +38,7 @@ for env in ({"AURA_IVF_ORDER": 0}, {"AURA_IVF_ORDER": 1}, {"AURA_IVF_ORDER": 0},
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(); hf.retrieve_batch(q, K); e1.record(); torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1))
-    print(env, " ".join(f"{t:.1f}" for t in ts), flush=True)
+    r = hf.retrieve_batch(q, K)
+    if ref is None: ref = r
+    same = torch.equal(r[0], ref[0]) and torch.equal(r[1], ref[1])
+    print(env, " ".join(f"{t:.1f}" for t in ts), "same_as_first", same, flush=True)
