@@ -53,6 +53,7 @@ struct IvfBatchArgs {
   int cap_plists;
   u64* partial;             // [cap_plists][GT_L]: one sorted list per (pair, chunk), at pbase[c] + chunk * nq_c + rel
   int use_gthr, spread;     // tuning switches (experiments)
+  int list_major;           // the bank copy behind the kernel's tensor map holds every list contiguously (CSR order)
   int l2_hint;              // bit 0: single-tile lists evict-first, bit 1: multi-tile lists evict-last, bit 2: query rows evict-last
   int sync_polls;           // sibling CTAs of a cluster wait at most this many polls for each other per tile (0: never)
   const u64* ceil_keys;     // per query: only keys strictly below are eligible (multi-round top-k), may be null
@@ -86,8 +87,8 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 
 template <bool TF32, bool CEIL>
 __global__ void __launch_bounds__(IB_THREADS, 1)
-ivf_gemm_kernel(const unsigned char* __restrict__ qmat, const unsigned char* __restrict__ bank, const int row_pitch,
-                const IvfBatchArgs a) {
+ivf_gemm_kernel(const __grid_constant__ CUtensorMap tmap_lm, const unsigned char* __restrict__ qmat,
+                const unsigned char* __restrict__ bank, const int row_pitch, const IvfBatchArgs a) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int S = a.n_stages;
@@ -107,9 +108,11 @@ ivf_gemm_kernel(const unsigned char* __restrict__ qmat, const unsigned char* __r
   constexpr int ELEMS_PER_SLAB = TF32 ? 32 : 64;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < S; ++s) { mbar_init(&full[s], 128); mbar_init(&empty[s], 1); }
+    // full: one asynchronous arrival per producer thread, plus the expect-tx arrival of the TMA box in list-major mode
+    for (int s = 0; s < S; ++s) { mbar_init(&full[s], a.list_major ? 129 : 128); mbar_init(&empty[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4); }
     *sync_ctr = 0u;
+    if (a.list_major) tc::tma_prefetch_desc(&tmap_lm);
     fence_mbar_init();
   }
   if (warp == 0) { tc::tmem_alloc(tmem_slot, 512); tc::tmem_relinquish(); }
@@ -173,9 +176,30 @@ ivf_gemm_kernel(const unsigned char* __restrict__ qmat, const unsigned char* __r
             }
           }
         }
-        int rb[16];                   // bank rows of B-tile rows prow + 16*i
+        int rb[16];                   // bank rows of B-tile rows prow + 16*i (unused with the list-major copy)
 #pragma unroll
-        for (int i = 0; i < 16; ++i) rb[i] = a.list_rows[lb + min(cr + prow + 16 * i, r1 - 1)];
+        for (int i = 0; i < 16; ++i) rb[i] = a.list_major ? 0 : a.list_rows[lb + min(cr + prow + 16 * i, r1 - 1)];
+        if (a.list_major) {
+          // the bank has a resident copy with every list contiguous: the B tile is one TMA box per k-block (256
+          // consecutive rows, streamed from HBM like the exact-search kernel); only the query rows are gathered
+          for (int kb = 0; kb < a.k_blocks; ++kb) {
+            tc::mbar_wait_guarded(&empty[stage], phase ^ 1u);
+            unsigned char* sp = ring + (size_t)stage * GT_STAGE_BYTES;
+            if (pt == 0) {
+              mbar_arrive_expect_tx(&full[stage], (unsigned)(GT_STAGE_BYTES - GT_A_BYTES));
+              tc::tma_load_2d(sp + GT_A_BYTES, &tmap_lm, kb * ELEMS_PER_SLAB, lb + cr, &full[stage], pol_b);
+            }
+            const unsigned sa0 = ring_u32 + (uint32_t)stage * GT_STAGE_BYTES + dst_off;
+            const size_t koff = (size_t)kb * GT_SLAB;
+            const bool in = (int)koff + pj * 16 < row_pitch;
+            const size_t ko1 = in ? koff : 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) cp_async16(sa0 + i * 16 * GT_SLAB, qsrc[i] + ko1, in ? 16u : 0u, pol_a);
+            cp_async_arrive_noinc(&full[stage]);
+            if (++stage == S) { stage = 0; phase ^= 1u; }
+          }
+          continue;
+        }
         // k-blocks go in PAIRS into two consecutive stages: the two 128-byte pieces of a row are adjacent in memory
         // and are requested back to back, so DRAM serves them from one open page (256 B per row visit, not 128 B)
         for (int kb = 0; kb < a.k_blocks; kb += 2) {
@@ -530,9 +554,9 @@ extern "C" size_t aura_ivf_search_batch_workspace_bytes(int n_queries, int d, in
 
 extern "C" int aura_ivf_search_batch(const void* rows, int dtype, int64_t n_rows, int d, const float* queries, int n_queries,
                                      const float* centroids, int n_centroid_rows, int nprobe, const int32_t* list_offsets,
-                                     const int32_t* list_rows, const float* scale, const float* bias, int k, int64_t row_base,
-                                     float eps, int64_t* out_idx, float* out_score, int32_t* out_uncertain, void* workspace,
-                                     size_t workspace_bytes, void* stream) {
+                                     const int32_t* list_rows, const void* rows_by_list, const float* scale, const float* bias,
+                                     int k, int64_t row_base, float eps, int64_t* out_idx, float* out_score,
+                                     int32_t* out_uncertain, void* workspace, size_t workspace_bytes, void* stream) {
   AURA_REQUIRE(dtype == AURA_F32 || dtype == AURA_BF16, AURA_ERR_INVALID_ARG, "aura_ivf_search_batch: bad dtype %d", dtype);
   AURA_REQUIRE(n_rows >= 1 && n_rows < 0x7fffffffll && d >= 1 && n_queries >= 1 && n_centroid_rows >= 1, AURA_ERR_INVALID_ARG,
                "aura_ivf_search_batch: n_rows=%lld d=%d n_queries=%d n_centroid_rows=%d", (long long)n_rows, d, n_queries,
@@ -608,7 +632,16 @@ extern "C" int aura_ivf_search_batch(const void* rows, int dtype, int64_t n_rows
   { const char* e = getenv("AURA_IVF_L2HINT"); a.l2_hint = e ? atoi(e) : 3; }
   { const char* e = getenv("AURA_IVF_SYNC_POLLS"); a.sync_polls = e ? atoi(e) : 512; }
   const size_t smem = (size_t)stages * GT_STAGE_BYTES + fixed + 1024;
-  typedef void (*IvfKern)(const unsigned char*, const unsigned char*, int, const IvfBatchArgs);
+  CUtensorMap tmap_lm;
+  memset(&tmap_lm, 0, sizeof(tmap_lm));
+  a.list_major = 0;
+  if (rows_by_list != nullptr) {
+    AURA_REQUIRE((reinterpret_cast<uintptr_t>(rows_by_list) & 15) == 0, AURA_ERR_UNSUPPORTED, "aura_ivf_search_batch: rows_by_list must be 16-byte aligned");
+    const int trc = encode_tmap_2d(&tmap_lm, rows_by_list, eb, bf16, n_rows, d, GT_BN);
+    if (trc != AURA_OK) return trc;
+    a.list_major = 1;
+  }
+  typedef void (*IvfKern)(const CUtensorMap, const unsigned char*, const unsigned char*, int, const IvfBatchArgs);
   IvfKern kern0 = bf16 ? ivf_gemm_kernel<false, false> : ivf_gemm_kernel<true, false>;    // first round: no ceiling
   IvfKern kern1 = bf16 ? ivf_gemm_kernel<false, true> : ivf_gemm_kernel<true, true>;
   AURA_CUDA_OK(cudaFuncSetAttribute(kern0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -641,7 +674,7 @@ extern "C" int aura_ivf_search_batch(const void* rows, int dtype, int64_t n_rows
   for (int r = 0; r < rounds; ++r) {
     if (r > 0) AURA_CUDA_OK(cudaMemsetAsync(gthr, 0, (size_t)n_queries * 4, st));
     a.ceil_keys = r ? ceil_buf : nullptr;
-    AURA_CUDA_OK(cudaLaunchKernelEx(&cfg, r ? kern1 : kern0, reinterpret_cast<const unsigned char*>(bf16 ? (const void*)qb : (const void*)qn),
+    AURA_CUDA_OK(cudaLaunchKernelEx(&cfg, r ? kern1 : kern0, tmap_lm, reinterpret_cast<const unsigned char*>(bf16 ? (const void*)qb : (const void*)qn),
                                     reinterpret_cast<const unsigned char*>(rows), d * eb, a));
     f.round = r;
     ivf_finish_kernel<<<n_queries, 128, 0, st>>>(f);
@@ -657,6 +690,32 @@ extern "C" int aura_ivf_search_batch(const void* rows, int dtype, int64_t n_rows
 
 /* Diagnostics: number of work items the last aura_ivf_search_batch call on this workspace generated, and the capacity
  * of its work table (a call whose items exceed the capacity hands every query back to the per-query path). */
+// ---- list-major resident copy: out[p] = rows[list_rows[p]] (one warp per row, 16-byte pieces) ----
+__global__ void __launch_bounds__(256) ivf_pack_lists_kernel(const uint4* __restrict__ rows, const int* __restrict__ list_rows,
+                                                             long long n, int vec_per_row, uint4* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  for (long long p = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); p < n; p += (long long)gridDim.x * (blockDim.x >> 5)) {
+    const uint4* src = rows + (size_t)list_rows[p] * vec_per_row;
+    uint4* dst = out + (size_t)p * vec_per_row;
+    for (int v = lane; v < vec_per_row; v += 32) __stcs(dst + v, __ldcs(src + v));
+  }
+}
+
+extern "C" int aura_ivf_pack_lists(const void* rows, int dtype, int d, const int32_t* list_rows, int64_t n_listed,
+                                   void* rows_by_list, void* stream) {
+  AURA_REQUIRE(dtype == AURA_F32 || dtype == AURA_BF16, AURA_ERR_INVALID_ARG, "aura_ivf_pack_lists: bad dtype %d", dtype);
+  AURA_REQUIRE(rows && list_rows && rows_by_list && d >= 1 && n_listed >= 0, AURA_ERR_INVALID_ARG, "aura_ivf_pack_lists: bad argument");
+  const size_t pitch = (size_t)d * (dtype == AURA_BF16 ? 2 : 4);
+  AURA_REQUIRE(pitch % 16 == 0 && (reinterpret_cast<uintptr_t>(rows) & 15) == 0 && (reinterpret_cast<uintptr_t>(rows_by_list) & 15) == 0,
+               AURA_ERR_UNSUPPORTED, "aura_ivf_pack_lists: rows must be 16-byte aligned with a 16-byte multiple pitch (d=%d)", d);
+  if (n_listed == 0) return AURA_OK;
+  ivf_pack_lists_kernel<<<sm_count() * 8, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint4*>(rows), list_rows, (long long)n_listed,
+                                                                             (int)(pitch / 16), reinterpret_cast<uint4*>(rows_by_list));
+  AURA_CUDA_OK(cudaGetLastError());
+  note_launches(1);
+  return AURA_OK;
+}
+
 extern "C" int aura_ivf_search_batch_items(const void* workspace, int n_queries, int d, int n_centroid_rows, int nprobe,
                                            int32_t* host_items, int32_t* host_cap, void* stream) {
   AURA_REQUIRE(workspace && host_items && host_cap, AURA_ERR_INVALID_ARG, "aura_ivf_search_batch_items: null pointer");

@@ -59,7 +59,8 @@ class HippocampalFormation(nn.Module):
                  centroid_rows: Optional[int] = None,
                  nprobe: int = 8,
                  bank_dtype: torch.dtype = torch.float32,
-                 track_ids: bool = True):
+                 track_ids: bool = True,
+                 list_major_copy: bool = False):
         super().__init__()
         if not torch.cuda.is_available():
             raise AuraLibraryError("HippocampalFormation (B200 build) needs a CUDA device: the retrieval path has "
@@ -106,6 +107,11 @@ class HippocampalFormation(nn.Module):
         self.centroids_k = int(centroids_k)
         self.centroids_update_interval = 512
         self.nprobe = int(nprobe)                       # reference literal 8 (:262)
+        # batched centroid path: keep a second copy of the bank with every inverted list contiguous (2x bank memory), so
+        # list tiles stream from HBM by TMA instead of being gathered row by row; re-packed after every list rebuild
+        self.list_major_copy = bool(list_major_copy)
+        self._bank_by_list: Optional[torch.Tensor] = None
+        self._by_list_valid = False
         self.ivf_strict = True                          # batched centroid path: re-run uncertified queries exactly (ops.ivf_search_batched)
         rows = int(centroid_rows) if centroid_rows is not None else max(256, self.centroids_k)
         self.register_buffer('centroids', torch.zeros(rows, feature_dim, **f32))
@@ -285,6 +291,7 @@ class HippocampalFormation(nn.Module):
         counts_f[:min(rows_c, counts_f.numel())] = full[:counts_f.numel()]
         self.centroid_counts = counts_f                                       # rebinding quirk kept (:369,:374)
         self._lists_dirty = False
+        self._by_list_valid = False
         self._index_ready = True
 
     def _ensure_lists(self) -> None:
@@ -292,6 +299,18 @@ class HippocampalFormation(nn.Module):
             ops.ivf_build_lists(self._cid, self.memory_count, self._centroid_buffer_rows(), self._list_offsets,
                                 self._list_rows)
             self._lists_dirty = False
+            self._by_list_valid = False
+
+    def _rows_by_list(self) -> Optional[torch.Tensor]:
+        """The list-major copy of the bank (None unless `list_major_copy`), re-packed if the lists changed."""
+        if not self.list_major_copy:
+            return None
+        if self._bank_by_list is None:
+            self._bank_by_list = torch.empty_like(self.memory_features)
+        if not self._by_list_valid:
+            ops.ivf_pack_lists(self.memory_features, self._list_rows, self.memory_count, self._bank_by_list)
+            self._by_list_valid = True
+        return self._bank_by_list
 
     # ------------------------------------------------------------------ queries
     def _row_terms(self, location) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -339,7 +358,7 @@ class HippocampalFormation(nn.Module):
                 idx, score = ops.ivf_search_batched(self.memory_features, m, q, self.centroids, nprobe,
                                                     self._list_offsets, self._list_rows, kk, scale, bias,
                                                     eps=ops.TC_EPS_COS * 0.5 * self._max_strength(),
-                                                    strict=self.ivf_strict)
+                                                    strict=self.ivf_strict, rows_by_list=self._rows_by_list())
             else:
                 idx, score = ops.ivf_search(self.memory_features, m, q, self.centroids, nprobe, self._list_offsets,
                                             self._list_rows, kk, scale, bias)

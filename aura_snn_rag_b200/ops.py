@@ -375,15 +375,29 @@ def allpairs_topk(rows: torch.Tensor, k: int = 32, inv_norm: Optional[torch.Tens
     return out_idx, out_score
 
 
+def ivf_pack_lists(rows: torch.Tensor, list_rows: torch.Tensor, n_listed: int, out: torch.Tensor) -> torch.Tensor:
+    """out[p] = rows[list_rows[p]], p < n_listed: the list-major resident copy of the bank (aura_ivf_pack_lists)."""
+    rows = _dev(rows, "rows")
+    if out.dtype != rows.dtype or out.shape[1] != rows.shape[1] or out.shape[0] < n_listed or not out.is_contiguous():
+        raise ValueError("out must be a contiguous [>= n_listed, d] tensor of the bank's dtype")
+    check(_lib.load().aura_ivf_pack_lists(rows.data_ptr(), _dtype_code(rows), rows.shape[1], list_rows.data_ptr(), n_listed,
+                                          out.data_ptr(), _stream()), "aura_ivf_pack_lists")
+    return out
+
+
 TC_IVF_MIN_BATCH = 64          # list-major grouped GEMM pays off once lists are shared by several queries
 
 
 def ivf_search_batched(rows: torch.Tensor, n_rows: int, queries: torch.Tensor, centroids: torch.Tensor, nprobe: int,
                        list_offsets: torch.Tensor, list_rows: torch.Tensor, k: int, scale: Optional[torch.Tensor],
                        bias: Optional[torch.Tensor] = None, row_base: int = 0, eps: float = TC_EPS_COS,
-                       stats: Optional[dict] = None, strict: bool = True) -> Tuple[torch.Tensor, torch.Tensor]:
+                       stats: Optional[dict] = None, strict: bool = True,
+                       rows_by_list: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
     """Centroid-path query for a block of queries: list-major tensor-core pass (aura_ivf_search_batch), then the
     per-query path for the queries it hands back.
+
+    rows_by_list : optional resident copy of the bank in list order (`ivf_pack_lists`); list tiles are then streamed
+                   by TMA instead of gathered row by row.  Results do not depend on it.
 
     strict=True  : every flagged query (result not certified exact among its candidates, or no candidates) is re-run
                    through the per-query path - results equal `ivf_search` bit for bit.
@@ -406,7 +420,7 @@ def ivf_search_batched(rows: torch.Tensor, n_rows: int, queries: torch.Tensor, c
     ws = _workspace(lib.aura_ivf_search_batch_workspace_bytes(b, d, c, nprobe), dev, "ivfbatch")
     check(lib.aura_ivf_search_batch(rows.data_ptr(), _dtype_code(rows), n_rows, d, queries.data_ptr(), b,
                                     centroids.data_ptr(), c, nprobe, list_offsets.data_ptr(), list_rows.data_ptr(),
-                                    _ptr(scale), _ptr(bias), k, row_base, float(eps), out_idx.data_ptr(),
+                                    _ptr(rows_by_list), _ptr(scale), _ptr(bias), k, row_base, float(eps), out_idx.data_ptr(),
                                     out_score.data_ptr(), flags.data_ptr(), ws.data_ptr(), ws.numel(), _stream()),
           "aura_ivf_search_batch")
     if stats is not None:

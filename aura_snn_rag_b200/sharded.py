@@ -209,6 +209,7 @@ class ShardedIndex:
         self._all_reduce(local_counts)
         hf.centroid_counts = local_counts[:max(hf.centroids_k, 1)].clone()
         hf._lists_dirty = False
+        hf._by_list_valid = False
         hf._index_ready = True
 
     def search(self, queries: torch.Tensor, k: int, exact: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:

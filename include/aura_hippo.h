@@ -148,16 +148,25 @@ int aura_ivf_search(const void* rows, int dtype, int64_t n_rows, int d, const fl
                     void* stream);
 
 /* Block-of-queries form of aura_ivf_search: the (query, probe) pairs are sorted by list and every probed list is
- * scored ONCE against the group of queries probing it (ragged grouped GEMM on tcgen05, operands gathered by row id with
- * TMA gather4), so a batch reads each probed list once instead of once per query.  Results: exact fp32 scores of the
- * best candidates (same re-score + certification as aura_batch_topk); out_uncertain[b] = 1 hands query b back to
- * aura_ivf_search (uncertified result, no candidates, or work table overflow).  k <= 18, d*sizeof(elem) % 16 == 0. */
+ * scored ONCE per group of <= 128 queries probing it (ragged grouped GEMM on tcgen05; query rows and bank rows gathered
+ * by row id with 16-byte cp.async into the swizzled operand layout), so a batch reads each probed list once instead of
+ * once per query.  rows_by_list (may be NULL): a resident copy of the bank in CSR order made by aura_ivf_pack_lists for
+ * these list_offsets / list_rows - list tiles are then streamed as TMA boxes instead of gathered.  Results: exact fp32
+ * scores of the best candidates (same re-score + certification as aura_batch_topk, read from `rows`);
+ * out_uncertain[b] = 1 hands query b back to aura_ivf_search (uncertified result, no candidates, or work table
+ * overflow).  k <= 114, d*sizeof(elem) % 16 == 0. */
 size_t aura_ivf_search_batch_workspace_bytes(int n_queries, int d, int n_centroid_rows, int nprobe);
 int aura_ivf_search_batch(const void* rows, int dtype, int64_t n_rows, int d, const float* queries, int n_queries,
                           const float* centroids, int n_centroid_rows, int nprobe, const int32_t* list_offsets,
-                          const int32_t* list_rows, const float* scale, const float* bias, int k, int64_t row_base,
-                          float eps, int64_t* out_idx, float* out_score, int32_t* out_uncertain, void* workspace,
-                          size_t workspace_bytes, void* stream);
+                          const int32_t* list_rows, const void* rows_by_list, const float* scale, const float* bias, int k,
+                          int64_t row_base, float eps, int64_t* out_idx, float* out_score, int32_t* out_uncertain,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
+/* rows_by_list[p] = rows[list_rows[p]] for p < n_listed (same dtype, pitch d): the list-major resident copy of the bank
+ * (the layout an inverted-file index normally stores; the reference keeps insertion order only, hippocampal.py:211).
+ * Rebuild it whenever aura_ivf_build_lists ran. */
+int aura_ivf_pack_lists(const void* rows, int dtype, int d, const int32_t* list_rows, int64_t n_listed, void* rows_by_list,
+                        void* stream);
 
 /* diagnostics: work items generated by the last aura_ivf_search_batch call on `workspace` and the table capacity
  * (synchronises `stream`; not for hot paths) */

@@ -5,7 +5,7 @@ from aura_snn_rag_b200.hippocampal import HippocampalFormation
 M, D, C, P, B, K = int(sys.argv[1]) if len(sys.argv) > 1 else 4_000_000, 1024, 4096, 32, 4096, 10
 dev = torch.device("cuda:0")
 hf = HippocampalFormation(n_place_cells=8, n_time_cells=4, n_grid_cells=4, max_memories=M, feature_dim=D, device="cuda:0",
-                          centroids_k=C, nprobe=P, track_ids=False)
+                          centroids_k=C, nprobe=P, track_ids=False, list_major_copy=bool(int(__import__("os").environ.get("LM", "0"))))
 hf.centroids_update_interval = 1 << 40
 g = torch.Generator(device=dev).manual_seed(1234)
 centres = torch.nn.functional.normalize(torch.randn(1024, D, device=dev, generator=g), dim=1)

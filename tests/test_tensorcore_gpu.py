@@ -225,3 +225,13 @@ def test_ivf_search_batched_equals_per_query_path(n, d, c, p, b, k, dt):
     assert stats["uncertain"] < b // 2              # the grouped pass itself must answer most queries
     assert torch.equal(s1, s2)
     assert torch.equal(i1, i2)
+    # list-major resident copy (list tiles streamed by TMA instead of gathered): same answers
+    packed = ops.ivf_pack_lists(rows, lrows, n, torch.empty_like(rows))
+    assert torch.equal(packed, rows[lrows.long()])
+    stats3 = {}
+    i3, s3 = ops.ivf_search_batched(rows, n, q, cent_d, p, offsets, lrows, k, scale, bias, eps=0.5 * ops.TC_EPS_COS,
+                                    stats=stats3, rows_by_list=packed)
+    torch.cuda.synchronize()
+    assert stats3["uncertain"] == stats["uncertain"]
+    assert torch.equal(s3, s2)
+    assert torch.equal(i3, i2)
