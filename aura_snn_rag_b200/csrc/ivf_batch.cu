@@ -462,13 +462,18 @@ __global__ void __launch_bounds__(128) ivf_finish_kernel(const IvfFinishArgs f) 
         block_bitonic_sort_desc(keys, IB_MERGE_CAP);
         n = GT_L;
       }
-      if (threadIdx.x < GT_L) keys[n + threadIdx.x] = f.partial[((size_t)f.pbase[c] + (size_t)j * nq + rel) * GT_L + threadIdx.x];
-      n += GT_L;
+      // a partial list is sorted and zero-padded: only its non-zero prefix is buffered (every warp reads the list so
+      // that the count stays uniform without a barrier; warp 0 stores)
+      const u64 key = f.partial[((size_t)f.pbase[c] + (size_t)j * nq + rel) * GT_L + (threadIdx.x & 31)];
+      const int cnt = __popc(__ballot_sync(0xffffffffu, key != 0ull));
+      if (threadIdx.x < cnt) keys[n + threadIdx.x] = key;
+      n += cnt;
     }
   }
   __syncthreads();
-  for (int i = n + threadIdx.x; i < IB_MERGE_CAP; i += blockDim.x) keys[i] = 0ull;
-  block_bitonic_sort_desc(keys, IB_MERGE_CAP);
+  const int n2 = max(64, next_pow2(n));       // sort only what was buffered
+  for (int i = n + threadIdx.x; i < n2; i += blockDim.x) keys[i] = 0ull;
+  block_bitonic_sort_desc(keys, n2);
   if (f.cand != nullptr) {
     for (int i = threadIdx.x; i < GT_L; i += blockDim.x) f.cand[(size_t)b * GT_MAX_L + f.round * GT_L + i] = keys[i];
     if (threadIdx.x == 0) {
@@ -482,7 +487,7 @@ __global__ void __launch_bounds__(128) ivf_finish_kernel(const IvfFinishArgs f) 
   ra.eps = f.eps; ra.k = f.k; ra.L = GT_L; ra.row_base = f.row_base;
   ra.out_idx = f.out_idx + (size_t)b * f.k; ra.out_score = f.out_score + (size_t)b * f.k;
   ra.uncertain = f.uncertain + b;
-  rescore_and_write(keys, IB_MERGE_CAP, ex, ra);
+  rescore_and_write(keys, n2, ex, ra);
   // no candidate at all (every probed list empty -> the reference scans all rows, hippocampal.py:269-270) or a
   // work table that did not fit: hand the query back to the per-query path
   if (threadIdx.x == 0 && (overflow || keys[0] == 0ull)) f.uncertain[b] = 1;
