@@ -425,15 +425,51 @@ __global__ void __launch_bounds__(128) gemm_topk_finish_kernel(const FinishArgs 
   const long long b = blockIdx.x;
   const int atile = (int)(b / GT_BM), r = (int)(b % GT_BM);
   const int n_in = f.n_groups * f.L;
-  for (int i = threadIdx.x; i < f.n2; i += blockDim.x) {
-    u64 key = 0ull;
-    if (i < n_in) {
-      const int g = i / f.L, s = i % f.L;
-      key = f.partial[((size_t)(g * f.n_atiles + atile) * f.L + s) * GT_BM + r];
+  int n2 = f.n2;          // keys actually sorted
+  __shared__ u64 tail_max;      // the floor key
+  __shared__ int n_kept;
+  bool filtered = false;
+  if (n_in > 256) {
+    // Many groups (a small query block spreads every query over all CTAs): a full sort of n_groups*L keys would dominate
+    // the step.  Every group list is sorted, so the L-th largest list HEAD is a floor: L keys (those heads) are at or above
+    // it, hence nothing below it can be among the best L.  Keep only keys >= floor (typically ~3L) and sort those.
+    if (threadIdx.x == 0) n_kept = 0;
+    const int h2 = next_pow2(f.n_groups);                       // <= n2: the key buffer doubles as head scratch
+    for (int g = threadIdx.x; g < h2; g += blockDim.x)
+      keys[g] = g < f.n_groups ? f.partial[((size_t)(g * f.n_atiles + atile) * f.L) * GT_BM + r] : 0ull;
+    block_bitonic_sort_desc(keys, h2);
+    if (threadIdx.x == 0) tail_max = f.n_groups >= f.L ? keys[f.L - 1] : 0ull;
+    __syncthreads();
+    const u64 floor_key = tail_max;
+    __syncthreads();                                            // heads are consumed: the buffer is reused for survivors
+    for (int g = threadIdx.x; g < f.n_groups; g += blockDim.x)       // thread = group: walk its sorted list down to the floor
+      for (int s = 0; s < f.L; ++s) {
+        const u64 key = f.partial[((size_t)(g * f.n_atiles + atile) * f.L + s) * GT_BM + r];
+        if (key == 0ull || key < floor_key) break;
+        const int pos = atomicAdd(&n_kept, 1);
+        if (pos < f.n2) keys[pos] = key;
+      }
+    __syncthreads();
+    const int kept = n_kept;
+    if (kept <= f.n2) {
+      n2 = max(64, next_pow2(kept));
+      if (n2 > f.n2) n2 = f.n2;
+      for (int i = kept + threadIdx.x; i < n2; i += blockDim.x) keys[i] = 0ull;
+      filtered = true;
     }
-    keys[i] = key;
+    __syncthreads();
   }
-  block_bitonic_sort_desc(keys, f.n2);
+  if (!filtered) {
+    for (int i = threadIdx.x; i < f.n2; i += blockDim.x) {
+      u64 key = 0ull;
+      if (i < n_in) {
+        const int g = i / f.L, s = i % f.L;
+        key = f.partial[((size_t)(g * f.n_atiles + atile) * f.L + s) * GT_BM + r];
+      }
+      keys[i] = key;
+    }
+  }
+  block_bitonic_sort_desc(keys, n2);
   if (f.cand != nullptr) {
     for (int i = threadIdx.x; i < GT_L; i += blockDim.x) f.cand[(size_t)b * GT_MAX_L + f.round * GT_L + i] = keys[i];
     if (threadIdx.x == 0) f.ceil_out[b] = keys[GT_L - 1];     // 0 = fewer than 32 were left: nothing below
@@ -443,7 +479,7 @@ __global__ void __launch_bounds__(128) gemm_topk_finish_kernel(const FinishArgs 
   if (f.rows == nullptr) {
     const float mul = f.a_scale ? f.a_scale[b] : 1.f;
     for (int i = threadIdx.x; i < f.k; i += blockDim.x) {
-      const u64 key = i < f.n2 ? keys[i] : 0ull;
+      const u64 key = i < n2 ? keys[i] : 0ull;
       f.out_idx[b * f.k + i] = key ? f.row_base + (long long)key_row(key) : -1ll;
       f.out_score[b * f.k + i] = key ? key_score(key) * mul : -INFINITY;
     }
@@ -453,7 +489,7 @@ __global__ void __launch_bounds__(128) gemm_topk_finish_kernel(const FinishArgs 
   ra.rows = f.rows; ra.bf16 = f.bf16; ra.d = f.d; ra.q = f.qn + (size_t)b * f.d; ra.scale = f.scale; ra.bias = f.bias;
   ra.eps = f.eps; ra.k = f.k; ra.L = f.L; ra.row_base = f.row_base;
   ra.out_idx = f.out_idx + b * f.k; ra.out_score = f.out_score + b * f.k; ra.uncertain = f.uncertain ? f.uncertain + b : nullptr;
-  rescore_and_write(keys, f.n2, ex, ra);
+  rescore_and_write(keys, n2, ex, ra);
 }
 
 // ================================================================================================
@@ -472,6 +508,7 @@ static constexpr int SB_QBLOCK_BYTES = SB_NQ * GT_SLAB;   // one K-slab of the q
 struct SmallBatchArgs {
   long long n_rows;
   int n_queries, k_blocks, n_stages, n_tiles;
+  int kbg;                 // K-slabs per stage: 1 = one 2-D box per slab; > 1 = one 3-D box (tmap_b from encode_tmap_kgroup)
   const float* scale; const float* bias;
   const unsigned* floor_ord;   // per query: orderable score no top-32 row can be below (0 = none), from a sample pre-pass
   u64* partial;            // [grid][GT_L][128]
@@ -486,7 +523,9 @@ smallbatch_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
   const int S = a.n_stages;
   unsigned char* qblk = smem;                                           // [k_blocks][SB_NQ rows][128 B]
   unsigned char* ring = qblk + (size_t)a.k_blocks * SB_QBLOCK_BYTES;    // [S][128 rows][128 B]
-  uint64_t* full = reinterpret_cast<uint64_t*>(ring + (size_t)S * SB_STAGE_BYTES);
+  const unsigned stage_bytes = (unsigned)a.kbg * SB_STAGE_BYTES;
+  const int n_kg = (a.k_blocks + a.kbg - 1) / a.kbg;
+  uint64_t* full = reinterpret_cast<uint64_t*>(ring + (size_t)S * stage_bytes);
   uint64_t* empty = full + SB_MAX_STAGES;
   uint64_t* tfull = empty + SB_MAX_STAGES;
   uint64_t* tempty = tfull + 2;
@@ -530,10 +569,13 @@ smallbatch_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
         tc::tma_load_2d(qblk + (size_t)kb * SB_QBLOCK_BYTES, &tmap_q, kb * ELEMS_PER_SLAB, 0, qfull, pol_q);
       int stage = 0; unsigned phase = 0;
       for (int t = t_begin; t < t_end; ++t)
-        for (int kb = 0; kb < a.k_blocks; ++kb) {
+        for (int kg = 0; kg < n_kg; ++kg) {
           tc::mbar_wait_guarded(&empty[stage], phase ^ 1u);
-          mbar_arrive_expect_tx(&full[stage], SB_STAGE_BYTES);
-          tc::tma_load_2d(ring + (size_t)stage * SB_STAGE_BYTES, &tmap_b, kb * ELEMS_PER_SLAB, t * GT_BM, &full[stage], pol_b);
+          mbar_arrive_expect_tx(&full[stage], stage_bytes);      // a box past the last K-slab is zero-filled, bytes count in full
+          if (a.kbg == 1)
+            tc::tma_load_2d(ring + (size_t)stage * stage_bytes, &tmap_b, kg * ELEMS_PER_SLAB, t * GT_BM, &full[stage], pol_b);
+          else
+            tc::tma_load_3d(ring + (size_t)stage * stage_bytes, &tmap_b, 0, t * GT_BM, kg * a.kbg, &full[stage], pol_b);
           if (++stage == S) { stage = 0; phase ^= 1u; }
         }
     }
@@ -547,14 +589,17 @@ smallbatch_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
         tc::mbar_wait_guarded(&tempty[acc], acc_phase ^ 1u);
         tc::tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * SB_NQ;
-        for (int kb = 0; kb < a.k_blocks; ++kb) {
+        for (int kg = 0; kg < n_kg; ++kg) {
           tc::mbar_wait_guarded(&full[stage], phase);
           tc::tc_fence_after();
-          const uint64_t da = tc::make_smem_desc_sw128(ring + (size_t)stage * SB_STAGE_BYTES);
-          const uint64_t db = tc::make_smem_desc_sw128(qblk + (size_t)kb * SB_QBLOCK_BYTES);
+          for (int kbi = 0; kbi < a.kbg && kg * a.kbg + kbi < a.k_blocks; ++kbi) {
+            const int kb = kg * a.kbg + kbi;
+            const uint64_t da = tc::make_smem_desc_sw128(ring + (size_t)stage * stage_bytes + (size_t)kbi * SB_STAGE_BYTES);
+            const uint64_t db = tc::make_smem_desc_sw128(qblk + (size_t)kb * SB_QBLOCK_BYTES);
 #pragma unroll
-          for (int j = 0; j < GT_SLAB / 32; ++j)
-            tc::umma<TF32>(d_tmem, da + (uint64_t)(2 * j), db + (uint64_t)(2 * j), idesc, (kb | j) != 0 ? 1u : 0u);
+            for (int j = 0; j < GT_SLAB / 32; ++j)
+              tc::umma<TF32>(d_tmem, da + (uint64_t)(2 * j), db + (uint64_t)(2 * j), idesc, (kb | j) != 0 ? 1u : 0u);
+          }
           tc::umma_commit(&empty[stage]);
           if (++stage == S) { stage = 0; phase ^= 1u; }
         }
@@ -673,6 +718,22 @@ int encode_tmap_2d(CUtensorMap* map, const void* base, int elem_bytes, bool bf16
   return AURA_OK;
 }
 
+int encode_tmap_kgroup(CUtensorMap* map, const void* base, int elem_bytes, bool bf16, long long n_rows, int d, int box_rows, int kgroup) {
+  EncodeTiledFn fn = encode_fn();
+  AURA_REQUIRE(fn != nullptr, AURA_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  const int elems = GT_SLAB / elem_bytes;
+  AURA_REQUIRE(d % elems == 0, AURA_ERR_UNSUPPORTED, "encode_tmap_kgroup: d=%d is not a multiple of %d", d, elems);
+  const cuuint64_t gdim[3] = {(cuuint64_t)elems, (cuuint64_t)n_rows, (cuuint64_t)(d / elems)};
+  const cuuint64_t gstride[2] = {(cuuint64_t)d * elem_bytes, (cuuint64_t)GT_SLAB};
+  const cuuint32_t box[3] = {(cuuint32_t)elems, (cuuint32_t)box_rows, (cuuint32_t)kgroup};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  const CUresult r = fn(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
+                        const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  AURA_REQUIRE(r == CUDA_SUCCESS, AURA_ERR_CUDA, "cuTensorMapEncodeTiled (3-D) failed with CUresult %d", (int)r);
+  return AURA_OK;
+}
+
 struct GemmPlan {
   int two_cta;     // CTA-pair kernel: n_atiles is even, grid is a multiple of 2
   int n_atiles, n_ctiles, n_groups, grid, L, n_stages, k_blocks, n2;
@@ -775,7 +836,7 @@ __global__ void __launch_bounds__(128) sample_floor_kernel(const u64* __restrict
   if (threadIdx.x == 0) floor_ord[q] = (unsigned)(keys[GT_L - 1] >> 32);
 }
 
-struct SmallPlan { int grid, n_stages, k_blocks, n_tiles, n2; size_t smem; };
+struct SmallPlan { int grid, n_stages, k_blocks, n_tiles, n2, kbg; size_t smem; };
 
 static bool make_small_plan(long long n_rows, int d, int elem_bytes, int n_queries, SmallPlan* p) {
   // measured on B200 (1M x 768 fp32): 693 / 804 us at B = 8 / 16 against 764 / 869 us for the 128-row-tile kernel;
@@ -789,10 +850,16 @@ static bool make_small_plan(long long n_rows, int d, int elem_bytes, int n_queri
   const size_t fixed = (2 * SB_MAX_STAGES + 5) * 8 + 16;
   const size_t cap = (size_t)max_smem_optin() - 1024;
   if (qbytes + fixed + 3 * (size_t)SB_STAGE_BYTES > cap) return false;
-  int stages = (int)((cap - qbytes - fixed) / SB_STAGE_BYTES);
+  // K-slabs per stage: each bank row is visited for kbg*128 contiguous bytes per box instead of 128
+  int kbg = 1;
+  if (const char* e = getenv("AURA_SB_KBG")) kbg = atoi(e);
+  if (kbg < 1 || d % elems != 0) kbg = 1;
+  while (kbg > 1 && (cap - qbytes - fixed) / ((size_t)kbg * SB_STAGE_BYTES) < 2) kbg >>= 1;
+  p->kbg = kbg;
+  int stages = (int)((cap - qbytes - fixed) / ((size_t)kbg * SB_STAGE_BYTES));
   if (stages > SB_MAX_STAGES) stages = SB_MAX_STAGES;
   p->n_stages = stages;
-  p->smem = qbytes + (size_t)stages * SB_STAGE_BYTES + fixed + 1024;
+  p->smem = qbytes + (size_t)stages * kbg * SB_STAGE_BYTES + fixed + 1024;
   p->n_tiles = (int)((n_rows + GT_BM - 1) / GT_BM);
   const int sms = sm_count();
   p->grid = p->n_tiles < sms ? p->n_tiles : sms;
@@ -806,7 +873,7 @@ static int launch_smallbatch(const CUtensorMap& tq, const CUtensorMap& tb, long 
                              const float* bias, const unsigned* floor_ord, const SmallPlan& p, int grid, u64* partial,
                              bool bf16, cudaStream_t st) {
   SmallBatchArgs a;
-  a.n_rows = n_rows; a.n_queries = n_queries; a.k_blocks = p.k_blocks; a.n_stages = p.n_stages;
+  a.n_rows = n_rows; a.n_queries = n_queries; a.k_blocks = p.k_blocks; a.n_stages = p.n_stages; a.kbg = p.kbg;
   a.n_tiles = (int)((n_rows + GT_BM - 1) / GT_BM);
   a.scale = scale; a.bias = bias; a.floor_ord = floor_ord; a.partial = partial;
   void (*kern)(const CUtensorMap, const CUtensorMap, const SmallBatchArgs) =
@@ -826,7 +893,7 @@ static int run_smallbatch(const void* q_mat, int n_queries, const void* rows, lo
   CUtensorMap tq, tb;
   int rc = encode_tmap_2d(&tq, q_mat, eb, bf16, n_queries, d, SB_NQ);
   if (rc != AURA_OK) return rc;
-  rc = encode_tmap_2d(&tb, rows, eb, bf16, n_rows, d, GT_BM);
+  rc = p.kbg > 1 ? encode_tmap_kgroup(&tb, rows, eb, bf16, n_rows, d, GT_BM, p.kbg) : encode_tmap_2d(&tb, rows, eb, bf16, n_rows, d, GT_BM);
   if (rc != AURA_OK) return rc;
   // sample pre-pass: one tile per CTA over the first rows gives every query a floor under its final 32nd-best score, so
   // the per-warp lists of the main pass start selective instead of each paying its own warm-up
