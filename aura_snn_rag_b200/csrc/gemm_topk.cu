@@ -492,168 +492,6 @@ __global__ void __launch_bounds__(128) gemm_topk_finish_kernel(const FinishArgs 
   rescore_and_write(keys, n2, ex, ra);
 }
 
-// ================================================================================================
-// Small query blocks (B <= 32): roles swapped - the BANK tile is the M operand (128 rows -> TMEM lanes), the whole
-// normalised query block is the N operand and stays resident in shared memory for the kernel's lifetime, so the only
-// stream is the bank (HBM-bound, like the single-query scan, for any B <= 32 - the production block size of
-// MemoryAugmentedLayer, colab_l4_training.py:91).  Epilogue thread = bank row; per (warp, query) a register-distributed
-// WarpTopK behind a warp-uniform threshold, exactly the structure of the scan kernel; CTA merge -> partial lists in the
-// layout gemm_topk_finish_kernel reads -> exact fp32 re-score + certification.
-// ================================================================================================
-static constexpr int SB_NQ = 32;                          // query columns (UMMA N)
-static constexpr int SB_STAGE_BYTES = GT_BM * GT_SLAB;    // one 128-row K-slab of the bank: 16 KB
-static constexpr int SB_MAX_STAGES = 8;
-static constexpr int SB_QBLOCK_BYTES = SB_NQ * GT_SLAB;   // one K-slab of the query block: 4 KB
-
-struct SmallBatchArgs {
-  long long n_rows;
-  int n_queries, k_blocks, n_stages, n_tiles;
-  int kbg;                 // K-slabs per stage: 1 = one 2-D box per slab; > 1 = one 3-D box (tmap_b from encode_tmap_kgroup)
-  const float* scale; const float* bias;
-  const unsigned* floor_ord;   // per query: orderable score no top-32 row can be below (0 = none), from a sample pre-pass
-  u64* partial;            // [grid][GT_L][128]
-};
-
-template <bool TF32>
-__global__ void __launch_bounds__(GT_THREADS, 1)
-smallbatch_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_b,
-                       const SmallBatchArgs a) {
-  extern __shared__ unsigned char smem_raw[];
-  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  const int S = a.n_stages;
-  unsigned char* qblk = smem;                                           // [k_blocks][SB_NQ rows][128 B]
-  unsigned char* ring = qblk + (size_t)a.k_blocks * SB_QBLOCK_BYTES;    // [S][128 rows][128 B]
-  const unsigned stage_bytes = (unsigned)a.kbg * SB_STAGE_BYTES;
-  const int n_kg = (a.k_blocks + a.kbg - 1) / a.kbg;
-  uint64_t* full = reinterpret_cast<uint64_t*>(ring + (size_t)S * stage_bytes);
-  uint64_t* empty = full + SB_MAX_STAGES;
-  uint64_t* tfull = empty + SB_MAX_STAGES;
-  uint64_t* tempty = tfull + 2;
-  uint64_t* qfull = tempty + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(qfull + 1);
-  u64* merge = reinterpret_cast<u64*>(ring);                            // CTA merge scratch once the ring has drained
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr int ELEMS_PER_SLAB = TF32 ? 32 : 64;
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4); }
-    mbar_init(qfull, 1);
-    fence_mbar_init();
-    tc::tma_prefetch_desc(&tmap_q);
-    tc::tma_prefetch_desc(&tmap_b);
-  }
-  if (warp == 1) { tc::tmem_alloc(tmem_slot, 2 * SB_NQ); tc::tmem_relinquish(); }
-  tc::tc_fence_before();
-  __syncthreads();
-  tc::tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  const int t_begin = (int)(((long long)a.n_tiles * blockIdx.x) / gridDim.x);
-  const int t_end = (int)(((long long)a.n_tiles * (blockIdx.x + 1)) / gridDim.x);
-
-  // lists start filled with a sentinel at the sample floor (row field 0 = invalid row 0xFFFFFFFF): anything scoring
-  // below the floor is rejected by the ordinary threshold test from the first tile on; sentinels are dropped at the merge
-  WarpTopK<1> tk[SB_NQ];
-#pragma unroll
-  for (int c = 0; c < SB_NQ; ++c) {
-    const u64 f = (a.floor_ord != nullptr && c < a.n_queries) ? ((u64)a.floor_ord[c] << 32) : 0ull;
-    tk[c].e[0] = f;
-    tk[c].thr = f;
-  }
-
-  if (warp == 0) {
-    if (lane == 0) {
-      const uint64_t pol_b = l2_policy_evict_first(), pol_q = l2_policy_evict_last();
-      mbar_arrive_expect_tx(qfull, (unsigned)(a.k_blocks * SB_QBLOCK_BYTES));
-      for (int kb = 0; kb < a.k_blocks; ++kb)
-        tc::tma_load_2d(qblk + (size_t)kb * SB_QBLOCK_BYTES, &tmap_q, kb * ELEMS_PER_SLAB, 0, qfull, pol_q);
-      int stage = 0; unsigned phase = 0;
-      for (int t = t_begin; t < t_end; ++t)
-        for (int kg = 0; kg < n_kg; ++kg) {
-          tc::mbar_wait_guarded(&empty[stage], phase ^ 1u);
-          mbar_arrive_expect_tx(&full[stage], stage_bytes);      // a box past the last K-slab is zero-filled, bytes count in full
-          if (a.kbg == 1)
-            tc::tma_load_2d(ring + (size_t)stage * stage_bytes, &tmap_b, kg * ELEMS_PER_SLAB, t * GT_BM, &full[stage], pol_b);
-          else
-            tc::tma_load_3d(ring + (size_t)stage * stage_bytes, &tmap_b, 0, t * GT_BM, kg * a.kbg, &full[stage], pol_b);
-          if (++stage == S) { stage = 0; phase ^= 1u; }
-        }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = tc::make_idesc(TF32 ? 2 : 1, GT_BM, SB_NQ);
-      tc::mbar_wait_guarded(qfull, 0u);
-      int stage = 0; unsigned phase = 0, tile_n = 0;
-      for (int t = t_begin; t < t_end; ++t, ++tile_n) {
-        const unsigned acc = tile_n & 1u, acc_phase = (tile_n >> 1) & 1u;
-        tc::mbar_wait_guarded(&tempty[acc], acc_phase ^ 1u);
-        tc::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * SB_NQ;
-        for (int kg = 0; kg < n_kg; ++kg) {
-          tc::mbar_wait_guarded(&full[stage], phase);
-          tc::tc_fence_after();
-          for (int kbi = 0; kbi < a.kbg && kg * a.kbg + kbi < a.k_blocks; ++kbi) {
-            const int kb = kg * a.kbg + kbi;
-            const uint64_t da = tc::make_smem_desc_sw128(ring + (size_t)stage * stage_bytes + (size_t)kbi * SB_STAGE_BYTES);
-            const uint64_t db = tc::make_smem_desc_sw128(qblk + (size_t)kb * SB_QBLOCK_BYTES);
-#pragma unroll
-            for (int j = 0; j < GT_SLAB / 32; ++j)
-              tc::umma<TF32>(d_tmem, da + (uint64_t)(2 * j), db + (uint64_t)(2 * j), idesc, (kb | j) != 0 ? 1u : 0u);
-          }
-          tc::umma_commit(&empty[stage]);
-          if (++stage == S) { stage = 0; phase ^= 1u; }
-        }
-        tc::umma_commit(&tfull[acc]);
-      }
-    }
-  } else {
-    const int quarter = warp & 3;
-    const int te = quarter * 32 + lane;
-    unsigned tile_n = 0;
-    for (int t = t_begin; t < t_end; ++t, ++tile_n) {
-      const unsigned acc = tile_n & 1u, acc_phase = (tile_n >> 1) & 1u;
-      const long long row = (long long)t * GT_BM + te;
-      const bool valid = row < a.n_rows;
-      const float sc = valid ? (a.scale ? a.scale[row] : 1.f) : 0.f;
-      const float bi = valid ? (a.bias ? a.bias[row] : 0.f) : 0.f;
-      tc::mbar_wait_guarded(&tfull[acc], acc_phase);
-      tc::tc_fence_after();
-      float v[32];
-      tc::tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * SB_NQ, v);
-      tc::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[acc]);        // the accumulator is in registers: release it early
-#pragma unroll
-      for (int c = 0; c < SB_NQ; ++c) {
-        if (c < a.n_queries) {                         // uniform
-          const u64 key = valid ? make_key(fmaf(v[c], sc, bi), (unsigned)row) : 0ull;
-          unsigned pend = __ballot_sync(FULL, key > tk[c].thr);
-          while (pend) {
-            const int src = __ffs(pend) - 1;
-            pend &= pend - 1u;
-            const u64 kx = __shfl_sync(FULL, key, src);
-            if (kx > tk[c].thr) tk[c].insert(kx, lane);
-          }
-        }
-      }
-    }
-  }
-  // ---- CTA merge per query: 4 warps x 32 keys -> best 32 -> partial[blockIdx.x][s][query] ----
-  __syncthreads();
-#pragma unroll 1
-  for (int c = 0; c < a.n_queries; ++c) {
-    u64 mine = 0ull;
-#pragma unroll
-    for (int cc = 0; cc < SB_NQ; ++cc) if (cc == c) mine = tk[cc].e[0];
-    if ((mine & 0xFFFFFFFFull) == 0ull) mine = 0ull;       // floor sentinel / empty slot
-    if (warp >= 2) merge[(warp - 2) * 32 + lane] = mine;
-    block_bitonic_sort_desc(merge, 128);
-    if (threadIdx.x < GT_L) a.partial[((size_t)blockIdx.x * GT_L + threadIdx.x) * GT_BM + c] = merge[threadIdx.x];
-    __syncthreads();
-  }
-  if (warp == 1) { tc::tc_fence_after(); tc::tmem_dealloc(tmem_base, 2 * SB_NQ); }
-}
-
 // multi-round tail: the candidates of all rounds (already in descending approximate order) -> exact re-score + certify
 struct CandRescoreArgs {
   const u64* cand; int n_cand;      // n_cand = rounds * 32
@@ -715,22 +553,6 @@ int encode_tmap_2d(CUtensorMap* map, const void* base, int elem_bytes, bool bf16
                         const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   AURA_REQUIRE(r == CUDA_SUCCESS, AURA_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
-  return AURA_OK;
-}
-
-int encode_tmap_kgroup(CUtensorMap* map, const void* base, int elem_bytes, bool bf16, long long n_rows, int d, int box_rows, int kgroup) {
-  EncodeTiledFn fn = encode_fn();
-  AURA_REQUIRE(fn != nullptr, AURA_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
-  const int elems = GT_SLAB / elem_bytes;
-  AURA_REQUIRE(d % elems == 0, AURA_ERR_UNSUPPORTED, "encode_tmap_kgroup: d=%d is not a multiple of %d", d, elems);
-  const cuuint64_t gdim[3] = {(cuuint64_t)elems, (cuuint64_t)n_rows, (cuuint64_t)(d / elems)};
-  const cuuint64_t gstride[2] = {(cuuint64_t)d * elem_bytes, (cuuint64_t)GT_SLAB};
-  const cuuint32_t box[3] = {(cuuint32_t)elems, (cuuint32_t)box_rows, (cuuint32_t)kgroup};
-  const cuuint32_t estr[3] = {1, 1, 1};
-  const CUresult r = fn(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
-                        const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  AURA_REQUIRE(r == CUDA_SUCCESS, AURA_ERR_CUDA, "cuTensorMapEncodeTiled (3-D) failed with CUresult %d", (int)r);
   return AURA_OK;
 }
 
@@ -798,10 +620,10 @@ static size_t align256(size_t v) { return (v + 255) / 256 * 256; }
 
 static int run_gemm_topk(const void* a_mat, long long n_a_rows, long long a_row_first, const void* b_mat, long long n_b_rows,
                          int d, bool bf16, const float* scale, const float* bias, bool exclude_self, const GemmPlan& p,
-                         u64* partial, cudaStream_t st, const u64* ceil_keys = nullptr) {
+                         u64* partial, cudaStream_t st, const u64* ceil_keys = nullptr, long long a_rows_alloc = 0) {
   const int eb = bf16 ? 2 : 4;
   CUtensorMap ta, tb;
-  int rc = encode_tmap_2d(&ta, a_mat, eb, bf16, n_a_rows, d, GT_BM);
+  int rc = encode_tmap_2d(&ta, a_mat, eb, bf16, a_rows_alloc > n_a_rows ? a_rows_alloc : n_a_rows, d, GT_BM);
   if (rc != AURA_OK) return rc;
   rc = encode_tmap_2d(&tb, b_mat, eb, bf16, n_b_rows, d, p.two_cta ? GT_BM : GT_BN);   // a CTA pair loads half of B each
   if (rc != AURA_OK) return rc;
@@ -822,102 +644,6 @@ static int run_gemm_topk(const void* a_mat, long long n_a_rows, long long a_row_
   AURA_CUDA_OK(cudaGetLastError());
   note_launches(1);
   return AURA_OK;
-}
-
-// floor[q] = orderable score of the GT_L-th best key of query q in a sample pass's partial lists (0 when fewer exist)
-__global__ void __launch_bounds__(128) sample_floor_kernel(const u64* __restrict__ partial, int n_groups, int n2,
-                                                           unsigned* __restrict__ floor_ord) {
-  extern __shared__ __align__(16) unsigned char fsm[];
-  u64* keys = reinterpret_cast<u64*>(fsm);
-  const int q = blockIdx.x;
-  for (int i = threadIdx.x; i < n2; i += blockDim.x)
-    keys[i] = i < n_groups * GT_L ? partial[((size_t)(i / GT_L) * GT_L + (i % GT_L)) * GT_BM + q] : 0ull;
-  block_bitonic_sort_desc(keys, n2);
-  if (threadIdx.x == 0) floor_ord[q] = (unsigned)(keys[GT_L - 1] >> 32);
-}
-
-struct SmallPlan { int grid, n_stages, k_blocks, n_tiles, n2, kbg; size_t smem; };
-
-static bool make_small_plan(long long n_rows, int d, int elem_bytes, int n_queries, SmallPlan* p) {
-  // measured on B200 (1M x 768 fp32): 693 / 804 us at B = 8 / 16 against 764 / 869 us for the 128-row-tile kernel;
-  // at B = 32 the 32 per-query list updates per tile make it slower (1064 vs 838 us), so it serves B <= 16
-  int max_b = 16;
-  if (const char* e = getenv("AURA_SMALLBATCH")) max_b = atoi(e) == 0 ? 0 : SB_NQ;
-  if (n_queries > max_b) return false;
-  const int elems = GT_SLAB / elem_bytes;
-  p->k_blocks = (d + elems - 1) / elems;
-  const size_t qbytes = (size_t)p->k_blocks * SB_QBLOCK_BYTES;
-  const size_t fixed = (2 * SB_MAX_STAGES + 5) * 8 + 16;
-  const size_t cap = (size_t)max_smem_optin() - 1024;
-  if (qbytes + fixed + 3 * (size_t)SB_STAGE_BYTES > cap) return false;
-  // K-slabs per stage: each bank row is visited for kbg*128 contiguous bytes per box instead of 128
-  int kbg = 1;
-  if (const char* e = getenv("AURA_SB_KBG")) kbg = atoi(e);
-  if (kbg < 1 || d % elems != 0) kbg = 1;
-  while (kbg > 1 && (cap - qbytes - fixed) / ((size_t)kbg * SB_STAGE_BYTES) < 2) kbg >>= 1;
-  p->kbg = kbg;
-  int stages = (int)((cap - qbytes - fixed) / ((size_t)kbg * SB_STAGE_BYTES));
-  if (stages > SB_MAX_STAGES) stages = SB_MAX_STAGES;
-  p->n_stages = stages;
-  p->smem = qbytes + (size_t)stages * kbg * SB_STAGE_BYTES + fixed + 1024;
-  p->n_tiles = (int)((n_rows + GT_BM - 1) / GT_BM);
-  const int sms = sm_count();
-  p->grid = p->n_tiles < sms ? p->n_tiles : sms;
-  int n2 = 2;
-  while (n2 < p->grid * GT_L) n2 <<= 1;
-  p->n2 = n2;
-  return true;
-}
-
-static int launch_smallbatch(const CUtensorMap& tq, const CUtensorMap& tb, long long n_rows, int n_queries, const float* scale,
-                             const float* bias, const unsigned* floor_ord, const SmallPlan& p, int grid, u64* partial,
-                             bool bf16, cudaStream_t st) {
-  SmallBatchArgs a;
-  a.n_rows = n_rows; a.n_queries = n_queries; a.k_blocks = p.k_blocks; a.n_stages = p.n_stages; a.kbg = p.kbg;
-  a.n_tiles = (int)((n_rows + GT_BM - 1) / GT_BM);
-  a.scale = scale; a.bias = bias; a.floor_ord = floor_ord; a.partial = partial;
-  void (*kern)(const CUtensorMap, const CUtensorMap, const SmallBatchArgs) =
-      bf16 ? smallbatch_topk_kernel<false> : smallbatch_topk_kernel<true>;
-  AURA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
-  kern<<<grid, GT_THREADS, p.smem, st>>>(tq, tb, a);
-  AURA_CUDA_OK(cudaGetLastError());
-  note_launches(1);
-  return AURA_OK;
-}
-
-// floor_ord: SB_NQ unsigned of caller scratch
-static int run_smallbatch(const void* q_mat, int n_queries, const void* rows, long long n_rows, int d, bool bf16,
-                          const float* scale, const float* bias, const SmallPlan& p, u64* partial, unsigned* floor_ord,
-                          cudaStream_t st) {
-  const int eb = bf16 ? 2 : 4;
-  CUtensorMap tq, tb;
-  int rc = encode_tmap_2d(&tq, q_mat, eb, bf16, n_queries, d, SB_NQ);
-  if (rc != AURA_OK) return rc;
-  rc = p.kbg > 1 ? encode_tmap_kgroup(&tb, rows, eb, bf16, n_rows, d, GT_BM, p.kbg) : encode_tmap_2d(&tb, rows, eb, bf16, n_rows, d, GT_BM);
-  if (rc != AURA_OK) return rc;
-  // sample pre-pass: one tile per CTA over the first rows gives every query a floor under its final 32nd-best score, so
-  // the per-warp lists of the main pass start selective instead of each paying its own warm-up
-  const long long sample = (long long)p.grid * GT_BM;
-  const unsigned* fl = nullptr;
-  // off by default: measured slower (the pre-pass + floor kernel cost ~200 us, list warm-up was not the bottleneck)
-  const bool use_floor = n_rows >= 16 * sample && getenv("AURA_SMALLBATCH_FLOOR") != nullptr;
-  if (use_floor) {
-    rc = launch_smallbatch(tq, tb, sample, n_queries, scale, bias, nullptr, p, p.grid, partial, bf16, st);
-    if (rc != AURA_OK) return rc;
-    const size_t fsmem = (size_t)p.n2 * 8;
-    AURA_CUDA_OK(cudaFuncSetAttribute(sample_floor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
-    sample_floor_kernel<<<n_queries, 128, fsmem, st>>>(partial, p.grid, p.n2, floor_ord);
-    AURA_CUDA_OK(cudaGetLastError());
-    note_launches(1);
-    fl = floor_ord;
-  }
-  return launch_smallbatch(tq, tb, n_rows, n_queries, scale, bias, fl, p, p.grid, partial, bf16, st);
-}
-
-// partial-list region of aura_batch_topk: large enough for either kernel (the small-batch kernel writes one list block per CTA)
-static size_t batch_partial_bytes(const GemmPlan& p) {
-  const size_t small = (size_t)sm_count() * GT_L * GT_BM * 8;
-  return p.partial_bytes > small ? p.partial_bytes : small;
 }
 
 static int check_shapes(const char* who, const void* rows, int dtype, long long n_rows, int d, int k, int k_max = GT_L) {
@@ -1124,7 +850,8 @@ extern "C" size_t aura_batch_topk_workspace_bytes(int64_t n_rows, int d, int dty
   GemmPlan p;
   if (n_queries < 1 || n_rows < 1 || d < 1 || k < 1) return 0;
   if (!make_gemm_plan(n_queries, n_rows, d, dtype == AURA_BF16 ? 2 : 4, k, true, &p)) return 0;
-  return align256(batch_partial_bytes(p)) + align256((size_t)n_queries * d * 4) + align256((size_t)n_queries * d * 2) + 512 +
+  const size_t n_pad = ((size_t)n_queries + GT_BM - 1) / GT_BM * GT_BM;     // query block padded to whole A tiles
+  return align256(p.partial_bytes) + align256(n_pad * d * 4) + align256(n_pad * d * 2) + 512 +
          align256((size_t)n_queries * GT_MAX_L * 8) + align256((size_t)n_queries * 8);
 }
 
@@ -1145,13 +872,18 @@ extern "C" int aura_batch_topk(const void* rows, int dtype, int64_t n_rows, int 
   cudaStream_t st = (cudaStream_t)stream;
   unsigned char* ws = reinterpret_cast<unsigned char*>(workspace);
   u64* partial = reinterpret_cast<u64*>(ws);
-  float* qn = reinterpret_cast<float*>(ws + align256(batch_partial_bytes(p)));
-  __nv_bfloat16* qb = bf16 ? reinterpret_cast<__nv_bfloat16*>(ws + align256(batch_partial_bytes(p)) + align256((size_t)n_queries * d * 4))
-                           : nullptr;
+  // the normalised query block is padded with zero rows to whole 128-row A tiles: the A-tile TMA box then never leaves
+  // the tensor (out-of-bounds fill measured ~20 % slower per step at B = 32 than a fully resident tile)
+  const size_t n_pad = ((size_t)n_queries + GT_BM - 1) / GT_BM * GT_BM;
+  float* qn = reinterpret_cast<float*>(ws + align256(p.partial_bytes));
+  __nv_bfloat16* qb = bf16 ? reinterpret_cast<__nv_bfloat16*>(ws + align256(p.partial_bytes) + align256(n_pad * d * 4)) : nullptr;
   normalize_queries_kernel<<<(n_queries + 7) / 8, 256, 0, st>>>(queries, n_queries, d, qn, qb);
   note_launches(1);
-  const size_t off_floor = align256(batch_partial_bytes(p)) + align256((size_t)n_queries * d * 4) + align256((size_t)n_queries * d * 2);
-  unsigned* floor_ord = reinterpret_cast<unsigned*>(ws + off_floor);
+  if (n_pad > (size_t)n_queries) {
+    AURA_CUDA_OK(cudaMemsetAsync(qn + (size_t)n_queries * d, 0, (n_pad - n_queries) * d * 4, st));
+    if (qb) AURA_CUDA_OK(cudaMemsetAsync(qb + (size_t)n_queries * d, 0, (n_pad - n_queries) * d * 2, st));
+  }
+  const size_t off_floor = align256(p.partial_bytes) + align256(n_pad * d * 4) + align256(n_pad * d * 2);
   u64* cand = reinterpret_cast<u64*>(ws + off_floor + 512);
   u64* ceil_buf = cand + align256((size_t)n_queries * GT_MAX_L * 8) / 8;
   const int rounds = (k + 14 + GT_L - 1) / GT_L;          // 32 candidates per round; k <= 18 needs one
@@ -1161,23 +893,12 @@ extern "C" int aura_batch_topk(const void* rows, int dtype, int64_t n_rows, int 
   f.scale = scale; f.bias = bias; f.eps = eps; f.a_scale = nullptr;
   f.out_idx = reinterpret_cast<long long*>(out_idx); f.out_score = out_score; f.uncertain = out_uncertain;
   f.cand = nullptr; f.ceil_out = nullptr; f.round = 0;
-  SmallPlan sp;
-  bool used_small = false;
-  if (rounds == 1 && make_small_plan(n_rows, d, bf16 ? 2 : 4, n_queries, &sp)) {
-    used_small = true;
-    // 5 <= B <= 16: bank tile as the M operand, query block resident in shared memory
-    rc = run_smallbatch(a_mat, n_queries, rows, n_rows, d, bf16, scale, bias, sp, partial, floor_ord, st);
-    if (rc != AURA_OK) return rc;
-    p.n_atiles = 1; p.n_groups = sp.grid; p.L = GT_L; p.n2 = sp.n2;
-  }
   f.partial = partial; f.n_atiles = p.n_atiles; f.n_groups = p.n_groups; f.L = p.L; f.n2 = p.n2;
   const size_t fsmem = ((size_t)p.n2 + GT_MAX_L) * 8;
   AURA_CUDA_OK(cudaFuncSetAttribute(gemm_topk_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
   if (rounds == 1) {
-    if (!used_small) {
-      rc = run_gemm_topk(a_mat, n_queries, 0, rows, n_rows, d, bf16, scale, bias, false, p, partial, st);
-      if (rc != AURA_OK) return rc;
-    }
+    rc = run_gemm_topk(a_mat, n_queries, 0, rows, n_rows, d, bf16, scale, bias, false, p, partial, st, nullptr, (long long)n_pad);
+    if (rc != AURA_OK) return rc;
     gemm_topk_finish_kernel<<<n_queries, 128, fsmem, st>>>(f);
     AURA_CUDA_OK(cudaGetLastError());
     note_launches(1);
@@ -1188,7 +909,7 @@ extern "C" int aura_batch_topk(const void* rows, int dtype, int64_t n_rows, int 
   // without gaps or repeats; all candidates are then re-scored exactly and certified like the one-round case.
   f.cand = cand; f.ceil_out = ceil_buf;
   for (int r = 0; r < rounds; ++r) {
-    rc = run_gemm_topk(a_mat, n_queries, 0, rows, n_rows, d, bf16, scale, bias, false, p, partial, st, r ? ceil_buf : nullptr);
+    rc = run_gemm_topk(a_mat, n_queries, 0, rows, n_rows, d, bf16, scale, bias, false, p, partial, st, r ? ceil_buf : nullptr, (long long)n_pad);
     if (rc != AURA_OK) return rc;
     f.round = r;
     gemm_topk_finish_kernel<<<n_queries, 128, fsmem, st>>>(f);

@@ -26,14 +26,6 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
       ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(policy)
       : "memory");
 }
-__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar,
-                                            uint64_t policy) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
-      " [%0], [%1, {%3, %4, %5}], [%2], %6;"
-      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "l"(policy)
-      : "memory");
-}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -315,10 +307,6 @@ __device__ __forceinline__ void rescore_and_write(const u64* keys, int n2, u64* 
 // ---- host: tensor-map encode through the runtime's driver entry point (no -lcuda link dependency) ----
 // 2-D row-major matrix [n_rows, d] of `elem_bytes`-byte elements; box = [128 bytes of K, box_rows], SWIZZLE_128B.
 int encode_tmap_2d(CUtensorMap* map, const void* base, int elem_bytes, bool bf16, long long n_rows, int d, int box_rows);
-// 3-D view (slab element, row, K-slab) of the same matrix: one box = box_rows rows x kgroup consecutive 128-byte K-slabs, laid
-// out in shared memory as kgroup standard K-major slabs - every row is visited once for kgroup*128 contiguous bytes.
-// Needs d*elem_bytes % 128 == 0.
-int encode_tmap_kgroup(CUtensorMap* map, const void* base, int elem_bytes, bool bf16, long long n_rows, int d, int box_rows, int kgroup);
 
 
 // kmeans.cu: exclusive scan of counts[0..n) -> offsets[0..n] (and cursor := offsets), single CTA

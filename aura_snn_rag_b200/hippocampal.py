@@ -379,7 +379,7 @@ class HippocampalFormation(nn.Module):
         """Exact top-k of a query block over all live rows: tcgen05 shortlist + exact fp32 re-score for blocks of
         >= TC_MIN_BATCH queries (identical results to the scan, see ops.exact_topk_batched), else the streaming scan."""
         m = self.memory_count
-        if q.shape[0] >= ops.TC_MIN_BATCH and ops.batch_topk_supported(self.memory_features, k) and m >= 1024:
+        if q.shape[0] >= ops.tc_min_batch(self.memory_features) and ops.batch_topk_supported(self.memory_features, k) and m >= 1024:
             return ops.exact_topk_batched(self.memory_features, q, k, scale, bias, n_rows=m,
                                           eps=ops.TC_EPS_COS * score_per_cos)
         return ops.scan_topk(self.memory_features, q, k, scale, bias, n_rows=m)
@@ -423,7 +423,7 @@ class HippocampalFormation(nn.Module):
         m = self.memory_count
         kk = min(int(k), m)
         if defer:
-            if not (q.shape[0] >= ops.TC_MIN_BATCH and ops.batch_topk_supported(self.memory_features, kk) and m >= 1024):
+            if not (q.shape[0] >= ops.tc_min_batch(self.memory_features) and ops.batch_topk_supported(self.memory_features, kk) and m >= 1024):
                 idx, score = ops.scan_topk(self.memory_features, q, kk, self._inv_norm, None, n_rows=m)
                 return idx, score, torch.zeros(q.shape[0], dtype=torch.int32, device=self.device), q
             idx, score, flags = ops.exact_topk_batched(self.memory_features, q, kk, self._inv_norm, None, n_rows=m,

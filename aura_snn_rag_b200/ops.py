@@ -287,7 +287,15 @@ def ivf_search(rows: torch.Tensor, n_rows: int, queries: torch.Tensor, centroids
 
 # ---------------------------------------------------------------------------- tensor-core paths
 TC_MAX_K = 114                 # tensor-core paths: 32 candidates per round, up to 4 rounds, margin 14 (k <= 18: one round)
-TC_MIN_BATCH = 5               # below this the CUDA-core streaming scan is faster (measured on B200: B=4 scan 690 us)
+TC_MIN_BATCH = 3               # fp32 bank: below this the CUDA-core streaming scan is faster
+TC_MIN_BATCH_BF16 = 2          # bf16 bank
+
+
+def tc_min_batch(rows: torch.Tensor) -> int:
+    """Smallest query block that goes to the tensor-core path.  B200, 1M x 768: the scan takes 470 / 498 / 687 us at
+    B = 1 / 2 / 3 (fp32) and 273 / 376 / 748 us (bf16); the tensor-core path 530-560 us (fp32) and 315-366 us (bf16) for
+    any B <= 128."""
+    return TC_MIN_BATCH_BF16 if rows.dtype == torch.bfloat16 else TC_MIN_BATCH
 TC_EPS_COS = 2.0 ** -9 + 1e-4   # |tensor-core cosine - fp32 cosine| bound: both operands rounded to 11 bits + fp32 sums
 
 

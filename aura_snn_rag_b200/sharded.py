@@ -56,7 +56,7 @@ class ShardedBank:
         """Exact local search: the tensor-core path for query blocks (flags deferred), the streaming scan otherwise."""
         def search(q, k):
             n = self.rows.shape[0]
-            if q.shape[0] >= ops.TC_MIN_BATCH and ops.batch_topk_supported(self.rows, k) and n >= 1024:
+            if q.shape[0] >= ops.tc_min_batch(self.rows) and ops.batch_topk_supported(self.rows, k) and n >= 1024:
                 return ops.exact_topk_batched(self.rows, q, k, self.scale, self.bias, row_base=self.row_base, defer=True)
             return ops.scan_topk(self.rows, q, k, self.scale, self.bias, row_base=self.row_base)
 

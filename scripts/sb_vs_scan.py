@@ -17,7 +17,7 @@ def t(fn, n=6):
 for dt in (torch.float32,) if one else (torch.float32, torch.bfloat16):
     rows = torch.randn(M, D, device=dev, generator=g).to(dt)
     inv = ops.row_inv_norms(rows)
-    for B in (16,) if one else (1, 2, 4, 8, 16, 32, 64, 128):
+    for B in (16,) if one else (1, 2, 3, 4, 8, 16, 32, 64, 128, 256):
         q = torch.randn(B, D, device=dev, generator=g)
         ts = t(lambda: ops.scan_topk(rows, q, K, inv, None))
         tb = t(lambda: ops.batch_topk(rows, q, K, inv, None))
