@@ -445,32 +445,62 @@ __global__ void __launch_bounds__(128) ivf_finish_kernel(const IvfFinishArgs f) 
   __shared__ u64 ex[GT_MAX_L];
   const int b = blockIdx.x;
   const bool overflow = *f.n_items > f.cap_items || f.pbase[f.n_lists] > f.cap_plists;
-  int n = 0;   // keys buffered so far (uniform across the CTA)
-  for (int p = 0; p < f.nprobe && !overflow; ++p) {
-    const long long c = f.probes[(size_t)b * f.nprobe + p];
-    if (c < 0 || c >= f.n_lists) continue;
-    const int len = f.list_offsets[c + 1] - f.list_offsets[c];
-    if (len == 0) continue;
-    int n_ch, ch_rows;
-    ib_chunks(len, n_ch, ch_rows);
-    const int rel = f.pos_of_pair[(size_t)b * f.nprobe + p] - f.q_off[c];
-    const int nq = f.q_off[c + 1] - f.q_off[c];
-    for (int j = 0; j < n_ch; ++j) {
-      if (n + GT_L > IB_MERGE_CAP) {        // buffer full: keep the best GT_L so far
-        __syncthreads();
-        for (int i = n + threadIdx.x; i < IB_MERGE_CAP; i += blockDim.x) keys[i] = 0ull;
-        block_bitonic_sort_desc(keys, IB_MERGE_CAP);
-        n = GT_L;
+  // Partial lists of this query: one per (probe, chunk of the probed list), each sorted and zero-padded.  Two passes, a
+  // warp per probe so that the dependent table reads of different probes overlap:
+  //   1. the list HEADS; the GT_L-th largest head is a floor - GT_L keys (those heads) are at or above it, so nothing
+  //      below it can be among the best GT_L;
+  //   2. every list's keys >= floor (at most GT_L lists x GT_L keys) are buffered and sorted.
+  __shared__ const u64* lptr[AURA_MAX_NPROBE];   // first partial list of probe p
+  __shared__ int lstride[AURA_MAX_NPROBE];       // distance between the chunks' lists, in keys
+  __shared__ int lcnt[AURA_MAX_NPROBE];          // chunks (0: probe has no list)
+  __shared__ int n_heads, n_kept;
+  __shared__ u64 floor_s;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) { n_heads = 0; n_kept = 0; }
+  for (int p = threadIdx.x; p < f.nprobe; p += blockDim.x) {
+    int cnt = 0, stride = 0;
+    const u64* ptr = nullptr;
+    const long long c = overflow ? -1 : f.probes[(size_t)b * f.nprobe + p];
+    if (c >= 0 && c < f.n_lists) {
+      const int len = f.list_offsets[c + 1] - f.list_offsets[c];
+      if (len > 0) {
+        int n_ch, ch_rows;
+        ib_chunks(len, n_ch, ch_rows);
+        const int rel = f.pos_of_pair[(size_t)b * f.nprobe + p] - f.q_off[c];
+        const int nq = f.q_off[c + 1] - f.q_off[c];
+        cnt = n_ch; stride = nq * GT_L;
+        ptr = f.partial + ((size_t)f.pbase[c] + rel) * GT_L;
       }
-      // a partial list is sorted and zero-padded: only its non-zero prefix is buffered (every warp reads the list so
-      // that the count stays uniform without a barrier; warp 0 stores)
-      const u64 key = f.partial[((size_t)f.pbase[c] + (size_t)j * nq + rel) * GT_L + (threadIdx.x & 31)];
-      const int cnt = __popc(__ballot_sync(0xffffffffu, key != 0ull));
-      if (threadIdx.x < cnt) keys[n + threadIdx.x] = key;
-      n += cnt;
     }
+    lptr[p] = ptr; lstride[p] = stride; lcnt[p] = cnt;
   }
   __syncthreads();
+  for (int p = warp; p < f.nprobe; p += 4)
+    for (int j = lane; j < lcnt[p]; j += 32) {
+      const u64 head = lptr[p][(size_t)j * lstride[p]];
+      if (head != 0ull) keys[atomicAdd(&n_heads, 1)] = head;     // <= nprobe * IB_MAX_CHUNKS = IB_MERGE_CAP heads
+    }
+  __syncthreads();
+  const int nh = n_heads;
+  const int h2 = max(64, next_pow2(nh));
+  for (int i = nh + threadIdx.x; i < h2; i += blockDim.x) keys[i] = 0ull;
+  block_bitonic_sort_desc(keys, h2);
+  if (threadIdx.x == 0) floor_s = nh >= GT_L ? keys[GT_L - 1] : 0ull;
+  __syncthreads();
+  const u64 floor_key = floor_s;
+  __syncthreads();                                               // heads consumed: the buffer now takes the survivors
+  for (int p = warp; p < f.nprobe; p += 4)
+    for (int j = 0; j < lcnt[p]; ++j) {
+      const u64 key = lptr[p][(size_t)j * lstride[p] + lane];
+      const unsigned m = __ballot_sync(0xffffffffu, key != 0ull && key >= floor_key);
+      if (m == 0u) continue;
+      int base = 0;
+      if (lane == 0) base = atomicAdd(&n_kept, __popc(m));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if ((m >> lane) & 1u) keys[base + __popc(m & ((1u << lane) - 1u))] = key;
+    }
+  __syncthreads();
+  const int n = n_kept;
   const int n2 = max(64, next_pow2(n));       // sort only what was buffered
   for (int i = n + threadIdx.x; i < n2; i += blockDim.x) keys[i] = 0ull;
   block_bitonic_sort_desc(keys, n2);
