@@ -38,6 +38,10 @@ sys.path.insert(0, ROOT)
 N_ROWS, DIM, TOPK = 1_000_000, 768, 10
 SEED_DATA, SEED_QUERY = 1234, 4321
 METRIC = "queries/sec at recall@10>=ref (exact top-10, 1M x 768 fp32)"
+# DRAM bytes per launch of the two dominant kernels on this workload, from the committed `ncu --set full` captures
+# (profiles/r01_ncu_k6_raw.csv, profiles/r01_ncu_scan_raw.csv): both equal the 3.072 GB of the bank read once.
+NCU_TRAFFIC_K6 = 3.079249e9 + 3.445504e6
+NCU_TRAFFIC_SCAN = 3.076065e9 + 3.531264e6
 
 
 def load_peaks():
@@ -362,7 +366,9 @@ def run_ours(args):
             "value": 1e3 / sq_ms, "unit": "queries/s", "ms_per_query": sq_ms, "ms_min": ts[0],
             "roofline": {"bound": "hbm", "achieved": sq_bytes / sq_ms / 1e6, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": sq_bytes / sq_ms / 1e6 / peaks["hbm_gbs"], "frac_of_nominal_8TBs": sq_bytes / sq_ms / 1e6 / 8000.0,
-                         "traffic": None, "kernel": "scan_topk_kernel<f32,QB=1>", "peak_source": peaks["source"]}}
+                         "traffic": NCU_TRAFFIC_SCAN if (N_ROWS, DIM) == (1_000_000, 768) else None,
+                         "traffic_source": "profiles/r01_ncu_scan_raw.csv (dram__bytes_read.sum + dram__bytes_write.sum, one launch)",
+                         "kernel": "scan_topk_kernel<f32,QB=1>", "peak_source": peaks["source"]}}
 
     if world == 1:
         # same-box GPU bar: what the reference's own statements cost when torch runs them on this B200
@@ -398,7 +404,9 @@ def run_ours(args):
         tf = flops / world / (step_ms / 1e3) / 1e12
         roof = {"bound": "tensor", "achieved": tf, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
                 "frac": tf / peaks["bf16_tflops_sustained"],
-                "frac_of_tf32_peak": tf / (0.5 * peaks["bf16_tflops_sustained"]), "traffic": None,
+                "frac_of_tf32_peak": tf / (0.5 * peaks["bf16_tflops_sustained"]),
+                "traffic": NCU_TRAFFIC_K6 if (N_ROWS, DIM, B) == (1_000_000, 768, 1024) else None,
+                "traffic_source": "profiles/r01_ncu_k6_raw.csv (dram__bytes_read.sum + dram__bytes_write.sum, one launch)",
                 "kernel": args.kernel_name, "algorithmic_flops_per_launch": flops / world,
                 "algorithmic_bytes_per_launch": alg_bytes / world, "timing": "whole step (kernel share in profiles/)",
                 "peak_source": peaks["source"] + " (bf16 sustained; tf32 dense peak = half)"}

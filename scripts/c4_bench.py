@@ -62,6 +62,20 @@ res["exact_batch_ms"] = ms
 res["exact_qps"] = B / ms * 1e3
 hits = (iv_idx.unsqueeze(2) == ex_idx.unsqueeze(1)).any(dim=2).float().sum(dim=1) / K
 res["recall_at_10"] = float(hits.mean())
+# list-major resident copy (2x bank memory): list tiles streamed by TMA instead of gathered
+hf.list_major_copy = True
+hf._ensure_lists()
+hf._bank_by_list = torch.empty_like(hf.memory_features)
+ms, _ = timed(lambda: ops.ivf_pack_lists(hf.memory_features, hf._list_rows, hf.memory_count, hf._bank_by_list), iters=2, warm=1)
+res["pack_lists_ms"] = ms
+ms, (lm_idx, lm_sc) = timed(lambda: hf.retrieve_batch(q, K), iters=2, warm=1)
+res["ivf_batch_list_major_ms"] = ms
+res["ivf_list_major_qps"] = B / ms * 1e3
+res["ivf_list_major_bytes_per_s_TB"] = res["probed_list_bytes_GB"] / ms
+res["list_major_same_result"] = bool(torch.equal(lm_idx, iv_idx) and torch.equal(lm_sc, iv_sc))
+hf.list_major_copy = False
+hf._bank_by_list = None
+torch.cuda.empty_cache()
 ms1, _ = timed(lambda: hf.retrieve_batch(q[:1], K), iters=20, warm=3)
 res["ivf_single_query_ms"] = ms1
 ms, _ = timed(lambda: ops.ivf_coarse(q, hf.centroids, P), iters=3, warm=1)
