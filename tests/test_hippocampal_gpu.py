@@ -347,3 +347,42 @@ def test_bf16_bank_tracks_the_fp32_reference(name, monkeypatch):
         np.testing.assert_allclose([s for _, s in res], g_sc[:n_ret], atol=1e-2)
         overlap.append(len({int(i[1:]) for i, _ in res} & set(g_ids[:n_ret].tolist())) / n_ret)
     assert np.mean(overlap) > 0.9
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+def test_list_major_copy_gives_the_same_answers_and_follows_writes(dt, monkeypatch):
+    """`list_major_copy=True` (bank copy in inverted-list order, list tiles streamed by TMA) must not change a single
+    result of the batched centroid path, also after writes and a rebuild have re-ordered the lists."""
+    import aura_snn_rag_b200.hippocampal as hmod
+    clock = _Clock()
+    monkeypatch.setattr(hmod, "time", types.SimpleNamespace(time=clock.time))
+    g = torch.Generator().manual_seed(77)
+    centres = torch.randn(40, 96, generator=g)
+    rows = centres[torch.randint(0, 40, (9000,), generator=g)] + 0.3 * torch.randn(9000, 96, generator=g)
+
+    def make(lm):
+        hf = hmod.HippocampalFormation(n_place_cells=4, n_time_cells=2, n_grid_cells=2, max_memories=12000, feature_dim=96,
+                                       centroids_k=64, nprobe=6, bank_dtype=dt, track_ids=False, list_major_copy=lm)
+        hf.centroids_update_interval = 1 << 30
+        hf.create_episodic_memories(rows[:8000])
+        hf.rebuild_centroids(seed_rows=torch.arange(0, 8000, 125)[:64])
+        return hf
+
+    a, b = make(False), make(True)
+    q = rows[torch.randint(0, 8000, (150,), generator=g)] + 0.05 * torch.randn(150, 96, generator=g)
+    ia, sa = a.retrieve_batch(q, k=10)
+    ib, sb = b.retrieve_batch(q, k=10)
+    assert b._bank_by_list is not None and b._by_list_valid and a._bank_by_list is None
+    assert torch.equal(b._bank_by_list[:8000], b.memory_features[b._list_rows[:8000].long()])
+    assert torch.equal(ia, ib) and torch.equal(sa, sb)
+    for hf in (a, b):                        # online writes append to lists: the copy must be re-packed before the next batch
+        hf.create_episodic_memories(rows[8000:])
+    assert not b._by_list_valid or b._lists_dirty
+    ia, sa = a.retrieve_batch(q, k=10)
+    ib, sb = b.retrieve_batch(q, k=10)
+    assert b._by_list_valid and torch.equal(ia, ib) and torch.equal(sa, sb)
+    for hf in (a, b):
+        hf.rebuild_centroids(seed_rows=torch.arange(0, 9000, 140)[:64])
+    ia, sa = a.retrieve_batch(q, k=10)
+    ib, sb = b.retrieve_batch(q, k=10)
+    assert torch.equal(ia, ib) and torch.equal(sa, sb)
