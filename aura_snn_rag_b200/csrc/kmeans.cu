@@ -277,8 +277,115 @@ __global__ void __launch_bounds__(256) online_assign_kernel(const void* __restri
   for (int e = threadIdx.x; e < d; e += blockDim.x) {
     const float f = BF16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(rows)[(size_t)row * d + e])
                          : reinterpret_cast<const float*>(rows)[(size_t)row * d + e];
-    cent[(size_t)c * d + e] = (1.0f - eta) * cent[(size_t)c * d + e] + eta * f;  // :228
+    cent[(size_t)c * d + e] = __fadd_rn(__fmul_rn(1.0f - eta, cent[(size_t)c * d + e]), __fmul_rn(eta, f));  // :228, no contraction
   }
+}
+
+// ------------------------------------------------------------------ K1b: a run of writes in ONE cooperative launch
+// The writes are inherently sequential (each may move a centroid the next one is compared with), so the one-launch-per-
+// write form above is launch- and L2-latency bound (~30 us per write at 4096 x 1024).  Here a persistent grid keeps the
+// centroids STATIONARY: CTA b owns the contiguous slice [b*per, (b+1)*per) and holds it in shared memory for the whole
+// run (4096 x 1024 fp32 = 16 MB = 113 KB per SM).  Per write: every CTA scores its slice against the new row from shared
+// memory, publishes its best key, one grid barrier, every CTA reads the 148 keys, and only the owner of the winner updates
+// its slice - same arithmetic in the same order as online_assign_kernel, so the results are bit-identical.
+struct OnlineRunArgs {
+  const void* rows; long long first_row; int n_writes, d, n_live, per, in_smem;
+  float* cent; float* counts; int* cid_i32; float* cid_f32; int cid_stride;
+  u64* partial;                  // [2][gridDim.x] published slots, double-buffered by write parity, zeroed before the launch
+  unsigned long long* barrier;   // unused (kept zero)
+};
+
+template <bool BF16>
+__global__ void __launch_bounds__(256, 1) online_assign_run_kernel(const OnlineRunArgs a) {
+  extern __shared__ float osm[];
+  float* xs2 = osm;                      // [2][d] the row being written / the next one (prefetched)
+  float* cs = osm + 2 * a.d;             // [per][d] this CTA's centroid slice (in_smem)
+  __shared__ u64 warp_best[8];
+  __shared__ int s_arg;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int G = gridDim.x;
+  const int c0 = blockIdx.x * a.per, c1 = min(a.n_live, c0 + a.per);
+  auto load_row = [&](int w, float* dst) {
+    const long long row = a.first_row + w;
+    for (int e = threadIdx.x; e < a.d; e += blockDim.x)
+      dst[e] = BF16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(a.rows)[(size_t)row * a.d + e])
+                    : reinterpret_cast<const float*>(a.rows)[(size_t)row * a.d + e];
+  };
+  if (a.in_smem)
+    for (int i = threadIdx.x; i < (c1 - c0) * a.d; i += blockDim.x) cs[i] = a.cent[(size_t)c0 * a.d + i];
+  load_row(0, xs2);
+  __syncthreads();
+  for (int w = 0; w < a.n_writes; ++w) {
+    const long long row = a.first_row + w;
+    const float* xs = xs2 + (size_t)(w & 1) * a.d;
+    u64 best = 0ull;
+    for (int c = c0 + warp; c < c1; c += 8) {
+      const float* cp = a.in_smem ? cs + (size_t)(c - c0) * a.d : a.cent + (size_t)c * a.d;
+      float ss = 0.f;
+      for (int e = lane; e < a.d; e += 32) {
+        const float t = (a.in_smem ? cp[e] : __ldcg(cp + e)) - xs[e];
+        ss = fmaf(t, t, ss);
+      }
+      ss = warp_sum(ss);
+      const u64 key = make_key(-sqrtf(ss), (unsigned)c);
+      best = key > best ? key : best;
+    }
+    if (lane == 0) warp_best[warp] = best;
+    __syncthreads();
+    // Publish + barrier in one step: slot[parity][cta] = (orderable(-dist) : 32 | ~centroid : 16 | tag : 16).  A slot is
+    // ready when its tag is this write's; parity double-buffering keeps a fast CTA from overwriting a slot a slow one
+    // still polls (it cannot publish write w+2 before every CTA has published w+1, i.e. has finished reading w).
+    const unsigned tag = (unsigned)((w >> 1) + 1) & 0xFFFFu;
+    unsigned long long* slots = reinterpret_cast<unsigned long long*>(a.partial) + (size_t)(w & 1) * G;
+    if (threadIdx.x == 0) {
+      u64 b = 0ull;
+      for (int i = 0; i < 8; ++i) b = warp_best[i] > b ? warp_best[i] : b;
+      // b = 0 (no centroid in this slice can win: empty slice) still publishes a tagged, lowest-ranking slot
+      const u64 packed = (b & 0xFFFFFFFF00000000ull) | ((b & 0xFFFFull) << 16) | tag;
+      __stcg(slots + blockIdx.x, (unsigned long long)packed);
+    }
+    if (w + 1 < a.n_writes) load_row(w + 1, xs2 + (size_t)((w + 1) & 1) * a.d);     // overlaps the wait below
+    u64 m = 0ull;
+    for (int i = threadIdx.x; i < G; i += blockDim.x) {
+      unsigned long long p;
+      unsigned polls = 0;
+      while ((((p = *reinterpret_cast<volatile unsigned long long*>(slots + i))) & 0xFFFFull) != tag)
+        if (++polls > (1u << 27)) __trap();           // a lost CTA must not hang the GPU
+      m = (u64)p > m ? (u64)p : m;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      const u64 other = __shfl_xor_sync(0xffffffffu, m, o);
+      m = other > m ? other : m;
+    }
+    __syncthreads();                                    // warp_best was read by thread 0 above
+    if (lane == 0) warp_best[warp] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      u64 b = 0ull;
+      for (int i = 0; i < 8; ++i) b = warp_best[i] > b ? warp_best[i] : b;
+      s_arg = (int)(0xFFFFu - (unsigned)((b >> 16) & 0xFFFFull));     // key_row(): row = 0xFFFFFFFF - low word
+    }
+    __syncthreads();
+    const int c = s_arg;
+    if (c >= c0 && c < c1) {                            // owner: :225-230
+      const float cnt = a.counts[c] + 1.0f;
+      const float eta = 1.0f / fmaxf(cnt, 1.0f);
+      float* cp = a.in_smem ? cs + (size_t)(c - c0) * a.d : a.cent + (size_t)c * a.d;
+      for (int e = threadIdx.x; e < a.d; e += blockDim.x) {
+        const float old = a.in_smem ? cp[e] : __ldcg(cp + e);
+        cp[e] = __fadd_rn(__fmul_rn(1.0f - eta, old), __fmul_rn(eta, xs[e]));
+      }
+      __syncthreads();                                  // everyone has read counts[c]
+      if (threadIdx.x == 0) {
+        a.counts[c] = cnt;
+        a.cid_i32[row] = c;
+        if (a.cid_f32) a.cid_f32[(size_t)row * a.cid_stride] = (float)c;
+      }
+    }
+    __syncthreads();
+  }
+  if (a.in_smem)
+    for (int i = threadIdx.x; i < (c1 - c0) * a.d; i += blockDim.x) a.cent[(size_t)c0 * a.d + i] = cs[i];
 }
 
 void launch_row_sq_norms(const float* x, int n, int d, float* out, cudaStream_t st) {
@@ -424,7 +531,36 @@ extern "C" int aura_online_assign(const void* rows, int dtype, int d, int64_t fi
   cudaStream_t st = (cudaStream_t)stream;
   unsigned* counter = reinterpret_cast<unsigned*>(workspace);
   u64* partial = reinterpret_cast<u64*>(reinterpret_cast<unsigned char*>(workspace) + 256);
-  AURA_CUDA_OK(cudaMemsetAsync(counter, 0, 4, st));
+  AURA_CUDA_OK(cudaMemsetAsync(counter, 0, 8, st));
+  // a run of writes: one cooperative launch with the centroids stationary in shared memory (AURA_ONLINE_RUN=0: off)
+  static int coop = -1;
+  if (coop < 0) {
+    int dev = 0, v = 0;
+    coop = (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&v, cudaDevAttrCooperativeLaunch, dev) == cudaSuccess && v) ? 1 : 0;
+    if (const char* e = getenv("AURA_ONLINE_RUN")) coop = coop && atoi(e) != 0;
+  }
+  if (coop && n_writes >= 4 && n_live <= 0xFFFF) {    // 16-bit centroid field in the published slots
+    AURA_CUDA_OK(cudaMemsetAsync(workspace, 0, aura_online_assign_workspace_bytes(), st));
+    OnlineRunArgs a;
+    a.rows = rows; a.first_row = first_row; a.n_writes = n_writes; a.d = d; a.n_live = n_live;
+    a.cent = centroids; a.counts = counts; a.cid_i32 = cid_i32; a.cid_f32 = cid_f32; a.cid_stride = cid_stride;
+    a.partial = partial; a.barrier = reinterpret_cast<unsigned long long*>(workspace);
+    int G = sm_count();
+    if (G > n_live) G = n_live;
+    a.per = (n_live + G - 1) / G;
+    G = (n_live + a.per - 1) / a.per;
+    size_t smem = ((size_t)a.per * d + 2 * (size_t)d) * 4;
+    a.in_smem = smem + 1024 <= (size_t)max_smem_optin();
+    if (!a.in_smem) smem = 2 * (size_t)d * 4;
+    if (smem + 1024 <= (size_t)max_smem_optin()) {
+      void* kern = dtype == AURA_BF16 ? (void*)online_assign_run_kernel<true> : (void*)online_assign_run_kernel<false>;
+      AURA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      void* params[] = {(void*)&a};
+      AURA_CUDA_OK(cudaLaunchCooperativeKernel(kern, dim3(G), dim3(256), params, smem, st));
+      note_launches(1);
+      return AURA_OK;
+    }
+  }
   int grid = (n_live + 7) / 8;
   const int cap = sm_count() * 2;
   if (grid > cap) grid = cap;
