@@ -565,7 +565,14 @@ struct GemmPlan {
 static int list_len(int k, bool rescore) {
   // K6 keeps a margin of >= 14 candidates beyond k for the certified re-score; K7 needs exactly k
   // K6 keeps a margin of >= 14 candidates beyond k for the certified re-score, in up to GT_MAX_ROUNDS rounds of 32
-  if (rescore) return k + 14 <= GT_MAX_L ? GT_L : 0;
+  // the list is the epilogue's only non-trivial cost (an insertion is ~6 instructions per slot, and lists fill while the
+  // pipeline is still starting): k <= 10 - the reference's default k = 5 and the bench's k = 10 - keeps 24 instead of 32
+  if (rescore) {
+    static int small_ok = -1;
+    if (small_ok < 0) { const char* e = getenv("AURA_GEMM_L24"); small_ok = (e == nullptr || atoi(e) != 0) ? 1 : 0; }
+    if (small_ok && k + 14 <= GT_L_SMALL) return GT_L_SMALL;
+    return k + 14 <= GT_MAX_L ? GT_L : 0;
+  }
   return k <= GT_L ? GT_L : 0;
 }
 
@@ -580,6 +587,7 @@ static bool make_gemm_plan(long long n_a_rows, long long n_b_rows, int d, int el
   p->two_cta = 0;
   if (const char* e = getenv("AURA_GEMM_2CTA")) p->two_cta = (atoi(e) != 0 && (sms % 2) == 0 && force_L == 0 && p->n_atiles >= 2) ? 1 : 0;
   if (p->two_cta) p->n_atiles = (p->n_atiles + 1) / 2 * 2;
+  if (p->two_cta && p->L == GT_L_SMALL) p->L = GT_L;             // the pair kernel is instantiated for 32 only
   const int units = p->two_cta ? sms / 2 : sms;                 // schedulable units (pairs or CTAs)
   const int work_rows = p->two_cta ? p->n_atiles / 2 : p->n_atiles;
   int groups = units / work_rows;
@@ -635,6 +643,7 @@ static int run_gemm_topk(const void* a_mat, long long n_a_rows, long long a_row_
   void (*kern)(const CUtensorMap, const CUtensorMap, const GemmTopkArgs);
   const bool ceil = ceil_keys != nullptr;
   if (p.L == GT_L_ASSIGN) kern = bf16 ? gemm_topk_kernel<false, GT_L_ASSIGN, false> : gemm_topk_kernel<true, GT_L_ASSIGN, false>;
+  else if (p.L == GT_L_SMALL && !ceil && !p.two_cta) kern = bf16 ? gemm_topk_kernel<false, GT_L_SMALL, false> : gemm_topk_kernel<true, GT_L_SMALL, false>;
   else if (p.two_cta) kern = ceil ? (bf16 ? gemm_topk2_kernel<false, GT_L, true> : gemm_topk2_kernel<true, GT_L, true>)
                                   : (bf16 ? gemm_topk2_kernel<false, GT_L, false> : gemm_topk2_kernel<true, GT_L, false>);
   else kern = ceil ? (bf16 ? gemm_topk_kernel<false, GT_L, true> : gemm_topk_kernel<true, GT_L, true>)

@@ -193,6 +193,7 @@ static constexpr int GT_MAX_STAGES = 4;
 static constexpr int GT_THREADS = 192;       // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
 static constexpr int GT_L = 32;             // per-row list length kept by the epilogue (registers)
 static constexpr int GT_L_ASSIGN = 4;       // list length of the nearest-centroid variant
+static constexpr int GT_L_SMALL = 24;       // exact search with k <= 10 (k + 14 margin)
 static constexpr int GT_MAX_L = 128;           // most candidates a query can carry into the exact re-score (4 rounds x 32)
 static constexpr int GT_MAX_ROUNDS = GT_MAX_L / GT_L;
 
