@@ -88,6 +88,13 @@ class ShardedBank:
         any_flag = gathered[:, :, 2 * k].sum(dim=0)               # identical on every rank
         return out_idx, out_score, any_flag
 
+    def graphed(self, batch: int, k: int, allow_collective: bool = False) -> "GraphedSearch":
+        """A CUDA-graph capture of `search_deferred` for a fixed (batch, k); see `GraphedSearch`."""
+        if self.world > 1 and not allow_collective:
+            raise RuntimeError("GraphedSearch with world > 1 captures an NCCL collective (unverified here); "
+                               "pass allow_collective=True to try")
+        return GraphedSearch(self, batch, k)
+
     def search(self, queries: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
         """queries [B,d] identical on all ranks -> (global rows int64 [B,k], scores fp32 [B,k]) on all ranks."""
         return self.finalize(self.search_deferred(queries, k))
@@ -118,6 +125,10 @@ class ShardedBank:
     def finalize(self, h) -> Tuple[torch.Tensor, torch.Tensor]:
         idx, score, queries, k = h["idx"], h["score"], h["queries"], h["k"]
         if h["local"]:
+            if "event" in h:                              # graphed search: the flag count is already on its way
+                h["event"].synchronize()
+                if int(h["n_bad"][0]) == 0:
+                    return idx, score
             if h["flags"] is not None:
                 self._fixup(h["flags"], idx, score, queries, k)
             return idx, score
@@ -139,6 +150,64 @@ class ShardedBank:
             idx[bad] = i3
             score[bad] = s3
         return idx, score
+
+
+class GraphedSearch:
+    """One `ShardedBank` search of a fixed (batch, k) captured as a CUDA graph: local top-k kernels, pack, the NCCL
+    all-gather and the merge replay as ONE launch, so a step is no longer paced by the host issuing ~7 launches (at 8
+    GPUs a 1M-row bank leaves ~0.3 ms of kernel time per step, less than the launch gaps it replaces).
+
+    Verified on one GPU (bench: 2.34 -> 2.28 ms per 1024-query step).  With world > 1 the capture includes the NCCL
+    all-gather; on this image (torch 2.11, NCCL 2.28.9) a 2-rank capture hung, so `ShardedBank.graphed` refuses
+    world > 1 unless `allow_collective=True`.
+
+    The graph owns static buffers: `launch(queries)` copies the queries in, replays, and returns a handle for
+    `ShardedBank.finalize`; results stay valid until the next `launch` of the SAME object - keep two objects and alternate
+    them to have two searches in flight."""
+
+    def __init__(self, bank: "ShardedBank", batch: int, k: int, warmup: int = 3):
+        dev = bank.rows.device
+        if dev.type != "cuda":
+            raise RuntimeError("GraphedSearch needs a CUDA bank")
+        self.bank, self.k = bank, int(k)
+        self.q = torch.zeros(batch, bank.rows.shape[1], device=dev, dtype=torch.float32)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):          # communicator, workspaces and kernel attributes exist before capture
+                self._enqueue()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        lib = bank._ops._lib.load() if bank._ops is not None else None
+        n0 = lib.aura_kernel_launches() if lib is not None else 0
+        with torch.cuda.graph(self.graph, stream=side, capture_error_mode="thread_local"):
+            self.idx, self.score, self.flag, self.n_bad_dev = self._enqueue()
+        self.kernels_per_replay = int(lib.aura_kernel_launches() - n0) if lib is not None else 0   # library kernels in the graph
+        self._n_bad = torch.empty(1, dtype=torch.int64).pin_memory()
+
+    def _enqueue(self):
+        b = self.bank
+        res = b._local_search(self.q, self.k)
+        idx, score = res[0], res[1]
+        flags = res[2] if len(res) > 2 else None
+        if b.world > 1:
+            idx, score, flags = b._gather_merge(idx, score, self.k, flags)
+        if flags is None:
+            flags = torch.zeros(idx.shape[0], dtype=torch.int32, device=idx.device)
+        return idx, score, flags, (flags != 0).sum().reshape(1)
+
+    def launch(self, queries: torch.Tensor):
+        self.q.copy_(queries, non_blocking=True)
+        self.graph.replay()
+        self._n_bad.copy_(self.n_bad_dev, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.q.device))
+        if self.bank.world == 1:
+            return {"idx": self.idx, "score": self.score, "flags": self.flag, "queries": self.q, "k": self.k,
+                    "local": True, "n_bad": self._n_bad, "event": ev}
+        return {"idx": self.idx, "score": self.score, "any_flag": self.flag, "queries": self.q, "k": self.k,
+                "local": False, "checked": False, "n_bad": self._n_bad, "event": ev}
 
 
 class ShardedIndex:

@@ -253,9 +253,26 @@ def run_ours(args):
     # ---- leg 1: resident inputs.  Search i is finalised (certification flags checked) after search i+1 has been
     # enqueued, so the host's launch work overlaps the GPU's; every search is finalised inside the timed region.
     pending = [None]
+    # the step as one CUDA-graph launch (kernels + NCCL all-gather + merge), two graphs alternating so that two searches
+    # are in flight.  N=1 only: with the NCCL all-gather inside the capture the 2-rank run hung on this image (torch 2.11,
+    # NCCL 2.28.9), so sharded runs keep the eager launches; --no-graph or a failed capture does the same at N=1
+    graphs = None
+    if world == 1 and not args.no_graph:
+        try:
+            graphs = [shard.graphed(B, TOPK) for _ in range(2)]
+        except Exception as e:                               # noqa: BLE001 - report and measure the eager path instead
+            graphs = None
+            sys.stderr.write(f"[bench] CUDA-graph capture failed, using eager launches: {e}\n")
+    replays = [0]
+
+    def enqueue(q):
+        if graphs is None:
+            return shard.search_deferred(q, TOPK)
+        replays[0] += 1
+        return graphs[replays[0] % 2].launch(q)
 
     def step_resident(i):
-        h = shard.search_deferred(q_dev[(W + i) % n_batches], TOPK)
+        h = enqueue(q_dev[(W + i) % n_batches])
         if pending[0] is not None:
             shard.finalize(pending[0])
         pending[0] = h
@@ -268,9 +285,9 @@ def run_ours(args):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    l0 = lib.aura_kernel_launches()
+    l0, r0 = lib.aura_kernel_launches(), replays[0]
     ms = cuda_time_steps(step_resident, K, sync, barrier)
-    launches = lib.aura_kernel_launches() - l0
+    launches = lib.aura_kernel_launches() - l0 + (replays[0] - r0) * (graphs[0].kernels_per_replay if graphs else 0)
 
     # ---- leg 2: end to end through the public API, host buffers.  Every step: H2D of its pinned query batch, search,
     # D2H of rows + scores (+ certification flags).  N=1 keeps two batches in flight on two streams through the
@@ -327,7 +344,7 @@ def run_ours(args):
     else:
         def step_e2e(i):
             q = q_host[(W + i) % n_batches]          # pinned host memory; the API call does the H2D copy
-            idx, score = shard.search(q, TOPK)
+            idx, score = shard.finalize(enqueue(q)) if graphs else shard.search(q, TOPK)
             out_idx_host.copy_(idx, non_blocking=True)
             out_score_host.copy_(score, non_blocking=True)
             sync()
@@ -458,7 +475,8 @@ def main():
     ap.add_argument("--cpu-queries", type=int, default=24)
     ap.add_argument("--ref-queries-per-step", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--kernel-name", default="gemm_topk_kernel<tf32> (tcgen05 M128 N256, fused top-32) + exact fp32 re-score")
+    ap.add_argument("--no-graph", action="store_true", help="N=1: eager launches instead of one CUDA-graph launch per step")
+    ap.add_argument("--kernel-name", default="gemm_topk_kernel<tf32> (tcgen05 M128 N256, fused top-24) + exact fp32 re-score")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

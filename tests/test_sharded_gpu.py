@@ -112,3 +112,27 @@ def test_pack_and_merge_packed_equal_the_reference_merge():
     ref_s, ref_i = merge_topk(s2.permute(1, 0, 2).reshape(B, G * k), ids.permute(1, 0, 2).reshape(B, G * k), k)
     assert torch.equal(oi.cpu(), ref_i) and torch.equal(os_.cpu(), ref_s)
     assert fl.cpu().tolist() == [1 if b == 11 else 0 for b in range(B)]
+
+
+def test_graphed_search_equals_eager_search():
+    """`ShardedBank.graphed` (the whole search captured as one CUDA graph, static buffers) returns exactly what the eager
+    search returns, for several query batches replayed through two alternating graphs."""
+    from aura_snn_rag_b200 import ops
+    from aura_snn_rag_b200.sharded import ShardedBank
+    g = torch.Generator().manual_seed(5)
+    rows = torch.randn(20000, 128, generator=g).cuda()
+    bank = ShardedBank(rows, 1000, scale=ops.row_inv_norms(rows))
+    graphs = [bank.graphed(64, 10) for _ in range(2)]
+    assert graphs[0].kernels_per_replay >= 3          # normalise + tensor-core scoring + finish are inside the graph
+    pending = None
+    for i in range(5):
+        q = torch.randn(64, 128, generator=g).cuda()
+        ref_idx, ref_sc = bank.search(q, 10)
+        h = graphs[i % 2].launch(q)
+        if pending is not None:                       # results of the other graph are still intact
+            idx_p, sc_p = bank.finalize(pending[0])
+            assert torch.equal(idx_p, pending[1]) and torch.equal(sc_p, pending[2])
+        idx, sc = bank.finalize(h)
+        assert torch.equal(idx, ref_idx) and torch.equal(sc, ref_sc)
+        assert int(idx.min()) >= 1000                 # global row ids
+        pending = (h, ref_idx, ref_sc)
