@@ -11,9 +11,12 @@
 //           lists stay an index (int32 row ids) and the bank keeps the reference's insertion order.
 //           Gathers are 16-byte cp.async (LDGSTS) copies issued by 4 producer warps into the SWIZZLE_128B layout
 //           the UMMA descriptors expect (8 lanes cover one 128-byte row slab; chunk j of row r lands at
-//           r*128 + ((j ^ (r & 7)) << 4)), multi-stage via commit/wait groups, then fence.proxy.async + mbarrier
-//           arrive.  (TMA tile::gather4 gives the same layout - scripts/exp/gather4_test.cu - but measured only
-//           ~5 GB/s per SM on B200: 57 ms per C4 batch against 6 ms of list bytes at the HBM roofline.)
+//           r*128 + ((j ^ (r & 7)) << 4)); a stage's mbarrier receives each thread's arrival when its copies have
+//           landed (cp.async.mbarrier.arrive.noinc), the MMA thread adds fence.proxy.async.  (TMA tile::gather4 gives
+//           the same layout - scripts/exp/gather4_test.cu - but measured only ~5 GB/s per SM on B200: 57 ms per C4
+//           batch against 6 ms of list bytes at the HBM roofline.)
+//           Optional list-major mode (rows_by_list: a resident copy of the bank in CSR order made by
+//           aura_ivf_pack_lists): the B tile is one TMA box per k-block instead of 2048 gathered pieces.
 //   MMA / TMEM / epilogue as in gemm_topk.cu (tf32 from an fp32 bank, bf16 from a bf16 bank, per-row top-32 in
 //   registers), one partial list per (pair, chunk)
 // and a finish kernel merges a query's partial lists, re-scores the 32 best in exact fp32 and certifies the top-k
@@ -28,7 +31,6 @@ static constexpr int IB_CH_TILES = 8;                       // column tiles per 
 static constexpr int IB_CH_ROWS = IB_CH_TILES * GT_BN;      // 2048 list rows per item
 static constexpr int IB_MERGE_CAP = 2048;                   // keys the finish kernel sorts at a time
 static constexpr int IB_THREADS = 288;                      // warp 0 MMA, warps 1-4 epilogue, warps 5-8 gather producers
-static constexpr int IB_LOOKAHEAD = 2;                      // stages a producer thread keeps in flight behind the newest
 
 static constexpr int IB_MAX_CHUNKS = 16;                    // chunks per list: long lists get longer chunks, not more of them
 

@@ -88,6 +88,17 @@ class ShardedBank:
         any_flag = gathered[:, :, 2 * k].sum(dim=0)               # identical on every rank
         return out_idx, out_score, any_flag
 
+    def _flag_slot(self):
+        """A pinned scalar + event for the flag count of one search, from a small ring: allocating pinned memory per
+        search costs a cudaHostAlloc (tens of microseconds, serialised across the ranks of a box) on a 0.5 ms step.
+        Up to 8 searches may be pending at once."""
+        if not hasattr(self, "_slots"):
+            self._slots = [(torch.empty(1, dtype=torch.int64).pin_memory(), torch.cuda.Event()) for _ in range(8)]
+            self._slot_next = 0
+        slot = self._slots[self._slot_next % len(self._slots)]
+        self._slot_next += 1
+        return slot
+
     def graphed(self, batch: int, k: int, allow_collective: bool = False) -> "GraphedSearch":
         """A CUDA-graph capture of `search_deferred` for a fixed (batch, k); see `GraphedSearch`."""
         if self.world > 1 and not allow_collective:
@@ -115,9 +126,8 @@ class ShardedBank:
         h = {"idx": out_idx, "score": out_score, "any_flag": any_flag, "queries": queries, "k": k, "local": False,
              "checked": flags is None}
         if flags is not None and queries.is_cuda:
-            n_bad = torch.empty(1, dtype=torch.int64).pin_memory()
+            n_bad, ev = self._flag_slot()
             n_bad.copy_((any_flag != 0).sum().reshape(1), non_blocking=True)
-            ev = torch.cuda.Event()
             ev.record(torch.cuda.current_stream(queries.device))
             h["n_bad"], h["event"] = n_bad, ev
         return h
