@@ -58,3 +58,14 @@ def test_sharded_search_two_ranks_gloo(tmp_path):
     assert same[1:].all()
     # query 0 ties rows 7 and n//2+3 exactly: the merge must list the lower global row first
     assert r["idx"][0, 0].item() == 7 and r["idx"][0, 1].item() == n // 2 + 3
+
+
+def test_graphed_search_needs_a_cuda_bank():
+    """`ShardedBank.graphed` captures CUDA kernels: with a CPU bank (injected search / merge) it must refuse loudly."""
+    import pytest
+    import torch
+    from aura_snn_rag_b200.sharded import ShardedBank
+    rows = torch.randn(64, 8)
+    bank = ShardedBank(rows, 0, scale=torch.ones(64), local_search=lambda q, k: (None, None), merge=lambda *a: None)
+    with pytest.raises(RuntimeError):
+        bank.graphed(4, 2)
