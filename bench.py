@@ -164,8 +164,10 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": qps, "unit": "queries/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "C2: 1M x 768 fp32 exact top-10", "rows": N_ROWS, "d": DIM, "k": TOPK,
-                       "batch": per_step},
+            # same workload as our arm (its `config`); one step here is a bounded sample of a 1024-query batch
+            "config": {"workload": "C2: 1M x 768 fp32 exact brute-force top-10, batch of B queries per step",
+                       "rows": N_ROWS, "d": DIM, "k": TOPK, "batch": args.batch, "sharding": "none (host cores)",
+                       "sample_queries_per_step": per_step},
             "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": threads, "kind": "port",
                              "sample": f"{per_step} single-query retrieve_similar_memories calls per step through the "
                                        "oracle port of hippocampal.py:245-319 (the reference has no batched entry "
