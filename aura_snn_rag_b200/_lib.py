@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_PKG, "libaura_hippo.so")
 AURA_F32, AURA_BF16 = 0, 1
 AURA_MAX_K = 128
 AURA_MAX_NPROBE = 128
+AURA_IVF_EMPTY_OK = 1
 
 _p = C.c_void_p
 _i = C.c_int
@@ -46,9 +47,9 @@ SIGNATURES = {
     "aura_ivf_coarse_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "aura_ivf_coarse": (_i, [_p, _i, _i, _p, _i, _i, _p, _p, _sz, _p]),
     "aura_ivf_search_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
-    "aura_ivf_search": (_i, [_p, _i, _i64, _i, _p, _i, _p, _i, _i, _p, _p, _p, _p, _i, _i64, _p, _p, _p, _p, _sz, _p]),
+    "aura_ivf_search": (_i, [_p, _i, _i64, _i, _p, _i, _p, _i, _i, _p, _p, _p, _p, _i, _i64, _i, _p, _p, _p, _p, _sz, _p]),
     "aura_ivf_search_batch_workspace_bytes": (_sz, [_i, _i, _i, _i]),
-    "aura_ivf_search_batch": (_i, [_p, _i, _i64, _i, _p, _i, _p, _i, _i, _p, _p, _p, _p, _p, _i, _i64, _f, _p, _p, _p, _p, _sz, _p]),
+    "aura_ivf_search_batch": (_i, [_p, _i, _i64, _i, _p, _i, _p, _i, _i, _p, _p, _p, _p, _p, _i, _i64, _i, _f, _p, _p, _p, _p, _sz, _p]),
     "aura_ivf_pack_lists": (_i, [_p, _i, _i, _p, _i64, _p, _p]),
     "aura_ivf_search_batch_items": (_i, [_p, _i, _i, _i, _i, _p, _p, _p]),
     "aura_batch_topk_workspace_bytes": (_sz, [_i64, _i, _i, _i, _i]),
@@ -56,7 +57,7 @@ SIGNATURES = {
     "aura_allpairs_topk_workspace_bytes": (_sz, [_i64, _i64, _i, _i, _i]),
     "aura_allpairs_topk": (_i, [_p, _i, _i64, _i, _i64, _i64, _p, _i, _p, _p, _p, _sz, _p]),
     "aura_topk_merge": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _p]),
-    "aura_pack_topk": (_i, [_p, _p, _p, _i, _i, _p, _p]),
+    "aura_pack_topk": (_i, [_p, _p, _p, _i, _i, _p, _i64, _p, _p]),
     "aura_topk_merge_packed": (_i, [_p, _i, _i, _i, _p, _p, _p, _p]),
     "aura_gather_rows": (_i, [_p, _i, _i, _p, _i64, _p, _p]),
 }

@@ -64,7 +64,11 @@ def build(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write(l)
     objs = [j[1] for j in jobs]
     if force or any(j[2] for j in jobs) or not os.path.exists(LIB):
-        cmd = [nvcc, *ARCH, "-shared", "-o", LIB, *objs, "-lcudart_static", "-ldl", "-lrt", "-lpthread"]
+        # the SHARED CUDA runtime: inside a torch process the library then binds to the libcudart.so.12 torch already
+        # loaded (one runtime per process), and the .so does not embed the runtime's entry-point table
+        cudalib = os.path.join(os.path.dirname(os.path.dirname(nvcc)), "lib64")
+        cmd = [nvcc, *ARCH, "-shared", "--cudart", "shared", "-o", LIB, *objs, "-L" + cudalib,
+               "-Xlinker", "-rpath=" + cudalib, "-ldl", "-lrt", "-lpthread"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

@@ -25,13 +25,14 @@ int  cuda_fail(cudaError_t e, const char* what);
 int  sm_count();
 int  max_smem_optin();
 void note_launches(int n);  // kernels launched by this library in this process (aura_kernel_launches)
+int  env_int(const char* name, int dflt);  // tuning knob from the environment (callers cache it in a function-local static)
 
 // scan_topk.cu: shared launcher of aura_scan_topk (probes == nullptr) and aura_ivf_search
 size_t scan_workspace_bytes(int n_queries, int k);
 int launch_scan(const void* rows, int dtype, long long n_rows, int d, const float* queries, int n_queries,
                 const float* scale, const float* bias, int k, long long row_base, long long* out_idx, float* out_score,
                 void* workspace, const long long* probes, int nprobe, int n_lists, const int* list_offsets,
-                const int* list_rows, long long expected_rows, cudaStream_t st);
+                const int* list_rows, long long expected_rows, cudaStream_t st, int empty_ok);
 
 // kmeans.cu: out[i] = ||x_i||^2 for n fp32 rows
 void launch_row_sq_norms(const float* x, int n, int d, float* out, cudaStream_t st);

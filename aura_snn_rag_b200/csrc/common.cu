@@ -2,6 +2,7 @@
 // version.  (C ABI: include/aura_hippo.h.)
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <atomic>
 
 #include "aura_common.cuh"
@@ -18,6 +19,11 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
 }
 
 int cuda_fail(cudaError_t e, const char* what) {

@@ -563,13 +563,11 @@ struct GemmPlan {
 };
 
 static int list_len(int k, bool rescore) {
-  // K6 keeps a margin of >= 14 candidates beyond k for the certified re-score; K7 needs exactly k
   // K6 keeps a margin of >= 14 candidates beyond k for the certified re-score, in up to GT_MAX_ROUNDS rounds of 32
   // the list is the epilogue's only non-trivial cost (an insertion is ~6 instructions per slot, and lists fill while the
   // pipeline is still starting): k <= 10 - the reference's default k = 5 and the bench's k = 10 - keeps 24 instead of 32
   if (rescore) {
-    static int small_ok = -1;
-    if (small_ok < 0) { const char* e = getenv("AURA_GEMM_L24"); small_ok = (e == nullptr || atoi(e) != 0) ? 1 : 0; }
+    static const int small_ok = env_int("AURA_GEMM_L24", 1);
     if (small_ok && k + 14 <= GT_L_SMALL) return GT_L_SMALL;
     return k + 14 <= GT_MAX_L ? GT_L : 0;
   }
@@ -585,7 +583,8 @@ static bool make_gemm_plan(long long n_a_rows, long long n_b_rows, int d, int el
   const int sms = sm_count();
   // CTA pairs (cta_group::2) when there are at least two A tiles of real work; AURA_GEMM_2CTA=0/1 overrides
   p->two_cta = 0;
-  if (const char* e = getenv("AURA_GEMM_2CTA")) p->two_cta = (atoi(e) != 0 && (sms % 2) == 0 && force_L == 0 && p->n_atiles >= 2) ? 1 : 0;
+  static const int env_2cta = env_int("AURA_GEMM_2CTA", 0), env_groups = env_int("AURA_GEMM_GROUPS", 0), env_stages = env_int("AURA_GEMM_STAGES", 0);
+  if (env_2cta) p->two_cta = ((sms % 2) == 0 && force_L == 0 && p->n_atiles >= 2) ? 1 : 0;
   if (p->two_cta) p->n_atiles = (p->n_atiles + 1) / 2 * 2;
   if (p->two_cta && p->L == GT_L_SMALL) p->L = GT_L;             // the pair kernel is instantiated for 32 only
   const int units = p->two_cta ? sms / 2 : sms;                 // schedulable units (pairs or CTAs)
@@ -593,7 +592,7 @@ static bool make_gemm_plan(long long n_a_rows, long long n_b_rows, int d, int el
   int groups = units / work_rows;
   if (groups < 1) groups = 1;
   if (groups > p->n_ctiles) groups = p->n_ctiles;
-  if (const char* e = getenv("AURA_GEMM_GROUPS")) { const int v = atoi(e); if (v >= 1 && v <= p->n_ctiles) groups = v; }
+  if (env_groups >= 1 && env_groups <= p->n_ctiles) groups = env_groups;
   if (force_groups) groups = force_groups;
   p->n_groups = groups;
   const long long items = (long long)work_rows * groups;
@@ -612,7 +611,7 @@ static bool make_gemm_plan(long long n_a_rows, long long n_b_rows, int d, int el
     const size_t fixed = 2 * GT_BN * 8 + (2 * GT_MAX_STAGES + 4) * 8 + 16;
     stages = (int)((cap - fixed) / GT_STAGE_BYTES);
     if (stages > GT_MAX_STAGES) stages = GT_MAX_STAGES;
-    if (const char* e = getenv("AURA_GEMM_STAGES")) { const int v = atoi(e); if (v >= 2 && v <= stages) stages = v; }
+    if (env_stages >= 2 && env_stages <= stages) stages = env_stages;
     p->smem = (size_t)stages * GT_STAGE_BYTES + fixed + 1024;
   }
   if (stages < 2) return false;
@@ -743,7 +742,7 @@ __global__ void __launch_bounds__(256) assign_finish_kernel(const u64* __restric
 bool tc_assign_supported(const void* rows, int dtype, long long n_rows, int d, int n_cent) {
   const int eb = dtype == AURA_BF16 ? 2 : 4;
   if (((size_t)d * eb) % 16 != 0 || (reinterpret_cast<uintptr_t>(rows) & 15) != 0 || (d % 4) != 0) return false;
-  if (const char* e = getenv("AURA_ASSIGN_TC")) return atoi(e) != 0;
+  if (const char* e = getenv("AURA_ASSIGN_TC")) return atoi(e) != 0;   // test switch, flipped between calls (once per ABI call, not per launch)
   return (double)n_rows * n_cent >= 1.0e8 && n_cent >= 64;    // below that the exact SIMT kernel is fast enough
 }
 
@@ -789,7 +788,7 @@ int tc_assign(const void* rows, int dtype, long long n_rows, int d, const float*
 bool tc_coarse_supported(const float* queries, int n_queries, int d, const float* cent, int n_cent, int nprobe) {
   if ((d % 4) != 0 || ((reinterpret_cast<uintptr_t>(queries) | reinterpret_cast<uintptr_t>(cent)) & 15) != 0) return false;
   if (nprobe > GT_MAX_L) return false;
-  if (const char* e = getenv("AURA_COARSE_TC")) return atoi(e) != 0;
+  if (const char* e = getenv("AURA_COARSE_TC")) return atoi(e) != 0;   // test switch, flipped between calls
   return n_queries >= 64 && (double)n_queries * n_cent >= 2.5e5;
 }
 

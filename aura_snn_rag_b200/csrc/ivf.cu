@@ -158,7 +158,7 @@ extern "C" size_t aura_ivf_search_workspace_bytes(int n_queries, int d, int n_ce
 extern "C" int aura_ivf_search(const void* rows, int dtype, int64_t n_rows, int d, const float* queries, int n_queries,
                                const float* centroids, int n_centroid_rows, int nprobe, const int32_t* list_offsets,
                                const int32_t* list_rows, const float* scale, const float* bias, int k, int64_t row_base,
-                               int64_t* out_idx, float* out_score, int64_t* out_probes, void* workspace,
+                               int flags, int64_t* out_idx, float* out_score, int64_t* out_probes, void* workspace,
                                size_t workspace_bytes, void* stream) {
   AURA_REQUIRE(dtype == AURA_F32 || dtype == AURA_BF16, AURA_ERR_INVALID_ARG, "aura_ivf_search: bad dtype %d", dtype);
   AURA_REQUIRE(n_rows >= 1 && n_rows < 0x7fffffffll && d >= 1 && n_queries >= 1 && n_centroid_rows >= 1,
@@ -182,5 +182,5 @@ extern "C" int aura_ivf_search(const void* rows, int dtype, int64_t n_rows, int 
   long long expect = (long long)((double)n_rows * nprobe / n_centroid_rows) + 1;
   return launch_scan(rows, dtype, n_rows, d, queries, n_queries, scale, bias, k, row_base,
                      reinterpret_cast<long long*>(out_idx), out_score, scan_ws, probes, nprobe, n_centroid_rows,
-                     list_offsets, list_rows, expect, st);
+                     list_offsets, list_rows, expect, st, (flags & AURA_IVF_EMPTY_OK) ? 1 : 0);
 }

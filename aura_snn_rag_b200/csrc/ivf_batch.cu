@@ -439,6 +439,7 @@ struct IvfFinishArgs {
   const void* rows; int bf16; int d; const float* qn; const float* scale; const float* bias; float eps;
   int k; long long row_base; int spread, chunk_major;
   u64* cand; u64* ceil_out; int round; int* force_flag;   // multi-round mode (see gemm_topk.cu)
+  int empty_ok;             // a query without candidates is a valid empty result (row-sharded callers), not a hand-back
   long long* out_idx; float* out_score; int* uncertain;
 };
 
@@ -510,7 +511,7 @@ __global__ void __launch_bounds__(128) ivf_finish_kernel(const IvfFinishArgs f) 
     for (int i = threadIdx.x; i < GT_L; i += blockDim.x) f.cand[(size_t)b * GT_MAX_L + f.round * GT_L + i] = keys[i];
     if (threadIdx.x == 0) {
       f.ceil_out[b] = keys[GT_L - 1];
-      if (f.round == 0) f.force_flag[b] = (overflow || keys[0] == 0ull) ? 1 : 0;
+      if (f.round == 0) f.force_flag[b] = (overflow || (keys[0] == 0ull && !f.empty_ok)) ? 1 : 0;
     }
     return;
   }
@@ -522,7 +523,7 @@ __global__ void __launch_bounds__(128) ivf_finish_kernel(const IvfFinishArgs f) 
   rescore_and_write(keys, n2, ex, ra);
   // no candidate at all (every probed list empty -> the reference scans all rows, hippocampal.py:269-270) or a
   // work table that did not fit: hand the query back to the per-query path
-  if (threadIdx.x == 0 && (overflow || keys[0] == 0ull)) f.uncertain[b] = 1;
+  if (threadIdx.x == 0 && (overflow || (keys[0] == 0ull && !f.empty_ok))) f.uncertain[b] = 1;
 }
 
 static size_t a256(size_t v) { return (v + 255) / 256 * 256; }
@@ -592,7 +593,7 @@ extern "C" size_t aura_ivf_search_batch_workspace_bytes(int n_queries, int d, in
 extern "C" int aura_ivf_search_batch(const void* rows, int dtype, int64_t n_rows, int d, const float* queries, int n_queries,
                                      const float* centroids, int n_centroid_rows, int nprobe, const int32_t* list_offsets,
                                      const int32_t* list_rows, const void* rows_by_list, const float* scale, const float* bias,
-                                     int k, int64_t row_base, float eps, int64_t* out_idx, float* out_score,
+                                     int k, int64_t row_base, int flags, float eps, int64_t* out_idx, float* out_score,
                                      int32_t* out_uncertain, void* workspace, size_t workspace_bytes, void* stream) {
   AURA_REQUIRE(dtype == AURA_F32 || dtype == AURA_BF16, AURA_ERR_INVALID_ARG, "aura_ivf_search_batch: bad dtype %d", dtype);
   AURA_REQUIRE(n_rows >= 1 && n_rows < 0x7fffffffll && d >= 1 && n_queries >= 1 && n_centroid_rows >= 1, AURA_ERR_INVALID_ARG,
@@ -636,10 +637,13 @@ extern "C" int aura_ivf_search_batch(const void* rows, int dtype, int64_t n_rows
   // AURA_IVF_CLUSTER=2|4 launches the CTAs in clusters: the query tiles of one list chunk go to the CTAs of one cluster,
   // which pace each other tile by tile so the chunk is fetched from HBM once.  Measured at BASELINE config 4: within 2 %
   // of the plain launch (the few lists probed by thousands of queries have 32 sibling tiles, not 2-4), so it is off.
-  int cs = 1;
-  if (const char* e = getenv("AURA_IVF_CLUSTER")) cs = atoi(e);
+  static const int env_cs = env_int("AURA_IVF_CLUSTER", 1), env_order = env_int("AURA_IVF_ORDER", 1);
+  static const int env_gthr = env_int("AURA_IVF_GTHR", 1), env_spread = env_int("AURA_IVF_SPREAD", 1);
+  static const int env_l2 = env_int("AURA_IVF_L2HINT", 3), env_polls = env_int("AURA_IVF_SYNC_POLLS", 512);
+  static const int env_grid = env_int("AURA_IVF_GRID", 0);
+  int cs = env_cs;
   if (cs != 1 && cs != 2 && cs != 4) cs = 1;
-  if (const char* e = getenv("AURA_IVF_ORDER")) chunk_major = atoi(e);
+  chunk_major = env_order;
   const int n_pairs = n_queries * nprobe;
   AURA_CUDA_OK(cudaMemsetAsync(counts, 0, (size_t)n_centroid_rows * 4, st));
   ib_pair_hist_kernel<<<(n_pairs + 255) / 256, 256, 0, st>>>(probes, n_pairs, n_centroid_rows, counts);
@@ -664,10 +668,7 @@ extern "C" int aura_ivf_search_batch(const void* rows, int dtype, int64_t n_rows
   a.n_stages = stages;
   a.list_offsets = list_offsets; a.list_rows = list_rows; a.q_off = q_off; a.pair_of_pos = pair_of_pos;
   a.items = items; a.n_items = n_items; a.scale = scale; a.bias = bias; a.partial = partial; a.gthr = gthr; a.pbase = pbase; a.cap_plists = ib_cap_plists(n_queries, nprobe);
-  { const char* e = getenv("AURA_IVF_GTHR"); a.use_gthr = e ? atoi(e) : 1; }
-  { const char* e = getenv("AURA_IVF_SPREAD"); a.spread = e ? atoi(e) : 1; }
-  { const char* e = getenv("AURA_IVF_L2HINT"); a.l2_hint = e ? atoi(e) : 3; }
-  { const char* e = getenv("AURA_IVF_SYNC_POLLS"); a.sync_polls = e ? atoi(e) : 512; }
+  a.use_gthr = env_gthr; a.spread = env_spread; a.l2_hint = env_l2; a.sync_polls = env_polls;
   const size_t smem = (size_t)stages * GT_STAGE_BYTES + fixed + 1024;
   CUtensorMap tmap_lm;
   memset(&tmap_lm, 0, sizeof(tmap_lm));
@@ -695,6 +696,7 @@ extern "C" int aura_ivf_search_batch(const void* rows, int dtype, int64_t n_rows
   f.rows = rows; f.bf16 = bf16 ? 1 : 0; f.d = d; f.qn = qn; f.scale = scale; f.bias = bias; f.eps = eps; f.k = k;
   f.row_base = row_base; f.spread = a.spread; f.chunk_major = chunk_major; f.out_idx = reinterpret_cast<long long*>(out_idx); f.out_score = out_score; f.uncertain = out_uncertain;
   f.cand = rounds > 1 ? cand : nullptr; f.ceil_out = ceil_buf; f.round = 0; f.force_flag = force;
+  f.empty_ok = (flags & AURA_IVF_EMPTY_OK) ? 1 : 0;
   cudaLaunchConfig_t cfg = {};
   cudaLaunchAttribute cattr[1];
   cattr[0].id = cudaLaunchAttributeClusterDimension;
@@ -707,7 +709,7 @@ extern "C" int aura_ivf_search_batch(const void* rows, int dtype, int64_t n_rows
       cfg.gridDim = dim3(n_cl * cs);
     (void)cudaGetLastError();
   }
-  { const char* e = getenv("AURA_IVF_GRID"); if (e && atoi(e) >= cs) cfg.gridDim = dim3(atoi(e) / cs * cs); }
+  if (env_grid >= cs) cfg.gridDim = dim3(env_grid / cs * cs);
   for (int r = 0; r < rounds; ++r) {
     if (r > 0) AURA_CUDA_OK(cudaMemsetAsync(gthr, 0, (size_t)n_queries * 4, st));
     a.ceil_keys = r ? ceil_buf : nullptr;
@@ -754,13 +756,12 @@ extern "C" int aura_ivf_pack_lists(const void* rows, int dtype, int d, const int
 }
 
 extern "C" int aura_ivf_search_batch_items(const void* workspace, int n_queries, int d, int n_centroid_rows, int nprobe,
-                                           int32_t* host_items, int32_t* host_cap, void* stream) {
-  AURA_REQUIRE(workspace && host_items && host_cap, AURA_ERR_INVALID_ARG, "aura_ivf_search_batch_items: null pointer");
+                                           int32_t* items_out, int32_t* host_cap, void* stream) {
+  AURA_REQUIRE(workspace && items_out && host_cap, AURA_ERR_INVALID_ARG, "aura_ivf_search_batch_items: null pointer");
   const int cap = ib_cap_items(n_queries, nprobe, n_centroid_rows);
   const IbLayout L = ib_layout(n_queries, d, n_centroid_rows, nprobe, cap, ivf_coarse_ws_bytes(n_queries, d, n_centroid_rows, nprobe));
-  AURA_CUDA_OK(cudaMemcpyAsync(host_items, reinterpret_cast<const unsigned char*>(workspace) + L.n_items, 4,
-                               cudaMemcpyDeviceToHost, (cudaStream_t)stream));
-  AURA_CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));
+  AURA_CUDA_OK(cudaMemcpyAsync(items_out, reinterpret_cast<const unsigned char*>(workspace) + L.n_items, 4,
+                               cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   *host_cap = cap;
   return AURA_OK;
 }

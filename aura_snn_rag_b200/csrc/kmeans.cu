@@ -4,7 +4,7 @@
 // (per-write nearest-centroid + running mean).
 //
 // This file holds the CUDA-core (fp32 FMA) formulation: exact fp32 arithmetic, any d / C / M.
-// The tcgen05 formulation of the assign GEMM lives in gemm_sm100.cu; this one stays as the
+// The tcgen05 formulation of the assign GEMM lives in gemm_topk.cu (tc_assign); this one stays as the
 // exact-fp32 path for small problems and for re-checking rows whose two best centroids are
 // closer than the tensor-core rounding.
 #include "tc_common.cuh"

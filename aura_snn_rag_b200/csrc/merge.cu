@@ -76,12 +76,13 @@ extern "C" int aura_topk_merge(const float* in_score, const int64_t* in_idx, int
 namespace aura {
 __global__ void __launch_bounds__(256) pack_topk_kernel(const long long* __restrict__ idx, const float* __restrict__ score,
                                                         const int* __restrict__ flags, int n_queries, int k,
+                                                        const long long* __restrict__ id_map, long long id_base,
                                                         long long* __restrict__ payload) {
   const int w = 2 * k + 1;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (long long)n_queries * w; i += (long long)gridDim.x * blockDim.x) {
     const int b = (int)(i / w), j = (int)(i % w);
     long long v;
-    if (j < k) v = idx[(size_t)b * k + j];
+    if (j < k) { v = idx[(size_t)b * k + j]; if (v >= 0) v = id_map ? id_map[v] : v + id_base; }   // local row -> global id
     else if (j < 2 * k) v = (long long)__float_as_int(score[(size_t)b * k + (j - k)]);
     else v = flags ? (long long)flags[b] : 0ll;
     payload[i] = v;
@@ -133,12 +134,13 @@ __global__ void __launch_bounds__(256) merge_packed_kernel(const long long* __re
 }  // namespace aura
 
 extern "C" int aura_pack_topk(const int64_t* idx, const float* score, const int32_t* flags, int n_queries, int k,
-                              int64_t* payload, void* stream) {
+                              const int64_t* id_map, int64_t id_base, int64_t* payload, void* stream) {
   AURA_REQUIRE(n_queries >= 1 && k >= 1 && idx && score && payload, AURA_ERR_INVALID_ARG, "aura_pack_topk: bad argument");
   const long long n = (long long)n_queries * (2 * k + 1);
   int g = (int)((n + 255) / 256);
   if (g > sm_count() * 8) g = sm_count() * 8;
   pack_topk_kernel<<<g, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const long long*>(idx), score, flags, n_queries, k,
+                                                        reinterpret_cast<const long long*>(id_map), (long long)id_base,
                                                         reinterpret_cast<long long*>(payload));
   AURA_CUDA_OK(cudaGetLastError());
   note_launches(1);

@@ -54,6 +54,8 @@ struct ScanArgs {
   const int* list_offsets;  // [n_lists + 1]
   const int* list_rows;     // [n_rows_in_lists]
   int interleave;           // stage g of CTA b = b + it*grid (1) or a contiguous range (0)
+  int empty_ok;             // indirect mode: a query whose probed lists are all empty returns no result (row-sharded
+                            // callers) instead of scanning every row (hippocampal.py:269-270)
 };
 
 // ---- row . query-block dot products out of shared memory ---------------------------------------
@@ -163,7 +165,7 @@ __global__ void __launch_bounds__(32 * (NW + 1), 1) scan_topk_kernel(const ScanA
     }
     __syncthreads();
     const int t = pre[a.nprobe];
-    if (t > 0) { total = t; mapped = true; }  // no candidates -> all live rows, hippocampal.py:269-270
+    if (t > 0 || a.empty_ok) { total = t; mapped = true; }  // no candidates -> all live rows, hippocampal.py:269-270
   } else {
     __syncthreads();
   }
@@ -351,7 +353,7 @@ __global__ void __launch_bounds__(256) scan_topk_generic_kernel(const ScanArgs a
       s_total = t;
     }
     __syncthreads();
-    if (s_total > 0) { total = s_total; mapped = true; }
+    if (s_total > 0 || a.empty_ok) { total = s_total; mapped = true; }
   }
 
   WarpTopK<KPL> tk;
@@ -431,7 +433,7 @@ static void make_plan(long long expected_rows, int d, int dtype, int n_queries, 
     const size_t stage_budget = dtype == AURA_BF16 ? 65536 : 49152;   // bf16 rows: 4 rows per warp step want rpw % 4 == 0
     while (rpw * 2 <= 32 && (size_t)(rpw * 2) * SCAN_NW * row_bytes <= stage_budget) rpw *= 2;
     if (rpw < 2 && (size_t)2 * SCAN_NW * row_bytes * 2 + 8192 <= (size_t)smem_cap) rpw = 2;
-    if (const char* e = getenv("AURA_SCAN_RPW")) rpw = atoi(e);   // tuning knob (experiments only)
+    { static const int v = env_int("AURA_SCAN_RPW", 0); if (v) rpw = v; }   // tuning knob (experiments only)
     if (rpw < 1) rpw = 1;
     if (rpw > 32) rpw = 32;
     p->rows_per_stage = rpw * SCAN_NW;
@@ -444,8 +446,7 @@ static void make_plan(long long expected_rows, int d, int dtype, int n_queries, 
       p->n_stage_bufs = s > SCAN_MAX_STAGES ? SCAN_MAX_STAGES : s;
       // ~150 KB in flight per SM saturates HBM; a deeper ring only took L1 away and measured slower (6.48 vs 6.75 TB/s)
       while (p->n_stage_bufs > 3 && (size_t)p->n_stage_bufs * slot > 163840) --p->n_stage_bufs;
-      if (const char* e = getenv("AURA_SCAN_STAGES")) { const int v = atoi(e); if (v >= 2 && v <= s && v <= SCAN_MAX_STAGES) p->n_stage_bufs = v; }
-      if (const char* e = getenv("AURA_SCAN_STAGES")) { const int v = atoi(e); if (v >= 2 && v <= p->n_stage_bufs) p->n_stage_bufs = v; }
+      { static const int v = env_int("AURA_SCAN_STAGES", 0); if (v >= 2 && v <= s && v <= SCAN_MAX_STAGES) p->n_stage_bufs = v; }
       const size_t ring = (size_t)p->n_stage_bufs * slot;
       size_t mk = 1;  // largest power of two of keys that fits the ring, capped
       while (mk * 2 * 8 <= ring && mk * 2 <= (size_t)FINAL_MERGE_CAP) mk *= 2;
@@ -456,7 +457,7 @@ static void make_plan(long long expected_rows, int d, int dtype, int n_queries, 
       // a CTA should own at least ~2 stages, otherwise launch/merge overhead dominates
       long long g = (n_stages + 1) / 2;
       p->grid = (int)(g < 1 ? 1 : g > sms ? sms : g);
-      if (const char* e = getenv("AURA_SCAN_GRID")) { const int v = atoi(e); if (v >= 1 && v <= sms) p->grid = v; }
+      { static const int v = env_int("AURA_SCAN_GRID", 0); if (v >= 1 && v <= sms) p->grid = v; }
       p->n_qblocks = (n_queries + p->qb - 1) / p->qb;
     }
   }
@@ -475,7 +476,7 @@ template <bool BF16, int QB, bool INDIRECT>
 static cudaError_t launch_pipelined(const ScanPlan& p, const ScanArgs& a, cudaStream_t st) {
   void (*kern)(ScanArgs) = nullptr;
   // bf16 rows carry half the bytes per element: 4 rows per step keep enough loads / FMAs in flight per warp
-  const bool ru4 = BF16 && QB <= 2 && (p.rows_per_stage / SCAN_NW) % 4 == 0 && getenv("AURA_SCAN_RU2") == nullptr;
+  const bool ru4 = BF16 && QB <= 2 && (p.rows_per_stage / SCAN_NW) % 4 == 0 && env_int("AURA_SCAN_RU2", 0) == 0;
   switch (p.kpl) {
     case 1: kern = ru4 ? scan_topk_kernel<BF16, QB, 1, SCAN_NW, (BF16 && QB <= 2 ? 4 : SCAN_RU), INDIRECT>
                        : scan_topk_kernel<BF16, QB, 1, SCAN_NW, SCAN_RU, INDIRECT>; break;
@@ -499,7 +500,7 @@ size_t scan_workspace_bytes(int n_queries, int k) {
 int launch_scan(const void* rows, int dtype, long long n_rows, int d, const float* queries, int n_queries,
                 const float* scale, const float* bias, int k, long long row_base, long long* out_idx, float* out_score,
                 void* workspace, const long long* probes, int nprobe, int n_lists, const int* list_offsets,
-                const int* list_rows, long long expected_rows, cudaStream_t st) {
+                const int* list_rows, long long expected_rows, cudaStream_t st, int empty_ok) {
   const bool indirect = probes != nullptr;
   ScanPlan p;
   make_plan(indirect ? expected_rows : n_rows, d, dtype, n_queries, k, indirect, nprobe, &p);
@@ -521,7 +522,8 @@ int launch_scan(const void* rows, int dtype, long long n_rows, int d, const floa
   a.rows_per_stage = p.rows_per_stage; a.n_stage_bufs = p.n_stage_bufs;
   a.stage_bytes = p.stage_bytes; a.q_bytes = p.q_bytes; a.merge_keys = p.merge_keys;
   a.terms_bulk = ((reinterpret_cast<uintptr_t>(scale) | reinterpret_cast<uintptr_t>(bias)) & 15) == 0;
-  { const char* e = getenv("AURA_SCAN_INTERLEAVE"); a.interleave = e ? atoi(e) : 0; }
+  a.interleave = env_int("AURA_SCAN_INTERLEAVE", 0);
+  a.empty_ok = empty_ok;
   a.probes = probes; a.nprobe = nprobe; a.n_lists = n_lists; a.list_offsets = list_offsets; a.list_rows = list_rows;
 
   cudaError_t e;
@@ -575,5 +577,5 @@ extern "C" int aura_scan_topk(const void* rows, int dtype, int64_t n_rows, int d
                "aura_scan_topk: workspace too small (%zu bytes)", workspace_bytes);
   return launch_scan(rows, dtype, n_rows, d, queries, n_queries, scale, bias, k, row_base,
                      reinterpret_cast<long long*>(out_idx), out_score, workspace, nullptr, 0, 0, nullptr, nullptr, n_rows,
-                     (cudaStream_t)stream);
+                     (cudaStream_t)stream, 0);
 }

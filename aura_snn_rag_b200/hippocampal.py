@@ -129,6 +129,10 @@ class HippocampalFormation(nn.Module):
         self._host_stage: Dict[int, Tuple[torch.Tensor, torch.Tensor]] = {}   # pinned result staging per k
         self._terms_key = None        # (fp32 now, location key, version) the cached _scale/_bias belong to
         self._version = 0             # bumped by every write / decay
+        # upper bound of the live strengths, tracked on the host (a write sets strength 1, :215; decay scales all of
+        # them, :334): the tensor-core error bound scales with it and must not cost a device read per write
+        self._strength_bound = 1.0
+        self._derived_stale = False   # set by load_state_dict: derived buffers are recomputed before the next use
 
     # ------------------------------------------------------------------ reference attribute surface
     @property
@@ -186,6 +190,8 @@ class HippocampalFormation(nn.Module):
         else:
             idx = self.memory_count
             self.memory_count += 1
+        self._ensure_derived()
+        self._strength_bound = max(self._strength_bound, 1.0)
         feats = self._to_dev_f32(features).detach().reshape(1, -1).contiguous()
         now = time.time()
         ops.bank_write(self.memory_features, idx, feats, self.memory_metadata, self._inv_norm, now,
@@ -210,6 +216,8 @@ class HippocampalFormation(nn.Module):
         `create_episodic_memory` with one timestamp, including the sequential online-assign order and the
         periodic rebuild points.  Returns the [first, last+1) row range written.  The bank must have room
         (no FIFO overwrite in bulk mode)."""
+        self._ensure_derived()
+        self._strength_bound = max(self._strength_bound, 1.0)
         feats = self._to_dev_f32(features).detach()
         if feats.dim() == 1:
             feats = feats.unsqueeze(0)
@@ -253,6 +261,7 @@ class HippocampalFormation(nn.Module):
         if self.memory_count == 0:
             return
         ops.decay_strength(self.memory_metadata, self.memory_count, decay_rate)
+        self._strength_bound *= abs(1.0 - float(decay_rate))
         self._version += 1
 
     def decay(self, rate: float = 0.01) -> None:
@@ -263,6 +272,7 @@ class HippocampalFormation(nn.Module):
         """Sample k seeds, one Lloyd step, re-assign, counts (hippocampal.py:345-377)."""
         if self.memory_count == 0 or not self.use_centroid_index:
             return
+        self._ensure_derived()
         m = self.memory_count
         k = min(self.centroids_k, m)
         rows_c = self._centroid_buffer_rows()
@@ -320,8 +330,11 @@ class HippocampalFormation(nn.Module):
         loc = None
         loc_key = None
         if location is not None:
+            if isinstance(location, torch.Tensor) and location.is_cuda:
+                loc_key = ("dev", location.data_ptr(), location._version)   # no device read just to build a cache key
+            else:
+                loc_key = tuple(np.asarray(location, dtype=np.float32).reshape(-1).tolist())
             loc = self._to_dev_f32(location).reshape(-1).contiguous()
-            loc_key = tuple(loc.tolist())
         key = (now32, loc_key, self._version, self.memory_count)
         if key != self._terms_key:
             ops.row_terms(self.memory_metadata, self._inv_norm, now32, self.memory_count, self.memory_locations, loc,
@@ -338,10 +351,14 @@ class HippocampalFormation(nn.Module):
             q = q.unsqueeze(0)
         return q.contiguous()
 
-    def retrieve_batch(self, queries, k: int = 5, location=None, gather: bool = False, force_exact: bool = False):
+    def retrieve_batch(self, queries, k: int = 5, location=None, gather: bool = False, force_exact: bool = False,
+                       allow_empty: bool = False):
         """Batched form of `retrieve_similar_memories`: queries [B,d] -> (rows int64 [B,k'], scores fp32 [B,k'])
         with k' = min(k, memory_count); missing results are row -1 / score -inf.  `gather=True` also returns the
-        fp32 feature rows [B,k',d] (zeros for missing), replacing memory_augmented_layer.py:124-128."""
+        fp32 feature rows [B,k',d] (zeros for missing), replacing memory_augmented_layer.py:124-128.
+        `allow_empty` (row shards, `ShardedIndex`): a query whose probed lists hold none of THIS bank's rows gets no
+        result instead of the all-rows scan of :269-270, which the caller applies to the merged result."""
+        self._ensure_derived()
         q = self._queries(queries)
         m = self.memory_count
         if m == 0:
@@ -358,10 +375,11 @@ class HippocampalFormation(nn.Module):
                 idx, score = ops.ivf_search_batched(self.memory_features, m, q, self.centroids, nprobe,
                                                     self._list_offsets, self._list_rows, kk, scale, bias,
                                                     eps=ops.TC_EPS_COS * 0.5 * self._max_strength(),
-                                                    strict=self.ivf_strict, rows_by_list=self._rows_by_list())
+                                                    strict=self.ivf_strict, rows_by_list=self._rows_by_list(),
+                                                    allow_empty=allow_empty)
             else:
                 idx, score = ops.ivf_search(self.memory_features, m, q, self.centroids, nprobe, self._list_offsets,
-                                            self._list_rows, kk, scale, bias)
+                                            self._list_rows, kk, scale, bias, allow_empty=allow_empty)
         else:
             idx, score = self._exact(q, kk, scale, bias, 0.5 * self._max_strength())
         if gather:
@@ -369,11 +387,12 @@ class HippocampalFormation(nn.Module):
         return idx, score
 
     def _max_strength(self) -> float:
-        """Upper bound of the live strengths (the tensor-core error bound scales with it); cached per version."""
-        if getattr(self, "_max_strength_key", None) != self._version:
-            self._max_strength_val = float(self.memory_metadata[:self.memory_count, 0].abs().max()) if self.memory_count else 1.0
-            self._max_strength_key = self._version
-        return self._max_strength_val
+        """Upper bound of the live strengths (the tensor-core error bound scales with it), kept on the host."""
+        return self._strength_bound
+
+    def _ensure_derived(self) -> None:
+        if self._derived_stale:
+            self.refresh_derived()
 
     def _exact(self, q: torch.Tensor, k: int, scale, bias, score_per_cos: float):
         """Exact top-k of a query block over all live rows: tcgen05 shortlist + exact fp32 re-score for blocks of
@@ -419,8 +438,14 @@ class HippocampalFormation(nn.Module):
         sync: flags[b] != 0 marks the rare query whose result is not yet certified; pass everything to
         `exact_topk_fixup` once the flags have been read.  This lets a serving loop keep several batches in flight
         (bench.py's e2e leg); defer=False does the check itself."""
+        self._ensure_derived()
         q = self._queries(queries)
         m = self.memory_count
+        if m == 0:                                      # empty bank: nothing to rank (retrieve_batch does the same)
+            e = torch.empty(q.shape[0], 0, device=self.device)
+            if defer:
+                return e.long(), e, torch.zeros(q.shape[0], dtype=torch.int32, device=self.device), q
+            return (e.unsqueeze(-1).expand(-1, -1, q.shape[1]).contiguous(), e, e.long()) if gather else (e.long(), e)
         kk = min(int(k), m)
         if defer:
             if not (q.shape[0] >= ops.tc_min_batch(self.memory_features) and ops.batch_topk_supported(self.memory_features, kk) and m >= 1024):
@@ -446,6 +471,7 @@ class HippocampalFormation(nn.Module):
         (the O(n^2) "cognitive map" of README.md:39,64 / training_recipes.md:292-308, which the reference
         documents but never implements).  Returns (neighbour rows int64 [M,k'], similarities fp32 [M,k']),
         best first, k' = min(k, M-1); one tcgen05 GEMM with the top-k fused into its epilogue."""
+        self._ensure_derived()
         m = self.memory_count
         kk = min(int(k), m - 1)
         if kk < 1:
@@ -481,11 +507,14 @@ class HippocampalFormation(nn.Module):
     def refresh_derived(self) -> None:
         """Recompute everything derived from the registered buffers (inverse norms, int32 centroid ids, inverted
         lists) - call after `load_state_dict` or after writing `memory_features` / `memory_metadata` directly."""
+        # every row, not only the live ones: callers of the reference set `memory_count` by hand after a resume
+        self._derived_stale = False
+        ops.row_inv_norms(self.memory_features, out=self._inv_norm)
+        self._cid.copy_(self.memory_metadata[:, 2].to(torch.int32))
         m = self.memory_count
-        if m > 0:
-            ops.row_inv_norms(self.memory_features[:m], out=self._inv_norm[:m])
-            self._cid[:m] = self.memory_metadata[:m, 2].to(torch.int32)
+        self._strength_bound = float(self.memory_metadata[:m, 0].abs().max()) if m else 1.0   # one device read per resume
         self._lists_dirty = True
+        self._by_list_valid = False
         self._terms_key = None
         self._version += 1
 
@@ -526,3 +555,6 @@ class HippocampalFormation(nn.Module):
         if key in state_dict and state_dict[key].shape != self.centroid_counts.shape:
             self.centroid_counts = torch.zeros_like(state_dict[key], device=self.device)
         super()._load_from_state_dict(state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs)
+        # inverse norms, int32 centroid ids, inverted lists, cached score terms and the strength bound all derive from
+        # the buffers just replaced: recompute lazily before the next query or write
+        self._derived_stale = True

@@ -5,16 +5,36 @@ libaura_hippo.so.  All functions require CUDA tensors and raise otherwise.
 """
 from __future__ import annotations
 
+import functools
 from typing import Optional, Tuple
 
 import torch
 
 from . import _lib
-from ._lib import AURA_BF16, AURA_F32, AURA_MAX_K, check
+from ._lib import AURA_BF16, AURA_F32, AURA_IVF_EMPTY_OK, AURA_MAX_K, check
 
 
 def _stream() -> int:
+    """Handle of the current stream of the CURRENT device; every public entry runs under `_on_device`, which makes
+    the tensors' device current first (the library launches on cudaGetDevice())."""
     return torch.cuda.current_stream().cuda_stream
+
+
+def _on_device(fn):
+    """Run `fn` with the device of its first CUDA tensor argument current: the library reads cudaGetDevice() for its
+    launches and cached attributes, and `_stream()` / `_workspace` are per current device.  With the bank on cuda:1 and
+    cuda:0 current, an unguarded call would launch on GPU 0 against GPU 1 pointers (the reference class works on any
+    device index, hippocampal.py:50-53)."""
+    @functools.wraps(fn)
+    def wrapped(*args, **kwargs):
+        for a in args:
+            if isinstance(a, torch.Tensor):
+                if a.is_cuda and a.device.index != torch.cuda.current_device():
+                    with torch.cuda.device(a.device):
+                        return fn(*args, **kwargs)
+                break
+        return fn(*args, **kwargs)
+    return wrapped
 
 
 def _dtype_code(t: torch.Tensor) -> int:
@@ -38,18 +58,29 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
 
 
 _workspaces = {}
+_pinned_streams = set()      # (device index, stream handle) whose scratch pointers are baked into a captured CUDA graph
+_retired = []                # scratch tensors replaced on a pinned stream: kept alive, a graph may still replay into them
+
+
+def pin_workspaces(device: torch.device, stream_handle: int) -> None:
+    """Scratch buffers handed out on this stream are never freed from now on (`GraphedSearch`)."""
+    _pinned_streams.add((device.index, int(stream_handle)))
 
 
 def _workspace(nbytes: int, device: torch.device, tag: str = "ws") -> torch.Tensor:
     """Per-(device, stream) scratch, grown on demand (the library never allocates)."""
-    key = (device.index, _stream(), tag)
+    st = _stream()
+    key = (device.index, st, tag)
     ws = _workspaces.get(key)
     if ws is None or ws.numel() < nbytes:
+        if ws is not None and (device.index, st) in _pinned_streams:
+            _retired.append(ws)
         ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
         _workspaces[key] = ws
     return ws
 
 
+@_on_device
 def row_inv_norms(rows: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     rows = _dev(rows, "rows")
     n, d = rows.shape
@@ -60,6 +91,7 @@ def row_inv_norms(rows: torch.Tensor, out: Optional[torch.Tensor] = None) -> tor
     return out
 
 
+@_on_device
 def row_terms(metadata: torch.Tensor, inv_norm: torch.Tensor, now: float, n_rows: int,
               locations: Optional[torch.Tensor] = None, query_loc: Optional[torch.Tensor] = None,
               scale: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None):
@@ -80,11 +112,13 @@ def row_terms(metadata: torch.Tensor, inv_norm: torch.Tensor, now: float, n_rows
     return scale, bias
 
 
+@_on_device
 def decay_strength(metadata: torch.Tensor, n_rows: int, rate: float) -> None:
     metadata = _dev(metadata, "metadata")
     check(_lib.load().aura_decay_strength(metadata.data_ptr(), n_rows, float(rate), _stream()), "aura_decay_strength")
 
 
+@_on_device
 def scan_topk(rows: torch.Tensor, queries: torch.Tensor, k: int, scale: Optional[torch.Tensor],
               bias: Optional[torch.Tensor] = None, n_rows: Optional[int] = None, row_base: int = 0,
               out_idx: Optional[torch.Tensor] = None, out_score: Optional[torch.Tensor] = None
@@ -116,6 +150,7 @@ def scan_topk(rows: torch.Tensor, queries: torch.Tensor, k: int, scale: Optional
     return out_idx, out_score
 
 
+@_on_device
 def topk_merge(scores: torch.Tensor, idx: torch.Tensor, n_lists: int, k_in: int, k_out: int):
     scores = _dev(scores, "scores")
     idx = _dev(idx, "idx")
@@ -127,16 +162,20 @@ def topk_merge(scores: torch.Tensor, idx: torch.Tensor, n_lists: int, k_in: int,
     return out_s, out_i
 
 
-def pack_topk(idx: torch.Tensor, score: torch.Tensor, flags: Optional[torch.Tensor], out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """[B, 2k+1] int64 payload of one rank for the sharded all-gather (ids, score bits, certification flag)."""
+@_on_device
+def pack_topk(idx: torch.Tensor, score: torch.Tensor, flags: Optional[torch.Tensor], out: Optional[torch.Tensor] = None,
+              id_map: Optional[torch.Tensor] = None, id_base: int = 0) -> torch.Tensor:
+    """[B, 2k+1] int64 payload of one rank for the sharded all-gather (ids, score bits, certification flag).
+    Ids are id_map[idx] (int64 table: local row -> global memory id) or idx + id_base; missing results stay -1."""
     b, k = idx.shape
     if out is None:
         out = torch.empty(b, 2 * k + 1, dtype=torch.int64, device=idx.device)
-    check(_lib.load().aura_pack_topk(idx.data_ptr(), score.data_ptr(), _ptr(flags), b, k, out.data_ptr(), _stream()),
-          "aura_pack_topk")
+    check(_lib.load().aura_pack_topk(idx.data_ptr(), score.data_ptr(), _ptr(flags), b, k, _ptr(id_map), int(id_base),
+                                     out.data_ptr(), _stream()), "aura_pack_topk")
     return out
 
 
+@_on_device
 def topk_merge_packed(gathered: torch.Tensor, n_ranks: int, b: int, k: int):
     """Merge the rank-major gathered payloads [n_ranks*B, 2k+1] -> (idx [B,k], score [B,k], any_flag [B] int32)."""
     dev = gathered.device
@@ -148,6 +187,7 @@ def topk_merge_packed(gathered: torch.Tensor, n_ranks: int, b: int, k: int):
     return out_i, out_s, flag
 
 
+@_on_device
 def gather_rows(rows: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
     rows = _dev(rows, "rows")
     idx = _dev(idx, "idx")
@@ -159,6 +199,7 @@ def gather_rows(rows: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
 
 
 # ---------------------------------------------------------------------------- bank write
+@_on_device
 def bank_write(rows: torch.Tensor, first_row: int, features: torch.Tensor, metadata: torch.Tensor,
                inv_norm: torch.Tensor, timestamp: float, locations: Optional[torch.Tensor] = None,
                location: Optional[torch.Tensor] = None) -> None:
@@ -181,6 +222,7 @@ def bank_write(rows: torch.Tensor, first_row: int, features: torch.Tensor, metad
 
 
 # ---------------------------------------------------------------------------- centroid index
+@_on_device
 def kmeans_seed(rows: torch.Tensor, seed_rows: torch.Tensor, centroids: torch.Tensor) -> None:
     rows = _dev(rows, "rows")
     seed_rows = _dev(seed_rows, "seed_rows")
@@ -190,6 +232,7 @@ def kmeans_seed(rows: torch.Tensor, seed_rows: torch.Tensor, centroids: torch.Te
                                        seed_rows.numel(), centroids.data_ptr(), _stream()), "aura_kmeans_seed")
 
 
+@_on_device
 def kmeans_assign(rows: torch.Tensor, n_rows: int, centroids: torch.Tensor, n_centroids: int, assign: torch.Tensor,
                   cid_f32: Optional[torch.Tensor] = None, cid_stride: int = 1,
                   best: Optional[torch.Tensor] = None, inv_norm: Optional[torch.Tensor] = None) -> None:
@@ -203,6 +246,7 @@ def kmeans_assign(rows: torch.Tensor, n_rows: int, centroids: torch.Tensor, n_ce
                                  ws.numel(), _stream()), "aura_kmeans_assign")
 
 
+@_on_device
 def ivf_build_lists(cid: torch.Tensor, n_rows: int, n_lists: int, list_offsets: torch.Tensor,
                     list_rows: torch.Tensor) -> None:
     cid = _dev(cid, "cid")
@@ -212,6 +256,7 @@ def ivf_build_lists(cid: torch.Tensor, n_rows: int, n_lists: int, list_offsets: 
                                    ws.data_ptr(), ws.numel(), _stream()), "aura_ivf_build_lists")
 
 
+@_on_device
 def kmeans_list_sums(rows: torch.Tensor, list_offsets: torch.Tensor, list_rows: torch.Tensor, n_lists: int,
                      sums: torch.Tensor, counts: torch.Tensor) -> None:
     rows = _dev(rows, "rows")
@@ -220,16 +265,19 @@ def kmeans_list_sums(rows: torch.Tensor, list_offsets: torch.Tensor, list_rows: 
                                             _stream()), "aura_kmeans_list_sums")
 
 
+@_on_device
 def kmeans_finalize(sums: torch.Tensor, counts: torch.Tensor, n_centroids: int, centroids: torch.Tensor) -> None:
     check(_lib.load().aura_kmeans_finalize(sums.data_ptr(), counts.data_ptr(), n_centroids, centroids.shape[1],
                                            centroids.data_ptr(), _stream()), "aura_kmeans_finalize")
 
 
+@_on_device
 def ivf_list_counts(list_offsets: torch.Tensor, n_lists: int, counts_f32: torch.Tensor) -> None:
     check(_lib.load().aura_ivf_list_counts(list_offsets.data_ptr(), n_lists, counts_f32.data_ptr(), _stream()),
           "aura_ivf_list_counts")
 
 
+@_on_device
 def online_assign(rows: torch.Tensor, first_row: int, n_writes: int, centroids: torch.Tensor, n_live: int,
                   counts: torch.Tensor, cid_i32: torch.Tensor, cid_f32: Optional[torch.Tensor] = None,
                   cid_stride: int = 1) -> None:
@@ -241,6 +289,7 @@ def online_assign(rows: torch.Tensor, first_row: int, n_writes: int, centroids: 
                                  cid_stride, ws.data_ptr(), ws.numel(), _stream()), "aura_online_assign")
 
 
+@_on_device
 def ivf_coarse(queries: torch.Tensor, centroids: torch.Tensor, nprobe: int) -> torch.Tensor:
     queries = _dev(queries, "queries")
     centroids = _dev(centroids, "centroids")
@@ -256,10 +305,14 @@ def ivf_coarse(queries: torch.Tensor, centroids: torch.Tensor, nprobe: int) -> t
     return probes
 
 
+@_on_device
 def ivf_search(rows: torch.Tensor, n_rows: int, queries: torch.Tensor, centroids: torch.Tensor, nprobe: int,
                list_offsets: torch.Tensor, list_rows: torch.Tensor, k: int, scale: Optional[torch.Tensor],
-               bias: Optional[torch.Tensor] = None, row_base: int = 0, return_probes: bool = False):
-    """Centroid-path query: coarse probes + scan of the probed lists.  Returns (idx[B,k], score[B,k][, probes])."""
+               bias: Optional[torch.Tensor] = None, row_base: int = 0, return_probes: bool = False,
+               allow_empty: bool = False):
+    """Centroid-path query: coarse probes + scan of the probed lists.  Returns (idx[B,k], score[B,k][, probes]).
+    allow_empty: a query whose probed lists hold no row returns idx -1 / score -inf instead of scanning every row
+    (a row shard applies the reference's all-rows rule, hippocampal.py:269-270, to the MERGED result)."""
     rows = _dev(rows, "rows")
     queries = _dev(queries, "queries")
     if queries.dtype != torch.float32:
@@ -280,8 +333,9 @@ def ivf_search(rows: torch.Tensor, n_rows: int, queries: torch.Tensor, centroids
     ws = _workspace(lib.aura_ivf_search_workspace_bytes(b, d, c, nprobe, k), dev)
     check(lib.aura_ivf_search(rows.data_ptr(), _dtype_code(rows), n_rows, d, queries.data_ptr(), b,
                               centroids.data_ptr(), c, nprobe, list_offsets.data_ptr(), list_rows.data_ptr(),
-                              _ptr(scale), _ptr(bias), k, row_base, out_idx.data_ptr(), out_score.data_ptr(),
-                              _ptr(probes), ws.data_ptr(), ws.numel(), _stream()), "aura_ivf_search")
+                              _ptr(scale), _ptr(bias), k, row_base, AURA_IVF_EMPTY_OK if allow_empty else 0,
+                              out_idx.data_ptr(), out_score.data_ptr(), _ptr(probes), ws.data_ptr(), ws.numel(),
+                              _stream()), "aura_ivf_search")
     return (out_idx, out_score, probes) if return_probes else (out_idx, out_score)
 
 
@@ -303,6 +357,7 @@ def batch_topk_supported(rows: torch.Tensor, k: int) -> bool:
     return (rows.shape[1] * rows.element_size()) % 16 == 0 and rows.data_ptr() % 16 == 0 and 1 <= k <= TC_MAX_K
 
 
+@_on_device
 def batch_topk(rows: torch.Tensor, queries: torch.Tensor, k: int, scale: Optional[torch.Tensor],
                bias: Optional[torch.Tensor] = None, n_rows: Optional[int] = None, row_base: int = 0,
                eps: float = TC_EPS_COS) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
@@ -329,6 +384,7 @@ def batch_topk(rows: torch.Tensor, queries: torch.Tensor, k: int, scale: Optiona
     return out_idx, out_score, flags
 
 
+@_on_device
 def exact_topk_batched(rows: torch.Tensor, queries: torch.Tensor, k: int, scale: Optional[torch.Tensor],
                        bias: Optional[torch.Tensor] = None, n_rows: Optional[int] = None, row_base: int = 0,
                        eps: float = TC_EPS_COS, stats: Optional[dict] = None, defer: bool = False):
@@ -345,6 +401,7 @@ def exact_topk_batched(rows: torch.Tensor, queries: torch.Tensor, k: int, scale:
     return idx, score
 
 
+@_on_device
 def exact_topk_fixup(flags: torch.Tensor, idx: torch.Tensor, score: torch.Tensor, rows: torch.Tensor,
                      queries: torch.Tensor, k: int, scale: Optional[torch.Tensor], bias: Optional[torch.Tensor] = None,
                      n_rows: Optional[int] = None, row_base: int = 0, stats: Optional[dict] = None) -> int:
@@ -359,6 +416,7 @@ def exact_topk_fixup(flags: torch.Tensor, idx: torch.Tensor, score: torch.Tensor
     return int(bad.numel())
 
 
+@_on_device
 def allpairs_topk(rows: torch.Tensor, k: int = 32, inv_norm: Optional[torch.Tensor] = None,
                   n_rows: Optional[int] = None, a_first: int = 0, n_a: Optional[int] = None
                   ) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -383,6 +441,7 @@ def allpairs_topk(rows: torch.Tensor, k: int = 32, inv_norm: Optional[torch.Tens
     return out_idx, out_score
 
 
+@_on_device
 def ivf_pack_lists(rows: torch.Tensor, list_rows: torch.Tensor, n_listed: int, out: torch.Tensor) -> torch.Tensor:
     """out[p] = rows[list_rows[p]], p < n_listed: the list-major resident copy of the bank (aura_ivf_pack_lists)."""
     rows = _dev(rows, "rows")
@@ -396,11 +455,13 @@ def ivf_pack_lists(rows: torch.Tensor, list_rows: torch.Tensor, n_listed: int, o
 TC_IVF_MIN_BATCH = 64          # list-major grouped GEMM pays off once lists are shared by several queries
 
 
+@_on_device
 def ivf_search_batched(rows: torch.Tensor, n_rows: int, queries: torch.Tensor, centroids: torch.Tensor, nprobe: int,
                        list_offsets: torch.Tensor, list_rows: torch.Tensor, k: int, scale: Optional[torch.Tensor],
                        bias: Optional[torch.Tensor] = None, row_base: int = 0, eps: float = TC_EPS_COS,
                        stats: Optional[dict] = None, strict: bool = True,
-                       rows_by_list: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+                       rows_by_list: Optional[torch.Tensor] = None, allow_empty: bool = False
+                       ) -> Tuple[torch.Tensor, torch.Tensor]:
     """Centroid-path query for a block of queries: list-major tensor-core pass (aura_ivf_search_batch), then the
     per-query path for the queries it hands back.
 
@@ -428,23 +489,25 @@ def ivf_search_batched(rows: torch.Tensor, n_rows: int, queries: torch.Tensor, c
     ws = _workspace(lib.aura_ivf_search_batch_workspace_bytes(b, d, c, nprobe), dev, "ivfbatch")
     check(lib.aura_ivf_search_batch(rows.data_ptr(), _dtype_code(rows), n_rows, d, queries.data_ptr(), b,
                                     centroids.data_ptr(), c, nprobe, list_offsets.data_ptr(), list_rows.data_ptr(),
-                                    _ptr(rows_by_list), _ptr(scale), _ptr(bias), k, row_base, float(eps), out_idx.data_ptr(),
+                                    _ptr(rows_by_list), _ptr(scale), _ptr(bias), k, row_base,
+                                    AURA_IVF_EMPTY_OK if allow_empty else 0, float(eps), out_idx.data_ptr(),
                                     out_score.data_ptr(), flags.data_ptr(), ws.data_ptr(), ws.numel(), _stream()),
           "aura_ivf_search_batch")
     if stats is not None:
         import ctypes as _C
-        items, cap = _C.c_int32(0), _C.c_int32(0)
-        check(lib.aura_ivf_search_batch_items(ws.data_ptr(), b, d, c, nprobe, _C.addressof(items), _C.addressof(cap), _stream()),
+        items, cap = torch.zeros(1, dtype=torch.int32, device=dev), _C.c_int32(0)
+        check(lib.aura_ivf_search_batch_items(ws.data_ptr(), b, d, c, nprobe, items.data_ptr(), _C.addressof(cap), _stream()),
               "aura_ivf_search_batch_items")
-        stats["items"], stats["items_cap"] = items.value, cap.value
+        stats["items"], stats["items_cap"] = int(items.item()), cap.value
     if not strict:
-        flags = flags * (out_idx[:, 0] < 0).to(flags.dtype)        # keep only "no candidate at all"
+        # keep only "no candidate at all" (never flagged when allow_empty) and work-table overflow
+        flags = flags * (out_idx[:, 0] < 0).to(flags.dtype)
     bad = torch.nonzero(flags, as_tuple=False).squeeze(-1)
     if stats is not None:
         stats["uncertain"] = stats.get("uncertain", 0) + int(bad.numel())
     if bad.numel() > 0:
         i2, s2 = ivf_search(rows, n_rows, queries[bad].contiguous(), centroids, nprobe, list_offsets, list_rows, k, scale,
-                            bias, row_base)
+                            bias, row_base, allow_empty=allow_empty)
         out_idx[bad] = i2
         out_score[bad] = s2
     return out_idx, out_score

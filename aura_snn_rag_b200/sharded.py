@@ -182,6 +182,10 @@ class GraphedSearch:
         self.bank, self.k = bank, int(k)
         self.q = torch.zeros(batch, bank.rows.shape[1], device=dev, dtype=torch.float32)
         side = torch.cuda.Stream(device=dev)
+        if bank._ops is not None:
+            # the graph bakes in the raw pointers of this stream's scratch buffers: they must outlive the graph even if
+            # a later, larger request on the same stream handle re-allocates them (torch recycles stream handles)
+            bank._ops.pin_workspaces(dev, side.cuda_stream)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
             for _ in range(max(1, warmup)):          # communicator, workspaces and kernel attributes exist before capture
@@ -221,26 +225,40 @@ class GraphedSearch:
 
 
 class ShardedIndex:
-    """Row-sharded centroid index: every rank holds a `HippocampalFormation` over its own rows
-    (global rows [row_base, row_base + memory_count)), the centroids are replicated and kept bit-identical on all
-    ranks, every rank keeps its own CSR slice of every inverted list.
+    """Row-sharded centroid index: every rank holds a `HippocampalFormation` over its own rows, the
+    centroids are replicated and kept bit-identical on all ranks, every rank keeps its own CSR slice of every inverted
+    list.  Local row r of this rank is global memory `gid[r]`: initially the contiguous range
+    [row_base, row_base + memory_count); online writes append global ids n_total, n_total + 1, ... to the rank
+    `id % world` (the owner rule of SURVEY 8e), so the table stays ascending.
 
     rebuild : seed rows are fetched from their owners (sum all-reduce of a [k,d] block that only the owner fills),
               local assign -> local per-list fp64 sums + counts -> all-reduce -> identical new centroids everywhere
               -> local re-assign + local lists (hippocampal.py:345-377 distributed over ranks).
-    search  : replicated queries, local coarse + fine search with global row ids, all-gather, k-way merge
-              (`ShardedBank.search` plumbing).  nprobe means the same as in the single index, so recall is comparable.
+    write   : `create_episodic_memories(features)` with the SAME feature block on every rank: every rank runs the
+              sequential nearest-centroid + running-mean update (hippocampal.py:218-230) over all rows, in order, on a
+              staging copy - the replicas of the centroids and counts therefore never diverge - and stores only the
+              rows it owns.
+    search  : replicated queries, local coarse + fine search, ids mapped to global inside the pack kernel, ONE
+              all-gather, k-way merge.  nprobe means the same as in the single index, so recall is comparable.  A shard
+              whose slices of the probed lists are empty contributes nothing; the reference's "no candidates -> all
+              rows" rule (hippocampal.py:269-270) is applied to the merged result.
+    map     : `build_cognitive_map`: one all-gather of the rows, each rank scores its own rows against the whole bank.
 
     `all_reduce` / `all_gather` default to torch.distributed (NCCL on GPUs); they are injectable so that the
     arithmetic can be checked against a single index inside one process (tests/test_sharded_gpu.py).
     """
 
     def __init__(self, local, row_base: int, n_total: int, all_reduce: Optional[Callable] = None,
-                 all_gather: Optional[Callable] = None, world: Optional[int] = None):
+                 all_gather: Optional[Callable] = None, world: Optional[int] = None, rank: Optional[int] = None):
         self.local = local
         self.row_base = int(row_base)
         self.n_total = int(n_total)
         self.world = world if world is not None else (dist.get_world_size() if dist.is_initialized() else 1)
+        self.rank = rank if rank is not None else (dist.get_rank() if dist.is_initialized() else 0)
+        # local row -> global id; None while the shard is still the contiguous range it was built from
+        self.gid: Optional[torch.Tensor] = None
+        self.update_interval = int(getattr(local, "centroids_update_interval", 512))
+        local.centroids_update_interval = 1 << 62          # rebuild points are decided here, on the global count
         if all_reduce is None:
             def all_reduce(t):
                 if self.world > 1:
@@ -255,6 +273,26 @@ class ShardedIndex:
                 return out.view(self.world, *t.shape)
         self._all_reduce, self._all_gather = all_reduce, all_gather
 
+    # ------------------------------------------------------------------ ids
+    def _gid_table(self) -> torch.Tensor:
+        hf = self.local
+        if self.gid is None:
+            self.gid = torch.arange(self.row_base, self.row_base + hf.max_memories, device=hf.device, dtype=torch.int64)
+            self._gid_contiguous = hf.memory_count
+        return self.gid
+
+    def _local_rows_of(self, global_ids: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """(mask of the ids this rank owns, their local rows)."""
+        m = self.local.memory_count
+        if self.gid is None:
+            mine = (global_ids >= self.row_base) & (global_ids < self.row_base + m)
+            return mine, (global_ids[mine] - self.row_base)
+        table = self.gid[:m]
+        pos = torch.searchsorted(table, global_ids).clamp_(max=max(m - 1, 0))
+        mine = table[pos] == global_ids if m > 0 else torch.zeros_like(global_ids, dtype=torch.bool)
+        return mine, pos[mine]
+
+    # ------------------------------------------------------------------ build
     def rebuild_centroids(self, seed_rows_global: torch.Tensor) -> None:
         from . import ops
         hf = self.local
@@ -262,11 +300,11 @@ class ShardedIndex:
         k = min(hf.centroids_k, self.n_total)
         rows_c = hf.centroids.shape[0]
         seeds = seed_rows_global.to(device=dev, dtype=torch.int64)[:k]
-        mine = (seeds >= self.row_base) & (seeds < self.row_base + m)
+        mine, local_rows = self._local_rows_of(seeds)
         block = torch.zeros(k, hf.memory_features.shape[1], device=dev, dtype=torch.float32)
         if bool(mine.any()):
             tmp = torch.empty(int(mine.sum()), block.shape[1], device=dev, dtype=torch.float32)
-            ops.kmeans_seed(hf.memory_features, (seeds[mine] - self.row_base).contiguous(), tmp)
+            ops.kmeans_seed(hf.memory_features, local_rows.contiguous(), tmp)
             block[mine] = tmp
         self._all_reduce(block)                                   # every seed row has exactly one owner
         hf.centroids[:k] = block
@@ -291,21 +329,118 @@ class ShardedIndex:
         hf._by_list_valid = False
         hf._index_ready = True
 
-    def search(self, queries: torch.Tensor, k: int, exact: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
-        """(global rows int64 [B,k], scores [B,k]) on every rank; centroid path unless `exact`."""
+    # ------------------------------------------------------------------ online writes
+    def create_episodic_memories(self, features: torch.Tensor, seed_rows_fn: Optional[Callable] = None) -> Tuple[int, int]:
+        """Append n memories (global ids n_total .. n_total + n); `features` [n,d] must be identical on every rank.
+        Same semantics as n sequential `create_episodic_memory` calls on a single index, including the rebuild points
+        (every `update_interval` memories once the global count exceeds centroids_k, hippocampal.py:242-243);
+        `seed_rows_fn(count)` supplies the global seed rows of a triggered rebuild (default: randperm of the global
+        count, seeded by the count so that every rank draws the same rows).  Returns the global id range written."""
         from . import ops
         hf = self.local
-        idx, score = hf.retrieve_batch(queries, k=k, force_exact=exact)
-        idx = torch.where(idx >= 0, idx + self.row_base, idx)
+        dev = hf.device
+        feats = hf._to_dev_f32(features).detach()
+        if feats.dim() == 1:
+            feats = feats.unsqueeze(0)
+        feats = feats.contiguous()
+        n, d = feats.shape
+        first = self.n_total
+        gid = self._gid_table()
+        done = 0
+        while done < n:
+            nxt = (self.n_total // self.update_interval + 1) * self.update_interval
+            step = min(n - done, nxt - self.n_total)
+            blk = feats[done:done + step]
+            # staging bank: the rows exactly as the bank stores them (dtype conversion, inverse norms) + their metadata
+            st_rows = torch.empty(step, d, device=dev, dtype=hf.memory_features.dtype)
+            st_meta = torch.empty(step, 4, device=dev, dtype=torch.float32)
+            st_loc = torch.empty(step, hf.memory_locations.shape[1], device=dev, dtype=torch.float32)
+            st_inv = torch.empty(step, device=dev, dtype=torch.float32)
+            st_cid = torch.full((step,), -1, device=dev, dtype=torch.int32)
+            ops.bank_write(st_rows, 0, blk, st_meta, st_inv, hf_time(hf), st_loc, hf.current_location.contiguous())
+            if hf.use_centroid_index and hf._index_ready:
+                live = min(hf.centroids_k, hf.centroids.shape[0])
+                # every rank updates the replicated centroids with EVERY row, in order: replicas stay bit-identical
+                ops.online_assign(st_rows, 0, step, hf.centroids, live, hf.centroid_counts, st_cid, st_meta[:, 2], 4)
+            ids = torch.arange(self.n_total, self.n_total + step, device=dev, dtype=torch.int64)
+            own = (ids % self.world) == self.rank
+            n_own = int(own.sum())
+            m = hf.memory_count
+            if m + n_own > hf.max_memories:
+                raise ValueError(f"shard {self.rank}: {n_own} new rows do not fit ({m} of {hf.max_memories} used)")
+            if n_own:
+                hf.memory_features[m:m + n_own] = st_rows[own]
+                hf.memory_metadata[m:m + n_own] = st_meta[own]
+                hf.memory_locations[m:m + n_own] = st_loc[own]
+                hf._inv_norm[m:m + n_own] = st_inv[own]
+                hf._cid[m:m + n_own] = st_cid[own]
+                gid[m:m + n_own] = ids[own]
+                hf.memory_count = m + n_own
+                hf._lists_dirty = True
+                hf._version += 1
+            self.n_total += step
+            done += step
+            if hf.use_centroid_index and self.n_total % self.update_interval == 0 and self.n_total > hf.centroids_k:
+                if seed_rows_fn is not None:
+                    seeds = seed_rows_fn(self.n_total)
+                else:
+                    g = torch.Generator().manual_seed(self.n_total)
+                    seeds = torch.randperm(self.n_total, generator=g)[:hf.centroids_k]
+                self.rebuild_centroids(seeds)
+        return first, first + n
+
+    # ------------------------------------------------------------------ query
+    def search(self, queries: torch.Tensor, k: int, exact: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
+        """(global ids int64 [B,k], scores [B,k]) on every rank; centroid path unless `exact`."""
+        from . import ops
+        hf = self.local
+        idx, score = hf.retrieve_batch(queries, k=k, force_exact=exact, allow_empty=self.world > 1)
         if idx.shape[1] < k:                                       # a shard with fewer than k rows
             pad = k - idx.shape[1]
             idx = torch.cat([idx, idx.new_full((idx.shape[0], pad), -1)], dim=1)
             score = torch.cat([score, score.new_full((score.shape[0], pad), float("-inf"))], dim=1)
-        if self.world == 1:
-            return idx, score
         b = idx.shape[0]
-        payload = ops.pack_topk(idx.contiguous(), score.contiguous(), None)       # [B, 2k+1]
+        payload = ops.pack_topk(idx.contiguous(), score.contiguous(), None, id_map=self.gid,
+                                id_base=self.row_base)                             # [B, 2k+1], global ids
         gathered = self._all_gather(payload)                                       # [G, B, 2k+1], one collective
         g = gathered.shape[0]
         out_idx, out_score, _ = ops.topk_merge_packed(gathered.reshape(g * b, 2 * k + 1).contiguous(), g, b, k)
+        if not exact and self.world > 1 and hf._centroid_path():
+            # hippocampal.py:269-270 on the merged result: no candidate on ANY shard -> scan all rows (all ranks agree)
+            empty = torch.nonzero(out_idx[:, 0] < 0, as_tuple=False).squeeze(-1)
+            if empty.numel() > 0:
+                q = hf._queries(queries)
+                i2, s2 = self.search(q[empty].contiguous(), k, exact=True)
+                out_idx[empty] = i2
+                out_score[empty] = s2
         return out_idx, out_score
+
+    # ------------------------------------------------------------------ cognitive map
+    def build_cognitive_map(self, k: int = 32) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Sharded all-pairs map: ONE all-gather of the rows (padded to the largest shard), then every rank
+        scores its own rows (the A block) against the whole bank with the top-k fused (`aura_allpairs_topk`); no result
+        exchange.  Returns (global neighbour ids int64 [m_local, k], cosine fp32 [m_local, k]) for this rank's rows."""
+        from . import ops
+        hf = self.local
+        dev, m, d = hf.device, hf.memory_count, hf.memory_features.shape[1]
+        counts = self._all_gather(torch.tensor([m], device=dev, dtype=torch.int64)).reshape(-1)
+        counts_l = counts.tolist()
+        m_max = max(counts_l)
+        pad = torch.zeros(m_max, d, device=dev, dtype=hf.memory_features.dtype)
+        pad[:m] = hf.memory_features[:m]
+        everyone = self._all_gather(pad)                                         # [G, m_max, d]
+        ids = torch.full((m_max,), -1, device=dev, dtype=torch.int64)
+        ids[:m] = self._gid_table()[:m] if self.gid is not None else torch.arange(self.row_base, self.row_base + m, device=dev)
+        all_ids = self._all_gather(ids)                                          # [G, m_max]
+        bank = torch.cat([everyone[r, :c] for r, c in enumerate(counts_l)], 0).contiguous()
+        gids = torch.cat([all_ids[r, :c] for r, c in enumerate(counts_l)], 0)
+        a_first = sum(counts_l[:self.rank])
+        kk = min(int(k), bank.shape[0] - 1)
+        nbr, sim = ops.allpairs_topk(bank, kk, ops.row_inv_norms(bank), a_first=a_first, n_a=m)
+        return torch.where(nbr >= 0, gids[nbr.clamp(min=0)], nbr), sim
+
+
+def hf_time(hf) -> float:
+    """The wall clock through the module `hippocampal` imported (tests freeze it there)."""
+    from . import hippocampal as _h
+    return _h.time.time()

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define AURA_HIPPO_VERSION 100 /* 0.1.0 */
+#define AURA_HIPPO_VERSION 200 /* 0.2.0 */
 
 enum {
   AURA_OK = 0,
@@ -40,6 +40,11 @@ enum {
 
 /* element type of the memory bank rows */
 enum { AURA_F32 = 0, AURA_BF16 = 1 };
+
+/* flags of aura_ivf_search / aura_ivf_search_batch */
+#define AURA_IVF_EMPTY_OK 1   /* a query whose probed lists hold no LOCAL row returns no result (idx -1, score -inf)
+                                 instead of scanning every row: row-sharded callers apply hippocampal.py:269-270 to
+                                 the merged result, not per shard */
 
 #define AURA_MAX_K 128        /* largest k of any fused top-k */
 #define AURA_MAX_NPROBE 128   /* largest nprobe of aura_ivf_search */
@@ -134,7 +139,8 @@ int aura_online_assign(const void* rows, int dtype, int d, int64_t first_row, in
  *   as :261 does), nearest first, ties to the lower row (:262).  Blocks of >= 64 queries are scored as one
  *   TF32 tcgen05 GEMM (2 q.c - ||c||^2, nprobe <= 32); smaller blocks in exact fp32 difference form.
  * aura_ivf_search: coarse + scan of the probed inverted lists with the same score/top-k as
- *   aura_scan_topk.  A query whose probed lists are all empty scans every row (:269-270).
+ *   aura_scan_topk.  A query whose probed lists are all empty scans every row (:269-270) unless
+ *   flags & AURA_IVF_EMPTY_OK.
  *   Returned indices are bank rows (the reference returns candidate-local positions, :307-317:
  *   a documented bug this library does not reproduce). */
 size_t aura_ivf_coarse_workspace_bytes(int n_queries, int d, int n_centroid_rows, int nprobe);
@@ -143,7 +149,7 @@ int aura_ivf_coarse(const float* queries, int n_queries, int d, const float* cen
 size_t aura_ivf_search_workspace_bytes(int n_queries, int d, int n_centroid_rows, int nprobe, int k);
 int aura_ivf_search(const void* rows, int dtype, int64_t n_rows, int d, const float* queries, int n_queries,
                     const float* centroids, int n_centroid_rows, int nprobe, const int32_t* list_offsets,
-                    const int32_t* list_rows, const float* scale, const float* bias, int k, int64_t row_base,
+                    const int32_t* list_rows, const float* scale, const float* bias, int k, int64_t row_base, int flags,
                     int64_t* out_idx, float* out_score, int64_t* out_probes, void* workspace, size_t workspace_bytes,
                     void* stream);
 
@@ -159,8 +165,8 @@ size_t aura_ivf_search_batch_workspace_bytes(int n_queries, int d, int n_centroi
 int aura_ivf_search_batch(const void* rows, int dtype, int64_t n_rows, int d, const float* queries, int n_queries,
                           const float* centroids, int n_centroid_rows, int nprobe, const int32_t* list_offsets,
                           const int32_t* list_rows, const void* rows_by_list, const float* scale, const float* bias, int k,
-                          int64_t row_base, float eps, int64_t* out_idx, float* out_score, int32_t* out_uncertain,
-                          void* workspace, size_t workspace_bytes, void* stream);
+                          int64_t row_base, int flags, float eps, int64_t* out_idx, float* out_score,
+                          int32_t* out_uncertain, void* workspace, size_t workspace_bytes, void* stream);
 
 /* rows_by_list[p] = rows[list_rows[p]] for p < n_listed (same dtype, pitch d): the list-major resident copy of the bank
  * (the layout an inverted-file index normally stores; the reference keeps insertion order only, hippocampal.py:211).
@@ -168,10 +174,10 @@ int aura_ivf_search_batch(const void* rows, int dtype, int64_t n_rows, int d, co
 int aura_ivf_pack_lists(const void* rows, int dtype, int d, const int32_t* list_rows, int64_t n_listed, void* rows_by_list,
                         void* stream);
 
-/* diagnostics: work items generated by the last aura_ivf_search_batch call on `workspace` and the table capacity
- * (synchronises `stream`; not for hot paths) */
+/* diagnostics: work items generated by the last aura_ivf_search_batch call on `workspace` (enqueued copy into the DEVICE
+ * word items_out; like every entry point it does not synchronise) and the table capacity (host word) */
 int aura_ivf_search_batch_items(const void* workspace, int n_queries, int d, int n_centroid_rows, int nprobe,
-                                int32_t* host_items, int32_t* host_cap, void* stream);
+                                int32_t* items_out, int32_t* host_cap, void* stream);
 
 /* ---- batched exact search on the tensor cores (the batch the reference loops over one query at a
  * time, memory_augmented_layer.py:113-128; score of hippocampal.py:272-307) -------------------
@@ -201,10 +207,12 @@ int aura_topk_merge(const float* in_score, const int64_t* in_idx, int n_queries,
                     int k_out, float* out_score, int64_t* out_idx, void* stream);
 
 /* Sharded search, one collective per step: aura_pack_topk writes what a rank contributes to the all-gather,
- * payload[b] = { idx[b][0..k), score bits[b][0..k), flag[b] } as int64 [n_queries, 2k+1]; aura_topk_merge_packed merges the
- * rank-major gathered block [n_ranks, n_queries, 2k+1] (same order rule as aura_topk_merge) and ORs the flags. */
-int aura_pack_topk(const int64_t* idx, const float* score, const int32_t* flags, int n_queries, int k, int64_t* payload,
-                   void* stream);
+ * payload[b] = { id[b][0..k), score bits[b][0..k), flag[b] } as int64 [n_queries, 2k+1], where id = id_map[idx] when id_map
+ * is given (local row -> global memory id of a shard that took online writes), else idx + id_base; idx < 0 stays -1.
+ * aura_topk_merge_packed merges the rank-major gathered block [n_ranks, n_queries, 2k+1] (same order rule as
+ * aura_topk_merge) and ORs the flags. */
+int aura_pack_topk(const int64_t* idx, const float* score, const int32_t* flags, int n_queries, int k,
+                   const int64_t* id_map, int64_t id_base, int64_t* payload, void* stream);
 int aura_topk_merge_packed(const int64_t* gathered, int n_ranks, int n_queries, int k, float* out_score, int64_t* out_idx,
                            int32_t* any_flag, void* stream);
 
