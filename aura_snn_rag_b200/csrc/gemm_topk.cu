@@ -787,33 +787,121 @@ int tc_assign(const void* rows, int dtype, long long n_rows, int d, const float*
 
 bool tc_coarse_supported(const float* queries, int n_queries, int d, const float* cent, int n_cent, int nprobe) {
   if ((d % 4) != 0 || ((reinterpret_cast<uintptr_t>(queries) | reinterpret_cast<uintptr_t>(cent)) & 15) != 0) return false;
-  if (nprobe > GT_MAX_L) return false;
+  if (nprobe + 14 > GT_MAX_L) return false;            // shortlist = nprobe + margin, at most 4 rounds of 32
   if (const char* e = getenv("AURA_COARSE_TC")) return atoi(e) != 0;   // test switch, flipped between calls
   return n_queries >= 64 && (double)n_queries * n_cent >= 2.5e5;
 }
 
 size_t tc_coarse_workspace_bytes(int n_queries, int d, int n_cent, int nprobe) {
   GemmPlan p;
-  if (!make_gemm_plan(n_queries, n_cent, d, 4, nprobe < GT_L ? nprobe : GT_L, false, &p)) return 0;
+  if (!make_gemm_plan(n_queries, n_cent, d, 4, GT_L, false, &p)) return 0;
   return align256(p.partial_bytes) + 3 * align256((size_t)n_cent * 4) + align256((size_t)n_queries * nprobe * 4) + 512 +
          align256((size_t)n_queries * GT_MAX_L * 8) + align256((size_t)n_queries * 8);
 }
 
-__global__ void __launch_bounds__(128) cand_to_probes_kernel(const u64* __restrict__ cand, int nprobe, long long* __restrict__ probes) {
+// ---- exact finish of the tensor-core coarse stage -------------------------------------------------------------------
+// The TF32 GEMM only SHORTLISTS centroid rows (n_cand = 32 per round, at least 14 more than nprobe).  This kernel
+// re-scores the shortlist with the reference's own statement, dist = ||centroid - q||_2 in the difference form and in
+// exactly the operation order of coarse_dist_kernel (ivf.cu), ranks by (dist ascending, row ascending) like
+// coarse_select_kernel, and certifies: a row outside the shortlist has TF32 score s <= s_last, hence
+// dist^2 >= ||q||^2 - s_last - eps with eps bounding the TF32 rounding of 2 q.c plus the fp32 cancellation of the
+// expanded form; if the nprobe-th exact dist^2 is below that, the probes are provably the exact ones.  Otherwise (rare:
+// near-equidistant centroids, or the tied zero rows of a small index, hippocampal.py:261) the CTA scans ALL centroid rows
+// itself in exact fp32 - same arithmetic, same order - so every query leaves with the probes of the exact path and
+// nothing needs a host-side check.
+__device__ __forceinline__ float coarse_exact_dist(const float* __restrict__ cr, const float* __restrict__ qs, int d, int lane,
+                                                   bool vec) {
+  float acc = 0.f;
+  if (vec) {
+    const float4* c4 = reinterpret_cast<const float4*>(cr);
+    const float4* q4 = reinterpret_cast<const float4*>(qs);
+    const int d4 = d >> 2;
+    for (int e = lane; e < d4; e += 32) {
+      const float4 cv = c4[e], qv = q4[e];
+      const float t0 = cv.x - qv.x, t1 = cv.y - qv.y, t2 = cv.z - qv.z, t3 = cv.w - qv.w;
+      acc = fmaf(t0, t0, fmaf(t1, t1, fmaf(t2, t2, fmaf(t3, t3, acc))));
+    }
+  } else {
+    for (int e = lane; e < d; e += 32) { const float t = cr[e] - qs[e]; acc = fmaf(t, t, acc); }
+  }
+  return sqrtf(warp_sum(acc));
+}
+
+template <int KPL>
+__global__ void __launch_bounds__(128) coarse_rescore_kernel(const u64* __restrict__ cand, int n_cand, const float* __restrict__ queries,
+                                                             int d, const float* __restrict__ cent, int n_cent,
+                                                             const float* __restrict__ cmax, int nprobe,
+                                                             long long* __restrict__ probes, int* __restrict__ n_fallback) {
+  extern __shared__ __align__(16) float qs[];          // [d] this query (raw, as hippocampal.py:261 uses it)
+  __shared__ u64 ex[GT_MAX_L];
+  __shared__ u64 merge[4 * 32 * KPL];
+  __shared__ u64 best[32 * KPL];
+  __shared__ float qsq_w[4];
+  __shared__ float qsq_s;
+  __shared__ int slow;
   const int b = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* q = queries + (size_t)b * d;
+  float ss = 0.f;
+  for (int e = threadIdx.x; e < d; e += blockDim.x) { const float v = q[e]; qs[e] = v; ss = fmaf(v, v, ss); }
+  ss = warp_sum(ss);
+  if (lane == 0) qsq_w[warp] = ss;
+  __syncthreads();
+  if (threadIdx.x == 0) qsq_s = (qsq_w[0] + qsq_w[1]) + (qsq_w[2] + qsq_w[3]);
+  __syncthreads();
+  const bool vec = (d & 3) == 0 && ((reinterpret_cast<uintptr_t>(cent) & 15) == 0);
+  const u64* my = cand + (size_t)b * GT_MAX_L;
+  for (int i = warp; i < GT_MAX_L; i += 4) {
+    u64 key = 0ull;
+    const u64 ak = i < n_cand ? my[i] : 0ull;
+    if (ak != 0ull) {
+      const unsigned c = key_row(ak);
+      key = make_key(-coarse_exact_dist(cent + (size_t)c * d, qs, d, lane, vec), c);
+    }
+    if (lane == 0) ex[i] = key;
+  }
+  block_bitonic_sort_desc(ex, GT_MAX_L);
+  if (threadIdx.x == 0) {
+    int s = 0;
+    const u64 last = my[n_cand - 1];
+    if (last != 0ull && nprobe <= n_cand) {            // the shortlist is full: rows outside it exist
+      const float qn = sqrtf(qsq_s);
+      const float eps = 0.00390625f * 1.05f * qn * (*cmax) + 1e-5f * (qsq_s + (*cmax) * (*cmax));
+      const float bound = qsq_s - key_score(last) - eps;                    // every outside row: dist^2 >= bound
+      const u64 pth = ex[nprobe - 1];
+      const float dp = pth ? -key_score(pth) : INFINITY;
+      if (!(dp * dp < bound)) s = 1;
+    }
+    slow = s;
+  }
+  __syncthreads();
+  if (!slow) {
+    for (int i = threadIdx.x; i < nprobe; i += blockDim.x) {
+      const u64 key = ex[i];
+      probes[(size_t)b * nprobe + i] = key ? (long long)key_row(key) : -1ll;
+    }
+    return;
+  }
+  // exact scan of every centroid row by this CTA (coarse_dist_kernel + coarse_select_kernel for one query)
+  if (threadIdx.x == 0 && n_fallback) atomicAdd(n_fallback, 1);
+  WarpTopK<KPL> tk;
+  tk.init();
+  for (int c = warp; c < n_cent; c += 4) {
+    const u64 key = make_key(-coarse_exact_dist(cent + (size_t)c * d, qs, d, lane, vec), (unsigned)c);
+    if (key > tk.thr) tk.insert(key, lane);
+  }
+  publish_cta_topk<KPL>(tk, warp, lane, 4, merge, nprobe, best);
   for (int i = threadIdx.x; i < nprobe; i += blockDim.x) {
-    const u64 key = cand[(size_t)b * GT_MAX_L + i];
+    const u64 key = best[i];
     probes[(size_t)b * nprobe + i] = key ? (long long)key_row(key) : -1ll;
   }
 }
 
-// probes[b, 0..nprobe) = centroid rows nearest to query b, ranked by the TF32 score (no exact re-score: probe
-// selection is the approximate stage of the index by construction).
+// probes[b, 0..nprobe) = the nprobe centroid rows nearest to query b: TF32 shortlist, exact fp32 finish (above).
 int tc_coarse(const float* queries, int n_queries, int d, const float* cent, int n_cent, const float* csq, int nprobe,
               long long* probes, void* workspace, cudaStream_t st) {
   GemmPlan p;
-  const int k1 = nprobe < GT_L ? nprobe : GT_L;
-  AURA_REQUIRE(make_gemm_plan(n_queries, n_cent, d, 4, k1, false, &p), AURA_ERR_UNSUPPORTED, "tc_coarse: no plan");
+  AURA_REQUIRE(make_gemm_plan(n_queries, n_cent, d, 4, GT_L, false, &p), AURA_ERR_UNSUPPORTED, "tc_coarse: no plan");
   unsigned char* ws = reinterpret_cast<unsigned char*>(workspace);
   u64* partial = reinterpret_cast<u64*>(ws);
   float* scale2 = reinterpret_cast<float*>(ws + align256(p.partial_bytes));
@@ -822,18 +910,19 @@ int tc_coarse(const float* queries, int n_queries, int d, const float* cent, int
   float* dummy_score = cmax + align256((size_t)n_cent * 4) / 4;
   u64* cand = reinterpret_cast<u64*>(reinterpret_cast<unsigned char*>(dummy_score) + align256((size_t)n_queries * nprobe * 4) + 512);
   u64* ceil_buf = cand + align256((size_t)n_queries * GT_MAX_L * 8) / 8;
-  AURA_CUDA_OK(cudaMemsetAsync(cmax, 0, 4, st));
+  AURA_CUDA_OK(cudaMemsetAsync(cmax, 0, 8, st));        // cmax and the fallback counter behind it
   centroid_terms_kernel<<<(n_cent + 255) / 256, 256, 0, st>>>(csq, n_cent, scale2, neg_csq, cmax);
   note_launches(1);
   FinishArgs f;
-  f.partial = partial; f.n_atiles = p.n_atiles; f.n_groups = p.n_groups; f.L = p.L; f.n2 = p.n2; f.k = k1;
+  f.partial = partial; f.n_atiles = p.n_atiles; f.n_groups = p.n_groups; f.L = p.L; f.n2 = p.n2; f.k = GT_L;
   f.n_a_rows = n_queries; f.row_base = 0; f.rows = nullptr; f.bf16 = 0; f.d = d; f.qn = nullptr;
   f.scale = nullptr; f.bias = nullptr; f.eps = 0.f; f.a_scale = nullptr;
-  f.out_idx = probes; f.out_score = dummy_score; f.uncertain = nullptr; f.cand = nullptr; f.ceil_out = nullptr; f.round = 0;
+  f.out_idx = probes; f.out_score = dummy_score; f.uncertain = nullptr; f.cand = cand; f.ceil_out = ceil_buf; f.round = 0;
   const size_t fsmem = ((size_t)p.n2 + GT_MAX_L) * 8;
   AURA_CUDA_OK(cudaFuncSetAttribute(gemm_topk_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
-  const int rounds = (nprobe + GT_L - 1) / GT_L;
-  if (rounds > 1) { f.cand = cand; f.ceil_out = ceil_buf; }
+  // 32 shortlisted rows per round, at least 14 beyond nprobe (the margin of the exact searches)
+  int rounds = (nprobe + 14 + GT_L - 1) / GT_L;
+  if (rounds > GT_MAX_ROUNDS) rounds = GT_MAX_ROUNDS;
   for (int r = 0; r < rounds; ++r) {
     int rc = run_gemm_topk(queries, n_queries, 0, cent, n_cent, d, false, scale2, neg_csq, false, p, partial, st,
                            r ? ceil_buf : nullptr);
@@ -843,11 +932,20 @@ int tc_coarse(const float* queries, int n_queries, int d, const float* cent, int
     AURA_CUDA_OK(cudaGetLastError());
     note_launches(1);
   }
-  if (rounds > 1) {
-    cand_to_probes_kernel<<<n_queries, 128, 0, st>>>(cand, nprobe, probes);
-    AURA_CUDA_OK(cudaGetLastError());
-    note_launches(1);
+  int* n_fallback = reinterpret_cast<int*>(cmax) + 1;
+  const size_t rsmem = (size_t)d * 4;
+  if (nprobe <= 32) {
+    AURA_CUDA_OK(cudaFuncSetAttribute(coarse_rescore_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem));
+    coarse_rescore_kernel<1><<<n_queries, 128, rsmem, st>>>(cand, rounds * GT_L, queries, d, cent, n_cent, cmax, nprobe, probes, n_fallback);
+  } else if (nprobe <= 64) {
+    AURA_CUDA_OK(cudaFuncSetAttribute(coarse_rescore_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem));
+    coarse_rescore_kernel<2><<<n_queries, 128, rsmem, st>>>(cand, rounds * GT_L, queries, d, cent, n_cent, cmax, nprobe, probes, n_fallback);
+  } else {
+    AURA_CUDA_OK(cudaFuncSetAttribute(coarse_rescore_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem));
+    coarse_rescore_kernel<4><<<n_queries, 128, rsmem, st>>>(cand, rounds * GT_L, queries, d, cent, n_cent, cmax, nprobe, probes, n_fallback);
   }
+  AURA_CUDA_OK(cudaGetLastError());
+  note_launches(1);
   return AURA_OK;
 }
 

@@ -94,9 +94,20 @@ def test_index_state_matches_reference(case, monkeypatch):
 def test_queries_match_reference(case, monkeypatch):
     gold = load(case.name)
     hf, rows, queries, locs = build_cuda(case, gold, monkeypatch)
+    from aura_snn_rag_b200 import ops
     o, *_ = build_oracle(case, gold)            # CPU oracle in the same final state (patched semantics)
     o.time_fn.now = C.query_time(case)
-    state_equal = bool((hf.memory_metadata[:hf.memory_count, 2].cpu() == o.memory_metadata[:o.memory_count, 2]).all())
+    m = hf.memory_count
+    cid_gpu = hf.memory_metadata[:m, 2].cpu()
+    cid_ref = o.memory_metadata[:m, 2]
+    flipped = cid_gpu != cid_ref                      # near-equidistant rows may land in the other list (<= 0.5 %)
+    flipped_lists = set(cid_gpu[flipped].tolist()) | set(cid_ref[flipped].tolist())
+    import copy
+    o_gpu_state = copy.copy(o)                        # same bank, clock and code; index state of the CUDA build
+    o_gpu_state.memory_metadata = o.memory_metadata.clone()
+    o_gpu_state.memory_metadata[:m, 2] = cid_gpu
+    o_gpu_state.centroids = hf.centroids.cpu()
+    n_centroid_queries = n_strict = 0
     for qi, q in enumerate(queries):
         qt = torch.from_numpy(q)
         # exact path vs the reference's own output
@@ -116,16 +127,35 @@ def test_queries_match_reference(case, monkeypatch):
         # rows vs the patched oracle
         if not hf._centroid_path():
             continue
+        n_centroid_queries += 1
         g_sc = gold["asis_scores"][qi]
         n_ret = int((gold["asis_idnum"][qi] >= 0).sum())
         idx, sc = hf.retrieve_batch(qt, k=case.k)
         idx, sc = idx[0].cpu().numpy(), sc[0].cpu().numpy()
-        if state_equal:
+        # strictly comparable: same probe set on both sides and no probed list holds a flipped row (the candidate
+        # sets are then identical by construction); otherwise the two sides legitimately score different rows
+        nprobe = min(hf.nprobe, hf.centroids_k)
+        # (zeroed tail rows of the 256-row buffer tie exactly and own no rows: torch.topk may pick any of them, :261-262)
+        p_ref = {c for c in o.coarse_probe(qt).tolist() if c < hf.centroids_k}
+        p_gpu = {c for c in ops.ivf_coarse(qt.cuda(), hf.centroids, nprobe)[0].tolist() if c < hf.centroids_k}
+        if p_ref == p_gpu and not (p_ref & flipped_lists):
+            n_strict += 1
             prow, psc = o.retrieve_rows(qt, k=case.k, patched=True)
             _same_topk(idx[: len(prow)].tolist(), sc[: len(prow)].tolist(), prow.tolist(), psc.tolist())
             assert np.all(idx[len(prow):] == -1)
             if n_ret:   # the reference itself returned (it raises when k exceeds the candidate count)
                 np.testing.assert_allclose(sc[:n_ret], g_sc[:n_ret], rtol=RTOL, atol=1e-6)
+        # EVERY query, flipped rows or not: the oracle's query path on the CUDA build's own index state (its centroids
+        # and stored centroid ids) must return the same rows and scores
+        prow, psc = o_gpu_state.retrieve_rows(qt, k=case.k, patched=True)
+        _same_topk(idx[: len(prow)].tolist(), sc[: len(prow)].tolist(), prow.tolist(), psc.tolist())
+        assert np.all(idx[len(prow):] == -1)
+    # the comparison against the reference's OWN state must not be vacuous either
+    if n_centroid_queries:
+        frac = n_strict / n_centroid_queries
+        print(f"[{case.name}] {n_strict}/{n_centroid_queries} centroid-path queries compared against the reference state "
+              f"row for row; {int(flipped.sum())} of {m} assignments differ")
+        assert frac >= (0.9 if int(flipped.sum()) == 0 else 0.5), (n_strict, n_centroid_queries, int(flipped.sum()))
 
 
 def test_reference_structural_assertions(monkeypatch):
