@@ -526,6 +526,537 @@ __global__ void __launch_bounds__(128) ivf_finish_kernel(const IvfFinishArgs f) 
   if (threadIdx.x == 0 && (overflow || (keys[0] == 0ull && !f.empty_ok))) f.uncertain[b] = 1;
 }
 
+// =====================================================================================================================
+// List-major fine stage, rows-as-M formulation with ONE-PASS selection (round 2).
+//
+//   item  = (list c, group of <= NQ of the queries probing it, chunk of its rows)
+//   A (M) = 128 bank rows of the list per tile (TMA box from the list-major copy, or gathered by row id with cp.async)
+//   B (N) = the query group, N = 16..NQ columns (gathered from the normalised query block, 128 B x N per k-block)
+//   D     = [128 rows x N queries] fp32 in TMEM, two accumulator stages; two k-blocks (256 B of every row) per pipeline
+//           stage so that a row visit is 256 contiguous bytes in both modes.
+// Against the queries-as-M kernel above: a list probed by 16-32 queries fills the M = 128 tile with rows instead of
+// padding, the gathered operand shrinks from 16 KB to 2-4 KB per k-block, and the epilogue work per tile is
+// proportional to the live queries.  Three launches cover the lists by group size (NQ = 32 / 64 / 128) so that the ring
+// is as deep as the operands allow (5 x 40 KB, 4 x 48 KB, 3 x 64 KB).
+//
+// Selection (any k <= 114 in one pass).  Epilogue thread = bank row; for every query column it compares the score with
+// the query's threshold thr[q] (shared memory) and appends survivors (64-bit ranking keys) to the query's candidate
+// buffer of this CTA (global memory, L2-resident; counters in shared memory).  After every tile, one warp per query
+// - raises thr[q] to the bound other CTAs published for the query (gthr, atomicMax) and
+// - compacts a buffer that grew past Lc keys: exact selection of its L best keys by bisection on the key bits
+//   (registers only), thr[q] = L-th best score, which is also published to gthr.
+// A buffer holds <= Lc keys when a tile starts and a tile appends <= 128, so capacity Lc + 128 never overflows.  When
+// the item ends, its (at most L) keys at or above gthr are written to a result slot that the query links to; the finish
+// kernel gathers the slots of a query, takes the L best approximate keys - exactly the set the multi-round scheme
+// enumerated, because thresholds are always scores of an L-th best key of a SUBSET of the candidates and ties pass -
+// re-scores them in exact fp32 and certifies.
+// =====================================================================================================================
+static constexpr int IR_THREADS = 288;       // warp 0 MMA, warps 1-4 epilogue, warps 5-8 producers
+static constexpr int IR_BM = 128;            // list rows per tile (TMEM lanes)
+static constexpr int IR_MAX_STAGES = 6;
+static constexpr int IR_MAX_NQ = 128;
+static constexpr int IR_MAX_KPL = 12;        // candidate buffer capacity / 32
+static constexpr int IR_SECTIONS = 3;
+
+struct IvfRowsArgs {
+  int n_lists, nprobe, k_blocks, n_stages;
+  int nq_max;                 // 32 / 64 / 128: queries per item of this launch
+  int L, Lc, capq;            // shortlist length, compaction trigger, capacity of a candidate buffer
+  int section, cap_items;
+  const int* item_base;       // [IR_SECTIONS * n_lists + 1] exclusive scan of the per-(section, list) item counts
+  const int4* items;          // {list, query group, chunk, 0}
+  const int* list_offsets; const int* list_rows;
+  const int* q_off; const int* pair_of_pos;
+  const float* scale; const float* bias;
+  int list_major, l2_hint;
+  unsigned* gthr;             // [B] orderable lower bound of every query's final L-th best score
+  u64* cbuf;                  // [grid][nq_max][capq]
+  // results of the items: one slot of <= L keys per (item, query) that kept anything, allocated from a global counter;
+  // query b lists its slots in qslots[b][0 .. qn[b])
+  u64* slot_keys; int* slot_cnt; int* n_slots; int cap_slots;
+  int* qslots; int* qn; int qs_max; int* qflag;
+};
+
+// chunk geometry of the rows-as-M path: a list is cut into chunks only for load balance, and every (chunk, query) pair
+// costs a result slot, so lists probed by many queries - whose items are tensor-bound and long anyway - get longer chunks
+__host__ __device__ __forceinline__ void ir_chunks(int len, int nq, int& n_ch, int& ch_rows) {
+  int mult = nq / 32;
+  mult = mult < 1 ? 1 : mult > 8 ? 8 : mult;
+  const int target = IB_CH_ROWS * mult;                     // 2048 .. 16384 rows per chunk
+  n_ch = (len + target - 1) / target;
+  if (n_ch > IB_MAX_CHUNKS) n_ch = IB_MAX_CHUNKS;
+  if (n_ch < 1) { n_ch = 0; ch_rows = target; return; }
+  ch_rows = ((len + n_ch - 1) / n_ch + GT_BN - 1) / GT_BN * GT_BN;
+  n_ch = (len + ch_rows - 1) / ch_rows;
+}
+__host__ __device__ __forceinline__ int ir_section_of(int nq) { return nq <= 32 ? 0 : nq <= 64 ? 1 : 2; }
+__host__ __device__ __forceinline__ int ir_groups_of(int nq) { return nq <= 64 ? 1 : (nq + IR_MAX_NQ - 1) / IR_MAX_NQ; }
+
+// exact selection inside one candidate buffer by the whole warp: keep its L largest keys (in place, front of the
+// buffer), return the L-th largest key.  n <= 32 * IR_MAX_KPL keys, n >= L.
+__device__ __forceinline__ u64 ir_warp_compact(u64* buf, int n, int L, int lane) {
+  u64 kk[IR_MAX_KPL];
+#pragma unroll
+  for (int j = 0; j < IR_MAX_KPL; ++j) { const int i = lane + 32 * j; kk[j] = i < n ? buf[i] : 0ull; }
+  // bisection on the score bits: largest t with |{hi >= t}| >= L
+  unsigned lo = 0u, hi = 0xFFFFFFFFu;
+  while (lo < hi) {
+    const unsigned mid = lo + ((hi - lo) >> 1) + 1u;
+    int c = 0;
+#pragma unroll
+    for (int j = 0; j < IR_MAX_KPL; ++j) c += ((unsigned)(kk[j] >> 32) >= mid) ? 1 : 0;
+    c = __reduce_add_sync(FULL, c);
+    if (c >= L) lo = mid; else hi = mid - 1u;
+  }
+  const unsigned t = lo;
+  int c_gt = 0, c_eq = 0;
+#pragma unroll
+  for (int j = 0; j < IR_MAX_KPL; ++j) {
+    const unsigned h = (unsigned)(kk[j] >> 32);
+    c_gt += h > t ? 1 : 0;
+    c_eq += (h == t && kk[j] != 0ull) ? 1 : 0;
+  }
+  c_gt = __reduce_add_sync(FULL, c_gt);
+  c_eq = __reduce_add_sync(FULL, c_eq);
+  unsigned u = 0u;                               // keys with the threshold score: keep the (L - c_gt) lowest rows
+  if (c_gt + c_eq > L) {
+    const int want = L - c_gt;
+    unsigned l2 = 0u, h2 = 0xFFFFFFFFu;
+    while (l2 < h2) {
+      const unsigned mid = l2 + ((h2 - l2) >> 1) + 1u;
+      int c = 0;
+#pragma unroll
+      for (int j = 0; j < IR_MAX_KPL; ++j) c += ((unsigned)(kk[j] >> 32) == t && (unsigned)kk[j] >= mid) ? 1 : 0;
+      c = __reduce_add_sync(FULL, c);
+      if (c >= want) l2 = mid; else h2 = mid - 1u;
+    }
+    u = l2;
+  }
+  __syncwarp();
+  int base = 0;
+  const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+  for (int j = 0; j < IR_MAX_KPL; ++j) {
+    const unsigned h = (unsigned)(kk[j] >> 32);
+    const bool keep = kk[j] != 0ull && (h > t || (h == t && (unsigned)kk[j] >= u));
+    const unsigned m = __ballot_sync(FULL, keep);
+    if (keep) buf[base + __popc(m & lt)] = kk[j];
+    base += __popc(m);
+  }
+  __syncwarp();
+  return ((u64)t << 32) | (u64)u;
+}
+
+template <bool TF32>
+__global__ void __launch_bounds__(IR_THREADS, 1)
+ivf_rows_kernel(const __grid_constant__ CUtensorMap tmap_lm, const unsigned char* __restrict__ qmat,
+                const unsigned char* __restrict__ bank, const int row_pitch, const IvfRowsArgs a) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int S = a.n_stages, NQ = a.nq_max;
+  const unsigned b_bytes = (unsigned)NQ * GT_SLAB;                 // one k-block of the query group
+  const unsigned stage_bytes = 2u * (GT_A_BYTES + b_bytes);        // [A k0][A k1][B k0][B k1]
+  unsigned char* ring = smem;
+  float* thr_s = reinterpret_cast<float*>(ring + (size_t)S * stage_bytes);   // [IR_MAX_NQ]
+  int* cnt_s = reinterpret_cast<int*>(thr_s + IR_MAX_NQ);
+  int* base_s = cnt_s + IR_MAX_NQ;              // keys in the buffer right after its last compaction
+  int* qid_s = base_s + IR_MAX_NQ;
+  uint64_t* full = reinterpret_cast<uint64_t*>(qid_s + IR_MAX_NQ);
+  uint64_t* empty = full + IR_MAX_STAGES;
+  uint64_t* tfull = empty + IR_MAX_STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  // need_s[tile parity] == tile number + 1: some candidate buffer needs compaction after this tile.  Written during the
+  // tile's pass, read after the barrier that ends it; the same word is next written two tiles later, i.e. after the
+  // barrier of the tile in between, which every reader of this tile has passed - no reset, no race.
+  volatile unsigned* need_s = reinterpret_cast<volatile unsigned*>(tmem_slot + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int ELEMS_PER_SLAB = TF32 ? 32 : 64;
+  const uint32_t tmem_cols = NQ <= 32 ? 64u : NQ <= 64 ? 128u : 256u;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(&full[s], a.list_major ? 129 : 128); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4); }
+    need_s[0] = 0u; need_s[1] = 0u;
+    if (a.list_major) tc::tma_prefetch_desc(&tmap_lm);
+    fence_mbar_init();
+  }
+  if (warp == 0) { tc::tmem_alloc(tmem_slot, tmem_cols); tc::tmem_relinquish(); }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // this launch's section of the work table; a table that did not fit processes nothing (the finish kernel hands
+  // every query back)
+  const int total_items = a.item_base[IR_SECTIONS * a.n_lists];
+  const int item_lo = a.item_base[a.section * a.n_lists];
+  const int item_hi = total_items <= a.cap_items ? a.item_base[(a.section + 1) * a.n_lists] : item_lo;
+
+#define IR_DECODE_ITEM(item)                                                                                   \
+  const int4 it = a.items[item];                                                                               \
+  const int qb = a.q_off[it.x], nq = a.q_off[it.x + 1] - qb;                                                    \
+  const int n_qg = ir_groups_of(nq);                                                                           \
+  const int g_lo = (int)(((long long)nq * it.y) / n_qg), g_hi = (int)(((long long)nq * (it.y + 1)) / n_qg);     \
+  const int a0 = qb + g_lo, n_live = g_hi - g_lo;                                                              \
+  const int n_pad = max(16, (n_live + 15) & ~15);                                                              \
+  const int lb = a.list_offsets[it.x], len = a.list_offsets[it.x + 1] - lb;                                    \
+  int n_ch_, ch_rows_;                                                                                         \
+  ir_chunks(len, nq, n_ch_, ch_rows_);                                                                         \
+  const int r0 = it.z * ch_rows_, r1 = min(len, r0 + ch_rows_);
+
+  if (warp >= 5) {
+    // ===================== producers: 128 threads =====================
+    const int pt = threadIdx.x - 160;
+    const int prow = pt >> 3, pj = pt & 7;          // A gather: chunk pj of tile rows prow + 16*i
+    const uint32_t a_dst = (uint32_t)(prow * GT_SLAB + ((pj ^ (prow & 7)) << 4));
+    const uint32_t ring_u32 = smem_u32(ring);
+    const uint64_t pol_stream = (a.l2_hint & 1) ? l2_policy_evict_first() : l2_policy_evict_normal();
+    const uint64_t pol_keep = (a.l2_hint & 2) ? l2_policy_evict_last() : l2_policy_evict_normal();
+    const uint64_t pol_q = (a.l2_hint & 4) ? l2_policy_evict_last() : l2_policy_evict_normal();
+    int stage = 0; unsigned phase = 0;
+    for (int item = item_lo + (int)blockIdx.x; item < item_hi; item += (int)gridDim.x) {
+      IR_DECODE_ITEM(item)
+      // query pieces of this thread: piece p = pt + 128*i covers 16 bytes (chunk p & 7) of B row p >> 3
+      const unsigned char* qsrc[IR_MAX_NQ / 16];
+      uint32_t q_dst[IR_MAX_NQ / 16];
+#pragma unroll
+      for (int i = 0; i < IR_MAX_NQ / 16; ++i) {
+        const int row = (pt + 128 * i) >> 3;
+        const int src_row = min(row, n_live - 1);   // columns past the group re-load a valid query (their threshold is +inf)
+        qsrc[i] = row < n_pad ? qmat + (size_t)(a.pair_of_pos[a0 + src_row] / a.nprobe) * row_pitch + pj * 16 : nullptr;
+        q_dst[i] = (uint32_t)(row * GT_SLAB + ((pj ^ (row & 7)) << 4));
+      }
+      const uint64_t pol_b = n_qg > 1 ? pol_keep : pol_stream;   // rows of a list with several query groups are re-read from L2
+      for (int cr = r0; cr < r1; cr += IR_BM) {
+        int rb[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) rb[i] = a.list_major ? 0 : a.list_rows[lb + min(cr + prow + 16 * i, r1 - 1)];
+        for (int kb = 0; kb < a.k_blocks; kb += 2) {
+          const int nkb = min(2, a.k_blocks - kb);
+          tc::mbar_wait_guarded(&empty[stage], phase ^ 1u);
+          const uint32_t sp = ring_u32 + (uint32_t)stage * stage_bytes;
+          bool in_row[2]; size_t ko[2];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            in_row[h] = h < nkb && (int)((kb + h) * GT_SLAB) + pj * 16 < row_pitch;
+            ko[h] = in_row[h] ? (size_t)(kb + h) * GT_SLAB : 0;
+          }
+          if (a.list_major) {
+            if (pt == 0) {
+              mbar_arrive_expect_tx(&full[stage], (unsigned)(nkb * GT_A_BYTES));
+              unsigned char* spg = ring + (size_t)stage * stage_bytes;
+              for (int h = 0; h < nkb; ++h)
+                tc::tma_load_2d(spg + h * GT_A_BYTES, &tmap_lm, (kb + h) * ELEMS_PER_SLAB, lb + cr, &full[stage], pol_b);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const unsigned char* src = bank + (size_t)rb[i] * row_pitch + pj * 16;
+#pragma unroll
+              for (int h = 0; h < 2; ++h)
+                if (h < nkb) cp_async16(sp + h * GT_A_BYTES + a_dst + i * 16 * GT_SLAB, src + ko[h], in_row[h] ? 16u : 0u, pol_b);
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < IR_MAX_NQ / 16; ++i)
+            if (qsrc[i] != nullptr) {
+#pragma unroll
+              for (int h = 0; h < 2; ++h)
+                if (h < nkb) cp_async16(sp + 2 * GT_A_BYTES + h * b_bytes + q_dst[i], qsrc[i] + ko[h], in_row[h] ? 16u : 0u, pol_q);
+            }
+          cp_async_arrive_noinc(&full[stage]);
+          if (++stage == S) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+    cp_async_wait<0>();
+  } else if (warp == 0) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      int stage = 0; unsigned phase = 0, tile_n = 0;
+      for (int item = item_lo + (int)blockIdx.x; item < item_hi; item += (int)gridDim.x) {
+        IR_DECODE_ITEM(item)
+        (void)a0;
+        const uint32_t idesc = tc::make_idesc(TF32 ? 2 : 1, IR_BM, n_pad);
+        for (int cr = r0; cr < r1; cr += IR_BM, ++tile_n) {
+          const unsigned acc = tile_n & 1u, acc_phase = (tile_n >> 1) & 1u;
+          tc::mbar_wait_guarded(&tempty[acc], acc_phase ^ 1u);
+          tc::tc_fence_after();
+          const uint32_t d_tmem = tmem_base + acc * (uint32_t)NQ;
+          for (int kb = 0; kb < a.k_blocks; kb += 2) {
+            const int nkb = min(2, a.k_blocks - kb);
+            tc::mbar_wait_guarded(&full[stage], phase);
+            fence_proxy_async();                    // cp.async wrote through the generic proxy; the MMA reads through the async proxy
+            tc::tc_fence_after();
+            const unsigned char* sp = ring + (size_t)stage * stage_bytes;
+            for (int h = 0; h < nkb; ++h) {
+              const uint64_t da = tc::make_smem_desc_sw128(sp + h * GT_A_BYTES);
+              const uint64_t db = tc::make_smem_desc_sw128(sp + 2 * GT_A_BYTES + h * b_bytes);
+#pragma unroll
+              for (int j = 0; j < GT_SLAB / 32; ++j)
+                tc::umma<TF32>(d_tmem, da + (uint64_t)(2 * j), db + (uint64_t)(2 * j), idesc, ((kb + h) | j) != 0 ? 1u : 0u);
+            }
+            tc::umma_commit(&empty[stage]);
+            if (++stage == S) { stage = 0; phase ^= 1u; }
+          }
+          tc::umma_commit(&tfull[acc]);
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue: thread = one bank row of the tile =====================
+    const int quarter = warp & 3;                   // TMEM lane quarter this warp may access
+    const int te = quarter * 32 + lane;
+    const int et = threadIdx.x - 32;                // 0..127
+    const int wi = warp - 1;                        // 0..3: this warp maintains the queries q = wi (mod 4)
+    u64* my_cbuf = a.cbuf + (size_t)blockIdx.x * NQ * a.capq;
+    const int L = a.L, Lc = a.Lc, capq = a.capq;
+    unsigned tile_n = 0;
+    for (int item = item_lo + (int)blockIdx.x; item < item_hi; item += (int)gridDim.x) {
+      IR_DECODE_ITEM(item)
+      tc::named_bar_sync(1, 128);                   // the previous item's flush is complete
+      if (et < NQ) {
+        const bool live = et < n_live;
+        const int b = live ? a.pair_of_pos[a0 + et] / a.nprobe : 0;
+        qid_s[et] = b; cnt_s[et] = 0; base_s[et] = 0;
+        float t = INFINITY;                         // dead columns select nothing
+        if (live) { const unsigned g = *reinterpret_cast<volatile unsigned*>(a.gthr + b); t = g ? f32_from_orderable(g) : -INFINITY; }
+        thr_s[et] = t;
+      }
+      // per-row terms of the first tile; every later tile's are fetched while the previous one is processed
+      bool valid = r0 + te < r1;
+      int rid = valid ? a.list_rows[lb + r0 + te] : 0;
+      float sc = valid ? (a.scale ? a.scale[rid] : 1.f) : 0.f;
+      float bi = valid ? (a.bias ? a.bias[rid] : 0.f) : 0.f;
+      tc::named_bar_sync(1, 128);
+      int tiles_since_refresh = 0;
+      for (int cr = r0; cr < r1; cr += IR_BM, ++tile_n) {
+        const unsigned acc = tile_n & 1u, acc_phase = (tile_n >> 1) & 1u;
+        const bool valid_n = cr + IR_BM + te < r1;
+        const int rid_n = valid_n ? a.list_rows[lb + cr + IR_BM + te] : 0;
+        tc::mbar_wait_guarded(&tfull[acc], acc_phase);
+        tc::tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * (uint32_t)NQ;
+#pragma unroll 1
+        for (int c0 = 0; c0 < n_pad; c0 += 16) {
+          float v[16];
+          tc::tmem_ld_32x16(taddr + c0, v);
+          unsigned mask = 0u;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) mask |= (fmaf(v[j], sc, bi) >= thr_s[c0 + j]) ? (1u << j) : 0u;
+          if (!valid) mask = 0u;
+          while (mask) {                            // rare once the thresholds are warm
+            const int j = __ffs(mask) - 1;
+            mask &= mask - 1u;
+            const u64 key = make_key(fmaf(select16(v, j), sc, bi), (unsigned)rid);
+            const int pos = atomicAdd(&cnt_s[c0 + j], 1);
+            if (pos < capq) my_cbuf[(size_t)(c0 + j) * capq + pos] = key;
+            if (pos + 1 == L || pos >= Lc) need_s[acc] = tile_n + 1u;   // a buffer reached L keys for the first time, or outgrew Lc
+          }
+        }
+        tc::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[acc]);
+        const float sc_n = valid_n ? (a.scale ? a.scale[rid_n] : 1.f) : 0.f;
+        const float bi_n = valid_n ? (a.bias ? a.bias[rid_n] : 0.f) : 0.f;
+        tc::named_bar_sync(1, 128);                 // every append of this tile is visible
+        const bool refresh = ++tiles_since_refresh >= 4;      // pull the bounds other CTAs published every few tiles
+        if (need_s[acc] == tile_n + 1u || refresh) {
+          tiles_since_refresh = 0;
+          // lane l looks after query q = wi + 4*l
+          const int q = wi + 4 * lane;
+          bool need = false;
+          unsigned g = 0u;
+          if (q < n_live) {
+            g = *reinterpret_cast<volatile unsigned*>(a.gthr + qid_s[q]);
+            const int c = cnt_s[q];
+            if (c > capq) { a.qflag[qid_s[q]] = 1; cnt_s[q] = capq; }    // cannot happen by construction; never silently drop
+            need = c > Lc || (base_s[q] < L && c >= L);
+            if (!need && g != 0u) thr_s[q] = fmaxf(thr_s[q], f32_from_orderable(g));
+          }
+          unsigned todo = __ballot_sync(FULL, need);
+          while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1u;
+            const int qq = wi + 4 * src;
+            const unsigned gq = __shfl_sync(FULL, g, src);
+            const u64 kth = ir_warp_compact(my_cbuf + (size_t)qq * capq, min(cnt_s[qq], capq), L, lane);
+            if (lane == 0) {
+              const unsigned o = (unsigned)(kth >> 32);
+              cnt_s[qq] = L; base_s[qq] = L;
+              thr_s[qq] = fmaxf(thr_s[qq], f32_from_orderable(o > gq ? o : gq));
+              if (o > gq) atomicMax(a.gthr + qid_s[qq], o);     // L keys of this item alone are at or above it
+            }
+          }
+          tc::named_bar_sync(1, 128);
+        }
+        valid = valid_n; rid = rid_n; sc = sc_n; bi = bi_n;
+      }
+      // ---- item done: the keys of every query that can still matter go to a result slot ----
+      for (int q = wi; q < n_live; q += 4) {
+        const int b = qid_s[q];
+        u64* buf = my_cbuf + (size_t)q * capq;
+        int c = min(cnt_s[q], capq);
+        if (c > L || (c == L && base_s[q] < L)) {
+          const u64 kth = ir_warp_compact(buf, c, L, lane);
+          c = L;
+          if (lane == 0) atomicMax(a.gthr + b, (unsigned)(kth >> 32));
+        }
+        __syncwarp();
+        const unsigned g = *reinterpret_cast<volatile unsigned*>(a.gthr + b);
+        u64 kk[4];
+        unsigned m[4];
+        int total = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int i = lane + 32 * j;
+          kk[j] = i < c ? buf[i] : 0ull;
+          m[j] = __ballot_sync(FULL, kk[j] != 0ull && (unsigned)(kk[j] >> 32) >= g);
+          total += __popc(m[j]);
+        }
+        if (total > 0) {
+          int slot = 0;
+          if (lane == 0) {
+            slot = atomicAdd(a.n_slots, 1);
+            const int at = slot < a.cap_slots ? atomicAdd(a.qn + b, 1) : a.qs_max;
+            if (at < a.qs_max) { a.qslots[(size_t)b * a.qs_max + at] = slot; a.slot_cnt[slot] = total; }
+            else { a.qflag[b] = 1; slot = -1; }     // slot table or the query's slot list is full: hand the query back
+          }
+          slot = __shfl_sync(FULL, slot, 0);
+          if (slot >= 0) {
+            u64* dst = a.slot_keys + (size_t)slot * L;
+            int off = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if ((m[j] >> lane) & 1u) dst[off + __popc(m[j] & ((1u << lane) - 1u))] = kk[j];
+              off += __popc(m[j]);
+            }
+          }
+        }
+      }
+    }
+  }
+#undef IR_DECODE_ITEM
+  __syncthreads();
+  if (warp == 0) { tc::tc_fence_after(); tc::tmem_dealloc(tmem_base, tmem_cols); }
+}
+
+// ---- work table of the rows-as-M kernel: three sections by queries per list ----
+__global__ void __launch_bounds__(256) ir_item_count_kernel(const int* __restrict__ q_off, const int* __restrict__ list_offsets,
+                                                            int n_lists, int* __restrict__ items_c) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_lists) return;
+  const int nq = q_off[c + 1] - q_off[c], len = list_offsets[c + 1] - list_offsets[c];
+  int n_ch, ch_rows;
+  ir_chunks(len, nq, n_ch, ch_rows);
+  const int sec = ir_section_of(nq);
+  const int cnt = (nq > 0 && len > 0) ? ir_groups_of(nq) * n_ch : 0;
+  for (int s = 0; s < IR_SECTIONS; ++s) items_c[s * n_lists + c] = s == sec ? cnt : 0;
+}
+__global__ void __launch_bounds__(256) ir_item_fill_kernel(const int* __restrict__ item_base, const int* __restrict__ q_off,
+                                                           int n_lists, int cap, int4* __restrict__ items) {
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (c >= n_lists) return;
+  const int nq = q_off[c + 1] - q_off[c];
+  const int sec = ir_section_of(nq);
+  const int base = item_base[sec * n_lists + c], cnt = item_base[sec * n_lists + c + 1] - base;
+  const int n_qg = ir_groups_of(nq);
+  for (int i = lane; i < cnt; i += 32)
+    if (base + i < cap) items[base + i] = make_int4(c, i % n_qg, i / n_qg, 0);   // the groups of one chunk run side by side (L2)
+}
+
+// ---- finish: the result slots of one query -> its L best approximate keys -> exact re-score + certification ----
+static constexpr int IR_QS_MAX = 1024;       // result slots one query can link (8 x AURA_MAX_NPROBE)
+static constexpr int IR_HIST = 1024;
+struct IvfSlotFinishArgs {
+  const u64* slot_keys; const int* slot_cnt; int cap_slots; const int* qslots; const int* qn; int qs_max; const int* qflag;
+  const unsigned* gthr; const int* item_base; int n_lists, cap_items;
+  const void* rows; int bf16; int d; const float* qn_vec; const float* scale; const float* bias; float eps;
+  int k, L; long long row_base; int empty_ok;
+  long long* out_idx; float* out_score; int* uncertain;
+};
+__global__ void __launch_bounds__(128) ivf_slot_finish_kernel(const IvfSlotFinishArgs f) {
+  __shared__ u64 keys[IB_MERGE_CAP];
+  __shared__ u64 ex[GT_MAX_L];
+  __shared__ int slot_id[IR_QS_MAX];
+  __shared__ int slot_n[IR_QS_MAX];
+  __shared__ int hist[IR_HIST];
+  __shared__ int n_kept;
+  __shared__ unsigned s_max, s_t1;
+  const int b = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  bool overflow = f.item_base[IR_SECTIONS * f.n_lists] > f.cap_items || f.qflag[b] != 0;
+  const int ns = overflow ? 0 : min(f.qn[b], f.qs_max);
+  const unsigned g = f.gthr[b];
+  if (threadIdx.x == 0) { n_kept = 0; s_max = 0u; }
+  for (int i = threadIdx.x; i < ns; i += blockDim.x) {
+    const int sl = f.qslots[(size_t)b * f.qs_max + i];
+    slot_id[i] = sl; slot_n[i] = min(f.slot_cnt[sl], f.L);
+  }
+  __syncthreads();
+  // pass 1: everything at or above the bound the items agreed on (the max over items of an item's own L-th best)
+  unsigned my_max = 0u;
+  for (int i = warp; i < ns; i += 4) {
+    const u64* src = f.slot_keys + (size_t)slot_id[i] * f.L;
+    for (int j = lane; j < slot_n[i]; j += 32) {
+      const u64 key = src[j];
+      const unsigned o = (unsigned)(key >> 32);
+      if (o >= g) { const int pos = atomicAdd(&n_kept, 1); if (pos < IB_MERGE_CAP) keys[pos] = key; my_max = max(my_max, o); }
+    }
+  }
+  atomicMax(&s_max, my_max);
+  __syncthreads();
+  int kept = n_kept;
+  if (kept > IB_MERGE_CAP) {
+    // the neighbours are spread over many lists, so no single item's L-th best is a tight bound: refine it with a
+    // histogram of the scores between the bound and the best score, then collect again
+    const unsigned long long range = (unsigned long long)(s_max - g) + 1ull;
+    for (int i = threadIdx.x; i < IR_HIST; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    for (int i = warp; i < ns; i += 4) {
+      const u64* src = f.slot_keys + (size_t)slot_id[i] * f.L;
+      for (int j = lane; j < slot_n[i]; j += 32) {
+        const unsigned o = (unsigned)(src[j] >> 32);
+        if (o >= g) atomicAdd(&hist[(int)(((unsigned long long)(o - g) * IR_HIST) / range)], 1);
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int acc = 0, t = IR_HIST - 1;
+      for (; t > 0; --t) { acc += hist[t]; if (acc >= f.L) break; }      // bins >= t hold at least L keys (or t == 0: all of them)
+      // key in a bin >= t  <=>  (o - g) * IR_HIST >= t * range
+      s_t1 = g + (unsigned)(((unsigned long long)t * range + IR_HIST - 1) / IR_HIST);
+      n_kept = 0;
+    }
+    __syncthreads();
+    const unsigned t1 = s_t1;
+    for (int i = warp; i < ns; i += 4) {
+      const u64* src = f.slot_keys + (size_t)slot_id[i] * f.L;
+      for (int j = lane; j < slot_n[i]; j += 32) {
+        const u64 key = src[j];
+        if ((unsigned)(key >> 32) >= t1) { const int pos = atomicAdd(&n_kept, 1); if (pos < IB_MERGE_CAP) keys[pos] = key; }
+      }
+    }
+    __syncthreads();
+    kept = n_kept;
+    if (kept > IB_MERGE_CAP) { overflow = true; kept = 0; }            // thousands of keys inside one score bin: hand back
+  }
+  const int n2 = max(64, next_pow2(kept));
+  for (int i = kept + threadIdx.x; i < n2; i += blockDim.x) keys[i] = 0ull;
+  block_bitonic_sort_desc(keys, n2);
+  RescoreArgs ra;
+  ra.rows = f.rows; ra.bf16 = f.bf16; ra.d = f.d; ra.q = f.qn_vec + (size_t)b * f.d; ra.scale = f.scale; ra.bias = f.bias;
+  ra.eps = f.eps; ra.k = f.k; ra.L = f.L; ra.row_base = f.row_base;
+  ra.out_idx = f.out_idx + (size_t)b * f.k; ra.out_score = f.out_score + (size_t)b * f.k;
+  ra.uncertain = f.uncertain + b;
+  rescore_and_write(keys, n2, ex, ra);
+  // no candidate at all (every probed list empty -> the reference scans all rows, hippocampal.py:269-270, unless the
+  // caller is a row shard) or a table that did not fit: hand the query back to the per-query path
+  if (threadIdx.x == 0 && (overflow || (keys[0] == 0ull && !f.empty_ok))) f.uncertain[b] = 1;
+}
+
 static size_t a256(size_t v) { return (v + 255) / 256 * 256; }
 static int ib_cap_items(int n_queries, int nprobe, int n_lists) {
   const long long pairs = (long long)n_queries * nprobe;
@@ -581,13 +1112,181 @@ int launch_cand_rescore(const u64* cand, int n_cand, const void* rows, int bf16,
                         int* uncertain, int n_queries, cudaStream_t st, const int* force_flag);
 void launch_normalize_queries(const float* q, int n, int d, float* qn, __nv_bfloat16* qb, cudaStream_t st);
 
+// diagnostics of the last batch call on a workspace: {items, result slots used, most slots linked by one query, queries
+// flagged inside the kernel, queries without any slot}
+__global__ void __launch_bounds__(256) ir_stats_kernel(const int* __restrict__ item_base, int n_lists, const int* __restrict__ n_slots,
+                                                       const int* __restrict__ qn, const int* __restrict__ qflag, int n_queries,
+                                                       int* __restrict__ out) {
+  __shared__ int s_max, s_flag, s_empty;
+  if (threadIdx.x == 0) { s_max = 0; s_flag = 0; s_empty = 0; }
+  __syncthreads();
+  for (int b = threadIdx.x; b < n_queries; b += blockDim.x) {
+    atomicMax(&s_max, qn[b]);
+    if (qflag[b]) atomicAdd(&s_flag, 1);
+    if (qn[b] == 0) atomicAdd(&s_empty, 1);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) { out[0] = item_base[IR_SECTIONS * n_lists]; out[1] = *n_slots; out[2] = s_max; out[3] = s_flag; out[4] = s_empty; }
+}
+
+// ---- host side of the rows-as-M path -----------------------------------------------------------------------------
+static int ir_list_len(int k) {          // shortlist length: k + 14 margin, in the steps the multi-round scheme used
+  if (k + 14 <= GT_L_SMALL) return GT_L_SMALL;
+  if (k + 14 <= GT_L) return GT_L;
+  return (k + 14 + GT_L - 1) / GT_L * GT_L;
+}
+static constexpr int IR_CBUF_KEYS = IR_MAX_NQ * 32 * IR_MAX_KPL;   // candidate-buffer keys per CTA, largest geometry
+
+struct IrLayout {
+  size_t probes, counts, q_off, cursor, pair_of_pos, pos_of_pair, items_c, item_base, items, qn, qb, coarse, gthr, qcnt, qflag,
+      n_slots, qslots, slot_cnt, slot_keys, cbuf, total;
+  int cap_slots;
+};
+static IrLayout ir_layout(int n_queries, int d, int n_lists, int nprobe, int cap, size_t coarse_bytes) {
+  IrLayout L;
+  size_t o = 0;
+  const size_t pairs = (size_t)n_queries * nprobe;
+  L.probes = o; o += a256(pairs * 8);
+  L.counts = o; o += a256((size_t)n_lists * 4);
+  L.q_off = o; o += a256((size_t)(n_lists + 1) * 4);
+  L.cursor = o; o += a256((size_t)(IR_SECTIONS * n_lists + 1) * 4);
+  L.pair_of_pos = o; o += a256(pairs * 4);
+  L.pos_of_pair = o; o += a256(pairs * 4);
+  L.items_c = o; o += a256((size_t)IR_SECTIONS * n_lists * 4);
+  L.item_base = o; o += a256((size_t)(IR_SECTIONS * n_lists + 1) * 4);
+  L.items = o; o += a256((size_t)cap * 16);
+  L.qn = o; o += a256((size_t)n_queries * d * 4);
+  L.qb = o; o += a256((size_t)n_queries * d * 2);
+  L.coarse = o; o += a256(coarse_bytes);
+  L.gthr = o; o += a256((size_t)n_queries * 4);          // gthr, qcnt, qflag, n_slots are cleared with one memset
+  L.qcnt = o; o += a256((size_t)n_queries * 4);
+  L.qflag = o; o += a256((size_t)n_queries * 4);
+  L.n_slots = o; o += 256;
+  L.qslots = o; o += a256((size_t)n_queries * IR_QS_MAX * 4);
+  // one result slot per (item, query) that keeps anything: ~1 per (query, probe) plus one per extra chunk of a long list
+  L.cap_slots = (int)(4 * pairs + 4096 < 32000000 ? 4 * pairs + 4096 : 32000000);
+  L.slot_cnt = o; o += a256((size_t)L.cap_slots * 4);
+  L.slot_keys = o; o += a256((size_t)L.cap_slots * GT_MAX_L * 8);
+  L.cbuf = o; o += a256((size_t)sm_count() * IR_CBUF_KEYS * 8);
+  L.total = o;
+  return L;
+}
+
+static size_t ir_workspace_bytes(int n_queries, int d, int n_lists, int nprobe) {
+  const int cap = ib_cap_items(n_queries, nprobe, n_lists);
+  return ir_layout(n_queries, d, n_lists, nprobe, cap, ivf_coarse_ws_bytes(n_queries, d, n_lists, nprobe)).total;
+}
+
+static int ivf_rows_search(const void* rows, bool bf16, long long n_rows, int d, const float* queries, int n_queries,
+                           const float* centroids, int n_lists, int nprobe, const int* list_offsets, const int* list_rows,
+                           const void* rows_by_list, const float* scale, const float* bias, int k, long long row_base, int flags,
+                           float eps, long long* out_idx, float* out_score, int* out_uncertain, void* workspace, cudaStream_t st) {
+  const int eb = bf16 ? 2 : 4;
+  const int cap = ib_cap_items(n_queries, nprobe, n_lists);
+  const IrLayout Lo = ir_layout(n_queries, d, n_lists, nprobe, cap, ivf_coarse_ws_bytes(n_queries, d, n_lists, nprobe));
+  unsigned char* ws = reinterpret_cast<unsigned char*>(workspace);
+  long long* probes = reinterpret_cast<long long*>(ws + Lo.probes);
+  int* counts = reinterpret_cast<int*>(ws + Lo.counts);
+  int* q_off = reinterpret_cast<int*>(ws + Lo.q_off);
+  int* cursor = reinterpret_cast<int*>(ws + Lo.cursor);
+  int* pair_of_pos = reinterpret_cast<int*>(ws + Lo.pair_of_pos);
+  int* pos_of_pair = reinterpret_cast<int*>(ws + Lo.pos_of_pair);
+  int* items_c = reinterpret_cast<int*>(ws + Lo.items_c);
+  int* item_base = reinterpret_cast<int*>(ws + Lo.item_base);
+  int4* items = reinterpret_cast<int4*>(ws + Lo.items);
+  float* qn = reinterpret_cast<float*>(ws + Lo.qn);
+  __nv_bfloat16* qb = bf16 ? reinterpret_cast<__nv_bfloat16*>(ws + Lo.qb) : nullptr;
+  unsigned* gthr = reinterpret_cast<unsigned*>(ws + Lo.gthr);
+  AURA_CUDA_OK(cudaMemsetAsync(gthr, 0, Lo.qslots - Lo.gthr, st));     // gthr, qcnt, qflag, n_slots
+
+  int rc = ivf_run_coarse(queries, n_queries, d, centroids, n_lists, nprobe, probes, ws + Lo.coarse, st);
+  if (rc != AURA_OK) return rc;
+  launch_normalize_queries(queries, n_queries, d, qn, qb, st);
+  const int n_pairs = n_queries * nprobe;
+  AURA_CUDA_OK(cudaMemsetAsync(counts, 0, (size_t)n_lists * 4, st));
+  ib_pair_hist_kernel<<<(n_pairs + 255) / 256, 256, 0, st>>>(probes, n_pairs, n_lists, counts);
+  launch_scan_offsets(counts, n_lists, q_off, cursor, st);
+  ib_pair_scatter_kernel<<<(n_pairs + 255) / 256, 256, 0, st>>>(probes, n_pairs, n_lists, cursor, pair_of_pos, pos_of_pair);
+  ir_item_count_kernel<<<(n_lists + 255) / 256, 256, 0, st>>>(q_off, list_offsets, n_lists, items_c);
+  launch_scan_offsets(items_c, IR_SECTIONS * n_lists, item_base, cursor, st);
+  ir_item_fill_kernel<<<(n_lists * 32 + 255) / 256, 256, 0, st>>>(item_base, q_off, n_lists, cap, items);
+  note_launches(4);
+
+  static const int env_l2 = env_int("AURA_IVF_L2HINT", 3), env_grid = env_int("AURA_IVF_GRID", 0);
+  static const int env_stages = env_int("AURA_IVF_STAGES", 0);
+  IvfRowsArgs a;
+  a.n_lists = n_lists; a.nprobe = nprobe; a.cap_items = cap;
+  const int elems = GT_SLAB / eb;
+  a.k_blocks = (d + elems - 1) / elems;
+  a.L = ir_list_len(k);
+  a.Lc = a.L * 2 < 64 ? 64 : a.L * 2;
+  a.capq = a.Lc + IR_BM;
+  a.item_base = item_base; a.items = items; a.list_offsets = list_offsets; a.list_rows = list_rows;
+  a.q_off = q_off; a.pair_of_pos = pair_of_pos; a.scale = scale; a.bias = bias;
+  a.l2_hint = env_l2; a.gthr = gthr; a.cbuf = reinterpret_cast<u64*>(ws + Lo.cbuf);
+  a.slot_keys = reinterpret_cast<u64*>(ws + Lo.slot_keys); a.slot_cnt = reinterpret_cast<int*>(ws + Lo.slot_cnt);
+  a.n_slots = reinterpret_cast<int*>(ws + Lo.n_slots); a.cap_slots = Lo.cap_slots;
+  a.qslots = reinterpret_cast<int*>(ws + Lo.qslots); a.qn = reinterpret_cast<int*>(ws + Lo.qcnt);
+  a.qs_max = IR_QS_MAX; a.qflag = reinterpret_cast<int*>(ws + Lo.qflag);
+  CUtensorMap tmap_lm;
+  memset(&tmap_lm, 0, sizeof(tmap_lm));
+  a.list_major = 0;
+  if (rows_by_list != nullptr) {
+    AURA_REQUIRE((reinterpret_cast<uintptr_t>(rows_by_list) & 15) == 0, AURA_ERR_UNSUPPORTED, "aura_ivf_search_batch: rows_by_list must be 16-byte aligned");
+    const int trc = encode_tmap_2d(&tmap_lm, rows_by_list, eb, bf16, n_rows, d, IR_BM);
+    if (trc != AURA_OK) return trc;
+    a.list_major = 1;
+  }
+  typedef void (*IrKern)(const CUtensorMap, const unsigned char*, const unsigned char*, int, const IvfRowsArgs);
+  IrKern kern = bf16 ? ivf_rows_kernel<false> : ivf_rows_kernel<true>;
+  const size_t fixed = 4 * IR_MAX_NQ * 4 + (2 * IR_MAX_STAGES + 4) * 8 + 16;
+  const size_t smem_cap = (size_t)max_smem_optin() - 1024;
+  int grid = sm_count();
+  if (env_grid >= 1 && env_grid <= grid) grid = env_grid;
+  static const int nq_of_section[IR_SECTIONS] = {32, 64, 128};
+  size_t smem_max = 0;
+  int stages_of[IR_SECTIONS];
+  for (int s = 0; s < IR_SECTIONS; ++s) {
+    const size_t stage_bytes = 2 * ((size_t)GT_A_BYTES + (size_t)nq_of_section[s] * GT_SLAB);
+    int stages = (int)((smem_cap - fixed) / stage_bytes);
+    if (stages > IR_MAX_STAGES) stages = IR_MAX_STAGES;
+    if (env_stages >= 2 && env_stages < stages) stages = env_stages;
+    AURA_REQUIRE(stages >= 2, AURA_ERR_UNSUPPORTED, "aura_ivf_search_batch: needs 2 pipeline stages of shared memory");
+    stages_of[s] = stages;
+    const size_t smem = (size_t)stages * stage_bytes + fixed + 1024;
+    if (smem > smem_max) smem_max = smem;
+  }
+  AURA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+  for (int s = IR_SECTIONS - 1; s >= 0; --s) {       // the lists probed by the most queries first
+    a.section = s; a.nq_max = nq_of_section[s]; a.n_stages = stages_of[s];
+    const size_t stage_bytes = 2 * ((size_t)GT_A_BYTES + (size_t)a.nq_max * GT_SLAB);
+    const size_t smem = (size_t)a.n_stages * stage_bytes + fixed + 1024;
+    kern<<<grid, IR_THREADS, smem, st>>>(tmap_lm, reinterpret_cast<const unsigned char*>(bf16 ? (const void*)qb : (const void*)qn),
+                                         reinterpret_cast<const unsigned char*>(rows), d * eb, a);
+    AURA_CUDA_OK(cudaGetLastError());
+  }
+  IvfSlotFinishArgs f;
+  f.slot_keys = a.slot_keys; f.slot_cnt = a.slot_cnt; f.cap_slots = a.cap_slots; f.qslots = a.qslots; f.qn = a.qn;
+  f.qs_max = a.qs_max; f.qflag = a.qflag; f.gthr = gthr;
+  f.item_base = item_base; f.n_lists = n_lists; f.cap_items = cap;
+  f.rows = rows; f.bf16 = bf16 ? 1 : 0; f.d = d; f.qn_vec = qn; f.scale = scale; f.bias = bias; f.eps = eps;
+  f.k = k; f.L = a.L; f.row_base = row_base; f.empty_ok = (flags & AURA_IVF_EMPTY_OK) ? 1 : 0;
+  f.out_idx = out_idx; f.out_score = out_score; f.uncertain = out_uncertain;
+  ivf_slot_finish_kernel<<<n_queries, 128, 0, st>>>(f);
+  AURA_CUDA_OK(cudaGetLastError());
+  note_launches(IR_SECTIONS + 1);
+  return AURA_OK;
+}
+
 }  // namespace aura
 using namespace aura;
 
 extern "C" size_t aura_ivf_search_batch_workspace_bytes(int n_queries, int d, int n_centroid_rows, int nprobe) {
   if (n_queries < 1 || d < 1 || n_centroid_rows < 1 || nprobe < 1) return 0;
   const int cap = ib_cap_items(n_queries, nprobe, n_centroid_rows);
-  return ib_layout(n_queries, d, n_centroid_rows, nprobe, cap, ivf_coarse_ws_bytes(n_queries, d, n_centroid_rows, nprobe)).total;
+  const size_t old_bytes = ib_layout(n_queries, d, n_centroid_rows, nprobe, cap, ivf_coarse_ws_bytes(n_queries, d, n_centroid_rows, nprobe)).total;
+  const size_t new_bytes = ir_workspace_bytes(n_queries, d, n_centroid_rows, nprobe);
+  return old_bytes > new_bytes ? old_bytes : new_bytes;
 }
 
 extern "C" int aura_ivf_search_batch(const void* rows, int dtype, int64_t n_rows, int d, const float* queries, int n_queries,
@@ -611,6 +1310,11 @@ extern "C" int aura_ivf_search_batch(const void* rows, int dtype, int64_t n_rows
   AURA_REQUIRE(workspace_bytes >= aura_ivf_search_batch_workspace_bytes(n_queries, d, n_centroid_rows, nprobe),
                AURA_ERR_WORKSPACE, "aura_ivf_search_batch: workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
+  static const int use_old = env_int("AURA_IVF_OLD", 0);      // the queries-as-M kernel with rounds of 32 (A/B comparisons)
+  if (!use_old)
+    return ivf_rows_search(rows, bf16, n_rows, d, queries, n_queries, centroids, n_centroid_rows, nprobe, list_offsets, list_rows,
+                           rows_by_list, scale, bias, k, row_base, flags, eps, reinterpret_cast<long long*>(out_idx), out_score,
+                           out_uncertain, workspace, st);
   const int cap = ib_cap_items(n_queries, nprobe, n_centroid_rows);
   const IbLayout L = ib_layout(n_queries, d, n_centroid_rows, nprobe, cap, ivf_coarse_ws_bytes(n_queries, d, n_centroid_rows, nprobe));
   unsigned char* ws = reinterpret_cast<unsigned char*>(workspace);
@@ -759,9 +1463,13 @@ extern "C" int aura_ivf_search_batch_items(const void* workspace, int n_queries,
                                            int32_t* items_out, int32_t* host_cap, void* stream) {
   AURA_REQUIRE(workspace && items_out && host_cap, AURA_ERR_INVALID_ARG, "aura_ivf_search_batch_items: null pointer");
   const int cap = ib_cap_items(n_queries, nprobe, n_centroid_rows);
-  const IbLayout L = ib_layout(n_queries, d, n_centroid_rows, nprobe, cap, ivf_coarse_ws_bytes(n_queries, d, n_centroid_rows, nprobe));
-  AURA_CUDA_OK(cudaMemcpyAsync(items_out, reinterpret_cast<const unsigned char*>(workspace) + L.n_items, 4,
-                               cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  const IrLayout L = ir_layout(n_queries, d, n_centroid_rows, nprobe, cap, ivf_coarse_ws_bytes(n_queries, d, n_centroid_rows, nprobe));
+  const unsigned char* ws = reinterpret_cast<const unsigned char*>(workspace);
+  ir_stats_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const int*>(ws + L.item_base), n_centroid_rows,
+                                                       reinterpret_cast<const int*>(ws + L.n_slots),
+                                                       reinterpret_cast<const int*>(ws + L.qcnt),
+                                                       reinterpret_cast<const int*>(ws + L.qflag), n_queries, items_out);
+  AURA_CUDA_OK(cudaGetLastError());
   *host_cap = cap;
   return AURA_OK;
 }

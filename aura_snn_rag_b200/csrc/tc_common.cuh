@@ -176,6 +176,21 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float (&v)[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// this warp's 32 lanes x 16 consecutive fp32 columns
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
 __device__ __forceinline__ void named_bar_sync(int id, int n_threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n_threads) : "memory");
 }
@@ -205,6 +220,16 @@ __device__ __forceinline__ float select32(const float (&v)[32], int j) {
   for (int i = 0; i < 16; ++i) a[i] = (j & 16) ? v[i + 16] : v[i];
 #pragma unroll
   for (int i = 0; i < 8; ++i) b[i] = (j & 8) ? a[i + 8] : a[i];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) c[i] = (j & 4) ? b[i + 4] : b[i];
+  const float d0 = (j & 2) ? c[2] : c[0], d1 = (j & 2) ? c[3] : c[1];
+  return (j & 1) ? d1 : d0;
+}
+
+__device__ __forceinline__ float select16(const float (&v)[16], int j) {
+  float b[8], c[4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) b[i] = (j & 8) ? v[i + 8] : v[i];
 #pragma unroll
   for (int i = 0; i < 4; ++i) c[i] = (j & 4) ? b[i + 4] : b[i];
   const float d0 = (j & 2) ? c[2] : c[0], d1 = (j & 2) ? c[3] : c[1];

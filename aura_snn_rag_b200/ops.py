@@ -495,10 +495,13 @@ def ivf_search_batched(rows: torch.Tensor, n_rows: int, queries: torch.Tensor, c
           "aura_ivf_search_batch")
     if stats is not None:
         import ctypes as _C
-        items, cap = torch.zeros(1, dtype=torch.int32, device=dev), _C.c_int32(0)
+        items, cap = torch.zeros(8, dtype=torch.int32, device=dev), _C.c_int32(0)
         check(lib.aura_ivf_search_batch_items(ws.data_ptr(), b, d, c, nprobe, items.data_ptr(), _C.addressof(cap), _stream()),
               "aura_ivf_search_batch_items")
-        stats["items"], stats["items_cap"] = int(items.item()), cap.value
+        it = items.tolist()
+        stats["items"], stats["items_cap"] = it[0], cap.value
+        stats["slots"], stats["slots_per_query_max"], stats["kernel_flagged"], stats["no_candidates"] = it[1], it[2], it[3], it[4]
+        stats["handed_back"] = int(flags.sum())
     if not strict:
         # keep only "no candidate at all" (never flagged when allow_empty) and work-table overflow
         flags = flags * (out_idx[:, 0] < 0).to(flags.dtype)

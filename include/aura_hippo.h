@@ -174,8 +174,9 @@ int aura_ivf_search_batch(const void* rows, int dtype, int64_t n_rows, int d, co
 int aura_ivf_pack_lists(const void* rows, int dtype, int d, const int32_t* list_rows, int64_t n_listed, void* rows_by_list,
                         void* stream);
 
-/* diagnostics: work items generated by the last aura_ivf_search_batch call on `workspace` (enqueued copy into the DEVICE
- * word items_out; like every entry point it does not synchronise) and the table capacity (host word) */
+/* diagnostics of the last aura_ivf_search_batch call on `workspace`, written to the DEVICE words items_out[0..5) by an
+ * enqueued kernel (like every entry point it does not synchronise): {work items, result slots used, most slots linked by one
+ * query, queries flagged inside the kernel, queries without any candidate}; host_cap = work-table capacity */
 int aura_ivf_search_batch_items(const void* workspace, int n_queries, int d, int n_centroid_rows, int nprobe,
                                 int32_t* items_out, int32_t* host_cap, void* stream);
 

@@ -40,6 +40,11 @@ for lm in (False, True):
     e1.record(); torch.cuda.synchronize()
     res["list_major" if lm else "gather"] = {"ms_per_batch": e0.elapsed_time(e1) / ITERS,
                                              "top1_is_source": float((idx[:, 0] == pick).float().mean())}
+st = {}
+hf._ensure_lists(); sc_, bi_ = hf._row_terms(None)
+ops.ivf_search_batched(hf.memory_features, hf.memory_count, q, hf.centroids, P, hf._list_offsets, hf._list_rows, K, sc_, bi_,
+                       eps=ops.TC_EPS_COS * 0.5, stats=st, strict=False)
+res["stats"] = st
 res["list_bytes_GB"] = M * D * 2 / 1e9
 cnt = (hf._list_offsets[1:] - hf._list_offsets[:-1]).float()
 res["list_len_min_mean_max"] = [float(cnt.min()), float(cnt.mean()), float(cnt.max())]

@@ -12,10 +12,23 @@ class Emulator:
         self.barrier = threading.Barrier(world)
         self.slots = {}
         self.lock = threading.Lock()
+        # one rank runs at a time (the turn is handed over inside the collectives): the ranks share one GPU, one stream
+        # and therefore the per-stream scratch buffers of aura_snn_rag_b200.ops, which must not be used concurrently
+        self.turn = threading.Lock()
 
     def collectives(self, rank: int):
         state = {"n": 0}
-        world, slots, lock, barrier = self.world, self.slots, self.lock, self.barrier
+        world, slots, lock, turn = self.world, self.slots, self.lock, self.turn
+
+        class _Barrier:                      # wait without holding the turn
+            @staticmethod
+            def wait():
+                turn.release()
+                try:
+                    self.barrier.wait()
+                finally:
+                    turn.acquire()
+        barrier = _Barrier
 
         def all_reduce(t):
             key = ("r", state["n"]); state["n"] += 1
@@ -44,6 +57,7 @@ class Emulator:
         results, errors = [None] * self.world, []
 
         def body(rank):
+            self.turn.acquire()
             try:
                 torch.cuda.set_device(0)
                 ar, ag = self.collectives(rank)
@@ -51,6 +65,8 @@ class Emulator:
             except BaseException as e:          # noqa: BLE001 - surface it in the main thread
                 errors.append(e)
                 self.barrier.abort()
+            finally:
+                self.turn.release()
         threads = [threading.Thread(target=body, args=(r,)) for r in range(self.world)]
         [t.start() for t in threads]
         [t.join() for t in threads]
