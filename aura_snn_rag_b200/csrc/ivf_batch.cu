@@ -1310,8 +1310,14 @@ extern "C" int aura_ivf_search_batch(const void* rows, int dtype, int64_t n_rows
   AURA_REQUIRE(workspace_bytes >= aura_ivf_search_batch_workspace_bytes(n_queries, d, n_centroid_rows, nprobe),
                AURA_ERR_WORKSPACE, "aura_ivf_search_batch: workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
-  static const int use_old = env_int("AURA_IVF_OLD", 0);      // the queries-as-M kernel with rounds of 32 (A/B comparisons)
-  if (!use_old)
+  // Two formulations of the list-major fine stage.  Shortlists of <= 32 keys (k <= 18) fit the queries-as-M kernel's
+  // register lists and it is the faster one there (C4: 10.1 ms against 12.8 ms per batch); longer shortlists (k up to 114)
+  // would need one full pass per 32 keys, so they take the rows-as-M kernel with its one-pass selection (one C5 shard,
+  // k = 100: 16 ms against 46 ms).  AURA_IVF_ROWS=1|0 forces one of them (test switch, read once per call: the
+  // parity tests run every shape through both).
+  const int forced = env_int("AURA_IVF_ROWS", -1);
+  const bool rows_path = forced >= 0 ? forced != 0 : k + 14 > GT_L;
+  if (rows_path)
     return ivf_rows_search(rows, bf16, n_rows, d, queries, n_queries, centroids, n_centroid_rows, nprobe, list_offsets, list_rows,
                            rows_by_list, scale, bias, k, row_base, flags, eps, reinterpret_cast<long long*>(out_idx), out_score,
                            out_uncertain, workspace, st);

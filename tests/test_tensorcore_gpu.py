@@ -198,8 +198,12 @@ def test_tensorcore_coarse_probes_match_exact_coarse(monkeypatch):
                                             (20000, 100, 50, 8, 100, 10, torch.float32),
                                             (50000, 128, 64, 8, 90, 100, torch.float32),
                                             (30000, 256, 40, 6, 70, 40, torch.bfloat16)])
-def test_ivf_search_batched_equals_per_query_path(n, d, c, p, b, k, dt):
-    """List-major grouped-GEMM IVF (aura_ivf_search_batch) vs the per-query scan of the same probed lists."""
+@pytest.mark.parametrize("path", ["rows", "queries"])
+def test_ivf_search_batched_equals_per_query_path(n, d, c, p, b, k, dt, path, monkeypatch):
+    """List-major grouped-GEMM IVF (aura_ivf_search_batch) vs the per-query scan of the same probed lists, through both
+    formulations of the fine stage: rows-as-M with one-pass selection (default for k > 18) and queries-as-M with
+    register lists (default for k <= 18; k > 18 then takes rounds of 32)."""
+    monkeypatch.setenv("AURA_IVF_ROWS", "1" if path == "rows" else "0")
     ops = _ops()
     g = torch.Generator().manual_seed(n + c)
     centres = torch.randn(c // 2, d, generator=g)
