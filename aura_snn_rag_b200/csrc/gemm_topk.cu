@@ -188,7 +188,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             const float sc = fmaf(select32(v, j), t.x, t.y);
             const u64 key = make_key(sc, (unsigned)(col0 + c0 + j));
             if (key > e[L - 1] && (!CEIL || key < ceil_key)) {
-              list_insert_sorted<L>(e, key);
+              list_insert_sorted_asc<L>(e, key);
               if (e[L - 1] != 0ull) thr = key_score(e[L - 1]);
             }
           }
@@ -362,7 +362,7 @@ gemm_topk2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             const float2 t = sb[c0 + j];
             const u64 key = make_key(fmaf(select32(v, j), t.x, t.y), (unsigned)(col0 + c0 + j));
             if (key > e[L - 1] && (!CEIL || key < ceil_key)) {
-              list_insert_sorted<L>(e, key);
+              list_insert_sorted_asc<L>(e, key);
               if (e[L - 1] != 0ull) thr = key_score(e[L - 1]);
             }
           }
@@ -398,6 +398,33 @@ __global__ void __launch_bounds__(256) normalize_queries_kernel(const float* __r
   }
 }
 
+// Shadow mode: also the per-query certification bound.  With q~ = bf16(q/||q||), r~ = bf16(r):
+//   |q~.r~ - qn.r| = |q~.(r~ - r) + (q~ - qn).r| <= ||q~|| ||r~ - r|| + ||q~ - qn|| ||r||      (Cauchy-Schwarz on the ACTUAL
+// rounding-error vectors, not on worst-case per-element bounds), so in score units, with relerr >= ||r~ - r|| / ||r|| for
+// every bank row (aura_rows_to_bf16 keeps the maximum) and unit = max |scale_r| ||r||:
+//   eps_q = unit * ((1 + e_q) * relerr + e_q + 1e-4),   e_q = ||q~ - qn||     (1e-4: fp32 accumulation slack, as TC_EPS_COS)
+__global__ void __launch_bounds__(256) normalize_queries_eps_kernel(const float* __restrict__ q, int n, int d, float* __restrict__ qn,
+                                                                    __nv_bfloat16* __restrict__ qb, const float* __restrict__ relerr,
+                                                                    float unit, float* __restrict__ eps_q) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= n) return;
+  const float* x = q + (size_t)w * d;
+  float ss = 0.f;
+  for (int e = lane; e < d; e += 32) ss = fmaf(x[e], x[e], ss);
+  const float denom = fmaxf(sqrtf(warp_sum(ss)), 1e-12f);
+  float err = 0.f;
+  for (int e = lane; e < d; e += 32) {
+    const float v = x[e] / denom;
+    const __nv_bfloat16 b = __float2bfloat16_rn(v);
+    qn[(size_t)w * d + e] = v;
+    qb[(size_t)w * d + e] = b;
+    const float t = __bfloat162float(b) - v;
+    err = fmaf(t, t, err);
+  }
+  const float eq = sqrtf(warp_sum(err));
+  if (lane == 0) eps_q[w] = unit * ((1.f + eq) * (*relerr) + eq + 1e-4f);
+}
+
 void launch_normalize_queries(const float* q, int n, int d, float* qn, __nv_bfloat16* qb, cudaStream_t st) {
   normalize_queries_kernel<<<(n + 7) / 8, 256, 0, st>>>(q, n, d, qn, qb);
   note_launches(1);
@@ -412,6 +439,7 @@ struct FinishArgs {
   // re-score (K6) - null rows => no re-score (K7)
   const void* rows; int bf16; int d;
   const float* qn; const float* scale; const float* bias; float eps;
+  const float* eps_q;        // per-query certification bound (bf16 shadow mode), overrides eps when non-null
   const float* a_scale;      // K7: output score multiplier per A row (inv_norm of the row), may be null
   long long* out_idx; float* out_score; int* uncertain;
   // multi-round mode: append this round's 32 best approximate keys to cand[b][round*32..] and publish the new ceiling
@@ -487,7 +515,7 @@ __global__ void __launch_bounds__(128) gemm_topk_finish_kernel(const FinishArgs 
   }
   RescoreArgs ra;
   ra.rows = f.rows; ra.bf16 = f.bf16; ra.d = f.d; ra.q = f.qn + (size_t)b * f.d; ra.scale = f.scale; ra.bias = f.bias;
-  ra.eps = f.eps; ra.k = f.k; ra.L = f.L; ra.row_base = f.row_base;
+  ra.eps = f.eps_q ? f.eps_q[b] : f.eps; ra.k = f.k; ra.L = f.L; ra.row_base = f.row_base;
   ra.out_idx = f.out_idx + b * f.k; ra.out_score = f.out_score + b * f.k; ra.uncertain = f.uncertain ? f.uncertain + b : nullptr;
   rescore_and_write(keys, n2, ex, ra);
 }
@@ -642,6 +670,7 @@ static int run_gemm_topk(const void* a_mat, long long n_a_rows, long long a_row_
   void (*kern)(const CUtensorMap, const CUtensorMap, const GemmTopkArgs);
   const bool ceil = ceil_keys != nullptr;
   if (p.L == GT_L_ASSIGN) kern = bf16 ? gemm_topk_kernel<false, GT_L_ASSIGN, false> : gemm_topk_kernel<true, GT_L_ASSIGN, false>;
+  else if (p.L == GT_L_WIDE) kern = gemm_topk_kernel<false, GT_L_WIDE, false>;       // bf16 shadow shortlist
   else if (p.L == GT_L_SMALL && !ceil && !p.two_cta) kern = bf16 ? gemm_topk_kernel<false, GT_L_SMALL, false> : gemm_topk_kernel<true, GT_L_SMALL, false>;
   else if (p.two_cta) kern = ceil ? (bf16 ? gemm_topk2_kernel<false, GT_L, true> : gemm_topk2_kernel<true, GT_L, true>)
                                   : (bf16 ? gemm_topk2_kernel<false, GT_L, false> : gemm_topk2_kernel<true, GT_L, false>);
@@ -916,7 +945,7 @@ int tc_coarse(const float* queries, int n_queries, int d, const float* cent, int
   FinishArgs f;
   f.partial = partial; f.n_atiles = p.n_atiles; f.n_groups = p.n_groups; f.L = p.L; f.n2 = p.n2; f.k = GT_L;
   f.n_a_rows = n_queries; f.row_base = 0; f.rows = nullptr; f.bf16 = 0; f.d = d; f.qn = nullptr;
-  f.scale = nullptr; f.bias = nullptr; f.eps = 0.f; f.a_scale = nullptr;
+  f.scale = nullptr; f.bias = nullptr; f.eps = 0.f; f.eps_q = nullptr; f.a_scale = nullptr;
   f.out_idx = probes; f.out_score = dummy_score; f.uncertain = nullptr; f.cand = cand; f.ceil_out = ceil_buf; f.round = 0;
   const size_t fsmem = ((size_t)p.n2 + GT_MAX_L) * 8;
   AURA_CUDA_OK(cudaFuncSetAttribute(gemm_topk_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
@@ -956,22 +985,30 @@ extern "C" size_t aura_batch_topk_workspace_bytes(int64_t n_rows, int d, int dty
   GemmPlan p;
   if (n_queries < 1 || n_rows < 1 || d < 1 || k < 1) return 0;
   if (!make_gemm_plan(n_queries, n_rows, d, dtype == AURA_BF16 ? 2 : 4, k, true, &p)) return 0;
+  GemmPlan ps;                                   // fp32 bank searched through a bf16 shadow: longer lists, bf16 tiles
+  if (dtype == AURA_F32 && k + 14 <= GT_L_WIDE && make_gemm_plan(n_queries, n_rows, d, 2, k, true, &ps, GT_L_WIDE) &&
+      ps.partial_bytes > p.partial_bytes)
+    p.partial_bytes = ps.partial_bytes;
   const size_t n_pad = ((size_t)n_queries + GT_BM - 1) / GT_BM * GT_BM;     // query block padded to whole A tiles
   return align256(p.partial_bytes) + align256(n_pad * d * 4) + align256(n_pad * d * 2) + 512 +
-         align256((size_t)n_queries * GT_MAX_L * 8) + align256((size_t)n_queries * 8);
+         align256((size_t)n_queries * GT_MAX_L * 8) + align256((size_t)n_queries * 8) + align256((size_t)n_queries * 4);
 }
 
 extern "C" int aura_batch_topk(const void* rows, int dtype, int64_t n_rows, int d, const float* queries, int n_queries,
                                const float* scale, const float* bias, int k, int64_t row_base, float eps,
-                               int64_t* out_idx, float* out_score, int32_t* out_uncertain, void* workspace,
-                               size_t workspace_bytes, void* stream) {
+                               const void* shadow_bf16, const float* shadow_relerr, int64_t* out_idx, float* out_score,
+                               int32_t* out_uncertain, void* workspace, size_t workspace_bytes, void* stream) {
   int rc = check_shapes("aura_batch_topk", rows, dtype, n_rows, d, k, GT_MAX_L - 14);
   if (rc != AURA_OK) return rc;
   AURA_REQUIRE(n_queries >= 1 && queries && out_idx && out_score && workspace, AURA_ERR_INVALID_ARG,
                "aura_batch_topk: null pointer / n_queries=%d", n_queries);
-  const bool bf16 = dtype == AURA_BF16;
+  // bf16 shadow of an fp32 bank: the tensor cores shortlist from the shadow (kind::f16, half the bytes, twice the
+  // rate), the finish kernel re-scores from the fp32 rows - same exact results, `eps` must be the bf16 bound
+  const bool shadow = shadow_bf16 != nullptr && dtype == AURA_F32 && k + 14 <= GT_L_WIDE && (d % 8) == 0 &&
+                      (reinterpret_cast<uintptr_t>(shadow_bf16) & 15) == 0;
+  const bool bf16 = dtype == AURA_BF16 || shadow;
   GemmPlan p;
-  AURA_REQUIRE(make_gemm_plan(n_queries, n_rows, d, bf16 ? 2 : 4, k, true, &p), AURA_ERR_UNSUPPORTED,
+  AURA_REQUIRE(make_gemm_plan(n_queries, n_rows, d, bf16 ? 2 : 4, k, true, &p, shadow ? GT_L_WIDE : 0), AURA_ERR_UNSUPPORTED,
                "aura_batch_topk: no plan for n_queries=%d k=%d", n_queries, k);
   AURA_REQUIRE(workspace_bytes >= aura_batch_topk_workspace_bytes(n_rows, d, dtype, n_queries, k), AURA_ERR_WORKSPACE,
                "aura_batch_topk: workspace too small");
@@ -983,27 +1020,33 @@ extern "C" int aura_batch_topk(const void* rows, int dtype, int64_t n_rows, int 
   const size_t n_pad = ((size_t)n_queries + GT_BM - 1) / GT_BM * GT_BM;
   float* qn = reinterpret_cast<float*>(ws + align256(p.partial_bytes));
   __nv_bfloat16* qb = bf16 ? reinterpret_cast<__nv_bfloat16*>(ws + align256(p.partial_bytes) + align256(n_pad * d * 4)) : nullptr;
-  normalize_queries_kernel<<<(n_queries + 7) / 8, 256, 0, st>>>(queries, n_queries, d, qn, qb);
+  const size_t off_floor = align256(p.partial_bytes) + align256(n_pad * d * 4) + align256(n_pad * d * 2);
+  u64* cand = reinterpret_cast<u64*>(ws + off_floor + 512);
+  u64* ceil_buf = cand + align256((size_t)n_queries * GT_MAX_L * 8) / 8;
+  float* eps_q = reinterpret_cast<float*>(ceil_buf + align256((size_t)n_queries * 8) / 8);
+  const bool measured_bound = shadow && shadow_relerr != nullptr;     // eps is then the score-per-cosine unit (see header)
+  if (measured_bound)
+    normalize_queries_eps_kernel<<<(n_queries + 7) / 8, 256, 0, st>>>(queries, n_queries, d, qn, qb, shadow_relerr, eps, eps_q);
+  else
+    normalize_queries_kernel<<<(n_queries + 7) / 8, 256, 0, st>>>(queries, n_queries, d, qn, qb);
   note_launches(1);
   if (n_pad > (size_t)n_queries) {
     AURA_CUDA_OK(cudaMemsetAsync(qn + (size_t)n_queries * d, 0, (n_pad - n_queries) * d * 4, st));
     if (qb) AURA_CUDA_OK(cudaMemsetAsync(qb + (size_t)n_queries * d, 0, (n_pad - n_queries) * d * 2, st));
   }
-  const size_t off_floor = align256(p.partial_bytes) + align256(n_pad * d * 4) + align256(n_pad * d * 2);
-  u64* cand = reinterpret_cast<u64*>(ws + off_floor + 512);
-  u64* ceil_buf = cand + align256((size_t)n_queries * GT_MAX_L * 8) / 8;
-  const int rounds = (k + 14 + GT_L - 1) / GT_L;          // 32 candidates per round; k <= 18 needs one
+  const int rounds = shadow ? 1 : (k + 14 + GT_L - 1) / GT_L;          // 32 candidates per round; k <= 18 needs one
   const void* a_mat = bf16 ? (const void*)qb : (const void*)qn;
+  const void* b_mat = shadow ? shadow_bf16 : rows;
   FinishArgs f;
-  f.k = k; f.n_a_rows = n_queries; f.row_base = row_base; f.rows = rows; f.bf16 = bf16 ? 1 : 0; f.d = d; f.qn = qn;
-  f.scale = scale; f.bias = bias; f.eps = eps; f.a_scale = nullptr;
+  f.k = k; f.n_a_rows = n_queries; f.row_base = row_base; f.rows = rows; f.bf16 = dtype == AURA_BF16 ? 1 : 0; f.d = d; f.qn = qn;
+  f.scale = scale; f.bias = bias; f.eps = eps; f.eps_q = measured_bound ? eps_q : nullptr; f.a_scale = nullptr;
   f.out_idx = reinterpret_cast<long long*>(out_idx); f.out_score = out_score; f.uncertain = out_uncertain;
   f.cand = nullptr; f.ceil_out = nullptr; f.round = 0;
   f.partial = partial; f.n_atiles = p.n_atiles; f.n_groups = p.n_groups; f.L = p.L; f.n2 = p.n2;
   const size_t fsmem = ((size_t)p.n2 + GT_MAX_L) * 8;
   AURA_CUDA_OK(cudaFuncSetAttribute(gemm_topk_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
   if (rounds == 1) {
-    rc = run_gemm_topk(a_mat, n_queries, 0, rows, n_rows, d, bf16, scale, bias, false, p, partial, st, nullptr, (long long)n_pad);
+    rc = run_gemm_topk(a_mat, n_queries, 0, b_mat, n_rows, d, bf16, scale, bias, false, p, partial, st, nullptr, (long long)n_pad);
     if (rc != AURA_OK) return rc;
     gemm_topk_finish_kernel<<<n_queries, 128, fsmem, st>>>(f);
     AURA_CUDA_OK(cudaGetLastError());
@@ -1024,6 +1067,43 @@ extern "C" int aura_batch_topk(const void* rows, int dtype, int64_t n_rows, int 
   }
   return launch_cand_rescore(cand, rounds * GT_L, rows, bf16 ? 1 : 0, d, qn, scale, bias, eps, k, row_base,
                              reinterpret_cast<long long*>(out_idx), out_score, out_uncertain, n_queries, st, nullptr);
+}
+
+namespace aura {
+// one warp per row: bf16 copy + the row's relative rounding error ||bf16(r) - r|| / ||r||, max-reduced into *relerr_max
+__global__ void __launch_bounds__(256) rows_to_bf16_kernel(const float* __restrict__ x, long long n_rows, int d,
+                                                           __nv_bfloat16* __restrict__ y, float* __restrict__ relerr_max) {
+  const int lane = threadIdx.x & 31;
+  float worst = 0.f;
+  for (long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n_rows; r += ((long long)gridDim.x * blockDim.x) >> 5) {
+    const float* xr = x + (size_t)r * d;
+    __nv_bfloat16* yr = y + (size_t)r * d;
+    float ee = 0.f, ss = 0.f;
+    for (int e = lane; e < d; e += 32) {
+      const float v = xr[e];
+      const __nv_bfloat16 b = __float2bfloat16_rn(v);
+      yr[e] = b;
+      const float t = __bfloat162float(b) - v;
+      ee = fmaf(t, t, ee); ss = fmaf(v, v, ss);
+    }
+    ee = warp_sum(ee); ss = warp_sum(ss);
+    if (ss > 0.f) worst = fmaxf(worst, sqrtf(ee / ss));
+  }
+  // round the bound UP a little: the sums above are themselves fp32
+  if (relerr_max != nullptr && lane == 0 && worst > 0.f) atomicMax(reinterpret_cast<int*>(relerr_max), __float_as_int(worst * 1.0001f));
+}
+}  // namespace aura
+
+extern "C" int aura_rows_to_bf16(const float* rows, int64_t n_rows, int d, void* out_bf16, float* relerr_max, void* stream) {
+  AURA_REQUIRE(n_rows >= 0 && d >= 1, AURA_ERR_INVALID_ARG, "aura_rows_to_bf16: n_rows=%lld d=%d", (long long)n_rows, d);
+  if (n_rows == 0) return AURA_OK;
+  AURA_REQUIRE(rows && out_bf16, AURA_ERR_INVALID_ARG, "aura_rows_to_bf16: null pointer");
+  long long blocks = (n_rows + 7) / 8;
+  if (blocks > (long long)sm_count() * 16) blocks = (long long)sm_count() * 16;
+  rows_to_bf16_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(rows, (long long)n_rows, d, reinterpret_cast<__nv_bfloat16*>(out_bf16), relerr_max);
+  AURA_CUDA_OK(cudaGetLastError());
+  note_launches(1);
+  return AURA_OK;
 }
 
 extern "C" size_t aura_allpairs_topk_workspace_bytes(int64_t n_a_rows, int64_t n_rows, int d, int dtype, int k) {
@@ -1055,7 +1135,7 @@ extern "C" int aura_allpairs_topk(const void* rows, int dtype, int64_t n_rows, i
   FinishArgs f;
   f.partial = partial; f.n_atiles = p.n_atiles; f.n_groups = p.n_groups; f.L = p.L; f.n2 = p.n2; f.k = k;
   f.n_a_rows = n_a_rows; f.row_base = 0; f.rows = nullptr; f.bf16 = 0; f.d = d; f.qn = nullptr;
-  f.scale = nullptr; f.bias = nullptr; f.eps = 0.f; f.a_scale = inv_norm ? inv_norm + a_row_first : nullptr;
+  f.scale = nullptr; f.bias = nullptr; f.eps = 0.f; f.eps_q = nullptr; f.a_scale = inv_norm ? inv_norm + a_row_first : nullptr;
   f.out_idx = reinterpret_cast<long long*>(out_idx); f.out_score = out_score; f.uncertain = nullptr; f.cand = nullptr; f.ceil_out = nullptr; f.round = 0;
   const size_t fsmem = ((size_t)p.n2 + GT_MAX_L) * 8;
   AURA_CUDA_OK(cudaFuncSetAttribute(gemm_topk_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));

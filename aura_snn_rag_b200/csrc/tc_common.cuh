@@ -209,6 +209,7 @@ static constexpr int GT_THREADS = 192;       // warp 0 TMA, warp 1 MMA, warps 2-
 static constexpr int GT_L = 32;             // per-row list length kept by the epilogue (registers)
 static constexpr int GT_L_ASSIGN = 4;       // list length of the nearest-centroid variant
 static constexpr int GT_L_SMALL = 24;       // exact search with k <= 10 (k + 14 margin)
+static constexpr int GT_L_WIDE = 48;        // bf16 shadow shortlist of an fp32 bank: the wider rounding bound needs more margin
 static constexpr int GT_MAX_L = 128;           // most candidates a query can carry into the exact re-score (4 rounds x 32)
 static constexpr int GT_MAX_ROUNDS = GT_MAX_L / GT_L;
 
@@ -246,6 +247,20 @@ __device__ __forceinline__ void list_insert_sorted(u64 (&e)[L], u64 key) {
     e[i] = ci ? (cp ? e[i - 1] : key) : e[i];
   }
   e[0] = key > e[0] ? key : e[0];
+}
+
+// Same list, for streams whose keys arrive in ASCENDING ROW order (the dense kernels walk the bank's columns left to
+// right): a key that ties an entry on the score has the higher row and ranks below it, so comparing the 32 score bits
+// alone reproduces the 64-bit order at half the compare cost.
+template <int L>
+__device__ __forceinline__ void list_insert_sorted_asc(u64 (&e)[L], u64 key) {
+  const unsigned kh = (unsigned)(key >> 32);
+#pragma unroll
+  for (int i = L - 1; i >= 1; --i) {
+    const bool ci = kh > (unsigned)(e[i] >> 32), cp = kh > (unsigned)(e[i - 1] >> 32);
+    e[i] = ci ? (cp ? e[i - 1] : key) : e[i];
+  }
+  e[0] = kh > (unsigned)(e[0] >> 32) ? key : e[0];
 }
 
 // Per-lane partial of dot(bank row, fp32 query) in exactly the operation order of scan_topk.cu (lane-strided 128-bit

@@ -60,7 +60,8 @@ class HippocampalFormation(nn.Module):
                  nprobe: int = 8,
                  bank_dtype: torch.dtype = torch.float32,
                  track_ids: bool = True,
-                 list_major_copy: bool = False):
+                 list_major_copy: bool = False,
+                 bf16_shadow: bool = False):
         super().__init__()
         if not torch.cuda.is_available():
             raise AuraLibraryError("HippocampalFormation (B200 build) needs a CUDA device: the retrieval path has "
@@ -113,6 +114,11 @@ class HippocampalFormation(nn.Module):
         self._bank_by_list: Optional[torch.Tensor] = None
         self._by_list_valid = False
         self.ivf_strict = True                          # batched centroid path: re-run uncertified queries exactly (ops.ivf_search_batched)
+        # exact search of query blocks over an fp32 bank: shortlist on a bf16 copy of the bank (+50 % memory, twice the
+        # tensor rate, half the bytes), exact fp32 re-score from the fp32 rows - same certified results
+        self.bf16_shadow = bool(bf16_shadow) and bank_dtype == torch.float32
+        self._shadow: Optional[ops.Bf16Shadow] = None
+        self._shadow_dirty = [0, 0]                     # [lo, hi) rows written since the shadow was last refreshed
         rows = int(centroid_rows) if centroid_rows is not None else max(256, self.centroids_k)
         self.register_buffer('centroids', torch.zeros(rows, feature_dim, **f32))
         self.register_buffer('centroid_counts', torch.zeros(rows, **f32))
@@ -196,6 +202,7 @@ class HippocampalFormation(nn.Module):
         now = time.time()
         ops.bank_write(self.memory_features, idx, feats, self.memory_metadata, self._inv_norm, now,
                        self.memory_locations, self.current_location.contiguous())
+        self._mark_shadow_dirty(idx, idx + 1)
         if self.use_centroid_index and self._index_ready:
             live = min(self.centroids_k, self._centroid_buffer_rows())          # :220
             ops.online_assign(self.memory_features, idx, 1, self.centroids, live, self.centroid_counts, self._cid,
@@ -231,6 +238,7 @@ class HippocampalFormation(nn.Module):
         now = time.time()
         ops.bank_write(self.memory_features, first, feats, self.memory_metadata, self._inv_norm, now,
                        self.memory_locations, self.current_location.contiguous())
+        self._mark_shadow_dirty(first, first + n)
         self._cid[first:first + n].fill_(-1)
         done = 0
         interval = self.centroids_update_interval
@@ -394,13 +402,35 @@ class HippocampalFormation(nn.Module):
         if self._derived_stale:
             self.refresh_derived()
 
+    def _mark_shadow_dirty(self, lo: int, hi: int) -> None:
+        d = self._shadow_dirty
+        if d[0] == d[1]:
+            d[0], d[1] = lo, hi
+        else:
+            d[0], d[1] = min(d[0], lo), max(d[1], hi)
+
+    def _shadow_rows(self) -> Optional["ops.Bf16Shadow"]:
+        """The bf16 shadow of the fp32 bank, refreshed for the rows written since the last call (None unless enabled)."""
+        if not self.bf16_shadow:
+            return None
+        if self._shadow is None:
+            self._shadow = ops.Bf16Shadow(self.memory_features, n_rows=self.memory_count)
+            self._shadow_dirty = [0, 0]
+        lo, hi = self._shadow_dirty
+        if hi > lo:
+            self._shadow.refresh(self.memory_features, lo, min(hi, self.memory_features.shape[0]))
+            self._shadow_dirty = [0, 0]
+        return self._shadow
+
     def _exact(self, q: torch.Tensor, k: int, scale, bias, score_per_cos: float):
         """Exact top-k of a query block over all live rows: tcgen05 shortlist + exact fp32 re-score for blocks of
         >= TC_MIN_BATCH queries (identical results to the scan, see ops.exact_topk_batched), else the streaming scan."""
         m = self.memory_count
         if q.shape[0] >= ops.tc_min_batch(self.memory_features) and ops.batch_topk_supported(self.memory_features, k) and m >= 1024:
-            return ops.exact_topk_batched(self.memory_features, q, k, scale, bias, n_rows=m,
-                                          eps=ops.TC_EPS_COS * score_per_cos)
+            shadow = self._shadow_rows() if k <= ops.TC_SHADOW_MAX_K else None
+            # with the shadow the bound is measured per query; eps is then just the score-per-cosine unit
+            eps = score_per_cos if shadow is not None else ops.TC_EPS_COS * score_per_cos
+            return ops.exact_topk_batched(self.memory_features, q, k, scale, bias, n_rows=m, eps=eps, shadow=shadow)
         return ops.scan_topk(self.memory_features, q, k, scale, bias, n_rows=m)
 
     def retrieve_similar_memories(self, query_features, location=None, k: int = 5) -> List[Tuple[Union[str, int], float]]:
@@ -451,8 +481,10 @@ class HippocampalFormation(nn.Module):
             if not (q.shape[0] >= ops.tc_min_batch(self.memory_features) and ops.batch_topk_supported(self.memory_features, kk) and m >= 1024):
                 idx, score = ops.scan_topk(self.memory_features, q, kk, self._inv_norm, None, n_rows=m)
                 return idx, score, torch.zeros(q.shape[0], dtype=torch.int32, device=self.device), q
+            shadow = self._shadow_rows() if kk <= ops.TC_SHADOW_MAX_K else None
             idx, score, flags = ops.exact_topk_batched(self.memory_features, q, kk, self._inv_norm, None, n_rows=m,
-                                                       eps=ops.TC_EPS_COS, defer=True)
+                                                       eps=1.0 if shadow is not None else ops.TC_EPS_COS,
+                                                       defer=True, shadow=shadow)
             return idx, score, flags, q
         idx, score = self._exact(q, kk, self._inv_norm, None, 1.0)
         if gather:
@@ -515,6 +547,7 @@ class HippocampalFormation(nn.Module):
         self._strength_bound = float(self.memory_metadata[:m, 0].abs().max()) if m else 1.0   # one device read per resume
         self._lists_dirty = True
         self._by_list_valid = False
+        self._shadow_dirty = [0, self.memory_features.shape[0]]
         self._terms_key = None
         self._version += 1
 

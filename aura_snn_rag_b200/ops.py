@@ -351,17 +351,53 @@ def tc_min_batch(rows: torch.Tensor) -> int:
     any B <= 128."""
     return TC_MIN_BATCH_BF16 if rows.dtype == torch.bfloat16 else TC_MIN_BATCH
 TC_EPS_COS = 2.0 ** -9 + 1e-4   # |tensor-core cosine - fp32 cosine| bound: both operands rounded to 11 bits + fp32 sums
+TC_EPS_COS_BF16 = 2.0 ** -7 + 1e-4   # the same bound when both operands are rounded to bf16 (8 significant bits)
+TC_SHADOW_MAX_K = 34            # bf16 shadow shortlist keeps 48 candidates per query (k + 14 margin)
 
 
 def batch_topk_supported(rows: torch.Tensor, k: int) -> bool:
     return (rows.shape[1] * rows.element_size()) % 16 == 0 and rows.data_ptr() % 16 == 0 and 1 <= k <= TC_MAX_K
 
 
+class Bf16Shadow:
+    """bf16 copy of an fp32 bank for the tensor-core shortlist pass + the measured bound on its rounding error
+    (`relerr`, device scalar: max over converted rows of ||bf16(r) - r|| / ||r||; only ever raised)."""
+
+    def __init__(self, rows: torch.Tensor, n_rows: Optional[int] = None):
+        self.rows = torch.empty(rows.shape, dtype=torch.bfloat16, device=rows.device)
+        self.relerr = torch.zeros(1, dtype=torch.float32, device=rows.device)
+        self.refresh(rows, 0, rows.shape[0] if n_rows is None else n_rows)
+
+    def refresh(self, rows: torch.Tensor, lo: int, hi: int) -> None:
+        if hi > lo:
+            rows_to_bf16(rows, self.rows, first_row=lo, n_rows=hi - lo, relerr=self.relerr)
+
+
+@_on_device
+def rows_to_bf16(rows: torch.Tensor, out: Optional[torch.Tensor] = None, first_row: int = 0,
+                 n_rows: Optional[int] = None, relerr: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """bf16 shadow copy of fp32 bank rows [first_row, first_row + n_rows) (whole tensor by default)."""
+    rows = _dev(rows, "rows")
+    if rows.dtype != torch.float32:
+        raise TypeError("rows must be float32")
+    n = rows.shape[0] - first_row if n_rows is None else int(n_rows)
+    if out is None:
+        out = torch.empty(rows.shape, dtype=torch.bfloat16, device=rows.device)
+    if n > 0:
+        check(_lib.load().aura_rows_to_bf16(rows[first_row:].data_ptr(), n, rows.shape[1], out[first_row:].data_ptr(),
+                                            _ptr(relerr), _stream()), "aura_rows_to_bf16")
+    return out
+
+
 @_on_device
 def batch_topk(rows: torch.Tensor, queries: torch.Tensor, k: int, scale: Optional[torch.Tensor],
                bias: Optional[torch.Tensor] = None, n_rows: Optional[int] = None, row_base: int = 0,
-               eps: float = TC_EPS_COS) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
-    """Tensor-core shortlist + exact fp32 re-score.  Returns (idx[B,k], score[B,k], uncertain[B] int32)."""
+               eps: float = TC_EPS_COS, shadow=None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """Tensor-core shortlist + exact fp32 re-score.  Returns (idx[B,k], score[B,k], uncertain[B] int32).
+    shadow: a `Bf16Shadow` of the fp32 bank (or a bare bf16 tensor); the shortlist pass then reads it instead of the fp32
+    rows.  With a `Bf16Shadow`, `eps` is the score-per-cosine unit (max |scale_r| * ||r||: 1 for pure cosine) and the
+    certification bound is measured per query from the shadow's rounding error; with a bare tensor `eps` must be the
+    worst-case bound (TC_EPS_COS_BF16 per unit)."""
     rows = _dev(rows, "rows")
     queries = _dev(queries, "queries")
     if queries.dtype != torch.float32:
@@ -378,23 +414,29 @@ def batch_topk(rows: torch.Tensor, queries: torch.Tensor, k: int, scale: Optiona
     if nbytes == 0:
         raise _lib.AuraLibraryError(f"aura_batch_topk: unsupported shape n={n} d={d} B={b} k={k}")
     ws = _workspace(nbytes, dev, "batch")
+    relerr = None
+    if isinstance(shadow, Bf16Shadow):
+        shadow, relerr = shadow.rows, shadow.relerr
+    if shadow is not None and (shadow.dtype != torch.bfloat16 or shadow.shape[1] != d or shadow.shape[0] < n
+                               or not shadow.is_contiguous() or rows.dtype != torch.float32 or k > TC_SHADOW_MAX_K):
+        raise ValueError("bf16 shadow does not match the bank (fp32 rows, same shape, k <= TC_SHADOW_MAX_K)")
     check(lib.aura_batch_topk(rows.data_ptr(), code, n, d, queries.data_ptr(), b, _ptr(scale), _ptr(bias), k, row_base,
-                              float(eps), out_idx.data_ptr(), out_score.data_ptr(), flags.data_ptr(), ws.data_ptr(),
-                              ws.numel(), _stream()), "aura_batch_topk")
+                              float(eps), _ptr(shadow), _ptr(relerr), out_idx.data_ptr(), out_score.data_ptr(),
+                              flags.data_ptr(), ws.data_ptr(), ws.numel(), _stream()), "aura_batch_topk")
     return out_idx, out_score, flags
 
 
 @_on_device
 def exact_topk_batched(rows: torch.Tensor, queries: torch.Tensor, k: int, scale: Optional[torch.Tensor],
                        bias: Optional[torch.Tensor] = None, n_rows: Optional[int] = None, row_base: int = 0,
-                       eps: float = TC_EPS_COS, stats: Optional[dict] = None, defer: bool = False):
+                       eps: float = TC_EPS_COS, stats: Optional[dict] = None, defer: bool = False, shadow=None):
     """Exact top-k of a query block: tensor-core pass, then the exact streaming scan for the (rare) queries
     whose result could not be certified.  One small D2H read (the flag count) per call.
 
     defer=True returns (idx, score, flags) WITHOUT reading the flags: the caller must later call
     `exact_topk_fixup` with the same arguments for the flagged queries (ShardedBank does this after it has
     enqueued its collectives, so that the only host sync of a step comes after all of its work is queued)."""
-    idx, score, flags = batch_topk(rows, queries, k, scale, bias, n_rows, row_base, eps)
+    idx, score, flags = batch_topk(rows, queries, k, scale, bias, n_rows, row_base, eps, shadow)
     if defer:
         return idx, score, flags
     exact_topk_fixup(flags, idx, score, rows, queries, k, scale, bias, n_rows, row_base, stats)

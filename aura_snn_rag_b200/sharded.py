@@ -30,8 +30,10 @@ class ShardedBank:
     def __init__(self, local_rows: torch.Tensor, row_base: int, group=None,
                  scale: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None,
                  local_search: Optional[Callable] = None, merge: Optional[Callable] = None,
-                 stats: Optional[dict] = None):
+                 stats: Optional[dict] = None, shadow=None, score_unit: float = 1.0):
         self.rows = local_rows
+        self.shadow = shadow                  # ops.Bf16Shadow of an fp32 shard: the shortlist pass reads it (ops.batch_topk)
+        self.score_unit = float(score_unit)   # max |scale_r| * ||r|| (1 for pure cosine): unit of the certification bound
         self.row_base = int(row_base)
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -57,7 +59,9 @@ class ShardedBank:
         def search(q, k):
             n = self.rows.shape[0]
             if q.shape[0] >= ops.tc_min_batch(self.rows) and ops.batch_topk_supported(self.rows, k) and n >= 1024:
-                return ops.exact_topk_batched(self.rows, q, k, self.scale, self.bias, row_base=self.row_base, defer=True)
+                sh = self.shadow if k <= ops.TC_SHADOW_MAX_K else None
+                return ops.exact_topk_batched(self.rows, q, k, self.scale, self.bias, row_base=self.row_base, defer=True,
+                                              eps=self.score_unit * (1.0 if sh is not None else ops.TC_EPS_COS), shadow=sh)
             return ops.scan_topk(self.rows, q, k, self.scale, self.bias, row_base=self.row_base)
 
         def fixup(flags, idx, score, q, k):

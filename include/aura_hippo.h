@@ -186,11 +186,22 @@ int aura_ivf_search_batch_items(const void* workspace, int n_queries, int d, int
  * every (query,row) pair and keeps a per-query shortlist; the shortlist is re-scored in exact fp32 and the
  * result certified: out_uncertain[b] = 0 means the top-k of query b is provably the exact fp32 top-k given
  * that tensor-core scores are within `eps` (score units) of the exact ones; 1 means the caller must re-run
- * query b through aura_scan_topk.  Needs d*sizeof(elem) % 16 == 0 and k <= 63. */
+ * query b through aura_scan_topk.  Needs d*sizeof(elem) % 16 == 0 and k <= 114.
+ * shadow_bf16 (may be NULL): a bf16 copy of an fp32 bank (aura_rows_to_bf16, same row order).  The shortlist pass then
+ * runs on the copy (kind::f16: half the bytes, twice the tensor rate, 48 candidates per query; k <= 34) and the re-score
+ * still reads the fp32 rows, so certified results are the same exact fp32 top-k; `eps` must then bound the bf16 rounding
+ * (2^-7 per unit of |scale * ||row|||) - or, with shadow_relerr (DEVICE scalar >= ||bf16(r) - r|| / ||r|| over the bank rows,
+ * maintained by aura_rows_to_bf16), `eps` is just that unit, max |scale_r| * ||r||, and the bound is measured per query:
+ * unit * ((1 + e_q) * relerr + e_q + 1e-4) with e_q the rounding error norm of the normalised query. */
 size_t aura_batch_topk_workspace_bytes(int64_t n_rows, int d, int dtype, int n_queries, int k);
 int aura_batch_topk(const void* rows, int dtype, int64_t n_rows, int d, const float* queries, int n_queries,
-                    const float* scale, const float* bias, int k, int64_t row_base, float eps, int64_t* out_idx,
-                    float* out_score, int32_t* out_uncertain, void* workspace, size_t workspace_bytes, void* stream);
+                    const float* scale, const float* bias, int k, int64_t row_base, float eps, const void* shadow_bf16,
+                    const float* shadow_relerr, int64_t* out_idx, float* out_score, int32_t* out_uncertain, void* workspace,
+                    size_t workspace_bytes, void* stream);
+/* out_bf16[i] = bf16(rows[i]) (round to nearest even) for n_rows rows: builds / refreshes the shadow above.  relerr_max
+ * (DEVICE float, may be NULL; zero it before the first call) is raised to the largest relative rounding error
+ * ||bf16(r) - r|| / ||r|| of the rows converted. */
+int aura_rows_to_bf16(const float* rows, int64_t n_rows, int d, void* out_bf16, float* relerr_max, void* stream);
 
 /* ---- cognitive map: all-pairs cosine + top-k neighbours per row, self excluded ---------------------
  * (training_recipes.md:292-308; README.md:39,64 - documented upstream, never implemented.)

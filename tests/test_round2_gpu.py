@@ -25,7 +25,7 @@ def _same_topk(ids, sc, ref_ids, ref_sc, rtol=1e-4):
 @pytest.mark.parametrize("n,d,c,p,b,k,dt", [(60000, 128, 1024, 16, 256, 10, torch.float32),
                                             (80000, 96, 2048, 40, 160, 10, torch.float32),      # nprobe > 32: 2 shortlist rounds
                                             (50000, 128, 1024, 8, 300, 5, torch.bfloat16),
-                                            (60000, 128, 1024, 16, 200, 60, torch.float32)])     # k > 18: rows-as-M one-pass path
+                                            (60000, 128, 1024, 16, 256, 60, torch.float32)])     # k > 18: rows-as-M one-pass path
 def test_batched_ivf_with_tensorcore_coarse_matches_oracle(n, d, c, p, b, k, dt, monkeypatch):
     """B * C >= 2.5e5: the coarse stage is the TF32 GEMM shortlist + exact fp32 finish and the fine stage the list-major
     tensor-core pass.  Every query is compared with the ORACLE's centroid path (hippocampal.py:257-307, patched) run on

@@ -239,3 +239,64 @@ def test_ivf_search_batched_equals_per_query_path(n, d, c, p, b, k, dt, path, mo
     assert stats3["uncertain"] == stats["uncertain"]
     assert torch.equal(s3, s2)
     assert torch.equal(i3, i2)
+
+
+@pytest.mark.parametrize("n,d,b,k", [(50000, 256, 200, 10), (30000, 768, 64, 34), (20000, 128, 130, 5)])
+def test_bf16_shadow_shortlist_gives_the_exact_fp32_answers(n, d, b, k):
+    """fp32 bank searched through its bf16 shadow (kind::f16 shortlist of 48, exact fp32 re-score from the fp32 rows):
+    after the certified fix-up the results are the streaming scan's, bit for bit - also with near-duplicate rows, where
+    the bf16 scores cannot separate the candidates and the flags must fire."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(n + d)
+    bank = torch.randn(n, d, generator=g)
+    bank[1000:1200] = bank[999] + 1e-4 * torch.randn(200, d, generator=g)       # 200 near-duplicates of one row
+    rows = bank.to(DEV)
+    inv = ops.row_inv_norms(rows)
+    shadow = ops.Bf16Shadow(rows)
+    assert torch.equal(shadow.rows.cpu(), bank.to(torch.bfloat16))
+    rel = ((bank.to(torch.bfloat16).double() - bank.double()).norm(dim=1) / bank.double().norm(dim=1)).max()
+    assert float(rel) <= float(shadow.relerr) <= float(rel) * 1.001 + 1e-9          # the measured rounding-error bound
+    q = bank[torch.randint(0, n, (b,), generator=g)] + 0.1 * torch.randn(b, d, generator=g)
+    q[0] = bank[999]
+    q = q.to(DEV)
+    strength = 0.5 + 0.5 * torch.rand(n, generator=g)
+    strength[999:1200] = 1.0                                                      # the near-duplicates also tie on the score terms
+    strength = strength.to(DEV)
+    scale, bias = 0.5 * strength * inv, 0.05 * strength
+    i_ref, s_ref = ops.scan_topk(rows, q, k, scale, bias)
+    _, _, flags = ops.batch_topk(rows, q, k, scale, bias, eps=0.5, shadow=shadow)     # eps = unit: max |scale| * ||row||
+    assert int(flags[0]) == 1                                     # the near-duplicate query is handed back
+    if k <= 10:
+        assert int(flags.sum()) < b // 4                          # and with the usual margin (48 - k) most queries are certified
+    stats = {}
+    i_sh, s_sh = ops.exact_topk_batched(rows, q, k, scale, bias, eps=0.5, shadow=shadow, stats=stats)
+    assert torch.equal(i_sh, i_ref) and torch.equal(s_sh, s_ref)
+    # worst-case bound with a bare bf16 tensor: same answers, more hand-backs
+    i_w, s_w = ops.exact_topk_batched(rows, q, k, scale, bias, eps=0.5 * ops.TC_EPS_COS_BF16, shadow=shadow.rows)
+    assert torch.equal(i_w, i_ref) and torch.equal(s_w, s_ref)
+    i_tf, s_tf = ops.exact_topk_batched(rows, q, k, scale, bias, eps=0.5 * ops.TC_EPS_COS)
+    assert torch.equal(i_tf, i_ref) and torch.equal(s_tf, s_ref)
+
+
+def test_bf16_shadow_follows_writes(monkeypatch):
+    """HippocampalFormation(bf16_shadow=True): the shadow is refreshed for exactly the rows written since the last search."""
+    import types
+    import aura_snn_rag_b200.hippocampal as hmod
+    monkeypatch.setattr(hmod, "time", types.SimpleNamespace(time=lambda: 1.79e9))
+    g = torch.Generator().manual_seed(12)
+    rows = torch.randn(6000, 128, generator=g)
+
+    def make(shadow):
+        return hmod.HippocampalFormation(n_place_cells=4, n_time_cells=2, n_grid_cells=2, max_memories=8192, feature_dim=128,
+                                         use_centroid_index=False, track_ids=False, bf16_shadow=shadow)
+    a, b = make(False), make(True)
+    q = rows[:90] + 0.05 * torch.randn(90, 128, generator=g)
+    for lo, hi in ((0, 3000), (3000, 3001), (3001, 6000)):
+        for hf in (a, b):
+            hf.create_episodic_memories(rows[lo:hi])
+        ia, sa = a.retrieve_batch(q, 10)
+        ib, sb = b.retrieve_batch(q, 10)
+        assert torch.equal(ia, ib) and torch.equal(sa, sb)
+        assert torch.equal(b._shadow.rows[:hi].cpu(), rows[:hi].to(torch.bfloat16))
+        ea, eb = a.exact_topk(q, 7), b.exact_topk(q, 7)
+        assert torch.equal(ea[0], eb[0]) and torch.equal(ea[1], eb[1])
