@@ -60,6 +60,9 @@ SIGNATURES = {
     "aura_topk_merge": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _p]),
     "aura_pack_topk": (_i, [_p, _p, _p, _i, _i, _p, _i64, _p, _p]),
     "aura_topk_merge_packed": (_i, [_p, _i, _i, _i, _p, _p, _p, _p]),
+    "aura_peer_gather_buffer_bytes": (_sz, [_i, _i, _i]),
+    "aura_pack_scatter": (_i, [_p, _p, _p, _i, _i, _p, _i64, _p, _i, _i, _p, _p]),
+    "aura_merge_gathered": (_i, [_p, _i, _i, _i, _p, _p, _p, _p, _p]),
     "aura_gather_rows": (_i, [_p, _i, _i, _p, _i64, _p, _p]),
 }
 

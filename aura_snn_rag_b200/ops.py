@@ -187,6 +187,33 @@ def topk_merge_packed(gathered: torch.Tensor, n_ranks: int, b: int, k: int):
     return out_i, out_s, flag
 
 
+def peer_gather_buffer_bytes(n_ranks: int, n_queries: int, k: int) -> int:
+    return int(_lib.load().aura_peer_gather_buffer_bytes(n_ranks, n_queries, k))
+
+
+@_on_device
+def pack_scatter(idx: torch.Tensor, score: torch.Tensor, flags: Optional[torch.Tensor], peer_ptrs, rank: int, n_ranks: int,
+                 counters: torch.Tensor, id_map: Optional[torch.Tensor] = None, id_base: int = 0) -> None:
+    """Build this rank's [B, 2k+1] payload and store it into every rank's gather buffer (peer_ptrs: ctypes array of
+    the peer-mapped buffer addresses in rank order), then raise this rank's flag there (aura_pack_scatter)."""
+    b, k = idx.shape
+    check(_lib.load().aura_pack_scatter(idx.data_ptr(), score.data_ptr(), _ptr(flags), b, k, _ptr(id_map), int(id_base),
+                                        peer_ptrs, rank, n_ranks, counters.data_ptr(), _stream()), "aura_pack_scatter")
+
+
+@_on_device
+def merge_gathered(gather_buf: torch.Tensor, n_ranks: int, b: int, k: int, counters: torch.Tensor):
+    """Wait (on the device) for every rank's payload of the current step in the local gather buffer, then merge:
+    -> (idx [B,k], score [B,k], any_flag [B] int32)."""
+    dev = gather_buf.device
+    out_s = torch.empty(b, k, dtype=torch.float32, device=dev)
+    out_i = torch.empty(b, k, dtype=torch.int64, device=dev)
+    flag = torch.empty(b, dtype=torch.int32, device=dev)
+    check(_lib.load().aura_merge_gathered(gather_buf.data_ptr(), n_ranks, b, k, counters.data_ptr(), out_s.data_ptr(),
+                                          out_i.data_ptr(), flag.data_ptr(), _stream()), "aura_merge_gathered")
+    return out_i, out_s, flag
+
+
 @_on_device
 def gather_rows(rows: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
     rows = _dev(rows, "rows")

@@ -26,12 +26,50 @@ def shard_range(n_rows: int, rank: int, world: int) -> Tuple[int, int]:
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+class PeerGather:
+    """The all-gather + merge of a sharded search over peer memory (NVLink / NVSwitch) instead of a library collective:
+    one symmetric buffer per rank (`torch.distributed._symmetric_memory`: every rank maps every peer's buffer), into
+    which `aura_pack_scatter` stores this rank's payload on EVERY rank, and which `aura_merge_gathered` merges once the
+    flags of all ranks are up.  Two kernel launches per search, no host synchronisation, capturable in a CUDA graph.
+    world == 1 (tests): a plain local buffer."""
+
+    def __init__(self, world: int, rank: int, batch: int, k: int, device: torch.device, group=None):
+        import ctypes
+        from . import ops
+        self.world, self.rank, self.batch, self.k = world, rank, batch, k
+        n64 = (ops.peer_gather_buffer_bytes(world, batch, k) + 7) // 8
+        if world > 1:
+            import torch.distributed._symmetric_memory as symm
+            self.buf = symm.empty(n64, dtype=torch.int64, device=device)
+            self.buf.zero_()
+            torch.cuda.synchronize(device)
+            self.handle = symm.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
+            ptrs = [int(p) for p in self.handle.buffer_ptrs]
+            self.handle.barrier()                    # every buffer is zeroed before anyone stores into it
+        else:
+            self.buf = torch.zeros(n64, dtype=torch.int64, device=device)
+            self.handle = None
+            ptrs = [self.buf.data_ptr()]
+        self.ptrs = (ctypes.c_void_p * world)(*ptrs)
+        self.counters = torch.zeros(4, dtype=torch.int32, device=device)
+        self._ops = ops
+
+    def gather_merge(self, idx, score, flags, id_map=None, id_base: int = 0):
+        self._ops.pack_scatter(idx.contiguous(), score.contiguous(), flags, self.ptrs, self.rank, self.world, self.counters,
+                               id_map=id_map, id_base=id_base)
+        return self._ops.merge_gathered(self.buf, self.world, idx.shape[0], idx.shape[1], self.counters)
+
+
 class ShardedBank:
     def __init__(self, local_rows: torch.Tensor, row_base: int, group=None,
                  scale: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None,
                  local_search: Optional[Callable] = None, merge: Optional[Callable] = None,
-                 stats: Optional[dict] = None, shadow=None, score_unit: float = 1.0):
+                 stats: Optional[dict] = None, shadow=None, score_unit: float = 1.0, peer_gather: bool = False):
         self.rows = local_rows
+        # exchange the local top-k blocks through peer memory (PeerGather) instead of an NCCL all-gather; decided
+        # collectively at the first search, falls back to NCCL if the symmetric allocation is not available
+        self.peer_gather = bool(peer_gather)
+        self._peers = {}
         self.shadow = shadow                  # ops.Bf16Shadow of an fp32 shard: the shortlist pass reads it (ops.batch_topk)
         self.score_unit = float(score_unit)   # max |scale_r| * ||r|| (1 for pure cosine): unit of the certification bound
         self.row_base = int(row_base)
@@ -71,6 +109,10 @@ class ShardedBank:
 
     def _gather_merge(self, idx: torch.Tensor, score: torch.Tensor, k: int, flags: Optional[torch.Tensor]):
         b = idx.shape[0]
+        if self._packed and self.peer_gather:
+            pg = self._peer_gather_for(b, k, idx.device)
+            if pg is not None:
+                return pg.gather_merge(idx, score, flags)
         if self._packed:
             # product path: pack kernel -> ONE collective -> merge kernel (3 launches, no torch elementwise ops)
             payload = self._ops.pack_topk(idx.contiguous(), score.contiguous(), flags)
@@ -92,6 +134,28 @@ class ShardedBank:
         any_flag = gathered[:, :, 2 * k].sum(dim=0)               # identical on every rank
         return out_idx, out_score, any_flag
 
+    def _peer_gather_for(self, b: int, k: int, device) -> Optional[PeerGather]:
+        """The PeerGather of this (batch, k), created collectively on first use; None (for good) if any rank could not
+        set up symmetric memory."""
+        key = (b, k)
+        if key in self._peers:
+            return self._peers[key]
+        pg = None
+        try:
+            pg = PeerGather(self.world, self.rank, b, k, device, self.group)
+            ok = torch.ones(1, device=device)
+        except Exception as e:                                  # noqa: BLE001 - agreed on collectively below
+            import sys
+            sys.stderr.write(f"[aura] peer gather unavailable on rank {self.rank} ({e}); using the NCCL all-gather\n")
+            ok = torch.zeros(1, device=device)
+        if self.world > 1:
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+        if float(ok) < 1.0:
+            pg = None
+            self.peer_gather = False
+        self._peers[key] = pg
+        return pg
+
     def _flag_slot(self):
         """A pinned scalar + event for the flag count of one search, from a small ring: allocating pinned memory per
         search costs a cudaHostAlloc (tens of microseconds, serialised across the ranks of a box) on a 0.5 ms step.
@@ -105,9 +169,9 @@ class ShardedBank:
 
     def graphed(self, batch: int, k: int, allow_collective: bool = False) -> "GraphedSearch":
         """A CUDA-graph capture of `search_deferred` for a fixed (batch, k); see `GraphedSearch`."""
-        if self.world > 1 and not allow_collective:
+        if self.world > 1 and not (allow_collective or self.peer_gather):
             raise RuntimeError("GraphedSearch with world > 1 captures an NCCL collective (unverified here); "
-                               "pass allow_collective=True to try")
+                               "use peer_gather=True (exchange over peer memory) or pass allow_collective=True to try")
         return GraphedSearch(self, batch, k)
 
     def search(self, queries: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:

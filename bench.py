@@ -520,7 +520,10 @@ def run_ours(args):
     stats = {}
     # the product's sharded exact path: tcgen05 shortlist + fp32 re-score per shard, NCCL all-gather, k-way merge
     # (default) the shortlist pass reads a bf16 shadow of the fp32 bank; the re-score and every returned score are fp32
-    shard = ShardedBank(bank, lo, scale=hf._inv_norm, stats=stats, shadow=hf._shadow_rows(), score_unit=1.0)
+    # N > 1: the local top-k blocks are exchanged through peer memory (two launches, graph-capturable) unless
+    # --no-peer-gather, in which case (or if symmetric memory is unavailable) it is one NCCL all-gather per step
+    shard = ShardedBank(bank, lo, scale=hf._inv_norm, stats=stats, shadow=hf._shadow_rows(), score_unit=1.0,
+                        peer_gather=world > 1 and not args.no_peer_gather)
 
     # ---- queries: distinct batch per step, pinned host copies for the e2e leg
     gq = torch.Generator().manual_seed(SEED_QUERY)
@@ -541,11 +544,13 @@ def run_ours(args):
     # ---- leg 1: resident inputs.  Search i is finalised (certification flags checked) after search i+1 has been
     # enqueued, so the host's launch work overlaps the GPU's; every search is finalised inside the timed region.
     pending = [None]
-    # the step as one CUDA-graph launch (kernels + NCCL all-gather + merge), two graphs alternating so that two searches
-    # are in flight.  N=1 only: with the NCCL all-gather inside the capture the 2-rank run hung on this image (torch 2.11,
-    # NCCL 2.28.9), so sharded runs keep the eager launches; --no-graph or a failed capture does the same at N=1
+    # the step as one CUDA-graph launch (local kernels + exchange + merge), two graphs alternating so that two searches
+    # are in flight.  At N > 1 this needs the peer-memory exchange (an NCCL all-gather inside the capture hung on this
+    # image: torch 2.11, NCCL 2.28.9); --no-graph, --no-peer-gather or a failed capture fall back to eager launches
     graphs = None
-    if world == 1 and not args.no_graph:
+    if world > 1:
+        shard.search(q_dev[0], TOPK)                         # sets up (or gives up on) the peer-memory exchange, collectively
+    if (world == 1 or shard.peer_gather) and not args.no_graph:
         try:
             graphs = [shard.graphed(B, TOPK) for _ in range(2)]
         except Exception as e:                               # noqa: BLE001 - report and measure the eager path instead
@@ -705,6 +710,7 @@ def run_ours(args):
         del eager_query
         _log("single-query + torch-eager bars done; cuBLAS bars")
         extra["cublas_tf32"] = cublas_bars(bank, q_dev[3], dev)
+    shard_peer, graphed = bool(shard.peer_gather), graphs is not None
     legs = [x for x in args.legs.split(",") if x]
     if world == 1:
         # free the C2 bank before the larger workloads
@@ -769,6 +775,8 @@ def run_ours(args):
                         "h2d_bytes_per_step": B * DIM * 4,
                         "d2h_bytes_per_step": B * TOPK * 12 + (B * 4 if world == 1 else 0),
                         "pipelining": "2 batches in flight on 2 streams (deferred certification)" if world == 1 else "none"},
+                "exchange": ("none" if world == 1 else "peer-memory stores over NVLink (aura_pack_scatter / aura_merge_gathered)" if shard_peer
+                             else "NCCL all_gather_into_tensor"), "cuda_graph_step": graphed,
                 "gpu_launches": int(launches), "roofline": roof, "clocks": clocks, "top1_hit_rate": hit,
                 "uncertified_queries_rerun": int(stats.get("uncertain", 0))}
         line.update(extra)
@@ -808,6 +816,7 @@ def main():
     ap.add_argument("--ref-queries-per-step", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="N=1: eager launches instead of one CUDA-graph launch per step")
+    ap.add_argument("--no-peer-gather", action="store_true", help="N>1: exchange the local top-k blocks with an NCCL all-gather instead of peer-memory stores")
     ap.add_argument("--no-shadow", action="store_true", help="shortlist straight from the fp32 bank (TF32) instead of its bf16 shadow")
     ap.add_argument("--legs", default="c3,c4,c5", help="extra BASELINE-config legs to run after the headline workload ('' = none)")
     ap.add_argument("--c4-rows", type=int, default=10_000_000)

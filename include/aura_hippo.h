@@ -228,6 +228,20 @@ int aura_pack_topk(const int64_t* idx, const float* score, const int32_t* flags,
 int aura_topk_merge_packed(const int64_t* gathered, int n_ranks, int n_queries, int k, float* out_score, int64_t* out_idx,
                            int32_t* any_flag, void* stream);
 
+/* The same exchange over peer memory instead of a library collective (NVLink / NVSwitch, symmetric allocation): rank r
+ * owns a gather buffer of aura_peer_gather_buffer_bytes() bytes that every peer has mapped (zero it once);
+ * aura_pack_scatter builds this rank's payload and stores it into EVERY rank's buffer (peer_bufs_host[r], host array of
+ * device pointers in rank order) and raises its flag there; aura_merge_gathered waits, on the device, until every rank's
+ * flag for the current step is up and merges what landed in the local buffer.  `counters`: 4 zero-initialised device
+ * words private to this rank (the step numbers live there, so consecutive calls - and CUDA-graph replays - need no
+ * changing argument).  Every rank must issue the same sequence of pack / merge calls. */
+size_t aura_peer_gather_buffer_bytes(int n_ranks, int n_queries, int k);
+int aura_pack_scatter(const int64_t* idx, const float* score, const int32_t* flags, int n_queries, int k,
+                      const int64_t* id_map, int64_t id_base, void* const* peer_bufs_host, int rank, int n_ranks,
+                      uint32_t* counters, void* stream);
+int aura_merge_gathered(const void* gather_buf, int n_ranks, int n_queries, int k, uint32_t* counters, float* out_score,
+                        int64_t* out_idx, int32_t* any_flag, void* stream);
+
 /* Gather bank rows of a result block: out[b, j, :] = rows[idx[b, j]] (zeros when idx < 0), as fp32.
  * Replaces the per-result id_to_idx lookup + row copy of memory_augmented_layer.py:124-128. */
 int aura_gather_rows(const void* rows, int dtype, int d, const int64_t* idx, int64_t n_idx, float* out, void* stream);

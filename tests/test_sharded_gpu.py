@@ -279,3 +279,33 @@ def test_sharded_cognitive_map_equals_single_gpu_map(dt, monkeypatch):
         nbr, sim = results[r]
         assert torch.equal(nbr.cpu(), ref_nbr[lo:hi].cpu())
         assert torch.equal(sim.cpu(), ref_sim[lo:hi].cpu())
+
+
+def test_peer_gather_single_rank_equals_packed_merge():
+    """`PeerGather` (pack + scatter into the gather buffer + flag, device-side wait + merge) with one rank: same result as
+    pack -> merge_packed, over several steps (slot parity, step counters) and inside a CUDA graph."""
+    from aura_snn_rag_b200 import ops
+    from aura_snn_rag_b200.sharded import PeerGather
+    g = torch.Generator().manual_seed(9)
+    B, k = 33, 10
+    pg = PeerGather(1, 0, B, k, torch.device("cuda:0"))
+    for step in range(5):
+        sc = torch.randn(B, k, generator=g).sort(dim=1, descending=True).values.cuda()
+        ids = torch.randint(0, 10 ** 6, (B, k), generator=g).cuda()
+        fl = (torch.rand(B, generator=g) < 0.1).int().cuda()
+        ref_i, ref_s, ref_f = ops.topk_merge_packed(ops.pack_topk(ids, sc, fl, id_base=7), 1, B, k)
+        i, s_, f = pg.gather_merge(ids, sc, fl, id_base=7)
+        assert torch.equal(i, ref_i) and torch.equal(s_, ref_s) and torch.equal(f, ref_f)
+    assert pg.counters.tolist() == [5, 0, 5, 0]
+    sc = torch.randn(B, k, generator=g).sort(dim=1, descending=True).values.cuda()
+    ids = torch.randint(0, 10 ** 6, (B, k), generator=g).cuda()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=side):
+        out = pg.gather_merge(ids, sc, None)
+    for _ in range(3):
+        graph.replay()
+    torch.cuda.synchronize()
+    ref_i, ref_s, _ = ops.topk_merge_packed(ops.pack_topk(ids, sc, None), 1, B, k)
+    assert torch.equal(out[0], ref_i) and torch.equal(out[1], ref_s) and pg.counters.tolist() == [8, 0, 8, 0]
