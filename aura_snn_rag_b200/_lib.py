@@ -64,6 +64,7 @@ SIGNATURES = {
     "aura_pack_scatter": (_i, [_p, _p, _p, _i, _i, _p, _i64, _p, _i, _i, _p, _p]),
     "aura_merge_gathered": (_i, [_p, _i, _i, _i, _p, _p, _p, _p, _p]),
     "aura_gather_rows": (_i, [_p, _i, _i, _p, _i64, _p, _p]),
+    "aura_gather_context": (_i, [_p, _i, _i, _p, _p, _i, _i, _p, _p, _p]),
 }
 
 

@@ -517,9 +517,11 @@ __global__ void __launch_bounds__(128) gemm_topk_finish_kernel(const FinishArgs 
     return;
   }
   RescoreArgs ra;
+  ra.out_mul = 1.f;
   ra.rows = f.rows; ra.bf16 = f.bf16; ra.d = f.d; ra.q = f.qn + (size_t)b * f.d; ra.scale = f.scale; ra.bias = f.bias;
   ra.eps = f.eps_q ? f.eps_q[b] : f.eps; ra.k = f.k; ra.L = f.L; ra.row_base = f.row_base;
   ra.out_idx = f.out_idx + b * f.k; ra.out_score = f.out_score + b * f.k; ra.uncertain = f.uncertain ? f.uncertain + b : nullptr;
+  if (f.a_scale) ra.out_mul = f.a_scale[b];        // all-pairs over an fp32 bank: exact fp32 cosine of the k neighbours
   rescore_and_write(keys, n2, ex, ra);
 }
 
@@ -537,6 +539,7 @@ __global__ void __launch_bounds__(128) cand_rescore_kernel(const CandRescoreArgs
   for (int i = threadIdx.x; i < GT_MAX_L; i += blockDim.x) keys[i] = i < f.n_cand ? f.cand[(size_t)b * GT_MAX_L + i] : 0ull;
   __syncthreads();
   RescoreArgs ra;
+  ra.out_mul = 1.f;
   ra.rows = f.rows; ra.bf16 = f.bf16; ra.d = f.d; ra.q = f.qn + (size_t)b * f.d; ra.scale = f.scale; ra.bias = f.bias;
   ra.eps = f.eps; ra.k = f.k; ra.L = f.n_cand; ra.row_base = f.row_base;
   ra.out_idx = f.out_idx + b * f.k; ra.out_score = f.out_score + b * f.k; ra.uncertain = f.uncertain ? f.uncertain + b : nullptr;
@@ -623,6 +626,17 @@ static bool make_gemm_plan(long long n_a_rows, long long n_b_rows, int d, int el
   int groups = units / work_rows;
   if (groups < 1) groups = 1;
   if (groups > p->n_ctiles) groups = p->n_ctiles;
+  static const int env_l2groups = env_int("AURA_GEMM_L2GROUPS", 0);
+  if (env_l2groups && work_rows > units) {
+    // More A tiles than CTAs and a B matrix larger than L2 (all-pairs): every CTA streams the whole of B per A tile, the
+    // CTAs drift apart and B comes from DRAM again and again (C3: 52 GB read for a 0.4 GB bank = 0.58 TB/s, 9 % of HBM).
+    // Cutting B into L2-resident column groups (48 MB, all A tiles pass over a group before the next) removes the
+    // re-reads but was measured SLOWER, 124 ms against 90 ms at C3: every (A tile, group) item warms its top-32 lists up
+    // again and the finish kernel merges 9 lists per row, while the re-reads were never the limiter.  Opt-in only.
+    const long long b_bytes = n_b_rows * (long long)d * elem_bytes;
+    const long long min_groups = (b_bytes + (48ll << 20) - 1) / (48ll << 20);
+    if (min_groups > groups) groups = (int)(min_groups < p->n_ctiles ? min_groups : p->n_ctiles);
+  }
   if (env_groups >= 1 && env_groups <= p->n_ctiles) groups = env_groups;
   if (force_groups) groups = force_groups;
   p->n_groups = groups;
@@ -1139,6 +1153,12 @@ extern "C" int aura_allpairs_topk(const void* rows, int dtype, int64_t n_rows, i
   f.partial = partial; f.n_atiles = p.n_atiles; f.n_groups = p.n_groups; f.L = p.L; f.n2 = p.n2; f.k = k;
   f.n_a_rows = n_a_rows; f.row_base = 0; f.rows = nullptr; f.bf16 = 0; f.d = d; f.qn = nullptr;
   f.scale = nullptr; f.bias = nullptr; f.eps = 0.f; f.eps_q = nullptr; f.a_scale = inv_norm ? inv_norm + a_row_first : nullptr;
+  if (!bf16) {
+    // fp32 bank: the TF32 products only pick the k candidates; their cosines are recomputed in exact fp32 (row i as the
+    // "query", scale_j = 1/||row_j||, times 1/||row_i|| on output) and re-ranked, so returned scores meet the fp32 bar.
+    // (bf16 x bf16 products are exact in the fp32 accumulator: a bf16 bank needs no second look.)
+    f.rows = rows; f.qn = reinterpret_cast<const float*>(rows) + (size_t)a_row_first * d; f.scale = inv_norm;
+  }
   f.out_idx = reinterpret_cast<long long*>(out_idx); f.out_score = out_score; f.uncertain = nullptr; f.cand = nullptr; f.ceil_out = nullptr; f.round = 0;
   const size_t fsmem = ((size_t)p.n2 + GT_MAX_L) * 8;
   AURA_CUDA_OK(cudaFuncSetAttribute(gemm_topk_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));

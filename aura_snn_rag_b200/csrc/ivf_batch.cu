@@ -516,6 +516,7 @@ __global__ void __launch_bounds__(128) ivf_finish_kernel(const IvfFinishArgs f) 
     return;
   }
   RescoreArgs ra;
+  ra.out_mul = 1.f;
   ra.rows = f.rows; ra.bf16 = f.bf16; ra.d = f.d; ra.q = f.qn + (size_t)b * f.d; ra.scale = f.scale; ra.bias = f.bias;
   ra.eps = f.eps; ra.k = f.k; ra.L = GT_L; ra.row_base = f.row_base;
   ra.out_idx = f.out_idx + (size_t)b * f.k; ra.out_score = f.out_score + (size_t)b * f.k;
@@ -1047,6 +1048,7 @@ __global__ void __launch_bounds__(128) ivf_slot_finish_kernel(const IvfSlotFinis
   for (int i = kept + threadIdx.x; i < n2; i += blockDim.x) keys[i] = 0ull;
   block_bitonic_sort_desc(keys, n2);
   RescoreArgs ra;
+  ra.out_mul = 1.f;
   ra.rows = f.rows; ra.bf16 = f.bf16; ra.d = f.d; ra.q = f.qn_vec + (size_t)b * f.d; ra.scale = f.scale; ra.bias = f.bias;
   ra.eps = f.eps; ra.k = f.k; ra.L = f.L; ra.row_base = f.row_base;
   ra.out_idx = f.out_idx + (size_t)b * f.k; ra.out_score = f.out_score + (size_t)b * f.k;

@@ -180,6 +180,72 @@ extern "C" int aura_gather_rows(const void* rows, int dtype, int d, const int64_
   return AURA_OK;
 }
 
+// ---- memory injection context (memory_augmented_layer.py:185-188,192-193): for every query b,
+//   w = softmax(scores[b, 0..k))  (a missing result counts with score 0 and a zero row, exactly as the zero-padded
+//   tensors of retrieve_memories, :113-130, enter the reference's softmax),  context[b] = sum_j w_j * rows[idx[b, j]]
+// fused with the row gather: the [B, k, d] feature block is never materialised.  One CTA per query.
+namespace aura {
+template <bool BF16>
+__global__ void __launch_bounds__(256) gather_context_kernel(const void* __restrict__ rows, int d, const long long* __restrict__ idx,
+                                                             const float* __restrict__ score, int k, float* __restrict__ context,
+                                                             float* __restrict__ weights) {
+  __shared__ float w_s[AURA_MAX_K];
+  __shared__ long long r_s[AURA_MAX_K];
+  const int b = blockIdx.x;
+  if (threadIdx.x < 32) {
+    // softmax over k <= 128 scores by one warp, in the order torch's softmax uses: max, exp(x - max), sum, divide
+    float v[AURA_MAX_K / 32];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < AURA_MAX_K / 32; ++j) {
+      const int i = threadIdx.x + 32 * j;
+      long long r = -1; float sc = -INFINITY;
+      if (i < k) { r = idx[(size_t)b * k + i]; sc = r >= 0 ? score[(size_t)b * k + i] : 0.f; r_s[i] = r; }
+      v[j] = sc;
+      mx = fmaxf(mx, sc);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(FULL, mx, o));
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < AURA_MAX_K / 32; ++j) { v[j] = (threadIdx.x + 32 * j) < k ? expf(v[j] - mx) : 0.f; sum += v[j]; }
+    sum = warp_sum(sum);
+#pragma unroll
+    for (int j = 0; j < AURA_MAX_K / 32; ++j) {
+      const int i = threadIdx.x + 32 * j;
+      if (i < k) { const float w = v[j] / sum; w_s[i] = w; if (weights) weights[(size_t)b * k + i] = w; }
+    }
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < d; e += blockDim.x) {
+    float acc = 0.f;
+    for (int j = 0; j < k; ++j) {
+      const long long r = r_s[j];
+      if (r < 0) continue;
+      const float x = BF16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(rows)[(size_t)r * d + e])
+                           : reinterpret_cast<const float*>(rows)[(size_t)r * d + e];
+      acc = fmaf(w_s[j], x, acc);
+    }
+    context[(size_t)b * d + e] = acc;
+  }
+}
+}  // namespace aura
+
+extern "C" int aura_gather_context(const void* rows, int dtype, int d, const int64_t* idx, const float* score, int n_queries,
+                                   int k, float* context, float* weights, void* stream) {
+  AURA_REQUIRE(dtype == AURA_F32 || dtype == AURA_BF16, AURA_ERR_INVALID_ARG, "aura_gather_context: bad dtype %d", dtype);
+  if (n_queries <= 0) return AURA_OK;
+  AURA_REQUIRE(rows && idx && score && context && d >= 1 && k >= 1 && k <= AURA_MAX_K, AURA_ERR_INVALID_ARG,
+               "aura_gather_context: null pointer / d=%d k=%d", d, k);
+  if (dtype == AURA_BF16)
+    gather_context_kernel<true><<<n_queries, 256, 0, (cudaStream_t)stream>>>(rows, d, reinterpret_cast<const long long*>(idx), score, k, context, weights);
+  else
+    gather_context_kernel<false><<<n_queries, 256, 0, (cudaStream_t)stream>>>(rows, d, reinterpret_cast<const long long*>(idx), score, k, context, weights);
+  AURA_CUDA_OK(cudaGetLastError());
+  note_launches(1);
+  return AURA_OK;
+}
+
 extern "C" int aura_bank_write(void* rows, int dtype, int d, int64_t first_row, int n_new, const float* features,
                                float* locations, int spatial_dims, const float* location, float* metadata,
                                float timestamp, float* inv_norm, void* stream) {

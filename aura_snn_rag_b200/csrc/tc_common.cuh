@@ -297,6 +297,7 @@ struct RescoreArgs {
   const float* scale; const float* bias; float eps;
   int k, L; long long row_base;
   long long* out_idx; float* out_score; int* uncertain;   // already offset to this query
+  float out_mul;               // written score = exact score * out_mul (all-pairs: 1 / ||row_i||); ranking is unaffected
 };
 __device__ __forceinline__ void rescore_and_write(const u64* keys, int n2, u64* ex, const RescoreArgs& f) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -330,7 +331,7 @@ __device__ __forceinline__ void rescore_and_write(const u64* keys, int n2, u64* 
   for (int i = threadIdx.x; i < f.k; i += blockDim.x) {
     const u64 key = i < GT_MAX_L ? ex[i] : 0ull;
     f.out_idx[i] = key ? f.row_base + (long long)key_row(key) : -1ll;
-    f.out_score[i] = key ? key_score(key) : -INFINITY;
+    f.out_score[i] = key ? key_score(key) * f.out_mul : -INFINITY;
   }
   if (threadIdx.x == 0 && f.uncertain) {
     // rows outside the shortlist have approximate score <= s_L (the L-th best approximate score), hence exact

@@ -394,6 +394,20 @@ class HippocampalFormation(nn.Module):
             return idx, score, ops.gather_rows(self.memory_features, idx)
         return idx, score
 
+    def retrieve_context(self, queries, k: int = 5, location=None):
+        """What `MemoryAugmentedLayer` needs from the bank for its "concat" / "gate" injection, in one pass
+        (memory_augmented_layer.py:106-130 + :185-194): top-k search of the query block, then
+        context[b] = sum_j softmax(scores[b])_j * memory_features[row_j] with the reference's zero padding for
+        missing results.  Returns (context fp32 [B,d], scores [B,k] zero-padded like the reference's, rows int64 [B,k]);
+        the [B,k,d] feature block is never materialised."""
+        idx, score = self.retrieve_batch(queries, k=k, location=location)
+        if idx.shape[1] < k:                       # fewer than k memories stored: the reference pads to k (:111-112)
+            pad = k - idx.shape[1]
+            idx = torch.cat([idx, idx.new_full((idx.shape[0], pad), -1)], dim=1)
+            score = torch.cat([score, score.new_zeros(score.shape[0], pad)], dim=1)
+        ctx = ops.gather_context(self.memory_features, idx.contiguous(), score.contiguous())
+        return ctx, torch.where(idx >= 0, score, torch.zeros_like(score)), idx
+
     def _max_strength(self) -> float:
         """Upper bound of the live strengths (the tensor-core error bound scales with it), kept on the host."""
         return self._strength_bound
@@ -533,6 +547,33 @@ class HippocampalFormation(nn.Module):
                 b = self._ids.owner(j) if self.track_ids else j
                 if b is not None:
                     out[(a, b)] = 1.0 - s
+        return out
+
+    def cognitive_map_edges(self, k: int = 32):
+        """The k-NN edges of the cognitive map as a CSR graph for sleep-phase replay / consolidation consumers
+        (TODO.md:12 "sparse graph construction (k-NN edges)"; training_recipes.md:292-308 reads the dict view):
+        (indptr int64 [M+1], neighbours int64 [nnz], distance fp32 [nnz]), distance = 1 - cosine, nearest first inside
+        a row.  Device tensors; `cognitive_map` is the host dict over the same edges."""
+        if getattr(self, "_cmap", None) is None or getattr(self, "_cmap_version", None) != self._version \
+                or self._cmap[0].shape[1] != min(int(k), max(self.memory_count - 1, 0)):
+            self.build_cognitive_map(k)
+        nbr, sim = self._cmap
+        valid = nbr >= 0
+        indptr = torch.zeros(nbr.shape[0] + 1, dtype=torch.int64, device=self.device)
+        indptr[1:] = valid.sum(dim=1).cumsum(0)
+        return indptr, nbr[valid], (1.0 - sim[valid])
+
+    def replay_order(self, start_row: int, length: int, k: int = 32) -> List[int]:
+        """A replay trajectory over the map for the sleep phase (hippocampal_trainer.py:327-348 replays stored items):
+        greedy nearest-unvisited-neighbour walk from `start_row`, at most `length` memories (host-side, small)."""
+        indptr, nbr, _ = self.cognitive_map_edges(k)
+        indptr, nbr = indptr.cpu().tolist(), nbr.cpu().tolist()
+        seen, out, cur = {int(start_row)}, [int(start_row)], int(start_row)
+        while len(out) < length:
+            nxt = next((j for j in nbr[indptr[cur]:indptr[cur + 1]] if j not in seen), None)
+            if nxt is None:
+                break
+            seen.add(nxt); out.append(nxt); cur = nxt
         return out
 
     # ------------------------------------------------------------------ persistence / resume (SURVEY.md 8f rank 2)

@@ -225,6 +225,25 @@ def gather_rows(rows: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
     return out
 
 
+@_on_device
+def gather_context(rows: torch.Tensor, idx: torch.Tensor, score: torch.Tensor, return_weights: bool = False):
+    """context[b] = sum_j softmax(score[b])_j * rows[idx[b, j]] (missing results: score 0, zero row) - the memory context
+    of inject_memories' "concat" / "gate" modes (memory_augmented_layer.py:185-194) fused with the gather."""
+    rows = _dev(rows, "rows")
+    idx = _dev(idx, "idx")
+    score = _dev(score, "score")
+    b, k = idx.shape
+    d = rows.shape[1]
+    ctx = torch.empty(b, d, dtype=torch.float32, device=rows.device)
+    w = torch.empty(b, k, dtype=torch.float32, device=rows.device) if return_weights else None
+    if k > 0:
+        check(_lib.load().aura_gather_context(rows.data_ptr(), _dtype_code(rows), d, idx.data_ptr(), score.data_ptr(), b, k,
+                                              ctx.data_ptr(), _ptr(w), _stream()), "aura_gather_context")
+    else:
+        ctx.zero_()
+    return (ctx, w) if return_weights else ctx
+
+
 # ---------------------------------------------------------------------------- bank write
 @_on_device
 def bank_write(rows: torch.Tensor, first_row: int, features: torch.Tensor, metadata: torch.Tensor,

@@ -246,6 +246,14 @@ int aura_merge_gathered(const void* gather_buf, int n_ranks, int n_queries, int 
  * Replaces the per-result id_to_idx lookup + row copy of memory_augmented_layer.py:124-128. */
 int aura_gather_rows(const void* rows, int dtype, int d, const int64_t* idx, int64_t n_idx, float* out, void* stream);
 
+/* Memory-injection context of MemoryAugmentedLayer.inject_memories ("concat" / "gate" modes,
+ * memory_augmented_layer.py:185-188,192-193), fused with the row gather:
+ *   w[b, :] = softmax(score[b, :]) with a missing result (idx < 0) entering as score 0 / zero row - the zero padding of
+ *   retrieve_memories (:113-130) - and context[b, :] = sum_j w[b, j] * rows[idx[b, j]]   (fp32, [n_queries, d]).
+ * weights (may be NULL) receives w [n_queries, k].  k <= AURA_MAX_K. */
+int aura_gather_context(const void* rows, int dtype, int d, const int64_t* idx, const float* score, int n_queries, int k,
+                        float* context, float* weights, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -327,6 +327,30 @@ def cognitive_map_dict(ids: Sequence[str], nbr: torch.Tensor, sim: torch.Tensor)
 
 
 # ---------------------------------------------------------------------------
+# Batched caller: MemoryAugmentedLayer.retrieve_memories + inject_memories context
+# ---------------------------------------------------------------------------
+def retrieve_memories_batch(o: "OracleHippocampus", queries: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """memory_augmented_layer.py:106-130: one search per batch item (Python loop), zero-padded
+    features [B,k,D] and scores [B,k].  The reference looks features up through
+    ``id_to_idx``; with the patched row mapping that is ``memory_features[row]``."""
+    b, d = queries.shape
+    feats = torch.zeros(b, k, d)
+    scores = torch.zeros(b, k)
+    for i in range(b):                                       # :113
+        rows, sc = o.retrieve_rows(queries[i], k=k)          # :117-120
+        for j, (r, s) in enumerate(zip(rows.tolist(), sc.tolist())):
+            feats[i, j] = o.memory_features[r]               # :124-128
+            scores[i, j] = s
+    return feats, scores
+
+
+def inject_context(memory_features: torch.Tensor, memory_scores: torch.Tensor) -> torch.Tensor:
+    """memory_augmented_layer.py:185-188 (and :192-193): softmax-weighted mean of the retrieved rows, [B,1,D] -> [B,D]."""
+    weights = F.softmax(memory_scores, dim=-1).unsqueeze(-1)
+    return (memory_features * weights).sum(dim=1)
+
+
+# ---------------------------------------------------------------------------
 # Host-side helpers shared by tests (CPU merge for the gloo tests, recall)
 # ---------------------------------------------------------------------------
 def merge_topk(scores: torch.Tensor, ids: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:

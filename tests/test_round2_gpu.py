@@ -184,3 +184,81 @@ def test_load_state_dict_refreshes_derived_state_lazily(monkeypatch):
     e = make()
     i0, s0 = e.exact_topk(q[:3], 5)
     assert i0.shape == (3, 0) and s0.shape == (3, 0)
+
+
+def test_batched_caller_and_injection_context_match_the_reference(monkeypatch):
+    """`retrieve_batch(gather=True)` and the fused `retrieve_context` against outputs of the
+    REAL reference's MemoryAugmentedLayer.retrieve_memories + inject_memories("concat") (tests/golden/mal_batch.npz) and
+    against the oracle's restatement of that loop - not against this class's own per-item path."""
+    import os
+    import aura_snn_rag_b200.hippocampal as hmod
+    from aura_snn_rag_b200 import memory_api as api
+    from test_oracle_mal_golden import B, D, K, N, build_oracle, inputs
+    import cases as C
+    monkeypatch.setattr(hmod, "time", types.SimpleNamespace(time=lambda: C.T0))
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "mal_batch.npz"))
+    rows, hidden = inputs()
+    for tag, n_rows in (("full", N), ("tiny", 3)):
+        hf = hmod.HippocampalFormation(2, 8, 4, 4, max_memories=256, feature_dim=D, device="cuda")
+        hf.create_episodic_memories(torch.from_numpy(rows[:n_rows]), [f"m{i}" for i in range(n_rows)])
+        hf.memory_metadata[:n_rows] = torch.from_numpy(gold[f"{tag}_metadata"]).cuda()      # strengths after decay
+        hf._version += 1
+        q = torch.from_numpy(hidden).mean(dim=1).cuda()
+        feats, scores = api.retrieve_memories(hf, q, k=K)                                   # [B,K,D], [B,K], zero-padded
+        np.testing.assert_allclose(scores.cpu().numpy(), gold[f"{tag}_scores"], rtol=1e-4, atol=1e-6)
+        np.testing.assert_array_equal(feats.cpu().numpy(), gold[f"{tag}_features"])
+        ctx, sc2, idx = hf.retrieve_context(q, k=K)
+        injected = torch.from_numpy(hidden).cuda() + 0.1 * ctx.unsqueeze(1)                   # memory_augmented_layer.py:189-190
+        np.testing.assert_allclose(injected.cpu().numpy(), gold[f"{tag}_injected"], rtol=1e-4, atol=1e-6)
+        np.testing.assert_allclose(sc2.cpu().numpy(), gold[f"{tag}_scores"], rtol=1e-4, atol=1e-6)
+        # and the oracle's restatement of the same loop on the same state
+        from oracle.hippo_oracle import inject_context, retrieve_memories_batch
+        o, h = build_oracle(n_rows, gold[f"{tag}_metadata"])
+        f_o, s_o = retrieve_memories_batch(o, h.mean(dim=1), K)
+        np.testing.assert_allclose(ctx.cpu().numpy(), inject_context(f_o, s_o).numpy(), rtol=1e-4, atol=1e-6)
+    # a larger block through the tensor-core path (B >= 3) with the centroid index on, against the oracle loop
+    g = torch.Generator().manual_seed(5)
+    n, d, k = 5000, 128, 6
+    bank = torch.randn(n, d, generator=g)
+    hf = hmod.HippocampalFormation(2, 8, 4, 4, max_memories=8192, feature_dim=d, device="cuda", centroids_k=32, nprobe=4, track_ids=False)
+    hf.centroids_update_interval = 1 << 40
+    hf.create_episodic_memories(bank)
+    hf.rebuild_centroids(seed_rows=torch.arange(0, n, 150)[:32])
+    from oracle.hippo_oracle import OracleHippocampus, inject_context, retrieve_memories_batch
+    o = OracleHippocampus(max_memories=8192, feature_dim=d, centroids_k=32, centroid_rows=256, nprobe=4, time_fn=lambda: C.T0)
+    o.memory_features[:n] = bank
+    o.memory_metadata[:n] = hf.memory_metadata[:n].cpu()
+    o.memory_count = n
+    o.centroids = hf.centroids.cpu()
+    o._index_ready = True
+    q = bank[:40] + 0.2 * torch.randn(40, d, generator=g)
+    ctx, sc, idx = hf.retrieve_context(q, k=k)
+    f_o, s_o = retrieve_memories_batch(o, q, k)
+    np.testing.assert_allclose(sc.cpu().numpy(), s_o.numpy(), rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(ctx.cpu().numpy(), inject_context(f_o, s_o).numpy(), rtol=1e-4, atol=1e-5)
+
+
+def test_cognitive_map_edges_and_exact_fp32_scores():
+    """fp32 bank: the map's neighbour scores are exact fp32 cosines (re-scored, 1e-4 bar of the north star; the TF32
+    products only pick the candidates).  CSR edge view + replay walk for the sleep-phase consumer."""
+    from aura_snn_rag_b200 import HippocampalFormation
+    from oracle.hippo_oracle import cognitive_map_topk
+    g = torch.Generator().manual_seed(33)
+    n, d, k = 3000, 96, 12
+    centres = torch.randn(30, d, generator=g)
+    rows = centres[torch.randint(0, 30, (n,), generator=g)] + 0.5 * torch.randn(n, d, generator=g)
+    hf = HippocampalFormation(max_memories=4096, feature_dim=d, n_place_cells=4, n_time_cells=2, n_grid_cells=2,
+                              use_centroid_index=False, track_ids=False)
+    hf.create_episodic_memories(rows)
+    nbr, sim = hf.build_cognitive_map(k)
+    ref_i, ref_s = cognitive_map_topk(rows, k)
+    np.testing.assert_allclose(sim.cpu().numpy(), ref_s.numpy(), rtol=1e-4, atol=2e-6)
+    assert np.mean([len(set(a) & set(b)) / k for a, b in zip(nbr.cpu().tolist(), ref_i.tolist())]) > 0.995
+    assert bool((sim[:, :-1] >= sim[:, 1:]).all())
+    indptr, nb, dist = hf.cognitive_map_edges(k)
+    assert indptr.tolist() == list(range(0, n * k + 1, k)) and nb.numel() == n * k
+    np.testing.assert_allclose(dist.cpu().numpy(), (1.0 - sim).reshape(-1).cpu().numpy())
+    walk = hf.replay_order(5, 20, k)
+    assert walk[0] == 5 and len(walk) == len(set(walk)) == 20
+    for a, b in zip(walk[:-1], walk[1:]):
+        assert b in nbr[a].tolist()
