@@ -40,6 +40,10 @@ struct GemmTopkArgs {
   const float* bias;          // per B row, may be null (0)
   u64* partial;               // [n_atiles * n_groups][L][128]
   const u64* ceil_keys;       // per A row: only keys strictly below this one are eligible (multi-round top-k), may be null
+  unsigned* gthr;             // per A row, zeroed per launch, may be null: orderable score that the row's final L-th best
+                              // is known to reach - the largest L-th best any CTA (column group) has seen for the row so
+                              // far.  L keys at or above it exist, so no CTA needs to keep anything below it: the lists of
+                              // the n_groups CTAs sharing a row become as selective as one global list.
 };
 
 template <bool TF32, int L, bool CEIL>
@@ -145,6 +149,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const long long my_row = a.a_row_first + (long long)atile * GT_BM + te;   // global id of this A row
       const bool live = (long long)atile * GT_BM + te < a.n_a_rows;
       float thr = live ? -INFINITY : INFINITY;        // rows past the end of A never select anything
+      unsigned published = 0u;
       // multi-round selection (k > 18): round r only admits keys strictly below the 32nd key of round r-1
       const u64 ceil_key = (CEIL && live) ? a.ceil_keys[(long long)atile * GT_BM + te] : ~0ull;
       const float ceil_score = ceil_key == ~0ull ? INFINITY : key_score(ceil_key);
@@ -152,6 +157,10 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       for (int ct = ct0; ct < ct1; ++ct, ++tile_n) {
         const unsigned acc = tile_n & 1u, acc_phase = (tile_n >> 1) & 1u;
         const long long col0 = (long long)ct * GT_BN;
+        if (live && a.gthr != nullptr) {             // other column groups of this row may already have raised the bar
+          const unsigned g = *reinterpret_cast<volatile unsigned*>(a.gthr + (long long)atile * GT_BM + te);
+          if (g != 0u) thr = fmaxf(thr, f32_from_orderable(g));
+        }
         // stage the per-column terms of this tile (invalid columns -> NaN score, never selected)
         float2* sb = sbuf + acc * GT_BN;
 #pragma unroll
@@ -189,13 +198,17 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             const u64 key = make_key(sc, (unsigned)(col0 + c0 + j));
             if (key > e[L - 1] && (!CEIL || key < ceil_key)) {
               list_insert_sorted_asc<L>(e, key);
-              if (e[L - 1] != 0ull) thr = key_score(e[L - 1]);
+              if (e[L - 1] != 0ull) thr = fmaxf(thr, key_score(e[L - 1]));
             }
           }
         }
         tc::tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty[acc]);
+        if (live && a.gthr != nullptr && e[L - 1] != 0ull) {     // a full list: its L-th best bounds the row's final L-th best
+          const unsigned o = (unsigned)(e[L - 1] >> 32);
+          if (o > published) { atomicMax(a.gthr + (long long)atile * GT_BM + te, o); published = o; }
+        }
       }
       // flush this item's list: partial[item][s][te]
       u64* dst = a.partial + (size_t)item * L * GT_BM;
@@ -323,12 +336,17 @@ gemm_topk2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       const long long my_row = a.a_row_first + (long long)atile * GT_BM + te;
       const bool live = (long long)atile * GT_BM + te < a.n_a_rows;
       float thr = live ? -INFINITY : INFINITY;
+      unsigned published = 0u;
       const u64 ceil_key = (CEIL && live) ? a.ceil_keys[(long long)atile * GT_BM + te] : ~0ull;
       const float ceil_score = ceil_key == ~0ull ? INFINITY : key_score(ceil_key);
       if (ceil_key == 0ull) thr = INFINITY;
       for (int ct = ct0; ct < ct1; ++ct, ++tile_n) {
         const unsigned acc = tile_n & 1u, acc_phase = (tile_n >> 1) & 1u;
         const long long col0 = (long long)ct * GT_BN;
+        if (live && a.gthr != nullptr) {
+          const unsigned g = *reinterpret_cast<volatile unsigned*>(a.gthr + (long long)atile * GT_BM + te);
+          if (g != 0u) thr = fmaxf(thr, f32_from_orderable(g));
+        }
         float2* sb = sbuf + acc * GT_BN;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -363,13 +381,17 @@ gemm_topk2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             const u64 key = make_key(fmaf(select32(v, j), t.x, t.y), (unsigned)(col0 + c0 + j));
             if (key > e[L - 1] && (!CEIL || key < ceil_key)) {
               list_insert_sorted_asc<L>(e, key);
-              if (e[L - 1] != 0ull) thr = key_score(e[L - 1]);
+              if (e[L - 1] != 0ull) thr = fmaxf(thr, key_score(e[L - 1]));
             }
           }
         }
         tc::tc_fence_before();
         __syncwarp();
         if (lane == 0) tc::mbar_arrive_leader(&tempty[acc]);
+        if (live && a.gthr != nullptr && e[L - 1] != 0ull) {
+          const unsigned o = (unsigned)(e[L - 1] >> 32);
+          if (o > published) { atomicMax(a.gthr + (long long)atile * GT_BM + te, o); published = o; }
+        }
       }
       const int item1 = group * a.n_atiles + atile;            // layout gemm_topk_finish_kernel reads
       u64* dst = a.partial + (size_t)item1 * L * GT_BM;
@@ -672,7 +694,8 @@ static size_t align256(size_t v) { return (v + 255) / 256 * 256; }
 
 static int run_gemm_topk(const void* a_mat, long long n_a_rows, long long a_row_first, const void* b_mat, long long n_b_rows,
                          int d, bool bf16, const float* scale, const float* bias, bool exclude_self, const GemmPlan& p,
-                         u64* partial, cudaStream_t st, const u64* ceil_keys = nullptr, long long a_rows_alloc = 0) {
+                         u64* partial, cudaStream_t st, const u64* ceil_keys = nullptr, long long a_rows_alloc = 0,
+                         unsigned* gthr = nullptr) {
   const int eb = bf16 ? 2 : 4;
   CUtensorMap ta, tb;
   int rc = encode_tmap_2d(&ta, a_mat, eb, bf16, a_rows_alloc > n_a_rows ? a_rows_alloc : n_a_rows, d, GT_BM);
@@ -684,6 +707,9 @@ static int run_gemm_topk(const void* a_mat, long long n_a_rows, long long a_row_
   a.n_a_rows = n_a_rows; a.n_b_rows = n_b_rows; a.a_row_first = a_row_first;
   a.k_blocks = p.k_blocks; a.L = p.L; a.n_stages = p.n_stages; a.exclude_self = exclude_self ? 1 : 0;
   a.scale = scale; a.bias = bias; a.partial = partial; a.ceil_keys = ceil_keys;
+  static const int env_gthr = env_int("AURA_GEMM_GTHR", 1);
+  a.gthr = (env_gthr && p.n_groups > 1) ? gthr : nullptr;          // one group per row: nobody to share a bound with
+  if (a.gthr != nullptr) AURA_CUDA_OK(cudaMemsetAsync(a.gthr, 0, (size_t)p.n_atiles * GT_BM * 4, st));
   void (*kern)(const CUtensorMap, const CUtensorMap, const GemmTopkArgs);
   const bool ceil = ceil_keys != nullptr;
   if (p.L == GT_L_ASSIGN) kern = bf16 ? gemm_topk_kernel<false, GT_L_ASSIGN, false> : gemm_topk_kernel<true, GT_L_ASSIGN, false>;
@@ -842,7 +868,7 @@ size_t tc_coarse_workspace_bytes(int n_queries, int d, int n_cent, int nprobe) {
   GemmPlan p;
   if (!make_gemm_plan(n_queries, n_cent, d, 4, GT_L, false, &p)) return 0;
   return align256(p.partial_bytes) + 3 * align256((size_t)n_cent * 4) + align256((size_t)n_queries * nprobe * 4) + 512 +
-         align256((size_t)n_queries * GT_MAX_L * 8) + align256((size_t)n_queries * 8);
+         align256((size_t)n_queries * GT_MAX_L * 8) + align256((size_t)n_queries * 8) + align256((size_t)p.n_atiles * GT_BM * 4);
 }
 
 // ---- exact finish of the tensor-core coarse stage -------------------------------------------------------------------
@@ -971,7 +997,7 @@ int tc_coarse(const float* queries, int n_queries, int d, const float* cent, int
   if (rounds > GT_MAX_ROUNDS) rounds = GT_MAX_ROUNDS;
   for (int r = 0; r < rounds; ++r) {
     int rc = run_gemm_topk(queries, n_queries, 0, cent, n_cent, d, false, scale2, neg_csq, false, p, partial, st,
-                           r ? ceil_buf : nullptr);
+                           r ? ceil_buf : nullptr, 0, reinterpret_cast<unsigned*>(ceil_buf + align256((size_t)n_queries * 8) / 8));
     if (rc != AURA_OK) return rc;
     f.round = r;
     gemm_topk_finish_kernel<<<n_queries, 128, fsmem, st>>>(f);
@@ -1008,7 +1034,8 @@ extern "C" size_t aura_batch_topk_workspace_bytes(int64_t n_rows, int d, int dty
     p.partial_bytes = ps.partial_bytes;
   const size_t n_pad = ((size_t)n_queries + GT_BM - 1) / GT_BM * GT_BM;     // query block padded to whole A tiles
   return align256(p.partial_bytes) + align256(n_pad * d * 4) + align256(n_pad * d * 2) + 512 +
-         align256((size_t)n_queries * GT_MAX_L * 8) + align256((size_t)n_queries * 8) + align256((size_t)n_queries * 4);
+         align256((size_t)n_queries * GT_MAX_L * 8) + align256((size_t)n_queries * 8) + align256((size_t)n_queries * 4) +
+         align256(n_pad * 4);
 }
 
 extern "C" int aura_batch_topk(const void* rows, int dtype, int64_t n_rows, int d, const float* queries, int n_queries,
@@ -1025,7 +1052,14 @@ extern "C" int aura_batch_topk(const void* rows, int dtype, int64_t n_rows, int 
                       (reinterpret_cast<uintptr_t>(shadow_bf16) & 15) == 0;
   const bool bf16 = dtype == AURA_BF16 || shadow;
   GemmPlan p;
-  AURA_REQUIRE(make_gemm_plan(n_queries, n_rows, d, bf16 ? 2 : 4, k, true, &p, shadow ? GT_L_WIDE : 0), AURA_ERR_UNSUPPORTED,
+  // shortlist length of the shadow pass: 32 when k + 14 <= 32, else 48.  The list is the epilogue's cost (C2, batch 1024:
+  // 1.28 / 1.51 / 1.63 ms per kernel at L = 24 / 32 / 48), the margin is what certifies: with the measured rounding bound
+  // L = 32 certified all 51 200 bench queries, L = 24 handed back 1.7 % of them (each one a 0.45 ms exact scan).
+  // AURA_SHADOW_L = 24 | 32 | 48 overrides.
+  static const int env_shadow_l = env_int("AURA_SHADOW_L", 0);
+  int shadow_L = k + 14 <= GT_L ? GT_L : GT_L_WIDE;
+  if ((env_shadow_l == GT_L_SMALL || env_shadow_l == GT_L || env_shadow_l == GT_L_WIDE) && k + 14 <= env_shadow_l) shadow_L = env_shadow_l;
+  AURA_REQUIRE(make_gemm_plan(n_queries, n_rows, d, bf16 ? 2 : 4, k, true, &p, shadow ? shadow_L : 0), AURA_ERR_UNSUPPORTED,
                "aura_batch_topk: no plan for n_queries=%d k=%d", n_queries, k);
   AURA_REQUIRE(workspace_bytes >= aura_batch_topk_workspace_bytes(n_rows, d, dtype, n_queries, k), AURA_ERR_WORKSPACE,
                "aura_batch_topk: workspace too small");
@@ -1041,6 +1075,7 @@ extern "C" int aura_batch_topk(const void* rows, int dtype, int64_t n_rows, int 
   u64* cand = reinterpret_cast<u64*>(ws + off_floor + 512);
   u64* ceil_buf = cand + align256((size_t)n_queries * GT_MAX_L * 8) / 8;
   float* eps_q = reinterpret_cast<float*>(ceil_buf + align256((size_t)n_queries * 8) / 8);
+  unsigned* gthr = reinterpret_cast<unsigned*>(eps_q + align256((size_t)n_queries * 4) / 4);     // [n_pad]
   const bool measured_bound = shadow && shadow_relerr != nullptr;     // eps is then the score-per-cosine unit (see header)
   if (measured_bound)
     normalize_queries_eps_kernel<<<(n_queries + 7) / 8, 256, 0, st>>>(queries, n_queries, d, qn, qb, shadow_relerr, eps, eps_q);
@@ -1063,7 +1098,7 @@ extern "C" int aura_batch_topk(const void* rows, int dtype, int64_t n_rows, int 
   const size_t fsmem = ((size_t)p.n2 + GT_MAX_L) * 8;
   AURA_CUDA_OK(cudaFuncSetAttribute(gemm_topk_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
   if (rounds == 1) {
-    rc = run_gemm_topk(a_mat, n_queries, 0, b_mat, n_rows, d, bf16, scale, bias, false, p, partial, st, nullptr, (long long)n_pad);
+    rc = run_gemm_topk(a_mat, n_queries, 0, b_mat, n_rows, d, bf16, scale, bias, false, p, partial, st, nullptr, (long long)n_pad, gthr);
     if (rc != AURA_OK) return rc;
     gemm_topk_finish_kernel<<<n_queries, 128, fsmem, st>>>(f);
     AURA_CUDA_OK(cudaGetLastError());
@@ -1075,7 +1110,7 @@ extern "C" int aura_batch_topk(const void* rows, int dtype, int64_t n_rows, int 
   // without gaps or repeats; all candidates are then re-scored exactly and certified like the one-round case.
   f.cand = cand; f.ceil_out = ceil_buf;
   for (int r = 0; r < rounds; ++r) {
-    rc = run_gemm_topk(a_mat, n_queries, 0, rows, n_rows, d, bf16, scale, bias, false, p, partial, st, r ? ceil_buf : nullptr, (long long)n_pad);
+    rc = run_gemm_topk(a_mat, n_queries, 0, rows, n_rows, d, bf16, scale, bias, false, p, partial, st, r ? ceil_buf : nullptr, (long long)n_pad, gthr);
     if (rc != AURA_OK) return rc;
     f.round = r;
     gemm_topk_finish_kernel<<<n_queries, 128, fsmem, st>>>(f);
@@ -1127,7 +1162,7 @@ extern "C" size_t aura_allpairs_topk_workspace_bytes(int64_t n_a_rows, int64_t n
   GemmPlan p;
   if (n_a_rows < 1 || n_rows < 1 || d < 1 || k < 1) return 0;
   if (!make_gemm_plan(n_a_rows, n_rows, d, dtype == AURA_BF16 ? 2 : 4, k, false, &p)) return 0;
-  return align256(p.partial_bytes) + 256;
+  return align256(p.partial_bytes) + align256((size_t)p.n_atiles * GT_BM * 4) + 256;
 }
 
 extern "C" int aura_allpairs_topk(const void* rows, int dtype, int64_t n_rows, int d, int64_t a_row_first,
@@ -1147,7 +1182,8 @@ extern "C" int aura_allpairs_topk(const void* rows, int dtype, int64_t n_rows, i
   cudaStream_t st = (cudaStream_t)stream;
   u64* partial = reinterpret_cast<u64*>(workspace);
   const unsigned char* a_mat = reinterpret_cast<const unsigned char*>(rows) + (size_t)a_row_first * d * (bf16 ? 2 : 4);
-  rc = run_gemm_topk(a_mat, n_a_rows, a_row_first, rows, n_rows, d, bf16, inv_norm, nullptr, true, p, partial, st);
+  unsigned* gthr = reinterpret_cast<unsigned*>(reinterpret_cast<unsigned char*>(workspace) + align256(p.partial_bytes));
+  rc = run_gemm_topk(a_mat, n_a_rows, a_row_first, rows, n_rows, d, bf16, inv_norm, nullptr, true, p, partial, st, nullptr, 0, gthr);
   if (rc != AURA_OK) return rc;
   FinishArgs f;
   f.partial = partial; f.n_atiles = p.n_atiles; f.n_groups = p.n_groups; f.L = p.L; f.n2 = p.n2; f.k = k;

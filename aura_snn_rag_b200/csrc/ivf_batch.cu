@@ -584,8 +584,12 @@ __host__ __device__ __forceinline__ void ir_chunks(int len, int nq, int& n_ch, i
   int mult = nq / 32;
   mult = mult < 1 ? 1 : mult > 8 ? 8 : mult;
   const int target = IB_CH_ROWS * mult;                     // 2048 .. 16384 rows per chunk
+  // a list probed by many queries is already split into query groups: fewer, longer chunks there (every query that
+  // probes it pays one result slot per chunk)
+  const int groups = nq <= 64 ? 1 : (nq + 127) / 128;
+  const int max_ch = groups >= 8 ? 4 : groups >= 2 ? 8 : IB_MAX_CHUNKS;
   n_ch = (len + target - 1) / target;
-  if (n_ch > IB_MAX_CHUNKS) n_ch = IB_MAX_CHUNKS;
+  if (n_ch > max_ch) n_ch = max_ch;
   if (n_ch < 1) { n_ch = 0; ch_rows = target; return; }
   ch_rows = ((len + n_ch - 1) / n_ch + GT_BN - 1) / GT_BN * GT_BN;
   n_ch = (len + ch_rows - 1) / ch_rows;
@@ -1144,39 +1148,39 @@ struct IrLayout {
       n_slots, qslots, slot_cnt, slot_keys, cbuf, total;
   int cap_slots;
 };
-static IrLayout ir_layout(int n_queries, int d, int n_lists, int nprobe, int cap, size_t coarse_bytes) {
-  IrLayout L;
+static IrLayout ir_layout(int n_queries, int d, int n_lists, int nprobe, int cap, size_t coarse_bytes, int L) {
+  IrLayout Lo;
   size_t o = 0;
   const size_t pairs = (size_t)n_queries * nprobe;
-  L.probes = o; o += a256(pairs * 8);
-  L.counts = o; o += a256((size_t)n_lists * 4);
-  L.q_off = o; o += a256((size_t)(n_lists + 1) * 4);
-  L.cursor = o; o += a256((size_t)(IR_SECTIONS * n_lists + 1) * 4);
-  L.pair_of_pos = o; o += a256(pairs * 4);
-  L.pos_of_pair = o; o += a256(pairs * 4);
-  L.items_c = o; o += a256((size_t)IR_SECTIONS * n_lists * 4);
-  L.item_base = o; o += a256((size_t)(IR_SECTIONS * n_lists + 1) * 4);
-  L.items = o; o += a256((size_t)cap * 16);
-  L.qn = o; o += a256((size_t)n_queries * d * 4);
-  L.qb = o; o += a256((size_t)n_queries * d * 2);
-  L.coarse = o; o += a256(coarse_bytes);
-  L.gthr = o; o += a256((size_t)n_queries * 4);          // gthr, qcnt, qflag, n_slots are cleared with one memset
-  L.qcnt = o; o += a256((size_t)n_queries * 4);
-  L.qflag = o; o += a256((size_t)n_queries * 4);
-  L.n_slots = o; o += 256;
-  L.qslots = o; o += a256((size_t)n_queries * IR_QS_MAX * 4);
+  Lo.probes = o; o += a256(pairs * 8);
+  Lo.counts = o; o += a256((size_t)n_lists * 4);
+  Lo.q_off = o; o += a256((size_t)(n_lists + 1) * 4);
+  Lo.cursor = o; o += a256((size_t)(IR_SECTIONS * n_lists + 1) * 4);
+  Lo.pair_of_pos = o; o += a256(pairs * 4);
+  Lo.pos_of_pair = o; o += a256(pairs * 4);
+  Lo.items_c = o; o += a256((size_t)IR_SECTIONS * n_lists * 4);
+  Lo.item_base = o; o += a256((size_t)(IR_SECTIONS * n_lists + 1) * 4);
+  Lo.items = o; o += a256((size_t)cap * 16);
+  Lo.qn = o; o += a256((size_t)n_queries * d * 4);
+  Lo.qb = o; o += a256((size_t)n_queries * d * 2);
+  Lo.coarse = o; o += a256(coarse_bytes);
+  Lo.gthr = o; o += a256((size_t)n_queries * 4);          // gthr, qcnt, qflag, n_slots are cleared with one memset
+  Lo.qcnt = o; o += a256((size_t)n_queries * 4);
+  Lo.qflag = o; o += a256((size_t)n_queries * 4);
+  Lo.n_slots = o; o += 256;
+  Lo.qslots = o; o += a256((size_t)n_queries * IR_QS_MAX * 4);
   // one result slot per (item, query) that keeps anything: ~1 per (query, probe) plus one per extra chunk of a long list
-  L.cap_slots = (int)(4 * pairs + 4096 < 32000000 ? 4 * pairs + 4096 : 32000000);
-  L.slot_cnt = o; o += a256((size_t)L.cap_slots * 4);
-  L.slot_keys = o; o += a256((size_t)L.cap_slots * GT_MAX_L * 8);
-  L.cbuf = o; o += a256((size_t)sm_count() * IR_CBUF_KEYS * 8);
-  L.total = o;
-  return L;
+  Lo.cap_slots = (int)(8 * pairs + 4096 < 32000000 ? 8 * pairs + 4096 : 32000000);
+  Lo.slot_cnt = o; o += a256((size_t)Lo.cap_slots * 4);
+  Lo.slot_keys = o; o += a256((size_t)Lo.cap_slots * L * 8);
+  Lo.cbuf = o; o += a256((size_t)sm_count() * IR_CBUF_KEYS * 8);
+  Lo.total = o;
+  return Lo;
 }
 
-static size_t ir_workspace_bytes(int n_queries, int d, int n_lists, int nprobe) {
+static size_t ir_workspace_bytes(int n_queries, int d, int n_lists, int nprobe, int k) {
   const int cap = ib_cap_items(n_queries, nprobe, n_lists);
-  return ir_layout(n_queries, d, n_lists, nprobe, cap, ivf_coarse_ws_bytes(n_queries, d, n_lists, nprobe)).total;
+  return ir_layout(n_queries, d, n_lists, nprobe, cap, ivf_coarse_ws_bytes(n_queries, d, n_lists, nprobe), ir_list_len(k)).total;
 }
 
 static int ivf_rows_search(const void* rows, bool bf16, long long n_rows, int d, const float* queries, int n_queries,
@@ -1185,7 +1189,7 @@ static int ivf_rows_search(const void* rows, bool bf16, long long n_rows, int d,
                            float eps, long long* out_idx, float* out_score, int* out_uncertain, void* workspace, cudaStream_t st) {
   const int eb = bf16 ? 2 : 4;
   const int cap = ib_cap_items(n_queries, nprobe, n_lists);
-  const IrLayout Lo = ir_layout(n_queries, d, n_lists, nprobe, cap, ivf_coarse_ws_bytes(n_queries, d, n_lists, nprobe));
+  const IrLayout Lo = ir_layout(n_queries, d, n_lists, nprobe, cap, ivf_coarse_ws_bytes(n_queries, d, n_lists, nprobe), ir_list_len(k));
   unsigned char* ws = reinterpret_cast<unsigned char*>(workspace);
   long long* probes = reinterpret_cast<long long*>(ws + Lo.probes);
   int* counts = reinterpret_cast<int*>(ws + Lo.counts);
@@ -1283,11 +1287,11 @@ static int ivf_rows_search(const void* rows, bool bf16, long long n_rows, int d,
 }  // namespace aura
 using namespace aura;
 
-extern "C" size_t aura_ivf_search_batch_workspace_bytes(int n_queries, int d, int n_centroid_rows, int nprobe) {
-  if (n_queries < 1 || d < 1 || n_centroid_rows < 1 || nprobe < 1) return 0;
+extern "C" size_t aura_ivf_search_batch_workspace_bytes(int n_queries, int d, int n_centroid_rows, int nprobe, int k) {
+  if (n_queries < 1 || d < 1 || n_centroid_rows < 1 || nprobe < 1 || k < 1) return 0;
   const int cap = ib_cap_items(n_queries, nprobe, n_centroid_rows);
   const size_t old_bytes = ib_layout(n_queries, d, n_centroid_rows, nprobe, cap, ivf_coarse_ws_bytes(n_queries, d, n_centroid_rows, nprobe)).total;
-  const size_t new_bytes = ir_workspace_bytes(n_queries, d, n_centroid_rows, nprobe);
+  const size_t new_bytes = ir_workspace_bytes(n_queries, d, n_centroid_rows, nprobe, k);
   return old_bytes > new_bytes ? old_bytes : new_bytes;
 }
 
@@ -1309,7 +1313,7 @@ extern "C" int aura_ivf_search_batch(const void* rows, int dtype, int64_t n_rows
                "aura_ivf_search_batch: rows must be 16-byte aligned with a 16-byte multiple pitch (d=%d)", d);
   AURA_REQUIRE(rows && queries && centroids && list_offsets && list_rows && out_idx && out_score && out_uncertain && workspace,
                AURA_ERR_INVALID_ARG, "aura_ivf_search_batch: null pointer");
-  AURA_REQUIRE(workspace_bytes >= aura_ivf_search_batch_workspace_bytes(n_queries, d, n_centroid_rows, nprobe),
+  AURA_REQUIRE(workspace_bytes >= aura_ivf_search_batch_workspace_bytes(n_queries, d, n_centroid_rows, nprobe, k),
                AURA_ERR_WORKSPACE, "aura_ivf_search_batch: workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
   // Two formulations of the list-major fine stage.  Shortlists of <= 32 keys (k <= 18) fit the queries-as-M kernel's
@@ -1467,11 +1471,11 @@ extern "C" int aura_ivf_pack_lists(const void* rows, int dtype, int d, const int
   return AURA_OK;
 }
 
-extern "C" int aura_ivf_search_batch_items(const void* workspace, int n_queries, int d, int n_centroid_rows, int nprobe,
+extern "C" int aura_ivf_search_batch_items(const void* workspace, int n_queries, int d, int n_centroid_rows, int nprobe, int k,
                                            int32_t* items_out, int32_t* host_cap, void* stream) {
-  AURA_REQUIRE(workspace && items_out && host_cap, AURA_ERR_INVALID_ARG, "aura_ivf_search_batch_items: null pointer");
+  AURA_REQUIRE(workspace && items_out && host_cap && k >= 1, AURA_ERR_INVALID_ARG, "aura_ivf_search_batch_items: null pointer");
   const int cap = ib_cap_items(n_queries, nprobe, n_centroid_rows);
-  const IrLayout L = ir_layout(n_queries, d, n_centroid_rows, nprobe, cap, ivf_coarse_ws_bytes(n_queries, d, n_centroid_rows, nprobe));
+  const IrLayout L = ir_layout(n_queries, d, n_centroid_rows, nprobe, cap, ivf_coarse_ws_bytes(n_queries, d, n_centroid_rows, nprobe), ir_list_len(k));
   const unsigned char* ws = reinterpret_cast<const unsigned char*>(workspace);
   ir_stats_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const int*>(ws + L.item_base), n_centroid_rows,
                                                        reinterpret_cast<const int*>(ws + L.n_slots),

@@ -574,7 +574,7 @@ def ivf_search_batched(rows: torch.Tensor, n_rows: int, queries: torch.Tensor, c
     out_score = torch.empty(b, k, dtype=torch.float32, device=dev)
     flags = torch.empty(b, dtype=torch.int32, device=dev)
     lib = _lib.load()
-    ws = _workspace(lib.aura_ivf_search_batch_workspace_bytes(b, d, c, nprobe), dev, "ivfbatch")
+    ws = _workspace(lib.aura_ivf_search_batch_workspace_bytes(b, d, c, nprobe, k), dev, "ivfbatch")
     check(lib.aura_ivf_search_batch(rows.data_ptr(), _dtype_code(rows), n_rows, d, queries.data_ptr(), b,
                                     centroids.data_ptr(), c, nprobe, list_offsets.data_ptr(), list_rows.data_ptr(),
                                     _ptr(rows_by_list), _ptr(scale), _ptr(bias), k, row_base,
@@ -584,7 +584,7 @@ def ivf_search_batched(rows: torch.Tensor, n_rows: int, queries: torch.Tensor, c
     if stats is not None:
         import ctypes as _C
         items, cap = torch.zeros(8, dtype=torch.int32, device=dev), _C.c_int32(0)
-        check(lib.aura_ivf_search_batch_items(ws.data_ptr(), b, d, c, nprobe, items.data_ptr(), _C.addressof(cap), _stream()),
+        check(lib.aura_ivf_search_batch_items(ws.data_ptr(), b, d, c, nprobe, k, items.data_ptr(), _C.addressof(cap), _stream()),
               "aura_ivf_search_batch_items")
         it = items.tolist()
         stats["items"], stats["items_cap"] = it[0], cap.value

@@ -751,7 +751,7 @@ def run_ours(args):
                 "tensor_input": "tf32 (fp32 bank read directly)" if args.no_shadow else "bf16 (shadow copy of the fp32 bank)",
                 "traffic": ncu_traffic(tkey)[0] if (N_ROWS, DIM, B) == (1_000_000, 768, 1024) and world == 1 else None,
                 "traffic_source": ncu_traffic(tkey)[1],
-                "kernel": args.kernel_name if args.no_shadow else "gemm_topk_kernel<bf16, L=48> (tcgen05 M128 N256, fused top-48) on the bf16 shadow + exact fp32 re-score",
+                "kernel": args.kernel_name if args.no_shadow else "gemm_topk_kernel<bf16, L=32> (tcgen05 M128 N256, fused top-32) on the bf16 shadow + exact fp32 re-score",
                 "algorithmic_flops_per_launch": flops / world,
                 "algorithmic_bytes_per_launch": (alg_bytes if args.no_shadow else alg_bytes / 2) / world,
                 "timing": "whole step (kernel share in profiles/)",

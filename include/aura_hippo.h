@@ -161,7 +161,7 @@ int aura_ivf_search(const void* rows, int dtype, int64_t n_rows, int d, const fl
  * scores of the best candidates (same re-score + certification as aura_batch_topk, read from `rows`);
  * out_uncertain[b] = 1 hands query b back to aura_ivf_search (uncertified result, no candidates, or work table
  * overflow).  k <= 114, d*sizeof(elem) % 16 == 0. */
-size_t aura_ivf_search_batch_workspace_bytes(int n_queries, int d, int n_centroid_rows, int nprobe);
+size_t aura_ivf_search_batch_workspace_bytes(int n_queries, int d, int n_centroid_rows, int nprobe, int k);
 int aura_ivf_search_batch(const void* rows, int dtype, int64_t n_rows, int d, const float* queries, int n_queries,
                           const float* centroids, int n_centroid_rows, int nprobe, const int32_t* list_offsets,
                           const int32_t* list_rows, const void* rows_by_list, const float* scale, const float* bias, int k,
@@ -177,7 +177,7 @@ int aura_ivf_pack_lists(const void* rows, int dtype, int d, const int32_t* list_
 /* diagnostics of the last aura_ivf_search_batch call on `workspace`, written to the DEVICE words items_out[0..5) by an
  * enqueued kernel (like every entry point it does not synchronise): {work items, result slots used, most slots linked by one
  * query, queries flagged inside the kernel, queries without any candidate}; host_cap = work-table capacity */
-int aura_ivf_search_batch_items(const void* workspace, int n_queries, int d, int n_centroid_rows, int nprobe,
+int aura_ivf_search_batch_items(const void* workspace, int n_queries, int d, int n_centroid_rows, int nprobe, int k,
                                 int32_t* items_out, int32_t* host_cap, void* stream);
 
 /* ---- batched exact search on the tensor cores (the batch the reference loops over one query at a
@@ -188,7 +188,7 @@ int aura_ivf_search_batch_items(const void* workspace, int n_queries, int d, int
  * that tensor-core scores are within `eps` (score units) of the exact ones; 1 means the caller must re-run
  * query b through aura_scan_topk.  Needs d*sizeof(elem) % 16 == 0 and k <= 114.
  * shadow_bf16 (may be NULL): a bf16 copy of an fp32 bank (aura_rows_to_bf16, same row order).  The shortlist pass then
- * runs on the copy (kind::f16: half the bytes, twice the tensor rate, 48 candidates per query; k <= 34) and the re-score
+ * runs on the copy (kind::f16: half the bytes, twice the tensor rate, 32 candidates per query for k <= 18, 48 for k <= 34) and the re-score
  * still reads the fp32 rows, so certified results are the same exact fp32 top-k; `eps` must then bound the bf16 rounding
  * (2^-7 per unit of |scale * ||row|||) - or, with shadow_relerr (DEVICE scalar >= ||bf16(r) - r|| / ||r|| over the bank rows,
  * maintained by aura_rows_to_bf16), `eps` is just that unit, max |scale_r| * ||r||, and the bound is measured per query:
