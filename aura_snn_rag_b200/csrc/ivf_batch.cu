@@ -87,7 +87,9 @@ __device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-template <bool TF32, bool CEIL>
+// L = entries of the per-(query, chunk) register list: GT_L, or GT_L_SMALL when k <= 10 (the list is the epilogue's cost);
+// the partial lists in memory keep a stride of GT_L keys either way (unused entries are zero).
+template <bool TF32, bool CEIL, int L>
 __global__ void __launch_bounds__(IB_THREADS, 1)
 ivf_gemm_kernel(const __grid_constant__ CUtensorMap tmap_lm, const unsigned char* __restrict__ qmat,
                 const unsigned char* __restrict__ bank, const int row_pitch, const IvfBatchArgs a) {
@@ -299,9 +301,9 @@ ivf_gemm_kernel(const __grid_constant__ CUtensorMap tmap_lm, const unsigned char
       int n_ch_, ch_rows_;
       ib_chunks(len, n_ch_, ch_rows_);
       const int r0 = it.z * ch_rows_, r1 = min(len, r0 + ch_rows_);
-      u64 e[GT_L];
+      u64 e[L];
 #pragma unroll
-      for (int s = 0; s < GT_L; ++s) e[s] = 0ull;
+      for (int s = 0; s < L; ++s) e[s] = 0ull;
       const int my_pos = ib_pos_of_row(te, a.spread);
       const bool live = my_pos < n_a;
       float thr = live ? -INFINITY : INFINITY;
@@ -352,24 +354,24 @@ ivf_gemm_kernel(const __grid_constant__ CUtensorMap tmap_lm, const unsigned char
             mask &= mask - 1u;
             const float2 t = sb[c0 + j];
             const u64 key = make_key(fmaf(select32(v, j), t.x, t.y), (unsigned)rs[c0 + j]);
-            if (key > e[GT_L - 1] && (!CEIL || key < ceil_key)) {
-              list_insert_sorted<GT_L>(e, key);
-              if (e[GT_L - 1] != 0ull) thr = fmaxf(thr, key_score(e[GT_L - 1]));
+            if (key > e[L - 1] && (!CEIL || key < ceil_key)) {
+              list_insert_sorted<L>(e, key);
+              if (e[L - 1] != 0ull) thr = fmaxf(thr, key_score(e[L - 1]));
             }
           }
         }
         tc::tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty[acc]);
-        if (live && a.use_gthr && e[GT_L - 1] != 0ull) {   // a full list: its L-th best bounds the query's final L-th best from below
-          const unsigned o = (unsigned)(e[GT_L - 1] >> 32);
+        if (live && a.use_gthr && e[L - 1] != 0ull) {   // a full list: its L-th best bounds the query's final L-th best from below
+          const unsigned o = (unsigned)(e[L - 1] >> 32);
           if (o > published) { atomicMax(my_gthr, o); published = o; }
         }
       }
       if (live) {
         u64* dst = a.partial + ((size_t)a.pbase[it.x] + (size_t)it.z * nq + it.y * GT_BM + my_pos) * GT_L;
 #pragma unroll
-        for (int s = 0; s < GT_L; ++s) dst[s] = e[s];
+        for (int s = 0; s < GT_L; ++s) dst[s] = s < L ? e[s < L ? s : 0] : 0ull;
       }
     }
   }
@@ -438,6 +440,7 @@ struct IvfFinishArgs {
   const u64* partial;
   const void* rows; int bf16; int d; const float* qn; const float* scale; const float* bias; float eps;
   int k; long long row_base; int spread, chunk_major;
+  int L;                    // entries the GEMM kernel keeps per partial list (<= GT_L)
   u64* cand; u64* ceil_out; int round; int* force_flag;   // multi-round mode (see gemm_topk.cu)
   int empty_ok;             // a query without candidates is a valid empty result (row-sharded callers), not a hand-back
   long long* out_idx; float* out_score; int* uncertain;
@@ -488,7 +491,7 @@ __global__ void __launch_bounds__(128) ivf_finish_kernel(const IvfFinishArgs f) 
   const int h2 = max(64, next_pow2(nh));
   for (int i = nh + threadIdx.x; i < h2; i += blockDim.x) keys[i] = 0ull;
   block_bitonic_sort_desc(keys, h2);
-  if (threadIdx.x == 0) floor_s = nh >= GT_L ? keys[GT_L - 1] : 0ull;
+  if (threadIdx.x == 0) floor_s = nh >= f.L ? keys[f.L - 1] : 0ull;
   __syncthreads();
   const u64 floor_key = floor_s;
   __syncthreads();                                               // heads consumed: the buffer now takes the survivors
@@ -518,7 +521,7 @@ __global__ void __launch_bounds__(128) ivf_finish_kernel(const IvfFinishArgs f) 
   RescoreArgs ra;
   ra.out_mul = 1.f;
   ra.rows = f.rows; ra.bf16 = f.bf16; ra.d = f.d; ra.q = f.qn + (size_t)b * f.d; ra.scale = f.scale; ra.bias = f.bias;
-  ra.eps = f.eps; ra.k = f.k; ra.L = GT_L; ra.row_base = f.row_base;
+  ra.eps = f.eps; ra.k = f.k; ra.L = f.L; ra.row_base = f.row_base;
   ra.out_idx = f.out_idx + (size_t)b * f.k; ra.out_score = f.out_score + (size_t)b * f.k;
   ra.uncertain = f.uncertain + b;
   rescore_and_write(keys, n2, ex, ra);
@@ -1396,8 +1399,10 @@ extern "C" int aura_ivf_search_batch(const void* rows, int dtype, int64_t n_rows
     a.list_major = 1;
   }
   typedef void (*IvfKern)(const CUtensorMap, const unsigned char*, const unsigned char*, int, const IvfBatchArgs);
-  IvfKern kern0 = bf16 ? ivf_gemm_kernel<false, false> : ivf_gemm_kernel<true, false>;    // first round: no ceiling
-  IvfKern kern1 = bf16 ? ivf_gemm_kernel<false, true> : ivf_gemm_kernel<true, true>;
+  const bool small = k + 14 <= GT_L_SMALL;                  // k <= 10: 24-entry lists, one round
+  IvfKern kern0 = small ? (bf16 ? ivf_gemm_kernel<false, false, GT_L_SMALL> : ivf_gemm_kernel<true, false, GT_L_SMALL>)
+                        : (bf16 ? ivf_gemm_kernel<false, false, GT_L> : ivf_gemm_kernel<true, false, GT_L>);    // first round: no ceiling
+  IvfKern kern1 = bf16 ? ivf_gemm_kernel<false, true, GT_L> : ivf_gemm_kernel<true, true, GT_L>;
   AURA_CUDA_OK(cudaFuncSetAttribute(kern0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   AURA_CUDA_OK(cudaFuncSetAttribute(kern1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   u64* cand = reinterpret_cast<u64*>(ws + L.cand);
@@ -1410,6 +1415,7 @@ extern "C" int aura_ivf_search_batch(const void* rows, int dtype, int64_t n_rows
   f.n_items = n_items; f.cap_items = cap; f.nprobe = nprobe; f.n_lists = n_centroid_rows; f.partial = partial;
   f.pbase = pbase; f.cap_plists = a.cap_plists;
   f.rows = rows; f.bf16 = bf16 ? 1 : 0; f.d = d; f.qn = qn; f.scale = scale; f.bias = bias; f.eps = eps; f.k = k;
+  f.L = small ? GT_L_SMALL : GT_L;
   f.row_base = row_base; f.spread = a.spread; f.chunk_major = chunk_major; f.out_idx = reinterpret_cast<long long*>(out_idx); f.out_score = out_score; f.uncertain = out_uncertain;
   f.cand = rounds > 1 ? cand : nullptr; f.ceil_out = ceil_buf; f.round = 0; f.force_flag = force;
   f.empty_ok = (flags & AURA_IVF_EMPTY_OK) ? 1 : 0;

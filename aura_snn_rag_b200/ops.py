@@ -583,13 +583,18 @@ def ivf_search_batched(rows: torch.Tensor, n_rows: int, queries: torch.Tensor, c
           "aura_ivf_search_batch")
     if stats is not None:
         import ctypes as _C
-        items, cap = torch.zeros(8, dtype=torch.int32, device=dev), _C.c_int32(0)
-        check(lib.aura_ivf_search_batch_items(ws.data_ptr(), b, d, c, nprobe, k, items.data_ptr(), _C.addressof(cap), _stream()),
-              "aura_ivf_search_batch_items")
-        it = items.tolist()
-        stats["items"], stats["items_cap"] = it[0], cap.value
-        stats["slots"], stats["slots_per_query_max"], stats["kernel_flagged"], stats["no_candidates"] = it[1], it[2], it[3], it[4]
+        import os as _os
+        forced = _os.environ.get("AURA_IVF_ROWS")
+        rows_path = (forced != "0") if forced is not None else (k + 14 > 32)    # the library's dispatch rule (ivf_batch.cu)
+        stats["path"] = "rows-as-M, one-pass selection" if rows_path else "queries-as-M, register lists"
         stats["handed_back"] = int(flags.sum())
+        if rows_path:                       # work-table / result-slot diagnostics exist for this formulation only
+            items, cap = torch.zeros(8, dtype=torch.int32, device=dev), _C.c_int32(0)
+            check(lib.aura_ivf_search_batch_items(ws.data_ptr(), b, d, c, nprobe, k, items.data_ptr(), _C.addressof(cap), _stream()),
+                  "aura_ivf_search_batch_items")
+            it = items.tolist()
+            stats["items"], stats["items_cap"] = it[0], cap.value
+            stats["slots"], stats["slots_per_query_max"], stats["kernel_flagged"], stats["no_candidates"] = it[1], it[2], it[3], it[4]
     if not strict:
         # keep only "no candidate at all" (never flagged when allow_empty) and work-table overflow
         flags = flags * (out_idx[:, 0] < 0).to(flags.dtype)

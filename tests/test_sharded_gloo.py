@@ -69,3 +69,54 @@ def test_graphed_search_needs_a_cuda_bank():
     bank = ShardedBank(rows, 0, scale=torch.ones(64), local_search=lambda q, k: (None, None), merge=lambda *a: None)
     with pytest.raises(RuntimeError):
         bank.graphed(4, 2)
+
+
+def _index_worker(rank, world, port, q):
+    """Host-side logic of ShardedIndex on 2 gloo ranks: the default collectives, the global-id table that online writes
+    extend (owner = id % world), and the ownership look-up the sharded rebuild uses for its seed rows."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import types
+        from aura_snn_rag_b200.sharded import ShardedIndex, shard_range
+        n0 = 10
+        lo, hi = shard_range(n0, rank, world)
+        local = types.SimpleNamespace(memory_count=hi - lo, max_memories=32, device=torch.device("cpu"),
+                                      centroids_update_interval=512)
+        si = ShardedIndex(local, lo, n0)
+        assert si.world == world and si.rank == rank and local.centroids_update_interval > 1 << 60
+        t = torch.tensor([float(rank + 1), 10.0])
+        si._all_reduce(t)
+        assert t.tolist() == [3.0, 20.0]
+        g = si._all_gather(torch.tensor([[rank, rank * 7]]))
+        assert g.shape == (2, 1, 2) and g[:, 0, 1].tolist() == [0, 7]
+        # contiguous phase: ownership by range
+        seeds = torch.tensor([0, 4, 5, 9, 12])
+        mine, rows = si._local_rows_of(seeds)
+        assert mine.tolist() == [lo <= s < hi for s in seeds.tolist()]
+        assert rows.tolist() == [s - lo for s in seeds.tolist() if lo <= s < hi]
+        # 7 online writes: ids 10..16 go to rank id % 2, appended to the owner's table in ascending order
+        table = si._gid_table()
+        new = [i for i in range(n0, n0 + 7) if i % world == rank]
+        table[local.memory_count:local.memory_count + len(new)] = torch.tensor(new)
+        local.memory_count += len(new)
+        si.n_total = n0 + 7
+        ids = torch.arange(0, 20)
+        mine, rows = si._local_rows_of(ids)
+        owned = [i for i in range(20) if (lo <= i < hi) or (n0 <= i < n0 + 7 and i % world == rank)]
+        assert ids[mine].tolist() == owned
+        assert table[rows].tolist() == owned
+        q.put((rank, "ok"))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_index_host_logic_two_gloo_ranks():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_index_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    [p.join(120) for p in procs]
+    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
+    assert sorted(q.get(timeout=5) for _ in range(2)) == [(0, "ok"), (1, "ok")]
