@@ -49,8 +49,8 @@ SIGNATURES = {
     "aura_ivf_search_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "aura_ivf_search": (_i, [_p, _i, _i64, _i, _p, _i, _p, _i, _i, _p, _p, _p, _p, _i, _i64, _i, _p, _p, _p, _p, _sz, _p]),
     "aura_ivf_search_batch_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
-    "aura_ivf_search_batch": (_i, [_p, _i, _i64, _i, _p, _i, _p, _i, _i, _p, _p, _p, _p, _p, _i, _i64, _i, _f, _p, _p, _p, _p, _sz, _p]),
-    "aura_ivf_pack_lists": (_i, [_p, _i, _i, _p, _i64, _p, _p]),
+    "aura_ivf_search_batch": (_i, [_p, _i, _i64, _i, _p, _i, _p, _i, _i, _p, _p, _p, _i, _p, _p, _p, _i, _i64, _i, _f, _p, _p, _p, _p, _sz, _p]),
+    "aura_ivf_pack_lists": (_i, [_p, _i, _i, _p, _i64, _p, _i, _p, _p]),
     "aura_ivf_search_batch_items": (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _p]),
     "aura_batch_topk_workspace_bytes": (_sz, [_i64, _i, _i, _i, _i]),
     "aura_batch_topk": (_i, [_p, _i, _i64, _i, _p, _i, _p, _p, _i, _i64, _f, _p, _p, _p, _p, _p, _p, _sz, _p]),

@@ -447,6 +447,12 @@ __global__ void __launch_bounds__(256) normalize_queries_eps_kernel(const float*
   if (lane == 0) eps_q[w] = unit * ((1.f + eq) * (*relerr) + eq + 1e-4f);
 }
 
+void launch_normalize_queries_eps(const float* q, int n, int d, float* qn, __nv_bfloat16* qb, const float* relerr, float unit,
+                                  float* eps_q, cudaStream_t st) {
+  normalize_queries_eps_kernel<<<(n + 7) / 8, 256, 0, st>>>(q, n, d, qn, qb, relerr, unit, eps_q);
+  note_launches(1);
+}
+
 void launch_normalize_queries(const float* q, int n, int d, float* qn, __nv_bfloat16* qb, cudaStream_t st) {
   normalize_queries_kernel<<<(n + 7) / 8, 256, 0, st>>>(q, n, d, qn, qb);
   note_launches(1);

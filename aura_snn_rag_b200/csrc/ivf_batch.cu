@@ -441,6 +441,7 @@ struct IvfFinishArgs {
   const void* rows; int bf16; int d; const float* qn; const float* scale; const float* bias; float eps;
   int k; long long row_base; int spread, chunk_major;
   int L;                    // entries the GEMM kernel keeps per partial list (<= GT_L)
+  const float* eps_q;       // per-query certification bound (bf16 list-major shadow of an fp32 bank), overrides eps
   u64* cand; u64* ceil_out; int round; int* force_flag;   // multi-round mode (see gemm_topk.cu)
   int empty_ok;             // a query without candidates is a valid empty result (row-sharded callers), not a hand-back
   long long* out_idx; float* out_score; int* uncertain;
@@ -521,7 +522,7 @@ __global__ void __launch_bounds__(128) ivf_finish_kernel(const IvfFinishArgs f) 
   RescoreArgs ra;
   ra.out_mul = 1.f;
   ra.rows = f.rows; ra.bf16 = f.bf16; ra.d = f.d; ra.q = f.qn + (size_t)b * f.d; ra.scale = f.scale; ra.bias = f.bias;
-  ra.eps = f.eps; ra.k = f.k; ra.L = f.L; ra.row_base = f.row_base;
+  ra.eps = f.eps_q ? f.eps_q[b] : f.eps; ra.k = f.k; ra.L = f.L; ra.row_base = f.row_base;
   ra.out_idx = f.out_idx + (size_t)b * f.k; ra.out_score = f.out_score + (size_t)b * f.k;
   ra.uncertain = f.uncertain + b;
   rescore_and_write(keys, n2, ex, ra);
@@ -982,6 +983,7 @@ struct IvfSlotFinishArgs {
   const u64* slot_keys; const int* slot_cnt; int cap_slots; const int* qslots; const int* qn; int qs_max; const int* qflag;
   const unsigned* gthr; const int* item_base; int n_lists, cap_items;
   const void* rows; int bf16; int d; const float* qn_vec; const float* scale; const float* bias; float eps;
+  const float* eps_q;
   int k, L; long long row_base; int empty_ok;
   long long* out_idx; float* out_score; int* uncertain;
 };
@@ -1057,7 +1059,7 @@ __global__ void __launch_bounds__(128) ivf_slot_finish_kernel(const IvfSlotFinis
   RescoreArgs ra;
   ra.out_mul = 1.f;
   ra.rows = f.rows; ra.bf16 = f.bf16; ra.d = f.d; ra.q = f.qn_vec + (size_t)b * f.d; ra.scale = f.scale; ra.bias = f.bias;
-  ra.eps = f.eps; ra.k = f.k; ra.L = f.L; ra.row_base = f.row_base;
+  ra.eps = f.eps_q ? f.eps_q[b] : f.eps; ra.k = f.k; ra.L = f.L; ra.row_base = f.row_base;
   ra.out_idx = f.out_idx + (size_t)b * f.k; ra.out_score = f.out_score + (size_t)b * f.k;
   ra.uncertain = f.uncertain + b;
   rescore_and_write(keys, n2, ex, ra);
@@ -1106,7 +1108,7 @@ static IbLayout ib_layout(int n_queries, int d, int n_lists, int nprobe, int cap
   L.gthr = o; o += a256((size_t)n_queries * 4);
   L.cand = o; o += a256((size_t)n_queries * GT_MAX_L * 8);
   L.ceil = o; o += a256((size_t)n_queries * 8);
-  L.force = o; o += a256((size_t)n_queries * 4);
+  L.force = o; o += 2 * a256((size_t)n_queries * 4 + 256);     // force flags, then the per-query certification bounds
   L.total = o;
   return L;
 }
@@ -1120,6 +1122,8 @@ int launch_cand_rescore(const u64* cand, int n_cand, const void* rows, int bf16,
                         const float* bias, float eps, int k, long long row_base, long long* out_idx, float* out_score,
                         int* uncertain, int n_queries, cudaStream_t st, const int* force_flag);
 void launch_normalize_queries(const float* q, int n, int d, float* qn, __nv_bfloat16* qb, cudaStream_t st);
+void launch_normalize_queries_eps(const float* q, int n, int d, float* qn, __nv_bfloat16* qb, const float* relerr, float unit,
+                                  float* eps_q, cudaStream_t st);
 
 // diagnostics of the last batch call on a workspace: {items, result slots used, most slots linked by one query, queries
 // flagged inside the kernel, queries without any slot}
@@ -1147,7 +1151,7 @@ static int ir_list_len(int k) {          // shortlist length: k + 14 margin, in 
 static constexpr int IR_CBUF_KEYS = IR_MAX_NQ * 32 * IR_MAX_KPL;   // candidate-buffer keys per CTA, largest geometry
 
 struct IrLayout {
-  size_t probes, counts, q_off, cursor, pair_of_pos, pos_of_pair, items_c, item_base, items, qn, qb, coarse, gthr, qcnt, qflag,
+  size_t probes, counts, q_off, cursor, pair_of_pos, pos_of_pair, items_c, item_base, items, qn, qb, eps_q, coarse, gthr, qcnt, qflag,
       n_slots, qslots, slot_cnt, slot_keys, cbuf, total;
   int cap_slots;
 };
@@ -1166,6 +1170,7 @@ static IrLayout ir_layout(int n_queries, int d, int n_lists, int nprobe, int cap
   Lo.items = o; o += a256((size_t)cap * 16);
   Lo.qn = o; o += a256((size_t)n_queries * d * 4);
   Lo.qb = o; o += a256((size_t)n_queries * d * 2);
+  Lo.eps_q = o; o += a256((size_t)n_queries * 4);
   Lo.coarse = o; o += a256(coarse_bytes);
   Lo.gthr = o; o += a256((size_t)n_queries * 4);          // gthr, qcnt, qflag, n_slots are cleared with one memset
   Lo.qcnt = o; o += a256((size_t)n_queries * 4);
@@ -1186,10 +1191,13 @@ static size_t ir_workspace_bytes(int n_queries, int d, int n_lists, int nprobe, 
   return ir_layout(n_queries, d, n_lists, nprobe, cap, ivf_coarse_ws_bytes(n_queries, d, n_lists, nprobe), ir_list_len(k)).total;
 }
 
-static int ivf_rows_search(const void* rows, bool bf16, long long n_rows, int d, const float* queries, int n_queries,
+static int ivf_rows_search(const void* rows, bool bank_bf16, long long n_rows, int d, const float* queries, int n_queries,
                            const float* centroids, int n_lists, int nprobe, const int* list_offsets, const int* list_rows,
-                           const void* rows_by_list, const float* scale, const float* bias, int k, long long row_base, int flags,
-                           float eps, long long* out_idx, float* out_score, int* out_uncertain, void* workspace, cudaStream_t st) {
+                           const void* rows_by_list, bool lm_shadow, const float* shadow_relerr, const float* scale,
+                           const float* bias, int k, long long row_base, int flags, float eps, long long* out_idx,
+                           float* out_score, int* out_uncertain, void* workspace, cudaStream_t st) {
+  // lm_shadow: the list-major copy is a bf16 shadow of an fp32 bank - the tensor cores read bf16, the re-score reads fp32
+  const bool bf16 = bank_bf16 || lm_shadow;
   const int eb = bf16 ? 2 : 4;
   const int cap = ib_cap_items(n_queries, nprobe, n_lists);
   const IrLayout Lo = ir_layout(n_queries, d, n_lists, nprobe, cap, ivf_coarse_ws_bytes(n_queries, d, n_lists, nprobe), ir_list_len(k));
@@ -1210,7 +1218,9 @@ static int ivf_rows_search(const void* rows, bool bf16, long long n_rows, int d,
 
   int rc = ivf_run_coarse(queries, n_queries, d, centroids, n_lists, nprobe, probes, ws + Lo.coarse, st);
   if (rc != AURA_OK) return rc;
-  launch_normalize_queries(queries, n_queries, d, qn, qb, st);
+  float* eps_q = (lm_shadow && shadow_relerr) ? reinterpret_cast<float*>(ws + Lo.eps_q) : nullptr;
+  if (eps_q) launch_normalize_queries_eps(queries, n_queries, d, qn, qb, shadow_relerr, eps, eps_q, st);
+  else launch_normalize_queries(queries, n_queries, d, qn, qb, st);
   const int n_pairs = n_queries * nprobe;
   AURA_CUDA_OK(cudaMemsetAsync(counts, 0, (size_t)n_lists * 4, st));
   ib_pair_hist_kernel<<<(n_pairs + 255) / 256, 256, 0, st>>>(probes, n_pairs, n_lists, counts);
@@ -1278,7 +1288,8 @@ static int ivf_rows_search(const void* rows, bool bf16, long long n_rows, int d,
   f.slot_keys = a.slot_keys; f.slot_cnt = a.slot_cnt; f.cap_slots = a.cap_slots; f.qslots = a.qslots; f.qn = a.qn;
   f.qs_max = a.qs_max; f.qflag = a.qflag; f.gthr = gthr;
   f.item_base = item_base; f.n_lists = n_lists; f.cap_items = cap;
-  f.rows = rows; f.bf16 = bf16 ? 1 : 0; f.d = d; f.qn_vec = qn; f.scale = scale; f.bias = bias; f.eps = eps;
+  f.rows = rows; f.bf16 = bank_bf16 ? 1 : 0; f.d = d; f.qn_vec = qn; f.scale = scale; f.bias = bias; f.eps = eps;
+  f.eps_q = eps_q;
   f.k = k; f.L = a.L; f.row_base = row_base; f.empty_ok = (flags & AURA_IVF_EMPTY_OK) ? 1 : 0;
   f.out_idx = out_idx; f.out_score = out_score; f.uncertain = out_uncertain;
   ivf_slot_finish_kernel<<<n_queries, 128, 0, st>>>(f);
@@ -1300,9 +1311,10 @@ extern "C" size_t aura_ivf_search_batch_workspace_bytes(int n_queries, int d, in
 
 extern "C" int aura_ivf_search_batch(const void* rows, int dtype, int64_t n_rows, int d, const float* queries, int n_queries,
                                      const float* centroids, int n_centroid_rows, int nprobe, const int32_t* list_offsets,
-                                     const int32_t* list_rows, const void* rows_by_list, const float* scale, const float* bias,
-                                     int k, int64_t row_base, int flags, float eps, int64_t* out_idx, float* out_score,
-                                     int32_t* out_uncertain, void* workspace, size_t workspace_bytes, void* stream) {
+                                     const int32_t* list_rows, const void* rows_by_list, int lm_dtype, const float* shadow_relerr,
+                                     const float* scale, const float* bias, int k, int64_t row_base, int flags, float eps,
+                                     int64_t* out_idx, float* out_score, int32_t* out_uncertain, void* workspace,
+                                     size_t workspace_bytes, void* stream) {
   AURA_REQUIRE(dtype == AURA_F32 || dtype == AURA_BF16, AURA_ERR_INVALID_ARG, "aura_ivf_search_batch: bad dtype %d", dtype);
   AURA_REQUIRE(n_rows >= 1 && n_rows < 0x7fffffffll && d >= 1 && n_queries >= 1 && n_centroid_rows >= 1, AURA_ERR_INVALID_ARG,
                "aura_ivf_search_batch: n_rows=%lld d=%d n_queries=%d n_centroid_rows=%d", (long long)n_rows, d, n_queries,
@@ -1310,9 +1322,18 @@ extern "C" int aura_ivf_search_batch(const void* rows, int dtype, int64_t n_rows
   AURA_REQUIRE(nprobe >= 1 && nprobe <= AURA_MAX_NPROBE && nprobe <= n_centroid_rows, AURA_ERR_INVALID_ARG,
                "aura_ivf_search_batch: nprobe=%d", nprobe);
   AURA_REQUIRE(k >= 1 && k + 14 <= GT_MAX_L, AURA_ERR_UNSUPPORTED, "aura_ivf_search_batch: k=%d too large (max %d)", k, GT_MAX_L - 14);
-  const bool bf16 = dtype == AURA_BF16;
+  const bool bank_bf16 = dtype == AURA_BF16;
+  AURA_REQUIRE(rows_by_list == nullptr || lm_dtype == dtype || (lm_dtype == AURA_BF16 && dtype == AURA_F32), AURA_ERR_INVALID_ARG,
+               "aura_ivf_search_batch: the list-major copy must have the bank's dtype or be a bf16 shadow of an fp32 bank");
+  // a bf16 list-major SHADOW of an fp32 bank: tensor cores and HBM see bf16 (half the bytes, twice the rate), the finish
+  // kernel re-scores from the fp32 rows; eps is then the score-per-cosine unit and the bound is measured per query from
+  // shadow_relerr (as aura_batch_topk)
+  const bool lm_shadow = rows_by_list != nullptr && lm_dtype == AURA_BF16 && dtype == AURA_F32;
+  AURA_REQUIRE(!lm_shadow || ((d % 8) == 0 && shadow_relerr != nullptr), AURA_ERR_INVALID_ARG,
+               "aura_ivf_search_batch: a bf16 list-major shadow needs d %% 8 == 0 and its rounding-error scalar");
+  const bool bf16 = bank_bf16 || lm_shadow;          // element type the tensor cores read
   const int eb = bf16 ? 2 : 4;
-  AURA_REQUIRE(((size_t)d * eb) % 16 == 0 && (d % 4) == 0 && (reinterpret_cast<uintptr_t>(rows) & 15) == 0, AURA_ERR_UNSUPPORTED,
+  AURA_REQUIRE(((size_t)d * (bank_bf16 ? 2 : 4)) % 16 == 0 && (d % 4) == 0 && (reinterpret_cast<uintptr_t>(rows) & 15) == 0, AURA_ERR_UNSUPPORTED,
                "aura_ivf_search_batch: rows must be 16-byte aligned with a 16-byte multiple pitch (d=%d)", d);
   AURA_REQUIRE(rows && queries && centroids && list_offsets && list_rows && out_idx && out_score && out_uncertain && workspace,
                AURA_ERR_INVALID_ARG, "aura_ivf_search_batch: null pointer");
@@ -1325,11 +1346,12 @@ extern "C" int aura_ivf_search_batch(const void* rows, int dtype, int64_t n_rows
   // k = 100: 16 ms against 46 ms).  AURA_IVF_ROWS=1|0 forces one of them (test switch, read once per call: the
   // parity tests run every shape through both).
   const int forced = env_int("AURA_IVF_ROWS", -1);
-  const bool rows_path = forced >= 0 ? forced != 0 : k + 14 > GT_L;
+  // (the multi-round form of the queries-as-M kernel has no per-query bound: a bf16 shadow with k > 18 always goes rows-as-M)
+  const bool rows_path = (forced >= 0 ? forced != 0 : k + 14 > GT_L) || (lm_shadow && k + 14 > GT_L);
   if (rows_path)
-    return ivf_rows_search(rows, bf16, n_rows, d, queries, n_queries, centroids, n_centroid_rows, nprobe, list_offsets, list_rows,
-                           rows_by_list, scale, bias, k, row_base, flags, eps, reinterpret_cast<long long*>(out_idx), out_score,
-                           out_uncertain, workspace, st);
+    return ivf_rows_search(rows, bank_bf16, n_rows, d, queries, n_queries, centroids, n_centroid_rows, nprobe, list_offsets, list_rows,
+                           rows_by_list, lm_shadow, shadow_relerr, scale, bias, k, row_base, flags, eps,
+                           reinterpret_cast<long long*>(out_idx), out_score, out_uncertain, workspace, st);
   const int cap = ib_cap_items(n_queries, nprobe, n_centroid_rows);
   const IbLayout L = ib_layout(n_queries, d, n_centroid_rows, nprobe, cap, ivf_coarse_ws_bytes(n_queries, d, n_centroid_rows, nprobe));
   unsigned char* ws = reinterpret_cast<unsigned char*>(workspace);
@@ -1351,7 +1373,9 @@ extern "C" int aura_ivf_search_batch(const void* rows, int dtype, int64_t n_rows
 
   int rc = ivf_run_coarse(queries, n_queries, d, centroids, n_centroid_rows, nprobe, probes, ws + L.coarse, st);
   if (rc != AURA_OK) return rc;
-  launch_normalize_queries(queries, n_queries, d, qn, qb, st);
+  float* eps_q = lm_shadow ? reinterpret_cast<float*>(ws + L.force + a256((size_t)n_queries * 4 + 256)) : nullptr;
+  if (eps_q) launch_normalize_queries_eps(queries, n_queries, d, qn, qb, shadow_relerr, eps, eps_q, st);
+  else launch_normalize_queries(queries, n_queries, d, qn, qb, st);
   int chunk_major = 1;
   // AURA_IVF_CLUSTER=2|4 launches the CTAs in clusters: the query tiles of one list chunk go to the CTAs of one cluster,
   // which pace each other tile by tile so the chunk is fetched from HBM once.  Measured at BASELINE config 4: within 2 %
@@ -1414,7 +1438,8 @@ extern "C" int aura_ivf_search_batch(const void* rows, int dtype, int64_t n_rows
   f.probes = probes; f.pos_of_pair = pos_of_pair; f.q_off = q_off; f.item_base = item_base; f.list_offsets = list_offsets;
   f.n_items = n_items; f.cap_items = cap; f.nprobe = nprobe; f.n_lists = n_centroid_rows; f.partial = partial;
   f.pbase = pbase; f.cap_plists = a.cap_plists;
-  f.rows = rows; f.bf16 = bf16 ? 1 : 0; f.d = d; f.qn = qn; f.scale = scale; f.bias = bias; f.eps = eps; f.k = k;
+  f.rows = rows; f.bf16 = bank_bf16 ? 1 : 0; f.d = d; f.qn = qn; f.scale = scale; f.bias = bias; f.eps = eps; f.k = k;
+  f.eps_q = eps_q;
   f.L = small ? GT_L_SMALL : GT_L;
   f.row_base = row_base; f.spread = a.spread; f.chunk_major = chunk_major; f.out_idx = reinterpret_cast<long long*>(out_idx); f.out_score = out_score; f.uncertain = out_uncertain;
   f.cand = rounds > 1 ? cand : nullptr; f.ceil_out = ceil_buf; f.round = 0; f.force_flag = force;
@@ -1443,7 +1468,7 @@ extern "C" int aura_ivf_search_batch(const void* rows, int dtype, int64_t n_rows
     note_launches(2);
   }
   if (rounds > 1)
-    return launch_cand_rescore(cand, rounds * GT_L, rows, bf16 ? 1 : 0, d, qn, scale, bias, eps, k, row_base,
+    return launch_cand_rescore(cand, rounds * GT_L, rows, bank_bf16 ? 1 : 0, d, qn, scale, bias, eps, k, row_base,
                                reinterpret_cast<long long*>(out_idx), out_score, out_uncertain, n_queries, st, force);
   return AURA_OK;
 }
@@ -1462,16 +1487,47 @@ __global__ void __launch_bounds__(256) ivf_pack_lists_kernel(const uint4* __rest
   }
 }
 
+namespace aura {
+// fp32 bank -> bf16 list-major shadow: one warp per row, conversion + the row's relative rounding error (max-reduced)
+__global__ void __launch_bounds__(256) ivf_pack_lists_bf16_kernel(const float* __restrict__ rows, const int* __restrict__ list_rows,
+                                                                  long long n, int d, __nv_bfloat16* __restrict__ out,
+                                                                  float* __restrict__ relerr_max) {
+  const int lane = threadIdx.x & 31;
+  float worst = 0.f;
+  for (long long p = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); p < n; p += (long long)gridDim.x * (blockDim.x >> 5)) {
+    const float* src = rows + (size_t)list_rows[p] * d;
+    __nv_bfloat16* dst = out + (size_t)p * d;
+    float ee = 0.f, ss = 0.f;
+    for (int e = lane; e < d; e += 32) {
+      const float v = src[e];
+      const __nv_bfloat16 b = __float2bfloat16_rn(v);
+      dst[e] = b;
+      const float t = __bfloat162float(b) - v;
+      ee = fmaf(t, t, ee); ss = fmaf(v, v, ss);
+    }
+    ee = warp_sum(ee); ss = warp_sum(ss);
+    if (ss > 0.f) worst = fmaxf(worst, sqrtf(ee / ss));
+  }
+  if (relerr_max != nullptr && lane == 0 && worst > 0.f) atomicMax(reinterpret_cast<int*>(relerr_max), __float_as_int(worst * 1.0001f));
+}
+}  // namespace aura
+
 extern "C" int aura_ivf_pack_lists(const void* rows, int dtype, int d, const int32_t* list_rows, int64_t n_listed,
-                                   void* rows_by_list, void* stream) {
+                                   void* rows_by_list, int out_dtype, float* relerr_max, void* stream) {
   AURA_REQUIRE(dtype == AURA_F32 || dtype == AURA_BF16, AURA_ERR_INVALID_ARG, "aura_ivf_pack_lists: bad dtype %d", dtype);
+  AURA_REQUIRE(out_dtype == dtype || (out_dtype == AURA_BF16 && dtype == AURA_F32), AURA_ERR_INVALID_ARG,
+               "aura_ivf_pack_lists: the copy has the bank's dtype or is a bf16 shadow of an fp32 bank");
   AURA_REQUIRE(rows && list_rows && rows_by_list && d >= 1 && n_listed >= 0, AURA_ERR_INVALID_ARG, "aura_ivf_pack_lists: bad argument");
   const size_t pitch = (size_t)d * (dtype == AURA_BF16 ? 2 : 4);
   AURA_REQUIRE(pitch % 16 == 0 && (reinterpret_cast<uintptr_t>(rows) & 15) == 0 && (reinterpret_cast<uintptr_t>(rows_by_list) & 15) == 0,
                AURA_ERR_UNSUPPORTED, "aura_ivf_pack_lists: rows must be 16-byte aligned with a 16-byte multiple pitch (d=%d)", d);
   if (n_listed == 0) return AURA_OK;
-  ivf_pack_lists_kernel<<<sm_count() * 8, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint4*>(rows), list_rows, (long long)n_listed,
-                                                                             (int)(pitch / 16), reinterpret_cast<uint4*>(rows_by_list));
+  if (out_dtype != dtype)
+    ivf_pack_lists_bf16_kernel<<<sm_count() * 8, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float*>(rows), list_rows, (long long)n_listed, d,
+                                                                                 reinterpret_cast<__nv_bfloat16*>(rows_by_list), relerr_max);
+  else
+    ivf_pack_lists_kernel<<<sm_count() * 8, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint4*>(rows), list_rows, (long long)n_listed,
+                                                                            (int)(pitch / 16), reinterpret_cast<uint4*>(rows_by_list));
   AURA_CUDA_OK(cudaGetLastError());
   note_launches(1);
   return AURA_OK;

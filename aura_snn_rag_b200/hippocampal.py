@@ -60,7 +60,7 @@ class HippocampalFormation(nn.Module):
                  nprobe: int = 8,
                  bank_dtype: torch.dtype = torch.float32,
                  track_ids: bool = True,
-                 list_major_copy: bool = False,
+                 list_major_copy: Union[bool, str] = False,
                  bf16_shadow: bool = False):
         super().__init__()
         if not torch.cuda.is_available():
@@ -110,9 +110,13 @@ class HippocampalFormation(nn.Module):
         self.nprobe = int(nprobe)                       # reference literal 8 (:262)
         # batched centroid path: keep a second copy of the bank with every inverted list contiguous (2x bank memory), so
         # list tiles stream from HBM by TMA instead of being gathered row by row; re-packed after every list rebuild
-        self.list_major_copy = bool(list_major_copy)
+        # list_major_copy="bf16" over an fp32 bank keeps that copy in bf16 (a list-major SHADOW, +0.5x bank memory): the
+        # tensor-core pass reads half the bytes at twice the rate, results are still re-scored from the fp32 rows and
+        # certified with a per-query bound measured from the copy's rounding error
         self._bank_by_list: Optional[torch.Tensor] = None
+        self._lm_relerr: Optional[torch.Tensor] = None
         self._by_list_valid = False
+        self.set_list_major_copy(list_major_copy)
         self.ivf_strict = True                          # batched centroid path: re-run uncertified queries exactly (ops.ivf_search_batched)
         # exact search of query blocks over an fp32 bank: shortlist on a bf16 copy of the bank (+50 % memory, twice the
         # tensor rate, half the bytes), exact fp32 re-score from the fp32 rows - same certified results
@@ -319,14 +323,32 @@ class HippocampalFormation(nn.Module):
             self._lists_dirty = False
             self._by_list_valid = False
 
+    def set_list_major_copy(self, mode: Union[bool, str]) -> None:
+        """False: no copy; True / 'bank': a copy in the bank's dtype; 'bf16': a bf16 copy (a shadow when the bank is fp32).
+        Drops the copy held for another mode; the next batched centroid-path query packs the new one."""
+        if isinstance(mode, str) and mode.lower() not in ("bf16", "bank"):
+            raise ValueError("list_major_copy must be a bool, 'bank' or 'bf16'")
+        bank = self.memory_features
+        lm_bf16 = (isinstance(mode, str) and mode.lower() == "bf16" and bank.dtype == torch.float32
+                   and bank.shape[1] % 8 == 0)
+        if lm_bf16 != getattr(self, "_lm_bf16", None) or not mode:
+            self._bank_by_list, self._lm_relerr, self._by_list_valid = None, None, False
+        self._lm_bf16 = lm_bf16
+        self.list_major_copy = bool(mode)
+
     def _rows_by_list(self) -> Optional[torch.Tensor]:
         """The list-major copy of the bank (None unless `list_major_copy`), re-packed if the lists changed."""
         if not self.list_major_copy:
             return None
         if self._bank_by_list is None:
-            self._bank_by_list = torch.empty_like(self.memory_features)
+            if self._lm_bf16:
+                self._bank_by_list = torch.empty(self.memory_features.shape, dtype=torch.bfloat16, device=self.device)
+                self._lm_relerr = torch.zeros(1, dtype=torch.float32, device=self.device)
+            else:
+                self._bank_by_list = torch.empty_like(self.memory_features)
         if not self._by_list_valid:
-            ops.ivf_pack_lists(self.memory_features, self._list_rows, self.memory_count, self._bank_by_list)
+            ops.ivf_pack_lists(self.memory_features, self._list_rows, self.memory_count, self._bank_by_list,
+                               relerr=self._lm_relerr)
             self._by_list_valid = True
         return self._bank_by_list
 
@@ -380,11 +402,15 @@ class HippocampalFormation(nn.Module):
             self._ensure_lists()
             nprobe = min(self.nprobe, self.centroids_k, self._centroid_buffer_rows())   # :262
             if q.shape[0] >= ops.TC_IVF_MIN_BATCH and ops.batch_topk_supported(self.memory_features, kk):
+                by_list = self._rows_by_list()
+                # with a bf16 list-major shadow the bound is measured per query; eps is then the score-per-cosine unit
+                unit = 0.5 * self._max_strength()
                 idx, score = ops.ivf_search_batched(self.memory_features, m, q, self.centroids, nprobe,
                                                     self._list_offsets, self._list_rows, kk, scale, bias,
-                                                    eps=ops.TC_EPS_COS * 0.5 * self._max_strength(),
-                                                    strict=self.ivf_strict, rows_by_list=self._rows_by_list(),
-                                                    allow_empty=allow_empty)
+                                                    eps=unit if self._lm_bf16 else ops.TC_EPS_COS * unit,
+                                                    strict=self.ivf_strict, rows_by_list=by_list,
+                                                    allow_empty=allow_empty,
+                                                    lm_relerr=self._lm_relerr if self._lm_bf16 else None)
             else:
                 idx, score = ops.ivf_search(self.memory_features, m, q, self.centroids, nprobe, self._list_offsets,
                                             self._list_rows, kk, scale, bias, allow_empty=allow_empty)

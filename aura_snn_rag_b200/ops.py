@@ -530,13 +530,23 @@ def allpairs_topk(rows: torch.Tensor, k: int = 32, inv_norm: Optional[torch.Tens
 
 
 @_on_device
-def ivf_pack_lists(rows: torch.Tensor, list_rows: torch.Tensor, n_listed: int, out: torch.Tensor) -> torch.Tensor:
-    """out[p] = rows[list_rows[p]], p < n_listed: the list-major resident copy of the bank (aura_ivf_pack_lists)."""
+def ivf_pack_lists(rows: torch.Tensor, list_rows: torch.Tensor, n_listed: int, out: torch.Tensor,
+                   relerr: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[p] = rows[list_rows[p]], p < n_listed: the list-major resident copy of the bank (aura_ivf_pack_lists).
+    `out` has the bank's dtype, or is bfloat16 over an fp32 bank (a list-major bf16 SHADOW: half the bytes for the
+    tensor-core pass); `relerr` (device float[1]) is then reset and raised to the largest relative rounding error
+    ||bf16(r) - r|| / ||r|| of the packed rows, which the search turns into its per-query certification bound."""
     rows = _dev(rows, "rows")
-    if out.dtype != rows.dtype or out.shape[1] != rows.shape[1] or out.shape[0] < n_listed or not out.is_contiguous():
-        raise ValueError("out must be a contiguous [>= n_listed, d] tensor of the bank's dtype")
+    shadow = out.dtype == torch.bfloat16 and rows.dtype == torch.float32
+    if (out.dtype != rows.dtype and not shadow) or out.shape[1] != rows.shape[1] or out.shape[0] < n_listed or not out.is_contiguous():
+        raise ValueError("out must be a contiguous [>= n_listed, d] tensor of the bank's dtype (or bfloat16 over an fp32 bank)")
+    if shadow:
+        if relerr is None or relerr.dtype != torch.float32 or relerr.numel() != 1 or relerr.device != rows.device:
+            raise ValueError("a bf16 list-major shadow needs relerr: a float32 device tensor of one element")
+        relerr.zero_()
     check(_lib.load().aura_ivf_pack_lists(rows.data_ptr(), _dtype_code(rows), rows.shape[1], list_rows.data_ptr(), n_listed,
-                                          out.data_ptr(), _stream()), "aura_ivf_pack_lists")
+                                          out.data_ptr(), _dtype_code(out), _ptr(relerr) if shadow else None, _stream()),
+          "aura_ivf_pack_lists")
     return out
 
 
@@ -548,13 +558,17 @@ def ivf_search_batched(rows: torch.Tensor, n_rows: int, queries: torch.Tensor, c
                        list_offsets: torch.Tensor, list_rows: torch.Tensor, k: int, scale: Optional[torch.Tensor],
                        bias: Optional[torch.Tensor] = None, row_base: int = 0, eps: float = TC_EPS_COS,
                        stats: Optional[dict] = None, strict: bool = True,
-                       rows_by_list: Optional[torch.Tensor] = None, allow_empty: bool = False
-                       ) -> Tuple[torch.Tensor, torch.Tensor]:
+                       rows_by_list: Optional[torch.Tensor] = None, allow_empty: bool = False,
+                       lm_relerr: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
     """Centroid-path query for a block of queries: list-major tensor-core pass (aura_ivf_search_batch), then the
     per-query path for the queries it hands back.
 
     rows_by_list : optional resident copy of the bank in list order (`ivf_pack_lists`); list tiles are then streamed
-                   by TMA instead of gathered row by row.  Results do not depend on it.
+                   by TMA instead of gathered row by row.  Results do not depend on it.  A bfloat16 copy of an fp32
+                   bank (with `lm_relerr`, both from `ivf_pack_lists`) halves the list bytes and doubles the tensor
+                   rate; `eps` is then the score-per-cosine unit (max |scale_r| * ||r||) and the certification bound
+                   is measured per query, as in `batch_topk` with a `Bf16Shadow`.  Results are re-scored from the
+                   fp32 rows either way.
 
     strict=True  : every flagged query (result not certified exact among its candidates, or no candidates) is re-run
                    through the per-query path - results equal `ivf_search` bit for bit.
@@ -575,9 +589,14 @@ def ivf_search_batched(rows: torch.Tensor, n_rows: int, queries: torch.Tensor, c
     flags = torch.empty(b, dtype=torch.int32, device=dev)
     lib = _lib.load()
     ws = _workspace(lib.aura_ivf_search_batch_workspace_bytes(b, d, c, nprobe, k), dev, "ivfbatch")
+    lm_code = _dtype_code(rows_by_list) if rows_by_list is not None else _dtype_code(rows)
+    lm_shadow = rows_by_list is not None and rows_by_list.dtype == torch.bfloat16 and rows.dtype == torch.float32
+    if lm_shadow and lm_relerr is None:
+        raise ValueError("a bf16 list-major shadow of an fp32 bank needs lm_relerr (ivf_pack_lists)")
     check(lib.aura_ivf_search_batch(rows.data_ptr(), _dtype_code(rows), n_rows, d, queries.data_ptr(), b,
                                     centroids.data_ptr(), c, nprobe, list_offsets.data_ptr(), list_rows.data_ptr(),
-                                    _ptr(rows_by_list), _ptr(scale), _ptr(bias), k, row_base,
+                                    _ptr(rows_by_list), lm_code, _ptr(lm_relerr) if lm_shadow else None,
+                                    _ptr(scale), _ptr(bias), k, row_base,
                                     AURA_IVF_EMPTY_OK if allow_empty else 0, float(eps), out_idx.data_ptr(),
                                     out_score.data_ptr(), flags.data_ptr(), ws.data_ptr(), ws.numel(), _stream()),
           "aura_ivf_search_batch")
@@ -585,7 +604,7 @@ def ivf_search_batched(rows: torch.Tensor, n_rows: int, queries: torch.Tensor, c
         import ctypes as _C
         import os as _os
         forced = _os.environ.get("AURA_IVF_ROWS")
-        rows_path = (forced != "0") if forced is not None else (k + 14 > 32)    # the library's dispatch rule (ivf_batch.cu)
+        rows_path = ((forced != "0") if forced is not None else (k + 14 > 32)) or (lm_shadow and k + 14 > 32)   # the library's dispatch rule (ivf_batch.cu)
         stats["path"] = "rows-as-M, one-pass selection" if rows_path else "queries-as-M, register lists"
         stats["handed_back"] = int(flags.sum())
         if rows_path:                       # work-table / result-slot diagnostics exist for this formulation only

@@ -342,25 +342,31 @@ def leg_c4(dev, peaks, gpu_index, args):
     res["exact_batch_ms"] = ex_ms
     out = {}
     sampler = ClockSampler(gpu_index); sampler.start()
-    for mode in ("gather", "list_major"):
-        hf.list_major_copy = mode == "list_major"
+    modes = {"gather": False, "list_major": True, "list_major_bf16": "bf16"}
+    for mode, lm in modes.items():
+        hf.set_list_major_copy(lm)             # drops the copy of the previous mode (fp32 copy: +41 GB, bf16 shadow: +20 GB)
+        torch.cuda.empty_cache()
         ms, reps, (idx, sc) = _median_timed(lambda: hf.retrieve_batch(q, K), reps=5, warm=2)
-        out[mode] = (ms, reps, idx)
+        out[mode] = (ms, reps, idx, sc)
     res["clocks"] = sampler.stop()
     res["recall_at_10_vs_exact"] = _recall(out["gather"][2], ex_idx, K)
     res["list_major_same_result"] = bool(torch.equal(out["gather"][2], out["list_major"][2]))
+    # the bf16 shadow only shortlists: rows and exact fp32 scores must equal the fp32 paths'
+    res["list_major_bf16_same_result"] = bool(torch.equal(out["gather"][2], out["list_major_bf16"][2])
+                                              and torch.equal(out["gather"][3], out["list_major_bf16"][3]))
     res["probed_list_bytes"] = list_bytes
-    for mode in ("gather", "list_major"):
-        ms, reps, _ = out[mode]
+    for mode in modes:
+        ms, reps, _, _ = out[mode]
         key = "ivf_c4_" + mode
         traffic, src = ncu_traffic(key)
+        # algorithmic bytes: the probed lists once, in the element type the fine-stage kernel streams
+        lb = list_bytes / 2 if mode == "list_major_bf16" else list_bytes
         res[mode] = {"ms_per_batch": ms, "ms_reps": reps, "queries_per_s": B / ms * 1e3,
-                     "roofline": {"bound": "hbm", "achieved": list_bytes / ms / 1e6, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                                  "frac": list_bytes / ms / 1e6 / peaks["hbm_gbs"], "traffic": traffic, "traffic_source": src,
-                                  "algorithmic_bytes_per_launch": list_bytes, "kernel": "aura_ivf_search_batch fine-stage kernel",
+                     "roofline": {"bound": "hbm", "achieved": lb / ms / 1e6, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                  "frac": lb / ms / 1e6 / peaks["hbm_gbs"], "traffic": traffic, "traffic_source": src,
+                                  "algorithmic_bytes_per_launch": lb, "kernel": "aura_ivf_search_batch fine-stage kernel",
                                   "timing": "whole call: coarse + work table + fine kernel + finish", "peak_source": peaks["source"]}}
-    hf.list_major_copy = False
-    hf._bank_by_list = None
+    hf.set_list_major_copy(False)
     torch.cuda.empty_cache()
     _log("c4: batch searches done; single query, writes, rebuild")
     ms1, _ = _timed(lambda: hf.retrieve_batch(q[:1], K), 20, warm=3)

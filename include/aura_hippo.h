@@ -158,21 +158,27 @@ int aura_ivf_search(const void* rows, int dtype, int64_t n_rows, int d, const fl
  * by row id with 16-byte cp.async into the swizzled operand layout), so a batch reads each probed list once instead of
  * once per query.  rows_by_list (may be NULL): a resident copy of the bank in CSR order made by aura_ivf_pack_lists for
  * these list_offsets / list_rows - list tiles are then streamed as TMA boxes instead of gathered.  Results: exact fp32
- * scores of the best candidates (same re-score + certification as aura_batch_topk, read from `rows`);
+ * scores of the best candidates (same re-score + certification as aura_batch_topk, read from `rows`).  lm_dtype is the
+ * element type of rows_by_list: the bank's, or AURA_BF16 for a bf16 SHADOW of an fp32 bank - the list tiles are then
+ * half the bytes and run at the bf16 tensor rate, `eps` is the score-per-cosine unit and the certification bound is
+ * measured per query from shadow_relerr (device scalar kept by aura_ivf_pack_lists), exactly as in aura_batch_topk;
  * out_uncertain[b] = 1 hands query b back to aura_ivf_search (uncertified result, no candidates, or work table
  * overflow).  k <= 114, d*sizeof(elem) % 16 == 0. */
 size_t aura_ivf_search_batch_workspace_bytes(int n_queries, int d, int n_centroid_rows, int nprobe, int k);
 int aura_ivf_search_batch(const void* rows, int dtype, int64_t n_rows, int d, const float* queries, int n_queries,
                           const float* centroids, int n_centroid_rows, int nprobe, const int32_t* list_offsets,
-                          const int32_t* list_rows, const void* rows_by_list, const float* scale, const float* bias, int k,
-                          int64_t row_base, int flags, float eps, int64_t* out_idx, float* out_score,
-                          int32_t* out_uncertain, void* workspace, size_t workspace_bytes, void* stream);
+                          const int32_t* list_rows, const void* rows_by_list, int lm_dtype, const float* shadow_relerr,
+                          const float* scale, const float* bias, int k, int64_t row_base, int flags, float eps,
+                          int64_t* out_idx, float* out_score, int32_t* out_uncertain, void* workspace,
+                          size_t workspace_bytes, void* stream);
 
-/* rows_by_list[p] = rows[list_rows[p]] for p < n_listed (same dtype, pitch d): the list-major resident copy of the bank
+/* rows_by_list[p] = rows[list_rows[p]] for p < n_listed (pitch d; out_dtype = dtype, or AURA_BF16 for a bf16 shadow of an
+ * fp32 bank, in which case relerr_max - DEVICE float, zero it first - is raised to the largest relative rounding error
+ * of the rows packed): the list-major resident copy of the bank
  * (the layout an inverted-file index normally stores; the reference keeps insertion order only, hippocampal.py:211).
  * Rebuild it whenever aura_ivf_build_lists ran. */
 int aura_ivf_pack_lists(const void* rows, int dtype, int d, const int32_t* list_rows, int64_t n_listed, void* rows_by_list,
-                        void* stream);
+                        int out_dtype, float* relerr_max, void* stream);
 
 /* diagnostics of the last aura_ivf_search_batch call on `workspace`, written to the DEVICE words items_out[0..5) by an
  * enqueued kernel (like every entry point it does not synchronise): {work items, result slots used, most slots linked by one

@@ -379,10 +379,11 @@ def test_bf16_bank_tracks_the_fp32_reference(name, monkeypatch):
     assert np.mean(overlap) > 0.9
 
 
-@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
-def test_list_major_copy_gives_the_same_answers_and_follows_writes(dt, monkeypatch):
+@pytest.mark.parametrize("dt,lm_mode", [(torch.float32, True), (torch.bfloat16, True), (torch.float32, "bf16")])
+def test_list_major_copy_gives_the_same_answers_and_follows_writes(dt, lm_mode, monkeypatch):
     """`list_major_copy=True` (bank copy in inverted-list order, list tiles streamed by TMA) must not change a single
-    result of the batched centroid path, also after writes and a rebuild have re-ordered the lists."""
+    result of the batched centroid path, also after writes and a rebuild have re-ordered the lists.  "bf16": the copy is
+    a bf16 shadow of the fp32 bank; results are re-scored from the fp32 rows and must still be identical."""
     import aura_snn_rag_b200.hippocampal as hmod
     clock = _Clock()
     monkeypatch.setattr(hmod, "time", types.SimpleNamespace(time=clock.time))
@@ -398,12 +399,13 @@ def test_list_major_copy_gives_the_same_answers_and_follows_writes(dt, monkeypat
         hf.rebuild_centroids(seed_rows=torch.arange(0, 8000, 125)[:64])
         return hf
 
-    a, b = make(False), make(True)
+    a, b = make(False), make(lm_mode)
     q = rows[torch.randint(0, 8000, (150,), generator=g)] + 0.05 * torch.randn(150, 96, generator=g)
     ia, sa = a.retrieve_batch(q, k=10)
     ib, sb = b.retrieve_batch(q, k=10)
     assert b._bank_by_list is not None and b._by_list_valid and a._bank_by_list is None
-    assert torch.equal(b._bank_by_list[:8000], b.memory_features[b._list_rows[:8000].long()])
+    assert torch.equal(b._bank_by_list[:8000], b.memory_features[b._list_rows[:8000].long()].to(b._bank_by_list.dtype))
+    assert (b._bank_by_list.dtype == torch.bfloat16) == (lm_mode == "bf16" or dt == torch.bfloat16)
     assert torch.equal(ia, ib) and torch.equal(sa, sb)
     for hf in (a, b):                        # online writes append to lists: the copy must be re-packed before the next batch
         hf.create_episodic_memories(rows[8000:])

@@ -183,6 +183,12 @@ def test_c4_scale_ivf_matches_oracle(kind, monkeypatch):
     hf.list_major_copy = True
     i3, s3 = hf.retrieve_batch(q, k)
     assert torch.equal(i3, idx) and torch.equal(s3, score)
+    # bf16 list-major shadow (half the list bytes; exact fp32 re-score + per-query measured certificate): same answers
+    hf.set_list_major_copy("bf16")
+    torch.cuda.empty_cache()
+    i4, s4 = hf.retrieve_batch(q, k)
+    assert hf._bank_by_list.dtype == torch.bfloat16
+    assert torch.equal(i4, idx) and torch.equal(s4, score)
 
 
 def test_c5_shard_ivf_matches_oracle(monkeypatch):

@@ -239,6 +239,21 @@ def test_ivf_search_batched_equals_per_query_path(n, d, c, p, b, k, dt, path, mo
     assert stats3["uncertain"] == stats["uncertain"]
     assert torch.equal(s3, s2)
     assert torch.equal(i3, i2)
+    # bf16 list-major SHADOW of an fp32 bank: the tensor cores read bf16 list tiles, the finish re-scores from the fp32
+    # rows under a per-query measured bound - after the strict fix-up the answers are still the per-query path's
+    if dt == torch.float32 and d % 8 == 0:
+        relerr = torch.zeros(1, device=DEV)
+        shadow = ops.ivf_pack_lists(rows, lrows, n, torch.empty(n, d, dtype=torch.bfloat16, device=DEV), relerr=relerr)
+        assert torch.equal(shadow, rows[lrows.long()].to(torch.bfloat16))
+        rel = ((bank.to(torch.bfloat16).double() - bank.double()).norm(dim=1) / bank.double().norm(dim=1)).max()
+        assert float(rel) <= float(relerr) <= float(rel) * 1.001 + 1e-9
+        stats4 = {}
+        i4, s4 = ops.ivf_search_batched(rows, n, q, cent_d, p, offsets, lrows, k, scale, bias, eps=0.5, stats=stats4,
+                                        rows_by_list=shadow, lm_relerr=relerr)       # eps = unit: max |scale| * ||row||
+        torch.cuda.synchronize()
+        assert stats4["uncertain"] < b // 2
+        assert torch.equal(s4, s2)
+        assert torch.equal(i4, i2)
 
 
 @pytest.mark.parametrize("n,d,b,k", [(50000, 256, 200, 10), (30000, 768, 64, 34), (20000, 128, 130, 5)])
