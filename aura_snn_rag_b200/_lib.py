@@ -16,6 +16,7 @@ AURA_F32, AURA_BF16 = 0, 1
 AURA_MAX_K = 128
 AURA_MAX_NPROBE = 128
 AURA_IVF_EMPTY_OK = 1
+AURA_IVF_MEASURED_EPS = 2
 
 _p = C.c_void_p
 _i = C.c_int

@@ -444,7 +444,8 @@ __global__ void __launch_bounds__(256) normalize_queries_eps_kernel(const float*
     err = fmaf(t, t, err);
   }
   const float eq = sqrtf(warp_sum(err));
-  if (lane == 0) eps_q[w] = unit * ((1.f + eq) * (*relerr) + eq + 1e-4f);
+  // relerr == nullptr: the bank rows are exact tensor-core operands (a bf16 bank) - only the query's rounding counts
+  if (lane == 0) eps_q[w] = unit * ((1.f + eq) * (relerr ? *relerr : 0.f) + eq + 1e-4f);
 }
 
 void launch_normalize_queries_eps(const float* q, int n, int d, float* qn, __nv_bfloat16* qb, const float* relerr, float unit,

@@ -1143,10 +1143,14 @@ __global__ void __launch_bounds__(256) ir_stats_kernel(const int* __restrict__ i
 }
 
 // ---- host side of the rows-as-M path -----------------------------------------------------------------------------
-static int ir_list_len(int k) {          // shortlist length: k + 14 margin, in the steps the multi-round scheme used
+static int ir_list_len(int k) {
+  // shortlist length.  Up to 32: the lengths of the queries-as-M kernel.  Beyond: k + 28 in steps of 32, capped at the
+  // 128 keys the re-score holds - the one-pass selection costs the same for any length (bisection over the candidate
+  // buffer), and the margin beyond k is what certifies a result on near-tie heavy data (k = 100 keeps 128, not 114)
   if (k + 14 <= GT_L_SMALL) return GT_L_SMALL;
   if (k + 14 <= GT_L) return GT_L;
-  return (k + 14 + GT_L - 1) / GT_L * GT_L;
+  const int want = (k + 28 + GT_L - 1) / GT_L * GT_L;
+  return want < GT_MAX_L ? want : GT_MAX_L;
 }
 static constexpr int IR_CBUF_KEYS = IR_MAX_NQ * 32 * IR_MAX_KPL;   // candidate-buffer keys per CTA, largest geometry
 
@@ -1193,7 +1197,7 @@ static size_t ir_workspace_bytes(int n_queries, int d, int n_lists, int nprobe, 
 
 static int ivf_rows_search(const void* rows, bool bank_bf16, long long n_rows, int d, const float* queries, int n_queries,
                            const float* centroids, int n_lists, int nprobe, const int* list_offsets, const int* list_rows,
-                           const void* rows_by_list, bool lm_shadow, const float* shadow_relerr, const float* scale,
+                           const void* rows_by_list, bool lm_shadow, bool measured, const float* shadow_relerr, const float* scale,
                            const float* bias, int k, long long row_base, int flags, float eps, long long* out_idx,
                            float* out_score, int* out_uncertain, void* workspace, cudaStream_t st) {
   // lm_shadow: the list-major copy is a bf16 shadow of an fp32 bank - the tensor cores read bf16, the re-score reads fp32
@@ -1218,8 +1222,8 @@ static int ivf_rows_search(const void* rows, bool bank_bf16, long long n_rows, i
 
   int rc = ivf_run_coarse(queries, n_queries, d, centroids, n_lists, nprobe, probes, ws + Lo.coarse, st);
   if (rc != AURA_OK) return rc;
-  float* eps_q = (lm_shadow && shadow_relerr) ? reinterpret_cast<float*>(ws + Lo.eps_q) : nullptr;
-  if (eps_q) launch_normalize_queries_eps(queries, n_queries, d, qn, qb, shadow_relerr, eps, eps_q, st);
+  float* eps_q = measured ? reinterpret_cast<float*>(ws + Lo.eps_q) : nullptr;
+  if (eps_q) launch_normalize_queries_eps(queries, n_queries, d, qn, qb, lm_shadow ? shadow_relerr : nullptr, eps, eps_q, st);
   else launch_normalize_queries(queries, n_queries, d, qn, qb, st);
   const int n_pairs = n_queries * nprobe;
   AURA_CUDA_OK(cudaMemsetAsync(counts, 0, (size_t)n_lists * 4, st));
@@ -1332,6 +1336,9 @@ extern "C" int aura_ivf_search_batch(const void* rows, int dtype, int64_t n_rows
   AURA_REQUIRE(!lm_shadow || ((d % 8) == 0 && shadow_relerr != nullptr), AURA_ERR_INVALID_ARG,
                "aura_ivf_search_batch: a bf16 list-major shadow needs d %% 8 == 0 and its rounding-error scalar");
   const bool bf16 = bank_bf16 || lm_shadow;          // element type the tensor cores read
+  // measured certification bound: eps is the score-per-cosine unit and the bound is computed per query from the ACTUAL
+  // rounding errors - of the query alone for a bf16 bank (its rows are exact operands), of query and rows for a shadow
+  const bool measured = lm_shadow || (bank_bf16 && (flags & AURA_IVF_MEASURED_EPS) != 0);
   const int eb = bf16 ? 2 : 4;
   AURA_REQUIRE(((size_t)d * (bank_bf16 ? 2 : 4)) % 16 == 0 && (d % 4) == 0 && (reinterpret_cast<uintptr_t>(rows) & 15) == 0, AURA_ERR_UNSUPPORTED,
                "aura_ivf_search_batch: rows must be 16-byte aligned with a 16-byte multiple pitch (d=%d)", d);
@@ -1346,11 +1353,11 @@ extern "C" int aura_ivf_search_batch(const void* rows, int dtype, int64_t n_rows
   // k = 100: 16 ms against 46 ms).  AURA_IVF_ROWS=1|0 forces one of them (test switch, read once per call: the
   // parity tests run every shape through both).
   const int forced = env_int("AURA_IVF_ROWS", -1);
-  // (the multi-round form of the queries-as-M kernel has no per-query bound: a bf16 shadow with k > 18 always goes rows-as-M)
-  const bool rows_path = (forced >= 0 ? forced != 0 : k + 14 > GT_L) || (lm_shadow && k + 14 > GT_L);
+  // (the multi-round form of the queries-as-M kernel has no per-query bound: a measured bound with k > 18 always goes rows-as-M)
+  const bool rows_path = (forced >= 0 ? forced != 0 : k + 14 > GT_L) || (measured && k + 14 > GT_L);
   if (rows_path)
     return ivf_rows_search(rows, bank_bf16, n_rows, d, queries, n_queries, centroids, n_centroid_rows, nprobe, list_offsets, list_rows,
-                           rows_by_list, lm_shadow, shadow_relerr, scale, bias, k, row_base, flags, eps,
+                           rows_by_list, lm_shadow, measured, shadow_relerr, scale, bias, k, row_base, flags, eps,
                            reinterpret_cast<long long*>(out_idx), out_score, out_uncertain, workspace, st);
   const int cap = ib_cap_items(n_queries, nprobe, n_centroid_rows);
   const IbLayout L = ib_layout(n_queries, d, n_centroid_rows, nprobe, cap, ivf_coarse_ws_bytes(n_queries, d, n_centroid_rows, nprobe));
@@ -1373,8 +1380,8 @@ extern "C" int aura_ivf_search_batch(const void* rows, int dtype, int64_t n_rows
 
   int rc = ivf_run_coarse(queries, n_queries, d, centroids, n_centroid_rows, nprobe, probes, ws + L.coarse, st);
   if (rc != AURA_OK) return rc;
-  float* eps_q = lm_shadow ? reinterpret_cast<float*>(ws + L.force + a256((size_t)n_queries * 4 + 256)) : nullptr;
-  if (eps_q) launch_normalize_queries_eps(queries, n_queries, d, qn, qb, shadow_relerr, eps, eps_q, st);
+  float* eps_q = measured ? reinterpret_cast<float*>(ws + L.force + a256((size_t)n_queries * 4 + 256)) : nullptr;
+  if (eps_q) launch_normalize_queries_eps(queries, n_queries, d, qn, qb, lm_shadow ? shadow_relerr : nullptr, eps, eps_q, st);
   else launch_normalize_queries(queries, n_queries, d, qn, qb, st);
   int chunk_major = 1;
   // AURA_IVF_CLUSTER=2|4 launches the CTAs in clusters: the query tiles of one list chunk go to the CTAs of one cluster,
@@ -1423,7 +1430,10 @@ extern "C" int aura_ivf_search_batch(const void* rows, int dtype, int64_t n_rows
     a.list_major = 1;
   }
   typedef void (*IvfKern)(const CUtensorMap, const unsigned char*, const unsigned char*, int, const IvfBatchArgs);
-  const bool small = k + 14 <= GT_L_SMALL;                  // k <= 10: 24-entry lists, one round
+  // k <= 10: 24-entry lists, one round (a bf16 shadow keeps 32: its measured bound is about as wide as the TF32 worst
+  // case while the bf16 scores scatter more, and every uncertified query costs a per-query scan)
+  static const int env_shadow_small = env_int("AURA_IVF_SHADOW_SMALL", 0);
+  const bool small = k + 14 <= GT_L_SMALL && (!lm_shadow || env_shadow_small);
   IvfKern kern0 = small ? (bf16 ? ivf_gemm_kernel<false, false, GT_L_SMALL> : ivf_gemm_kernel<true, false, GT_L_SMALL>)
                         : (bf16 ? ivf_gemm_kernel<false, false, GT_L> : ivf_gemm_kernel<true, false, GT_L>);    // first round: no ceiling
   IvfKern kern1 = bf16 ? ivf_gemm_kernel<false, true, GT_L> : ivf_gemm_kernel<true, true, GT_L>;

@@ -404,13 +404,16 @@ class HippocampalFormation(nn.Module):
             if q.shape[0] >= ops.TC_IVF_MIN_BATCH and ops.batch_topk_supported(self.memory_features, kk):
                 by_list = self._rows_by_list()
                 # with a bf16 list-major shadow the bound is measured per query; eps is then the score-per-cosine unit
+                # (so is it over a bf16 bank: only the query's rounding counts, the rows are exact operands)
                 unit = 0.5 * self._max_strength()
+                measured = self._lm_bf16 or self.memory_features.dtype == torch.bfloat16
                 idx, score = ops.ivf_search_batched(self.memory_features, m, q, self.centroids, nprobe,
                                                     self._list_offsets, self._list_rows, kk, scale, bias,
-                                                    eps=unit if self._lm_bf16 else ops.TC_EPS_COS * unit,
+                                                    eps=unit if measured else ops.TC_EPS_COS * unit,
                                                     strict=self.ivf_strict, rows_by_list=by_list,
                                                     allow_empty=allow_empty,
-                                                    lm_relerr=self._lm_relerr if self._lm_bf16 else None)
+                                                    lm_relerr=self._lm_relerr if self._lm_bf16 else None,
+                                                    measured_eps=measured)
             else:
                 idx, score = ops.ivf_search(self.memory_features, m, q, self.centroids, nprobe, self._list_offsets,
                                             self._list_rows, kk, scale, bias, allow_empty=allow_empty)

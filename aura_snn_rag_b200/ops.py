@@ -11,7 +11,7 @@ from typing import Optional, Tuple
 import torch
 
 from . import _lib
-from ._lib import AURA_BF16, AURA_F32, AURA_IVF_EMPTY_OK, AURA_MAX_K, check
+from ._lib import AURA_BF16, AURA_F32, AURA_IVF_EMPTY_OK, AURA_IVF_MEASURED_EPS, AURA_MAX_K, check
 
 
 def _stream() -> int:
@@ -559,7 +559,8 @@ def ivf_search_batched(rows: torch.Tensor, n_rows: int, queries: torch.Tensor, c
                        bias: Optional[torch.Tensor] = None, row_base: int = 0, eps: float = TC_EPS_COS,
                        stats: Optional[dict] = None, strict: bool = True,
                        rows_by_list: Optional[torch.Tensor] = None, allow_empty: bool = False,
-                       lm_relerr: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+                       lm_relerr: Optional[torch.Tensor] = None, measured_eps: bool = False
+                       ) -> Tuple[torch.Tensor, torch.Tensor]:
     """Centroid-path query for a block of queries: list-major tensor-core pass (aura_ivf_search_batch), then the
     per-query path for the queries it hands back.
 
@@ -569,6 +570,8 @@ def ivf_search_batched(rows: torch.Tensor, n_rows: int, queries: torch.Tensor, c
                    rate; `eps` is then the score-per-cosine unit (max |scale_r| * ||r||) and the certification bound
                    is measured per query, as in `batch_topk` with a `Bf16Shadow`.  Results are re-scored from the
                    fp32 rows either way.
+    measured_eps : bf16 bank: `eps` is the score-per-cosine unit and the bound is measured per query from the rounding
+                   error of the bf16 query copy (the rows are exact operands); ~1.7x tighter than TC_EPS_COS.
 
     strict=True  : every flagged query (result not certified exact among its candidates, or no candidates) is re-run
                    through the per-query path - results equal `ivf_search` bit for bit.
@@ -597,14 +600,16 @@ def ivf_search_batched(rows: torch.Tensor, n_rows: int, queries: torch.Tensor, c
                                     centroids.data_ptr(), c, nprobe, list_offsets.data_ptr(), list_rows.data_ptr(),
                                     _ptr(rows_by_list), lm_code, _ptr(lm_relerr) if lm_shadow else None,
                                     _ptr(scale), _ptr(bias), k, row_base,
-                                    AURA_IVF_EMPTY_OK if allow_empty else 0, float(eps), out_idx.data_ptr(),
+                                    (AURA_IVF_EMPTY_OK if allow_empty else 0) |
+                                    (AURA_IVF_MEASURED_EPS if measured_eps and rows.dtype == torch.bfloat16 else 0),
+                                    float(eps), out_idx.data_ptr(),
                                     out_score.data_ptr(), flags.data_ptr(), ws.data_ptr(), ws.numel(), _stream()),
           "aura_ivf_search_batch")
     if stats is not None:
         import ctypes as _C
         import os as _os
         forced = _os.environ.get("AURA_IVF_ROWS")
-        rows_path = ((forced != "0") if forced is not None else (k + 14 > 32)) or (lm_shadow and k + 14 > 32)   # the library's dispatch rule (ivf_batch.cu)
+        rows_path = ((forced != "0") if forced is not None else (k + 14 > 32)) or ((lm_shadow or (measured_eps and rows.dtype == torch.bfloat16)) and k + 14 > 32)   # the library's dispatch rule (ivf_batch.cu)
         stats["path"] = "rows-as-M, one-pass selection" if rows_path else "queries-as-M, register lists"
         stats["handed_back"] = int(flags.sum())
         if rows_path:                       # work-table / result-slot diagnostics exist for this formulation only

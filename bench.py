@@ -451,7 +451,10 @@ def leg_c5(dev, peaks, gpu_index, world, rank, args, m_total, shard_of):
     nq = 256
     ms_e, (ie, se) = _timed(lambda: idx_obj.search(q[:nq].contiguous(), K, exact=True), 1, warm=0, sync_all=sync_all)
     list_bytes = m * D * 2.0                                             # per GPU: every local list is probed by some query
-    traffic, src = ncu_traffic("ivf_c5_shard")
+    # the fine stage is three launches of ivf_rows_kernel (lists probed by > 64, <= 64, <= 32 queries): their sum
+    parts = [ncu_traffic("ivf_c5_shard_" + s) for s in ("heavy", "mid", "light")]
+    traffic = sum(p[0] for p in parts) if world == 1 and shard_of and all(p[0] is not None for p in parts) else None
+    src = "profiles/r02_c5_rows_raw.csv (sum of the three ivf_rows_kernel launches of one batch)" if traffic else None
     res.update({
         "relaxed": {"ms_per_batch": ms_rel, "ms_reps": reps_rel, "queries_per_s": B / ms_rel * 1e3},
         "strict": {"ms_per_batch": ms_str, "queries_per_s": B / ms_str * 1e3},

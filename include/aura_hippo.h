@@ -45,6 +45,10 @@ enum { AURA_F32 = 0, AURA_BF16 = 1 };
 #define AURA_IVF_EMPTY_OK 1   /* a query whose probed lists hold no LOCAL row returns no result (idx -1, score -inf)
                                  instead of scanning every row: row-sharded callers apply hippocampal.py:269-270 to
                                  the merged result, not per shard */
+#define AURA_IVF_MEASURED_EPS 2 /* aura_ivf_search_batch over a bf16 bank: `eps` is the score-per-cosine unit
+                                 (max |scale_r| * ||r||) and the certification bound is measured per query from the
+                                 rounding error of the bf16 query copy (the bank rows are exact tensor-core operands) -
+                                 about 1.7x tighter than the worst-case 2^-9 bound */
 
 #define AURA_MAX_K 128        /* largest k of any fused top-k */
 #define AURA_MAX_NPROBE 128   /* largest nprobe of aura_ivf_search */
@@ -161,7 +165,8 @@ int aura_ivf_search(const void* rows, int dtype, int64_t n_rows, int d, const fl
  * scores of the best candidates (same re-score + certification as aura_batch_topk, read from `rows`).  lm_dtype is the
  * element type of rows_by_list: the bank's, or AURA_BF16 for a bf16 SHADOW of an fp32 bank - the list tiles are then
  * half the bytes and run at the bf16 tensor rate, `eps` is the score-per-cosine unit and the certification bound is
- * measured per query from shadow_relerr (device scalar kept by aura_ivf_pack_lists), exactly as in aura_batch_topk;
+ * measured per query from shadow_relerr (device scalar kept by aura_ivf_pack_lists), exactly as in aura_batch_topk
+ * (flags & AURA_IVF_MEASURED_EPS asks for the measured bound over a bf16 bank);
  * out_uncertain[b] = 1 hands query b back to aura_ivf_search (uncertified result, no candidates, or work table
  * overflow).  k <= 114, d*sizeof(elem) % 16 == 0. */
 size_t aura_ivf_search_batch_workspace_bytes(int n_queries, int d, int n_centroid_rows, int nprobe, int k);

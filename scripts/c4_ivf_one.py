@@ -7,6 +7,7 @@ dev = torch.device("cuda:0")
 hf = HippocampalFormation(n_place_cells=8, n_time_cells=4, n_grid_cells=4, max_memories=M, feature_dim=D, device="cuda:0",
                           centroids_k=C, nprobe=P, track_ids=False, list_major_copy={"0": False, "1": True, "2": "bf16"}[__import__("os").environ.get("LM", "0")])
 hf.centroids_update_interval = 1 << 40
+hf.ivf_strict = bool(int(__import__('os').environ.get('STRICT', '1')))
 g = torch.Generator(device=dev).manual_seed(1234)
 centres = torch.nn.functional.normalize(torch.randn(1024, D, device=dev, generator=g), dim=1)
 for r0 in range(0, M, 1 << 18):

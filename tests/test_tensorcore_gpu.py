@@ -239,6 +239,15 @@ def test_ivf_search_batched_equals_per_query_path(n, d, c, p, b, k, dt, path, mo
     assert stats3["uncertain"] == stats["uncertain"]
     assert torch.equal(s3, s2)
     assert torch.equal(i3, i2)
+    # bf16 bank with the MEASURED per-query bound (only the query is rounded; eps = unit): same answers after the fix-up,
+    # and never more hand-backs than the worst-case bound gives
+    if dt == torch.bfloat16:
+        stats5 = {}
+        i5, s5 = ops.ivf_search_batched(rows, n, q, cent_d, p, offsets, lrows, k, scale, bias, eps=0.5, stats=stats5,
+                                        rows_by_list=packed, measured_eps=True)
+        torch.cuda.synchronize()
+        assert torch.equal(s5, s2) and torch.equal(i5, i2)
+        assert stats5["handed_back"] <= stats3["handed_back"]
     # bf16 list-major SHADOW of an fp32 bank: the tensor cores read bf16 list tiles, the finish re-scores from the fp32
     # rows under a per-query measured bound - after the strict fix-up the answers are still the per-query path's
     if dt == torch.float32 and d % 8 == 0:
