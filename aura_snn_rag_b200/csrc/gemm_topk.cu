@@ -44,10 +44,23 @@ struct GemmTopkArgs {
                               // is known to reach - the largest L-th best any CTA (column group) has seen for the row so
                               // far.  L keys at or above it exist, so no CTA needs to keep anything below it: the lists of
                               // the n_groups CTAs sharing a row become as selective as one global list.
+  // Sampled start threshold (K6 with one item per CTA): before its real pass every list (CTA x warpgroup) scores
+  // `sample_tiles / WG` tiles of its own column range in a cheap mode - a running best / second best per row, no list -
+  // and contributes its sample_j-th best to samp_min[row] (atomicMin).  Once all samp_total lists of the A tile have
+  // contributed (samp_cnt), samp_total * sample_j >= L distinct columns are known to score at or above samp_min[row],
+  // so it is a valid start threshold for every list of the row: the lists no longer fill through ~100 sorted insertions
+  // per row against a threshold of -inf while the tensor pipe waits.  0 = off.
+  int sample_tiles, sample_j, samp_total;
+  unsigned* samp_min;         // [n_atiles * 128], preset to 0xFFFFFFFF
+  unsigned* samp_cnt;         // [n_atiles], preset to 0
 };
 
-template <bool TF32, int L, bool CEIL>
-__global__ void __launch_bounds__(GT_THREADS, 1)
+// WG = number of epilogue warpgroups (1 or 2).  With two, warpgroup g drains accumulator stage g (every other tile of the
+// CTA) into its OWN per-row list: the epilogue is latency-bound (one warp per scheduler, dependent select chains), so two
+// warps per scheduler nearly double its throughput and a tile's epilogue may take two MMA tile times before the tensor
+// pipe waits.  The finish kernels simply see WG lists per (row, column group).
+template <bool TF32, int L, bool CEIL, int WG>
+__global__ void __launch_bounds__(64 + 128 * WG, 1)
 gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const GemmTopkArgs a) {
   extern __shared__ unsigned char smem_raw[];
@@ -55,8 +68,8 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int S = a.n_stages;
   unsigned char* ring = smem;
-  float2* sbuf = reinterpret_cast<float2*>(ring + (size_t)S * GT_STAGE_BYTES);   // [2][GT_BN] (scale, bias)
-  uint64_t* full = reinterpret_cast<uint64_t*>(sbuf + 2 * GT_BN);
+  float2* sbuf = reinterpret_cast<float2*>(ring + (size_t)S * GT_STAGE_BYTES);   // [4][GT_BN] (scale, bias): two halves per warpgroup
+  uint64_t* full = reinterpret_cast<uint64_t*>(sbuf + 4 * GT_BN);
   uint64_t* empty = full + GT_MAX_STAGES;
   uint64_t* tfull = empty + GT_MAX_STAGES;
   uint64_t* tempty = tfull + 2;
@@ -90,13 +103,15 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const int atile = item % a.n_atiles, group = item / a.n_atiles;
         const int ct0 = (int)(((long long)a.n_ctiles * group) / a.n_groups);
         const int ct1 = (int)(((long long)a.n_ctiles * (group + 1)) / a.n_groups);
-        for (int ct = ct0; ct < ct1; ++ct) {
+        // the sample tiles (the first of the range, scored twice: once for the start threshold, once for real), then the range
+        for (int t = -a.sample_tiles; t < ct1 - ct0; ++t) {
+          const int ct = ct0 + (t < 0 ? t + a.sample_tiles : t);
           for (int kb = 0; kb < a.k_blocks; ++kb) {
             tc::mbar_wait_guarded(&empty[stage], phase ^ 1u);
             unsigned char* sa = ring + (size_t)stage * GT_STAGE_BYTES;
             mbar_arrive_expect_tx(&full[stage], GT_STAGE_BYTES);
             tc::tma_load_2d(sa, &tmap_a, kb * ELEMS_PER_SLAB, atile * GT_BM, &full[stage], pol_a);
-            tc::tma_load_2d(sa + GT_A_BYTES, &tmap_b, kb * ELEMS_PER_SLAB, ct * GT_BN, &full[stage], pol_b);
+            tc::tma_load_2d(sa + GT_A_BYTES, &tmap_b, kb * ELEMS_PER_SLAB, ct * GT_BN, &full[stage], t < 0 ? pol_a : pol_b);
             if (++stage == S) { stage = 0; phase ^= 1u; }
           }
         }
@@ -112,7 +127,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const int group = item / a.n_atiles;
         const int ct0 = (int)(((long long)a.n_ctiles * group) / a.n_groups);
         const int ct1 = (int)(((long long)a.n_ctiles * (group + 1)) / a.n_groups);
-        for (int ct = ct0; ct < ct1; ++ct, ++tile_n) {
+        for (int ct = ct0 - a.sample_tiles; ct < ct1; ++ct, ++tile_n) {     // sample tiles first (same operand schedule as the producer)
           const unsigned acc = tile_n & 1u, acc_phase = (tile_n >> 1) & 1u;
           tc::mbar_wait_guarded(&tempty[acc], acc_phase ^ 1u);     // epilogue has drained this accumulator
           tc::tc_fence_after();
@@ -134,11 +149,13 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       }
     }
   } else {
-    // ===================== epilogue: 4 warps, thread = one A row =====================
+    // ===================== epilogue: WG warpgroups of 4 warps, thread = one A row =====================
+    const int wg = (warp - 2) >> 2;                 // warpgroup: drains accumulator stage wg (WG == 2) or both (WG == 1)
     const int quarter = warp & 3;                   // TMEM lane quarter this warp may access
     const int te = quarter * 32 + lane;             // A row inside the tile
-    const int et = threadIdx.x - 64;                // 0..127 among epilogue threads
-    unsigned tile_n = 0;
+    const int et = (threadIdx.x - 64) & 127;        // 0..127 inside the warpgroup
+    float2* sb_wg = sbuf + wg * 2 * GT_BN;          // this warpgroup's two (scale, bias) halves
+    unsigned tile_n = 0, my_tiles = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const int atile = item % a.n_atiles, group = item / a.n_atiles;
       const int ct0 = (int)(((long long)a.n_ctiles * group) / a.n_groups);
@@ -154,25 +171,98 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const u64 ceil_key = (CEIL && live) ? a.ceil_keys[(long long)atile * GT_BM + te] : ~0ull;
       const float ceil_score = ceil_key == ~0ull ? INFINITY : key_score(ceil_key);
       if (ceil_key == 0ull) thr = INFINITY;           // previous round already exhausted this row's candidates
-      for (int ct = ct0; ct < ct1; ++ct, ++tile_n) {
-        const unsigned acc = tile_n & 1u, acc_phase = (tile_n >> 1) & 1u;
+      if (a.sample_tiles > 0) {
+        // ---- sampled start threshold: cheap pass over this list's share of the sample tiles ----
+        float m1 = -INFINITY, m2 = -INFINITY;         // best and second best score of the sampled columns
+        for (int st = 0; st < a.sample_tiles; ++st, ++tile_n) {
+          if (WG == 2 && ((tile_n ^ (unsigned)wg) & 1u) != 0u) continue;
+          const unsigned acc = tile_n & 1u, acc_phase = (tile_n >> 1) & 1u;
+          const long long col0 = (long long)(ct0 + st) * GT_BN;
+          float2* sb = sb_wg + (my_tiles & 1u) * GT_BN;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const long long gc = col0 + et + h * 128;
+            float2 t;
+            if (gc < a.n_b_rows) { t.x = a.scale ? a.scale[gc] : 1.f; t.y = a.bias ? a.bias[gc] : 0.f; }
+            else { t.x = 0.f; t.y = -INFINITY; }      // invalid columns never raise a maximum
+            sb[et + h * 128] = t;
+          }
+          tc::named_bar_sync(1 + wg, 128);
+          tc::mbar_wait_guarded(&tfull[acc], acc_phase);
+          tc::tc_fence_after();
+          const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * GT_BN;
+#pragma unroll 1
+          for (int c0 = 0; c0 < GT_BN; c0 += 32) {
+            float v[32];
+            tc::tmem_ld_32x32(taddr + c0, v);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float2 t = sb[c0 + j];
+              const float sj = fmaf(v[j], t.x, t.y);
+              m2 = fmaxf(m2, fminf(m1, sj));
+              m1 = fmaxf(m1, sj);
+            }
+          }
+          tc::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty[acc]);
+          ++my_tiles;
+        }
+        const float mine = a.sample_j == 1 ? m1 : m2;
+        if (live && mine > -INFINITY) atomicMin(a.samp_min + (long long)atile * GT_BM + te, f32_orderable(mine));
+        __threadfence();
+        tc::named_bar_sync(1 + wg, 128);
+        // one thread per warpgroup announces the list and waits (bounded) for the other lists of this A tile; all of
+        // them are co-resident (one item per CTA).  A list that gives up simply starts without the bound.
+        volatile int* ok_flag = reinterpret_cast<volatile int*>(tmem_slot + 1 + wg);
+        if (et == 0) {
+          atomicAdd(a.samp_cnt + atile, 1u);
+          int ok = 0;
+          for (int spin = 0; spin < 20000; ++spin) {
+            if (*reinterpret_cast<volatile unsigned*>(a.samp_cnt + atile) >= (unsigned)a.samp_total) { ok = 1; break; }
+            __nanosleep(50);
+          }
+          __threadfence();
+          *ok_flag = ok;
+        }
+        tc::named_bar_sync(1 + wg, 128);
+        if (*ok_flag != 0 && live) {
+          const unsigned o = *reinterpret_cast<volatile unsigned*>(a.samp_min + (long long)atile * GT_BM + te);
+          if (o != 0xFFFFFFFFu) thr = fmaxf(thr, f32_from_orderable(o));
+        }
+      }
+      // first tile of this item that this warpgroup drains; the per-column terms of a tile are fetched one tile ahead
+      // (registers) and parked in the other half of the warpgroup's buffer, so their global-memory latency is never exposed
+      int ct = ct0;
+      if (WG == 2) { if (((tile_n ^ (unsigned)wg) & 1u) != 0u) { ++ct; } }
+      const unsigned tile_first = tile_n + (unsigned)(ct - ct0);
+      tile_n += (unsigned)(ct1 - ct0);                // running tile count of the CTA (accumulator stage = parity)
+      float2 tn[2];
+      auto fetch_terms = [&](int ctile) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const long long gc = (long long)ctile * GT_BN + et + h * 128;
+          if (gc < a.n_b_rows) { tn[h].x = a.scale ? a.scale[gc] : 1.f; tn[h].y = a.bias ? a.bias[gc] : 0.f; }
+          else { tn[h].x = 0.f; tn[h].y = __int_as_float(0x7fc00000); }      // invalid columns -> NaN score, never selected
+        }
+      };
+      if (ct < ct1) {
+        fetch_terms(ct);
+        float2* sb0 = sb_wg + (my_tiles & 1u) * GT_BN;
+        sb0[et] = tn[0]; sb0[et + 128] = tn[1];
+      }
+      unsigned tl = tile_first;
+      for (; ct < ct1; ct += WG, tl += WG, ++my_tiles) {
+        const unsigned acc = tl & 1u, acc_phase = (tl >> 1) & 1u;
         const long long col0 = (long long)ct * GT_BN;
-        if (live && a.gthr != nullptr) {             // other column groups of this row may already have raised the bar
+        if (live && a.gthr != nullptr) {             // other lists of this row may already have raised the bar
           const unsigned g = *reinterpret_cast<volatile unsigned*>(a.gthr + (long long)atile * GT_BM + te);
           if (g != 0u) thr = fmaxf(thr, f32_from_orderable(g));
         }
-        // stage the per-column terms of this tile (invalid columns -> NaN score, never selected)
-        float2* sb = sbuf + acc * GT_BN;
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int c = et + h * 128;
-          const long long gc = col0 + c;
-          float2 t;
-          if (gc < a.n_b_rows) { t.x = a.scale ? a.scale[gc] : 1.f; t.y = a.bias ? a.bias[gc] : 0.f; }
-          else { t.x = 0.f; t.y = __int_as_float(0x7fc00000); }
-          sb[c] = t;
-        }
-        tc::named_bar_sync(1, 128);
+        const float2* sb = sb_wg + (my_tiles & 1u) * GT_BN;
+        const bool more = ct + WG < ct1;
+        if (more) fetch_terms(ct + WG);               // in flight while this tile is processed
+        tc::named_bar_sync(1 + wg, 128);              // this tile's terms are staged (and the other half is free again)
         tc::mbar_wait_guarded(&tfull[acc], acc_phase);
         tc::tc_fence_after();
         const bool diag = a.exclude_self && my_row >= col0 && my_row < col0 + GT_BN;
@@ -205,13 +295,17 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         tc::tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty[acc]);
+        if (more) {                                   // park the next tile's terms in the half nobody reads any more
+          float2* sbn = sb_wg + ((my_tiles + 1u) & 1u) * GT_BN;
+          sbn[et] = tn[0]; sbn[et + 128] = tn[1];
+        }
         if (live && a.gthr != nullptr && e[L - 1] != 0ull) {     // a full list: its L-th best bounds the row's final L-th best
           const unsigned o = (unsigned)(e[L - 1] >> 32);
           if (o > published) { atomicMax(a.gthr + (long long)atile * GT_BM + te, o); published = o; }
         }
       }
-      // flush this item's list: partial[item][s][te]
-      u64* dst = a.partial + (size_t)item * L * GT_BM;
+      // flush this item's list: partial[(group * WG + wg) * n_atiles + atile][s][te]
+      u64* dst = a.partial + ((size_t)(group * WG + wg) * a.n_atiles + atile) * L * GT_BM;
 #pragma unroll
       for (int s = 0; s < L; ++s) dst[s * GT_BM + te] = e[s];
     }
@@ -621,6 +715,7 @@ int encode_tmap_2d(CUtensorMap* map, const void* base, int elem_bytes, bool bf16
 
 struct GemmPlan {
   int two_cta;     // CTA-pair kernel: n_atiles is even, grid is a multiple of 2
+  int wg;          // epilogue warpgroups per CTA = lists per (row, column group)
   int n_atiles, n_ctiles, n_groups, grid, L, n_stages, k_blocks, n2;
   size_t smem, partial_bytes;
 };
@@ -647,9 +742,13 @@ static bool make_gemm_plan(long long n_a_rows, long long n_b_rows, int d, int el
   // CTA pairs (cta_group::2) when there are at least two A tiles of real work; AURA_GEMM_2CTA=0/1 overrides
   p->two_cta = 0;
   static const int env_2cta = env_int("AURA_GEMM_2CTA", 0), env_groups = env_int("AURA_GEMM_GROUPS", 0), env_stages = env_int("AURA_GEMM_STAGES", 0);
-  if (env_2cta) p->two_cta = ((sms % 2) == 0 && force_L == 0 && p->n_atiles >= 2) ? 1 : 0;
+  if (env_2cta) p->two_cta = ((sms % 2) == 0 && (force_L == 0 || force_L == GT_L) && p->n_atiles >= 2) ? 1 : 0;
   if (p->two_cta) p->n_atiles = (p->n_atiles + 1) / 2 * 2;
   if (p->two_cta && p->L == GT_L_SMALL) p->L = GT_L;             // the pair kernel is instantiated for 32 only
+  // two epilogue warpgroups (one per accumulator stage) wherever the lists are long enough to cost something;
+  // AURA_GEMM_WG=1 keeps the single-warpgroup form (A/B measurements)
+  static const int env_wg = env_int("AURA_GEMM_WG", 2);
+  p->wg = (p->two_cta || p->L == GT_L_ASSIGN || p->L == GT_L_WIDE || env_wg == 1) ? 1 : 2;   // 48-entry lists: measured slower with two (register cap)
   const int units = p->two_cta ? sms / 2 : sms;                 // schedulable units (pairs or CTAs)
   const int work_rows = p->two_cta ? p->n_atiles / 2 : p->n_atiles;
   int groups = units / work_rows;
@@ -682,7 +781,7 @@ static bool make_gemm_plan(long long n_a_rows, long long n_b_rows, int d, int el
     if (stages > G2_MAX_STAGES) stages = G2_MAX_STAGES;
     p->smem = (size_t)stages * G2_STAGE_BYTES + fixed + 1024;
   } else {
-    const size_t fixed = 2 * GT_BN * 8 + (2 * GT_MAX_STAGES + 4) * 8 + 16;
+    const size_t fixed = 4 * GT_BN * 8 + (2 * GT_MAX_STAGES + 4) * 8 + 16;
     stages = (int)((cap - fixed) / GT_STAGE_BYTES);
     if (stages > GT_MAX_STAGES) stages = GT_MAX_STAGES;
     if (env_stages >= 2 && env_stages <= stages) stages = env_stages;
@@ -690,9 +789,9 @@ static bool make_gemm_plan(long long n_a_rows, long long n_b_rows, int d, int el
   }
   if (stages < 2) return false;
   p->n_stages = stages;
-  p->partial_bytes = (size_t)p->n_atiles * groups * p->L * GT_BM * 8;
+  p->partial_bytes = (size_t)p->n_atiles * groups * p->wg * p->L * GT_BM * 8;
   int n2 = 2;
-  while (n2 < groups * p->L) n2 <<= 1;
+  while (n2 < groups * p->wg * p->L) n2 <<= 1;
   p->n2 = n2;
   return ((size_t)n2 + GT_MAX_L) * 8 <= cap;
 }
@@ -702,7 +801,7 @@ static size_t align256(size_t v) { return (v + 255) / 256 * 256; }
 static int run_gemm_topk(const void* a_mat, long long n_a_rows, long long a_row_first, const void* b_mat, long long n_b_rows,
                          int d, bool bf16, const float* scale, const float* bias, bool exclude_self, const GemmPlan& p,
                          u64* partial, cudaStream_t st, const u64* ceil_keys = nullptr, long long a_rows_alloc = 0,
-                         unsigned* gthr = nullptr) {
+                         unsigned* gthr = nullptr, unsigned* samp = nullptr) {
   const int eb = bf16 ? 2 : 4;
   CUtensorMap ta, tb;
   int rc = encode_tmap_2d(&ta, a_mat, eb, bf16, a_rows_alloc > n_a_rows ? a_rows_alloc : n_a_rows, d, GT_BM);
@@ -715,19 +814,44 @@ static int run_gemm_topk(const void* a_mat, long long n_a_rows, long long a_row_
   a.k_blocks = p.k_blocks; a.L = p.L; a.n_stages = p.n_stages; a.exclude_self = exclude_self ? 1 : 0;
   a.scale = scale; a.bias = bias; a.partial = partial; a.ceil_keys = ceil_keys;
   static const int env_gthr = env_int("AURA_GEMM_GTHR", 1);
-  a.gthr = (env_gthr && p.n_groups > 1) ? gthr : nullptr;          // one group per row: nobody to share a bound with
+  a.gthr = (env_gthr && p.n_groups * p.wg > 1) ? gthr : nullptr;   // one list per row: nobody to share a bound with
   if (a.gthr != nullptr) AURA_CUDA_OK(cudaMemsetAsync(a.gthr, 0, (size_t)p.n_atiles * GT_BM * 4, st));
+  // sampled start threshold (see GemmTopkArgs): one item per CTA (all lists of an A tile co-resident), enough tiles per
+  // item to pay for scoring a few of them twice, and enough lists that their best or second best sample covers L
+  a.sample_tiles = 0; a.sample_j = 1; a.samp_total = 0; a.samp_min = nullptr; a.samp_cnt = nullptr;
+  static const int env_sample = env_int("AURA_GEMM_SAMPLE", -1);      // sample tiles per list; 0 = off, -1 = by range length
+  if (samp != nullptr && env_sample != 0 && ceil_keys == nullptr && !exclude_self && !p.two_cta &&
+      (long long)p.n_atiles * p.n_groups <= p.grid) {
+    const int lists = p.n_groups * p.wg;
+    const int j = (p.L + lists - 1) / lists;
+    const int per_item = p.n_ctiles / p.n_groups;
+    // C2 (217 tiles per CTA): 1516 / 1467 / 1445 / 1378 / 1369 / 1388 us per kernel with 0 / 1 / 2 / 4 / 6 / 8 tiles per
+    // list; one rank's share at 8 GPUs (27 tiles per CTA): 266 / 206 / 199 us with 0 / 1 / 2
+    int per_list = env_sample > 0 ? env_sample : per_item / 12;
+    if (per_list > 4 && env_sample < 0) per_list = 4;
+    if (per_list < 1) per_list = 1;
+    const int tiles = per_list * p.wg;
+    if (j <= 2 && per_item >= 4 * tiles) {
+      a.sample_tiles = tiles; a.sample_j = j; a.samp_total = lists;
+      a.samp_min = samp; a.samp_cnt = samp + (size_t)p.n_atiles * GT_BM;
+      AURA_CUDA_OK(cudaMemsetAsync(a.samp_min, 0xFF, (size_t)p.n_atiles * GT_BM * 4, st));
+      AURA_CUDA_OK(cudaMemsetAsync(a.samp_cnt, 0, (size_t)p.n_atiles * 4, st));
+    }
+  }
   void (*kern)(const CUtensorMap, const CUtensorMap, const GemmTopkArgs);
   const bool ceil = ceil_keys != nullptr;
-  if (p.L == GT_L_ASSIGN) kern = bf16 ? gemm_topk_kernel<false, GT_L_ASSIGN, false> : gemm_topk_kernel<true, GT_L_ASSIGN, false>;
-  else if (p.L == GT_L_WIDE) kern = gemm_topk_kernel<false, GT_L_WIDE, false>;       // bf16 shadow shortlist
-  else if (p.L == GT_L_SMALL && !ceil && !p.two_cta) kern = bf16 ? gemm_topk_kernel<false, GT_L_SMALL, false> : gemm_topk_kernel<true, GT_L_SMALL, false>;
+  const bool w2 = p.wg == 2;
+#define AURA_GT_KERN(TF, LL, CE) (w2 ? gemm_topk_kernel<TF, LL, CE, 2> : gemm_topk_kernel<TF, LL, CE, 1>)
+  if (p.L == GT_L_ASSIGN) kern = bf16 ? gemm_topk_kernel<false, GT_L_ASSIGN, false, 1> : gemm_topk_kernel<true, GT_L_ASSIGN, false, 1>;
+  else if (p.L == GT_L_WIDE) kern = AURA_GT_KERN(false, GT_L_WIDE, false);       // bf16 shadow shortlist
+  else if (p.L == GT_L_SMALL && !ceil && !p.two_cta) kern = bf16 ? AURA_GT_KERN(false, GT_L_SMALL, false) : AURA_GT_KERN(true, GT_L_SMALL, false);
   else if (p.two_cta) kern = ceil ? (bf16 ? gemm_topk2_kernel<false, GT_L, true> : gemm_topk2_kernel<true, GT_L, true>)
                                   : (bf16 ? gemm_topk2_kernel<false, GT_L, false> : gemm_topk2_kernel<true, GT_L, false>);
-  else kern = ceil ? (bf16 ? gemm_topk_kernel<false, GT_L, true> : gemm_topk_kernel<true, GT_L, true>)
-                   : (bf16 ? gemm_topk_kernel<false, GT_L, false> : gemm_topk_kernel<true, GT_L, false>);
+  else kern = ceil ? (bf16 ? AURA_GT_KERN(false, GT_L, true) : AURA_GT_KERN(true, GT_L, true))
+                   : (bf16 ? AURA_GT_KERN(false, GT_L, false) : AURA_GT_KERN(true, GT_L, false));
+#undef AURA_GT_KERN
   AURA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
-  kern<<<p.grid, GT_THREADS, p.smem, st>>>(ta, tb, a);     // the pair kernel carries __cluster_dims__(2,1,1)
+  kern<<<p.grid, p.two_cta ? GT_THREADS : 64 + 128 * p.wg, p.smem, st>>>(ta, tb, a);     // the pair kernel carries __cluster_dims__(2,1,1)
   AURA_CUDA_OK(cudaGetLastError());
   note_launches(1);
   return AURA_OK;
@@ -993,7 +1117,7 @@ int tc_coarse(const float* queries, int n_queries, int d, const float* cent, int
   centroid_terms_kernel<<<(n_cent + 255) / 256, 256, 0, st>>>(csq, n_cent, scale2, neg_csq, cmax);
   note_launches(1);
   FinishArgs f;
-  f.partial = partial; f.n_atiles = p.n_atiles; f.n_groups = p.n_groups; f.L = p.L; f.n2 = p.n2; f.k = GT_L;
+  f.partial = partial; f.n_atiles = p.n_atiles; f.n_groups = p.n_groups * p.wg; f.L = p.L; f.n2 = p.n2; f.k = GT_L;
   f.n_a_rows = n_queries; f.row_base = 0; f.rows = nullptr; f.bf16 = 0; f.d = d; f.qn = nullptr;
   f.scale = nullptr; f.bias = nullptr; f.eps = 0.f; f.eps_q = nullptr; f.a_scale = nullptr;
   f.out_idx = probes; f.out_score = dummy_score; f.uncertain = nullptr; f.cand = cand; f.ceil_out = ceil_buf; f.round = 0;
@@ -1035,14 +1159,19 @@ extern "C" size_t aura_batch_topk_workspace_bytes(int64_t n_rows, int d, int dty
   GemmPlan p;
   if (n_queries < 1 || n_rows < 1 || d < 1 || k < 1) return 0;
   if (!make_gemm_plan(n_queries, n_rows, d, dtype == AURA_BF16 ? 2 : 4, k, true, &p)) return 0;
-  GemmPlan ps;                                   // fp32 bank searched through a bf16 shadow: longer lists, bf16 tiles
-  if (dtype == AURA_F32 && k + 14 <= GT_L_WIDE && make_gemm_plan(n_queries, n_rows, d, 2, k, true, &ps, GT_L_WIDE) &&
-      ps.partial_bytes > p.partial_bytes)
-    p.partial_bytes = ps.partial_bytes;
+  // fp32 bank searched through a bf16 shadow: 32- or 48-entry lists over bf16 tiles (the plan fixes lists per row too)
+  if (dtype == AURA_F32 && k + 14 <= GT_L_WIDE) {
+    const int shadow_ls[3] = {GT_L_SMALL, GT_L, GT_L_WIDE};
+    for (int i = 0; i < 3; ++i) {
+      GemmPlan ps;
+      if (k + 14 <= shadow_ls[i] && make_gemm_plan(n_queries, n_rows, d, 2, k, true, &ps, shadow_ls[i]) && ps.partial_bytes > p.partial_bytes)
+        p.partial_bytes = ps.partial_bytes;
+    }
+  }
   const size_t n_pad = ((size_t)n_queries + GT_BM - 1) / GT_BM * GT_BM;     // query block padded to whole A tiles
   return align256(p.partial_bytes) + align256(n_pad * d * 4) + align256(n_pad * d * 2) + 512 +
          align256((size_t)n_queries * GT_MAX_L * 8) + align256((size_t)n_queries * 8) + align256((size_t)n_queries * 4) +
-         align256(n_pad * 4);
+         align256(n_pad * 4) + align256(n_pad * 4 + n_pad / GT_BM * 4);
 }
 
 extern "C" int aura_batch_topk(const void* rows, int dtype, int64_t n_rows, int d, const float* queries, int n_queries,
@@ -1083,6 +1212,7 @@ extern "C" int aura_batch_topk(const void* rows, int dtype, int64_t n_rows, int 
   u64* ceil_buf = cand + align256((size_t)n_queries * GT_MAX_L * 8) / 8;
   float* eps_q = reinterpret_cast<float*>(ceil_buf + align256((size_t)n_queries * 8) / 8);
   unsigned* gthr = reinterpret_cast<unsigned*>(eps_q + align256((size_t)n_queries * 4) / 4);     // [n_pad]
+  unsigned* samp = gthr + align256(n_pad * 4) / 4;                                               // [n_pad + n_pad / 128]
   const bool measured_bound = shadow && shadow_relerr != nullptr;     // eps is then the score-per-cosine unit (see header)
   if (measured_bound)
     normalize_queries_eps_kernel<<<(n_queries + 7) / 8, 256, 0, st>>>(queries, n_queries, d, qn, qb, shadow_relerr, eps, eps_q);
@@ -1101,11 +1231,11 @@ extern "C" int aura_batch_topk(const void* rows, int dtype, int64_t n_rows, int 
   f.scale = scale; f.bias = bias; f.eps = eps; f.eps_q = measured_bound ? eps_q : nullptr; f.a_scale = nullptr;
   f.out_idx = reinterpret_cast<long long*>(out_idx); f.out_score = out_score; f.uncertain = out_uncertain;
   f.cand = nullptr; f.ceil_out = nullptr; f.round = 0;
-  f.partial = partial; f.n_atiles = p.n_atiles; f.n_groups = p.n_groups; f.L = p.L; f.n2 = p.n2;
+  f.partial = partial; f.n_atiles = p.n_atiles; f.n_groups = p.n_groups * p.wg; f.L = p.L; f.n2 = p.n2;
   const size_t fsmem = ((size_t)p.n2 + GT_MAX_L) * 8;
   AURA_CUDA_OK(cudaFuncSetAttribute(gemm_topk_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
   if (rounds == 1) {
-    rc = run_gemm_topk(a_mat, n_queries, 0, b_mat, n_rows, d, bf16, scale, bias, false, p, partial, st, nullptr, (long long)n_pad, gthr);
+    rc = run_gemm_topk(a_mat, n_queries, 0, b_mat, n_rows, d, bf16, scale, bias, false, p, partial, st, nullptr, (long long)n_pad, gthr, samp);
     if (rc != AURA_OK) return rc;
     gemm_topk_finish_kernel<<<n_queries, 128, fsmem, st>>>(f);
     AURA_CUDA_OK(cudaGetLastError());
@@ -1193,7 +1323,7 @@ extern "C" int aura_allpairs_topk(const void* rows, int dtype, int64_t n_rows, i
   rc = run_gemm_topk(a_mat, n_a_rows, a_row_first, rows, n_rows, d, bf16, inv_norm, nullptr, true, p, partial, st, nullptr, 0, gthr);
   if (rc != AURA_OK) return rc;
   FinishArgs f;
-  f.partial = partial; f.n_atiles = p.n_atiles; f.n_groups = p.n_groups; f.L = p.L; f.n2 = p.n2; f.k = k;
+  f.partial = partial; f.n_atiles = p.n_atiles; f.n_groups = p.n_groups * p.wg; f.L = p.L; f.n2 = p.n2; f.k = k;
   f.n_a_rows = n_a_rows; f.row_base = 0; f.rows = nullptr; f.bf16 = 0; f.d = d; f.qn = nullptr;
   f.scale = nullptr; f.bias = nullptr; f.eps = 0.f; f.eps_q = nullptr; f.a_scale = inv_norm ? inv_norm + a_row_first : nullptr;
   if (!bf16) {

@@ -262,3 +262,36 @@ def test_cognitive_map_edges_and_exact_fp32_scores():
     assert walk[0] == 5 and len(walk) == len(set(walk)) == 20
     for a, b in zip(walk[:-1], walk[1:]):
         assert b in nbr[a].tolist()
+
+
+@pytest.mark.parametrize("n,d,b,k,dt,shadow", [(400_000, 64, 300, 10, torch.float32, True),      # 98 lists per row: best sample of each
+                                               (400_000, 64, 300, 10, torch.float32, False),
+                                               (120_000, 64, 1300, 10, torch.bfloat16, False),   # 26 lists per row: second best of each
+                                               (300_000, 128, 520, 18, torch.float32, True)])
+def test_sampled_start_threshold_keeps_exact_results(n, d, b, k, dt, shadow):
+    """Banks large enough that every list of the dense kernel starts from the sampled threshold (a few tiles of its own
+    column range scored in a cheap mode first, gemm_topk.cu): the threshold must be a true lower bound of every query's
+    L-th best score, i.e. results after the certified fix-up are still the exact scan's, bit for bit - including queries
+    whose best rows all sit in ONE list's range (clustered by row position) and rows with extreme scale / bias terms."""
+    from aura_snn_rag_b200 import ops
+    g = torch.Generator().manual_seed(n + b)
+    bank = torch.randn(n, d, generator=g)
+    # a block of rows near query 0 at the very end of the bank: all of its neighbours fall into the last list's range
+    bank[-300:] = bank[-301] + 0.05 * torch.randn(300, d, generator=g)
+    rows = bank.to(dt).cuda()
+    inv = ops.row_inv_norms(rows)
+    q = bank[torch.randint(0, n, (b,), generator=g)] + 0.2 * torch.randn(b, d, generator=g)
+    q[0] = bank[-301]
+    q = q.cuda()
+    strength = 0.5 + 0.5 * torch.rand(n, generator=g)
+    strength[::1000] = 5.0                                              # a few rows whose terms dominate their tile's maximum
+    strength = strength.cuda()
+    scale, bias = 0.5 * strength * inv, 0.05 * strength
+    sh = ops.Bf16Shadow(rows) if shadow else None
+    eps = 2.5 if shadow else 2.5 * (ops.TC_EPS_COS_BF16 if dt == torch.bfloat16 else ops.TC_EPS_COS)   # unit: max |scale| * ||row||
+    stats = {}
+    i1, s1 = ops.exact_topk_batched(rows, q, k, scale, bias, eps=eps, stats=stats, shadow=sh)
+    i2, s2 = ops.scan_topk(rows, q, k, scale, bias)
+    torch.cuda.synchronize()
+    assert stats["uncertain"] < b // 4
+    assert torch.equal(i1, i2) and torch.equal(s1, s2)
