@@ -380,6 +380,54 @@ ivf_gemm_kernel(const __grid_constant__ CUtensorMap tmap_lm, const unsigned char
   if (warp == 0) { tc::tc_fence_after(); tc::tmem_dealloc(tmem_base, 512); }
 }
 
+// ---- seeded start bound of the list-major fine stages ---------------------------------------------------
+// The fine-stage kernels select behind a per-query threshold that only becomes useful once SOME item has collected L keys
+// of the query; until then every item appends / inserts whatever it sees (C5 shard: 6.5 k appended keys per query for a
+// shortlist of 128, and the appends - not the tensor pipe - were a fifth of the batch).  This kernel scores, in exact fp32,
+// the first L rows of the query's nearest probed lists (probe order = nearest centroid first): any L candidate rows give a
+// lower bound of the final L-th best score - min over them - and rows of the nearest list are the likeliest to sit near
+// the top, so on clustered data the bound already rejects every row of the far lists.  The tensor-core score of a row
+// differs from its exact score by at most the certification bound eps, hence gthr[b] = min - eps.
+__global__ void __launch_bounds__(128) ivf_seed_gthr_kernel(const void* __restrict__ rows, int bf16, int d, const float* __restrict__ qn,
+                                                            const long long* __restrict__ probes, int nprobe, int n_lists,
+                                                            const int* __restrict__ list_offsets, const int* __restrict__ list_rows,
+                                                            const float* __restrict__ scale, const float* __restrict__ bias,
+                                                            float eps, const float* __restrict__ eps_q, int L,
+                                                            unsigned* __restrict__ gthr) {
+  __shared__ int s_row[GT_MAX_L];
+  __shared__ int s_n;
+  __shared__ float s_min[4];
+  const int b = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x < 32) {            // one warp walks the probes: positions [taken, taken + len) of the candidate list
+    int taken = 0;
+    for (int p = 0; p < nprobe && taken < L; ++p) {
+      const long long c = probes[(size_t)b * nprobe + p];
+      if (c < 0 || c >= n_lists) continue;
+      const int lb = list_offsets[c], len = min(list_offsets[c + 1] - lb, L - taken);
+      for (int i = lane; i < len; i += 32) s_row[taken + i] = list_rows[lb + i];
+      taken += len;
+    }
+    if (lane == 0) s_n = taken;
+  }
+  __syncthreads();
+  if (s_n < L) return;               // fewer than L candidates in all probed lists: no bound (every one of them is kept anyway)
+  const float* q = qn + (size_t)b * d;
+  float worst = INFINITY;
+  for (int i = warp; i < L; i += 4) {
+    const unsigned r = (unsigned)s_row[i];
+    const float dot = warp_sum(exact_dot_partial(rows, bf16, d, r, q, lane));
+    worst = fminf(worst, fmaf(dot, scale ? scale[r] : 1.f, bias ? bias[r] : 0.f));
+  }
+  if (lane == 0) s_min[warp] = worst;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const float m = fminf(fminf(s_min[0], s_min[1]), fminf(s_min[2], s_min[3])) - (eps_q ? eps_q[b] : eps);
+    // a non-finite bound (NaN rows) seeds nothing; 0 means "no bound" to the kernels, so a bound that maps to 0 is dropped too
+    if (m == m && m > -INFINITY) gthr[b] = f32_orderable(m);
+  }
+}
+
 // ---- work-table construction (all on device, no host sync) ----------------------------------------------
 __global__ void __launch_bounds__(256) ib_pair_hist_kernel(const long long* __restrict__ probes, int n_pairs, int n_lists,
                                                            int* __restrict__ counts) {
@@ -565,7 +613,8 @@ static constexpr int IR_SECTIONS = 3;
 
 struct IvfRowsArgs {
   int n_lists, nprobe, k_blocks, n_stages;
-  int nq_max;                 // 32 / 64 / 128: queries per item of this launch
+  int nq_max;                 // 32 / 64 / 128: queries per item of this launch (TMEM accumulator stride, buffer geometry)
+  int gmax;                   // query-group size of lists probed by more than 64 queries (IR_MAX_NQ, or what fits resident)
   int L, Lc, capq;            // shortlist length, compaction trigger, capacity of a candidate buffer
   int section, cap_items;
   const int* item_base;       // [IR_SECTIONS * n_lists + 1] exclusive scan of the per-(section, list) item counts
@@ -599,7 +648,7 @@ __host__ __device__ __forceinline__ void ir_chunks(int len, int nq, int& n_ch, i
   n_ch = (len + ch_rows - 1) / ch_rows;
 }
 __host__ __device__ __forceinline__ int ir_section_of(int nq) { return nq <= 32 ? 0 : nq <= 64 ? 1 : 2; }
-__host__ __device__ __forceinline__ int ir_groups_of(int nq) { return nq <= 64 ? 1 : (nq + IR_MAX_NQ - 1) / IR_MAX_NQ; }
+__host__ __device__ __forceinline__ int ir_groups_of(int nq, int gmax) { return nq <= 64 ? 1 : (nq + gmax - 1) / gmax; }
 
 // exact selection inside one candidate buffer by the whole warp: keep its L largest keys (in place, front of the
 // buffer), return the L-th largest key.  n <= 32 * IR_MAX_KPL keys, n >= L.
@@ -656,17 +705,24 @@ __device__ __forceinline__ u64 ir_warp_compact(u64* buf, int n, int L, int lane)
   return ((u64)t << 32) | (u64)u;
 }
 
-template <bool TF32>
+// RB ("resident B", bf16 list-major copy only): the query group of an item stays in shared memory for all of the item's
+// row tiles - k_blocks x [gmax x 128 B] swizzled slabs loaded once per item by one producer warp - and the ring carries
+// row tiles only.  The lists every query probes are re-read from L2 once per query group and the groups' operand once
+// per row tile: with both operands streamed, an M128 x N128 tile moves 392 KB through the SM per 3072 tensor clocks and
+// the kernel ran at ~24 % tensor-pipe utilisation, bound by the L2 -> SM path (ncu: r02_c5_rows).  Resident queries
+// take the query operand and its 16-byte cp.async gathers out of the tile loop (see the measurement at the launch site).
+template <bool TF32, bool RB>
 __global__ void __launch_bounds__(IR_THREADS, 1)
 ivf_rows_kernel(const __grid_constant__ CUtensorMap tmap_lm, const unsigned char* __restrict__ qmat,
                 const unsigned char* __restrict__ bank, const int row_pitch, const IvfRowsArgs a) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int S = a.n_stages, NQ = a.nq_max;
-  const unsigned b_bytes = (unsigned)NQ * GT_SLAB;                 // one k-block of the query group
-  const unsigned stage_bytes = 2u * (GT_A_BYTES + b_bytes);        // [A k0][A k1][B k0][B k1]
+  const unsigned b_bytes = (unsigned)(RB ? a.gmax : NQ) * GT_SLAB;    // one k-block of the query group
+  const unsigned stage_bytes = RB ? 2u * GT_A_BYTES : 2u * (GT_A_BYTES + b_bytes);   // [A k0][A k1]([B k0][B k1])
   unsigned char* ring = smem;
-  float* thr_s = reinterpret_cast<float*>(ring + (size_t)S * stage_bytes);   // [IR_MAX_NQ]
+  unsigned char* resb = ring + (size_t)S * stage_bytes;            // RB: [k_blocks][gmax x 128 B]
+  float* thr_s = reinterpret_cast<float*>(resb + (RB ? (size_t)a.k_blocks * b_bytes : 0));   // [IR_MAX_NQ]
   int* cnt_s = reinterpret_cast<int*>(thr_s + IR_MAX_NQ);
   int* base_s = cnt_s + IR_MAX_NQ;              // keys in the buffer right after its last compaction
   int* qid_s = base_s + IR_MAX_NQ;
@@ -674,7 +730,9 @@ ivf_rows_kernel(const __grid_constant__ CUtensorMap tmap_lm, const unsigned char
   uint64_t* empty = full + IR_MAX_STAGES;
   uint64_t* tfull = empty + IR_MAX_STAGES;
   uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* bfull = tempty + 2;                 // RB: the item's query slabs have landed (32 cp.async arrivals)
+  uint64_t* bfree = bfull + 1;                  // RB: the MMAs of the item have finished reading them
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bfree + 1);
   // need_s[tile parity] == tile number + 1: some candidate buffer needs compaction after this tile.  Written during the
   // tile's pass, read after the barrier that ends it; the same word is next written two tiles later, i.e. after the
   // barrier of the tile in between, which every reader of this tile has passed - no reset, no race.
@@ -685,8 +743,9 @@ ivf_rows_kernel(const __grid_constant__ CUtensorMap tmap_lm, const unsigned char
   const uint32_t tmem_cols = NQ <= 32 ? 64u : NQ <= 64 ? 128u : 256u;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < S; ++s) { mbar_init(&full[s], a.list_major ? 129 : 128); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < S; ++s) { mbar_init(&full[s], RB ? 1 : a.list_major ? 129 : 128); mbar_init(&empty[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4); }
+    mbar_init(bfull, 32); mbar_init(bfree, 1);
     need_s[0] = 0u; need_s[1] = 0u;
     if (a.list_major) tc::tma_prefetch_desc(&tmap_lm);
     fence_mbar_init();
@@ -706,7 +765,7 @@ ivf_rows_kernel(const __grid_constant__ CUtensorMap tmap_lm, const unsigned char
 #define IR_DECODE_ITEM(item)                                                                                   \
   const int4 it = a.items[item];                                                                               \
   const int qb = a.q_off[it.x], nq = a.q_off[it.x + 1] - qb;                                                    \
-  const int n_qg = ir_groups_of(nq);                                                                           \
+  const int n_qg = ir_groups_of(nq, a.gmax);                                                                   \
   const int g_lo = (int)(((long long)nq * it.y) / n_qg), g_hi = (int)(((long long)nq * (it.y + 1)) / n_qg);     \
   const int a0 = qb + g_lo, n_live = g_hi - g_lo;                                                              \
   const int n_pad = max(16, (n_live + 15) & ~15);                                                              \
@@ -715,7 +774,47 @@ ivf_rows_kernel(const __grid_constant__ CUtensorMap tmap_lm, const unsigned char
   ir_chunks(len, nq, n_ch_, ch_rows_);                                                                         \
   const int r0 = it.z * ch_rows_, r1 = min(len, r0 + ch_rows_);
 
-  if (warp >= 5) {
+  if (RB && warp >= 5) {
+    // ===================== producer (resident B): one warp; lane 0 also streams the row tiles by TMA =====================
+    if (warp == 5) {
+      const uint32_t resb_u32 = smem_u32(resb);
+      const uint64_t pol_stream = (a.l2_hint & 1) ? l2_policy_evict_first() : l2_policy_evict_normal();
+      const uint64_t pol_keep = (a.l2_hint & 2) ? l2_policy_evict_last() : l2_policy_evict_normal();
+      const uint64_t pol_q = (a.l2_hint & 4) ? l2_policy_evict_last() : l2_policy_evict_normal();
+      int stage = 0; unsigned phase = 0, item_n = 0;
+      const int pj = lane & 7, prow = lane >> 3;      // piece = 16 bytes (chunk pj) of B rows prow + 4*i
+      for (int item = item_lo + (int)blockIdx.x; item < item_hi; item += (int)gridDim.x, ++item_n) {
+        IR_DECODE_ITEM(item)
+        tc::mbar_wait_guarded(bfree, (item_n & 1u) ^ 1u);          // the previous item's MMAs are done with the slabs
+        for (int r = prow; r < n_pad; r += 4) {
+          const int src_row = min(r, n_live - 1);                  // columns past the group re-load a valid query (threshold +inf)
+          const unsigned char* src = qmat + (size_t)(a.pair_of_pos[a0 + src_row] / a.nprobe) * row_pitch + pj * 16;
+          const uint32_t dst = resb_u32 + (uint32_t)(r * GT_SLAB + ((pj ^ (r & 7)) << 4));
+          for (int kb = 0; kb < a.k_blocks; ++kb) {
+            const bool in = kb * GT_SLAB + pj * 16 < row_pitch;
+            cp_async16(dst + (uint32_t)kb * b_bytes, src + (in ? (size_t)kb * GT_SLAB : 0), in ? 16u : 0u, pol_q);
+          }
+        }
+        cp_async_arrive_noinc(bfull);
+        if (lane == 0) {
+          const uint64_t pol_b = n_qg > 1 ? pol_keep : pol_stream;   // rows of a list with several query groups are re-read from L2
+          for (int cr = r0; cr < r1; cr += IR_BM) {
+            for (int kb = 0; kb < a.k_blocks; kb += 2) {
+              const int nkb = min(2, a.k_blocks - kb);
+              tc::mbar_wait_guarded(&empty[stage], phase ^ 1u);
+              mbar_arrive_expect_tx(&full[stage], (unsigned)(nkb * GT_A_BYTES));
+              unsigned char* spg = ring + (size_t)stage * stage_bytes;
+              for (int h = 0; h < nkb; ++h)
+                tc::tma_load_2d(spg + h * GT_A_BYTES, &tmap_lm, (kb + h) * ELEMS_PER_SLAB, lb + cr, &full[stage], pol_b);
+              if (++stage == S) { stage = 0; phase ^= 1u; }
+            }
+          }
+        }
+        __syncwarp();
+      }
+      cp_async_wait<0>();
+    }
+  } else if (warp >= 5) {
     // ===================== producers: 128 threads =====================
     const int pt = threadIdx.x - 160;
     const int prow = pt >> 3, pj = pt & 7;          // A gather: chunk pj of tile rows prow + 16*i
@@ -784,11 +883,15 @@ ivf_rows_kernel(const __grid_constant__ CUtensorMap tmap_lm, const unsigned char
   } else if (warp == 0) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      int stage = 0; unsigned phase = 0, tile_n = 0;
-      for (int item = item_lo + (int)blockIdx.x; item < item_hi; item += (int)gridDim.x) {
+      int stage = 0; unsigned phase = 0, tile_n = 0, item_n = 0;
+      for (int item = item_lo + (int)blockIdx.x; item < item_hi; item += (int)gridDim.x, ++item_n) {
         IR_DECODE_ITEM(item)
         (void)a0;
         const uint32_t idesc = tc::make_idesc(TF32 ? 2 : 1, IR_BM, n_pad);
+        if (RB) {
+          tc::mbar_wait_guarded(bfull, item_n & 1u);    // this item's query slabs are resident
+          fence_proxy_async();
+        }
         for (int cr = r0; cr < r1; cr += IR_BM, ++tile_n) {
           const unsigned acc = tile_n & 1u, acc_phase = (tile_n >> 1) & 1u;
           tc::mbar_wait_guarded(&tempty[acc], acc_phase ^ 1u);
@@ -797,12 +900,12 @@ ivf_rows_kernel(const __grid_constant__ CUtensorMap tmap_lm, const unsigned char
           for (int kb = 0; kb < a.k_blocks; kb += 2) {
             const int nkb = min(2, a.k_blocks - kb);
             tc::mbar_wait_guarded(&full[stage], phase);
-            fence_proxy_async();                    // cp.async wrote through the generic proxy; the MMA reads through the async proxy
+            if (!RB) fence_proxy_async();           // cp.async wrote through the generic proxy; the MMA reads through the async proxy
             tc::tc_fence_after();
             const unsigned char* sp = ring + (size_t)stage * stage_bytes;
             for (int h = 0; h < nkb; ++h) {
               const uint64_t da = tc::make_smem_desc_sw128(sp + h * GT_A_BYTES);
-              const uint64_t db = tc::make_smem_desc_sw128(sp + 2 * GT_A_BYTES + h * b_bytes);
+              const uint64_t db = tc::make_smem_desc_sw128(RB ? resb + (size_t)(kb + h) * b_bytes : sp + 2 * GT_A_BYTES + h * b_bytes);
 #pragma unroll
               for (int j = 0; j < GT_SLAB / 32; ++j)
                 tc::umma<TF32>(d_tmem, da + (uint64_t)(2 * j), db + (uint64_t)(2 * j), idesc, ((kb + h) | j) != 0 ? 1u : 0u);
@@ -812,6 +915,7 @@ ivf_rows_kernel(const __grid_constant__ CUtensorMap tmap_lm, const unsigned char
           }
           tc::umma_commit(&tfull[acc]);
         }
+        if (RB) tc::umma_commit(bfree);             // every MMA that reads this item's slabs has completed when this arrives
       }
     }
   } else {
@@ -848,21 +952,46 @@ ivf_rows_kernel(const __grid_constant__ CUtensorMap tmap_lm, const unsigned char
         tc::mbar_wait_guarded(&tfull[acc], acc_phase);
         tc::tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * (uint32_t)NQ;
-#pragma unroll 1
-        for (int c0 = 0; c0 < n_pad; c0 += 16) {
-          float v[16];
-          tc::tmem_ld_32x16(taddr + c0, v);
+        // 32 columns per TMEM load, the next load in flight while the current columns are compared (the epilogue, not the
+        // tensor pipe, set the pace of this kernel: ncu r3b - 40 % of its samples sat in 16-column load -> wait -> compare
+        // round trips).  Columns past n_pad hold stale accumulators; their thresholds are +inf.
+        uint32_t va[32], vb[32];
+        auto scan32 = [&](const uint32_t (&vr)[32], int c0) {
           unsigned mask = 0u;
 #pragma unroll
-          for (int j = 0; j < 16; ++j) mask |= (fmaf(v[j], sc, bi) >= thr_s[c0 + j]) ? (1u << j) : 0u;
+          for (int j4 = 0; j4 < 32; j4 += 4) {
+            const float4 t4 = *reinterpret_cast<const float4*>(thr_s + c0 + j4);
+            mask |= (fmaf(__uint_as_float(vr[j4 + 0]), sc, bi) >= t4.x) ? (1u << (j4 + 0)) : 0u;
+            mask |= (fmaf(__uint_as_float(vr[j4 + 1]), sc, bi) >= t4.y) ? (1u << (j4 + 1)) : 0u;
+            mask |= (fmaf(__uint_as_float(vr[j4 + 2]), sc, bi) >= t4.z) ? (1u << (j4 + 2)) : 0u;
+            mask |= (fmaf(__uint_as_float(vr[j4 + 3]), sc, bi) >= t4.w) ? (1u << (j4 + 3)) : 0u;
+          }
           if (!valid) mask = 0u;
+          if (c0 + 32 > n_pad) mask &= (1u << (n_pad - c0)) - 1u;      // n_pad is a multiple of 16: never trust stale columns
           while (mask) {                            // rare once the thresholds are warm
             const int j = __ffs(mask) - 1;
             mask &= mask - 1u;
-            const u64 key = make_key(fmaf(select16(v, j), sc, bi), (unsigned)rid);
+            float vj = 0.f;
+#pragma unroll
+            for (int u = 0; u < 32; ++u) vj = (u == j) ? __uint_as_float(vr[u]) : vj;
+            const u64 key = make_key(fmaf(vj, sc, bi), (unsigned)rid);
             const int pos = atomicAdd(&cnt_s[c0 + j], 1);
             if (pos < capq) my_cbuf[(size_t)(c0 + j) * capq + pos] = key;
             if (pos + 1 == L || pos >= Lc) need_s[acc] = tile_n + 1u;   // a buffer reached L keys for the first time, or outgrew Lc
+          }
+        };
+        tc::tmem_ld_32x32_issue(taddr, va);
+        tc::tmem_ld_fence(va);
+#pragma unroll 1
+        for (int c0 = 0; c0 < n_pad; c0 += 64) {
+          const bool more_b = c0 + 32 < n_pad, more_a = c0 + 64 < n_pad;
+          if (more_b) tc::tmem_ld_32x32_issue(taddr + c0 + 32, vb);
+          scan32(va, c0);
+          if (more_b) {
+            tc::tmem_ld_fence(vb);
+            if (more_a) tc::tmem_ld_32x32_issue(taddr + c0 + 64, va);
+            scan32(vb, c0 + 32);
+            if (more_a) tc::tmem_ld_fence(va);
           }
         }
         tc::tc_fence_before();
@@ -954,24 +1083,24 @@ ivf_rows_kernel(const __grid_constant__ CUtensorMap tmap_lm, const unsigned char
 
 // ---- work table of the rows-as-M kernel: three sections by queries per list ----
 __global__ void __launch_bounds__(256) ir_item_count_kernel(const int* __restrict__ q_off, const int* __restrict__ list_offsets,
-                                                            int n_lists, int* __restrict__ items_c) {
+                                                            int n_lists, int gmax, int* __restrict__ items_c) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= n_lists) return;
   const int nq = q_off[c + 1] - q_off[c], len = list_offsets[c + 1] - list_offsets[c];
   int n_ch, ch_rows;
   ir_chunks(len, nq, n_ch, ch_rows);
   const int sec = ir_section_of(nq);
-  const int cnt = (nq > 0 && len > 0) ? ir_groups_of(nq) * n_ch : 0;
+  const int cnt = (nq > 0 && len > 0) ? ir_groups_of(nq, gmax) * n_ch : 0;
   for (int s = 0; s < IR_SECTIONS; ++s) items_c[s * n_lists + c] = s == sec ? cnt : 0;
 }
 __global__ void __launch_bounds__(256) ir_item_fill_kernel(const int* __restrict__ item_base, const int* __restrict__ q_off,
-                                                           int n_lists, int cap, int4* __restrict__ items) {
+                                                           int n_lists, int cap, int gmax, int4* __restrict__ items) {
   const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (c >= n_lists) return;
   const int nq = q_off[c + 1] - q_off[c];
   const int sec = ir_section_of(nq);
   const int base = item_base[sec * n_lists + c], cnt = item_base[sec * n_lists + c + 1] - base;
-  const int n_qg = ir_groups_of(nq);
+  const int n_qg = ir_groups_of(nq, gmax);
   for (int i = lane; i < cnt; i += 32)
     if (base + i < cap) items[base + i] = make_int4(c, i % n_qg, i / n_qg, 0);   // the groups of one chunk run side by side (L2)
 }
@@ -1225,22 +1354,44 @@ static int ivf_rows_search(const void* rows, bool bank_bf16, long long n_rows, i
   float* eps_q = measured ? reinterpret_cast<float*>(ws + Lo.eps_q) : nullptr;
   if (eps_q) launch_normalize_queries_eps(queries, n_queries, d, qn, qb, lm_shadow ? shadow_relerr : nullptr, eps, eps_q, st);
   else launch_normalize_queries(queries, n_queries, d, qn, qb, st);
+  static const int env_seed = env_int("AURA_IVF_SEED", 1);
+  if (env_seed) {
+    ivf_seed_gthr_kernel<<<n_queries, 128, 0, st>>>(rows, bank_bf16 ? 1 : 0, d, qn, probes, nprobe, n_lists, list_offsets, list_rows,
+                                                    scale, bias, eps, eps_q, ir_list_len(k), gthr);
+    note_launches(1);
+  }
   const int n_pairs = n_queries * nprobe;
   AURA_CUDA_OK(cudaMemsetAsync(counts, 0, (size_t)n_lists * 4, st));
   ib_pair_hist_kernel<<<(n_pairs + 255) / 256, 256, 0, st>>>(probes, n_pairs, n_lists, counts);
   launch_scan_offsets(counts, n_lists, q_off, cursor, st);
   ib_pair_scatter_kernel<<<(n_pairs + 255) / 256, 256, 0, st>>>(probes, n_pairs, n_lists, cursor, pair_of_pos, pos_of_pair);
-  ir_item_count_kernel<<<(n_lists + 255) / 256, 256, 0, st>>>(q_off, list_offsets, n_lists, items_c);
+  // geometry first: the query-group size of the heavy lists depends on whether their operand can stay resident
+  static const int env_l2 = env_int("AURA_IVF_L2HINT", 3), env_grid = env_int("AURA_IVF_GRID", 0);
+  static const int env_stages = env_int("AURA_IVF_STAGES", 0), env_rb = env_int("AURA_IVF_RB", 0);
+  const int elems = GT_SLAB / eb;
+  const int k_blocks = (d + elems - 1) / elems;
+  const size_t fixed = 4 * IR_MAX_NQ * 4 + (2 * IR_MAX_STAGES + 6) * 8 + 16;
+  const size_t smem_cap = (size_t)max_smem_optin() - 1024;
+  // resident-query mode (bf16 operands, list-major copy; opt-in AURA_IVF_RB=1): ring of 3 x 32 KB row-tile stages +
+  // k_blocks slabs of gmax queries (d = 768: 80).  Measured on one C5 shard: 12.28 ms for the heavy section against
+  // 10.8 ms with both operands streamed - the groups shrink from 128 to 80 queries, so the rows are streamed 1.6x as
+  // often and only 20 % of the L2 -> SM traffic is saved, while a ring of 96 KB covers less latency.  Kept for d <= 512,
+  // where all 128 queries fit.
+  int gmax = IR_MAX_NQ;
+  bool rb = false;
+  if (env_rb && bf16 && rows_by_list != nullptr && smem_cap > fixed + 3 * 2 * GT_A_BYTES) {
+    int fit = (int)((smem_cap - fixed - 3 * 2 * GT_A_BYTES) / ((size_t)k_blocks * GT_SLAB)) & ~15;
+    if (fit > IR_MAX_NQ) fit = IR_MAX_NQ;
+    if (fit >= 64) { rb = true; gmax = fit; }
+  }
+  ir_item_count_kernel<<<(n_lists + 255) / 256, 256, 0, st>>>(q_off, list_offsets, n_lists, gmax, items_c);
   launch_scan_offsets(items_c, IR_SECTIONS * n_lists, item_base, cursor, st);
-  ir_item_fill_kernel<<<(n_lists * 32 + 255) / 256, 256, 0, st>>>(item_base, q_off, n_lists, cap, items);
+  ir_item_fill_kernel<<<(n_lists * 32 + 255) / 256, 256, 0, st>>>(item_base, q_off, n_lists, cap, gmax, items);
   note_launches(4);
 
-  static const int env_l2 = env_int("AURA_IVF_L2HINT", 3), env_grid = env_int("AURA_IVF_GRID", 0);
-  static const int env_stages = env_int("AURA_IVF_STAGES", 0);
   IvfRowsArgs a;
-  a.n_lists = n_lists; a.nprobe = nprobe; a.cap_items = cap;
-  const int elems = GT_SLAB / eb;
-  a.k_blocks = (d + elems - 1) / elems;
+  a.n_lists = n_lists; a.nprobe = nprobe; a.cap_items = cap; a.gmax = gmax;
+  a.k_blocks = k_blocks;
   a.L = ir_list_len(k);
   a.Lc = a.L * 2 < 64 ? 64 : a.L * 2;
   a.capq = a.Lc + IR_BM;
@@ -1261,31 +1412,32 @@ static int ivf_rows_search(const void* rows, bool bank_bf16, long long n_rows, i
     a.list_major = 1;
   }
   typedef void (*IrKern)(const CUtensorMap, const unsigned char*, const unsigned char*, int, const IvfRowsArgs);
-  IrKern kern = bf16 ? ivf_rows_kernel<false> : ivf_rows_kernel<true>;
-  const size_t fixed = 4 * IR_MAX_NQ * 4 + (2 * IR_MAX_STAGES + 4) * 8 + 16;
-  const size_t smem_cap = (size_t)max_smem_optin() - 1024;
+  IrKern kern = bf16 ? ivf_rows_kernel<false, false> : ivf_rows_kernel<true, false>;
+  IrKern kern_rb = ivf_rows_kernel<false, true>;
   int grid = sm_count();
   if (env_grid >= 1 && env_grid <= grid) grid = env_grid;
   static const int nq_of_section[IR_SECTIONS] = {32, 64, 128};
-  size_t smem_max = 0;
+  size_t smem_max = 0, smem_of[IR_SECTIONS];
   int stages_of[IR_SECTIONS];
   for (int s = 0; s < IR_SECTIONS; ++s) {
-    const size_t stage_bytes = 2 * ((size_t)GT_A_BYTES + (size_t)nq_of_section[s] * GT_SLAB);
-    int stages = (int)((smem_cap - fixed) / stage_bytes);
+    const bool rb_s = rb && s == IR_SECTIONS - 1;
+    const size_t resident = rb_s ? (size_t)k_blocks * gmax * GT_SLAB : 0;
+    const size_t stage_bytes = rb_s ? 2 * (size_t)GT_A_BYTES : 2 * ((size_t)GT_A_BYTES + (size_t)nq_of_section[s] * GT_SLAB);
+    int stages = (int)((smem_cap - fixed - resident) / stage_bytes);
     if (stages > IR_MAX_STAGES) stages = IR_MAX_STAGES;
     if (env_stages >= 2 && env_stages < stages) stages = env_stages;
     AURA_REQUIRE(stages >= 2, AURA_ERR_UNSUPPORTED, "aura_ivf_search_batch: needs 2 pipeline stages of shared memory");
     stages_of[s] = stages;
-    const size_t smem = (size_t)stages * stage_bytes + fixed + 1024;
-    if (smem > smem_max) smem_max = smem;
+    smem_of[s] = (size_t)stages * stage_bytes + resident + fixed + 1024;
+    if (!rb_s && smem_of[s] > smem_max) smem_max = smem_of[s];
   }
   AURA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+  if (rb) AURA_CUDA_OK(cudaFuncSetAttribute(kern_rb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of[IR_SECTIONS - 1]));
   for (int s = IR_SECTIONS - 1; s >= 0; --s) {       // the lists probed by the most queries first
+    const bool rb_s = rb && s == IR_SECTIONS - 1;
     a.section = s; a.nq_max = nq_of_section[s]; a.n_stages = stages_of[s];
-    const size_t stage_bytes = 2 * ((size_t)GT_A_BYTES + (size_t)a.nq_max * GT_SLAB);
-    const size_t smem = (size_t)a.n_stages * stage_bytes + fixed + 1024;
-    kern<<<grid, IR_THREADS, smem, st>>>(tmap_lm, reinterpret_cast<const unsigned char*>(bf16 ? (const void*)qb : (const void*)qn),
-                                         reinterpret_cast<const unsigned char*>(rows), d * eb, a);
+    (rb_s ? kern_rb : kern)<<<grid, IR_THREADS, smem_of[s], st>>>(tmap_lm, reinterpret_cast<const unsigned char*>(bf16 ? (const void*)qb : (const void*)qn),
+                                                                   reinterpret_cast<const unsigned char*>(rows), d * eb, a);
     AURA_CUDA_OK(cudaGetLastError());
   }
   IvfSlotFinishArgs f;
@@ -1383,6 +1535,14 @@ extern "C" int aura_ivf_search_batch(const void* rows, int dtype, int64_t n_rows
   float* eps_q = measured ? reinterpret_cast<float*>(ws + L.force + a256((size_t)n_queries * 4 + 256)) : nullptr;
   if (eps_q) launch_normalize_queries_eps(queries, n_queries, d, qn, qb, lm_shadow ? shadow_relerr : nullptr, eps, eps_q, st);
   else launch_normalize_queries(queries, n_queries, d, qn, qb, st);
+  static const int env_seed = env_int("AURA_IVF_SEED", 1);
+  if (env_seed) {                    // start bound of round 0 (later rounds clear gthr: their keys lie below a ceiling)
+    static const int env_shadow_small0 = env_int("AURA_IVF_SHADOW_SMALL", 0);
+    const int seed_L = (k + 14 <= GT_L_SMALL && (!lm_shadow || env_shadow_small0)) ? GT_L_SMALL : GT_L;
+    ivf_seed_gthr_kernel<<<n_queries, 128, 0, st>>>(rows, bank_bf16 ? 1 : 0, d, qn, probes, nprobe, n_centroid_rows, list_offsets,
+                                                    list_rows, scale, bias, eps, eps_q, seed_L, gthr);
+    note_launches(1);
+  }
   int chunk_major = 1;
   // AURA_IVF_CLUSTER=2|4 launches the CTAs in clusters: the query tiles of one list chunk go to the CTAs of one cluster,
   // which pace each other tile by tile so the chunk is fetched from HBM once.  Measured at BASELINE config 4: within 2 %
