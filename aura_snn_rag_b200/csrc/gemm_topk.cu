@@ -218,9 +218,11 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         if (et == 0) {
           atomicAdd(a.samp_cnt + atile, 1u);
           int ok = 0;
-          for (int spin = 0; spin < 20000; ++spin) {
+          // the lists of an A tile finish their sample tiles within a few microseconds of each other; a list that is not
+          // there after ~100 us (its CTA is not resident yet: another kernel holds SMs) is not waited for
+          for (int spin = 0; spin < 128; ++spin) {
             if (*reinterpret_cast<volatile unsigned*>(a.samp_cnt + atile) >= (unsigned)a.samp_total) { ok = 1; break; }
-            __nanosleep(50);
+            __nanosleep(200);
           }
           __threadfence();
           *ok_flag = ok;
@@ -564,6 +566,8 @@ struct FinishArgs {
   const float* qn; const float* scale; const float* bias; float eps;
   const float* eps_q;        // per-query certification bound (bf16 shadow mode), overrides eps when non-null
   const float* a_scale;      // K7: output score multiplier per A row (inv_norm of the row), may be null
+  const unsigned* samp_min;  // sampled start bounds of the GEMM pass (may be null), part of the completeness floor
+  int deep;                  // second chance of the certificate (one-round K6 only)
   long long* out_idx; float* out_score; int* uncertain;
   // multi-round mode: append this round's 32 best approximate keys to cand[b][round*32..] and publish the new ceiling
   u64* cand; u64* ceil_out; int round;
@@ -572,7 +576,7 @@ struct FinishArgs {
 __global__ void __launch_bounds__(128) gemm_topk_finish_kernel(const FinishArgs f) {
   extern __shared__ __align__(16) unsigned char fsm[];
   u64* keys = reinterpret_cast<u64*>(fsm);              // [n2]
-  u64* ex = keys + f.n2;                                // [GT_MAX_L] exact keys
+  u64* ex = keys + f.n2;                                // [GT_DEEP] exact keys
   const long long b = blockIdx.x;
   const int atile = (int)(b / GT_BM), r = (int)(b % GT_BM);
   const int n_in = f.n_groups * f.L;
@@ -639,11 +643,29 @@ __global__ void __launch_bounds__(128) gemm_topk_finish_kernel(const FinishArgs 
     }
     return;
   }
+  // completeness floor of keys[] (second chance of rescore_and_write): a row that is in no list was rejected against its
+  // list's tail, a tail another list published, or the sampled start bound - all of them at most the largest list tail
+  // or the sampled bound; the head filter above dropped keys below floor_key only
+  __shared__ unsigned s_floor;
+  if (threadIdx.x == 0) {
+    unsigned fl = filtered ? (unsigned)(tail_max >> 32) : 0u;
+    if (f.samp_min != nullptr) { const unsigned o = f.samp_min[b]; if (o != 0xFFFFFFFFu && o > fl) fl = o; }
+    s_floor = fl;
+  }
+  __syncthreads();
+  {
+    unsigned fl = 0u;
+    for (int g = threadIdx.x; g < f.n_groups; g += blockDim.x)
+      fl = max(fl, (unsigned)(f.partial[((size_t)(g * f.n_atiles + atile) * f.L + (f.L - 1)) * GT_BM + r] >> 32));
+    if (fl != 0u) atomicMax(&s_floor, fl);
+  }
+  __syncthreads();
   RescoreArgs ra;
   ra.out_mul = 1.f;
   ra.rows = f.rows; ra.bf16 = f.bf16; ra.d = f.d; ra.q = f.qn + (size_t)b * f.d; ra.scale = f.scale; ra.bias = f.bias;
   ra.eps = f.eps_q ? f.eps_q[b] : f.eps; ra.k = f.k; ra.L = f.L; ra.row_base = f.row_base;
   ra.out_idx = f.out_idx + b * f.k; ra.out_score = f.out_score + b * f.k; ra.uncertain = f.uncertain ? f.uncertain + b : nullptr;
+  ra.deep = f.deep; ra.floor_score = s_floor ? f32_from_orderable(s_floor) : -INFINITY;
   if (f.a_scale) ra.out_mul = f.a_scale[b];        // all-pairs over an fp32 bank: exact fp32 cosine of the k neighbours
   rescore_and_write(keys, n2, ex, ra);
 }
@@ -665,6 +687,7 @@ __global__ void __launch_bounds__(128) cand_rescore_kernel(const CandRescoreArgs
   ra.out_mul = 1.f;
   ra.rows = f.rows; ra.bf16 = f.bf16; ra.d = f.d; ra.q = f.qn + (size_t)b * f.d; ra.scale = f.scale; ra.bias = f.bias;
   ra.eps = f.eps; ra.k = f.k; ra.L = f.n_cand; ra.row_base = f.row_base;
+  ra.deep = 0; ra.floor_score = 0.f;
   ra.out_idx = f.out_idx + b * f.k; ra.out_score = f.out_score + b * f.k; ra.uncertain = f.uncertain ? f.uncertain + b : nullptr;
   rescore_and_write(keys, GT_MAX_L, ex, ra);
   if (threadIdx.x == 0 && f.force_flag && f.uncertain && f.force_flag[b]) f.uncertain[b] = 1;
@@ -793,7 +816,7 @@ static bool make_gemm_plan(long long n_a_rows, long long n_b_rows, int d, int el
   int n2 = 2;
   while (n2 < groups * p->wg * p->L) n2 <<= 1;
   p->n2 = n2;
-  return ((size_t)n2 + GT_MAX_L) * 8 <= cap;
+  return ((size_t)n2 + GT_DEEP) * 8 <= cap;
 }
 
 static size_t align256(size_t v) { return (v + 255) / 256 * 256; }
@@ -819,6 +842,8 @@ static int run_gemm_topk(const void* a_mat, long long n_a_rows, long long a_row_
   // sampled start threshold (see GemmTopkArgs): one item per CTA (all lists of an A tile co-resident), enough tiles per
   // item to pay for scoring a few of them twice, and enough lists that their best or second best sample covers L
   a.sample_tiles = 0; a.sample_j = 1; a.samp_total = 0; a.samp_min = nullptr; a.samp_cnt = nullptr;
+  // the finish kernel reads samp[] as part of its completeness floor: "no bound" unless the pass below samples
+  if (samp != nullptr) AURA_CUDA_OK(cudaMemsetAsync(samp, 0xFF, (size_t)p.n_atiles * GT_BM * 4, st));
   static const int env_sample = env_int("AURA_GEMM_SAMPLE", -1);      // sample tiles per list; 0 = off, -1 = by range length
   if (samp != nullptr && env_sample != 0 && ceil_keys == nullptr && !exclude_self && !p.two_cta &&
       (long long)p.n_atiles * p.n_groups <= p.grid) {
@@ -834,7 +859,6 @@ static int run_gemm_topk(const void* a_mat, long long n_a_rows, long long a_row_
     if (j <= 2 && per_item >= 4 * tiles) {
       a.sample_tiles = tiles; a.sample_j = j; a.samp_total = lists;
       a.samp_min = samp; a.samp_cnt = samp + (size_t)p.n_atiles * GT_BM;
-      AURA_CUDA_OK(cudaMemsetAsync(a.samp_min, 0xFF, (size_t)p.n_atiles * GT_BM * 4, st));
       AURA_CUDA_OK(cudaMemsetAsync(a.samp_cnt, 0, (size_t)p.n_atiles * 4, st));
     }
   }
@@ -1119,9 +1143,9 @@ int tc_coarse(const float* queries, int n_queries, int d, const float* cent, int
   FinishArgs f;
   f.partial = partial; f.n_atiles = p.n_atiles; f.n_groups = p.n_groups * p.wg; f.L = p.L; f.n2 = p.n2; f.k = GT_L;
   f.n_a_rows = n_queries; f.row_base = 0; f.rows = nullptr; f.bf16 = 0; f.d = d; f.qn = nullptr;
-  f.scale = nullptr; f.bias = nullptr; f.eps = 0.f; f.eps_q = nullptr; f.a_scale = nullptr;
+  f.scale = nullptr; f.bias = nullptr; f.eps = 0.f; f.eps_q = nullptr; f.a_scale = nullptr; f.samp_min = nullptr; f.deep = 0;
   f.out_idx = probes; f.out_score = dummy_score; f.uncertain = nullptr; f.cand = cand; f.ceil_out = ceil_buf; f.round = 0;
-  const size_t fsmem = ((size_t)p.n2 + GT_MAX_L) * 8;
+  const size_t fsmem = ((size_t)p.n2 + GT_DEEP) * 8;
   AURA_CUDA_OK(cudaFuncSetAttribute(gemm_topk_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
   // 32 shortlisted rows per round, at least 14 beyond nprobe (the margin of the exact searches)
   int rounds = (nprobe + 14 + GT_L - 1) / GT_L;
@@ -1229,10 +1253,11 @@ extern "C" int aura_batch_topk(const void* rows, int dtype, int64_t n_rows, int 
   FinishArgs f;
   f.k = k; f.n_a_rows = n_queries; f.row_base = row_base; f.rows = rows; f.bf16 = dtype == AURA_BF16 ? 1 : 0; f.d = d; f.qn = qn;
   f.scale = scale; f.bias = bias; f.eps = eps; f.eps_q = measured_bound ? eps_q : nullptr; f.a_scale = nullptr;
+  f.samp_min = samp; f.deep = rounds == 1 ? 1 : 0;
   f.out_idx = reinterpret_cast<long long*>(out_idx); f.out_score = out_score; f.uncertain = out_uncertain;
   f.cand = nullptr; f.ceil_out = nullptr; f.round = 0;
   f.partial = partial; f.n_atiles = p.n_atiles; f.n_groups = p.n_groups * p.wg; f.L = p.L; f.n2 = p.n2;
-  const size_t fsmem = ((size_t)p.n2 + GT_MAX_L) * 8;
+  const size_t fsmem = ((size_t)p.n2 + GT_DEEP) * 8;
   AURA_CUDA_OK(cudaFuncSetAttribute(gemm_topk_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
   if (rounds == 1) {
     rc = run_gemm_topk(a_mat, n_queries, 0, b_mat, n_rows, d, bf16, scale, bias, false, p, partial, st, nullptr, (long long)n_pad, gthr, samp);
@@ -1326,6 +1351,7 @@ extern "C" int aura_allpairs_topk(const void* rows, int dtype, int64_t n_rows, i
   f.partial = partial; f.n_atiles = p.n_atiles; f.n_groups = p.n_groups * p.wg; f.L = p.L; f.n2 = p.n2; f.k = k;
   f.n_a_rows = n_a_rows; f.row_base = 0; f.rows = nullptr; f.bf16 = 0; f.d = d; f.qn = nullptr;
   f.scale = nullptr; f.bias = nullptr; f.eps = 0.f; f.eps_q = nullptr; f.a_scale = inv_norm ? inv_norm + a_row_first : nullptr;
+  f.samp_min = nullptr; f.deep = 0;
   if (!bf16) {
     // fp32 bank: the TF32 products only pick the k candidates; their cosines are recomputed in exact fp32 (row i as the
     // "query", scale_j = 1/||row_j||, times 1/||row_i|| on output) and re-ranked, so returned scores meet the fp32 bar.
@@ -1333,7 +1359,7 @@ extern "C" int aura_allpairs_topk(const void* rows, int dtype, int64_t n_rows, i
     f.rows = rows; f.qn = reinterpret_cast<const float*>(rows) + (size_t)a_row_first * d; f.scale = inv_norm;
   }
   f.out_idx = reinterpret_cast<long long*>(out_idx); f.out_score = out_score; f.uncertain = nullptr; f.cand = nullptr; f.ceil_out = nullptr; f.round = 0;
-  const size_t fsmem = ((size_t)p.n2 + GT_MAX_L) * 8;
+  const size_t fsmem = ((size_t)p.n2 + GT_DEEP) * 8;
   AURA_CUDA_OK(cudaFuncSetAttribute(gemm_topk_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
   gemm_topk_finish_kernel<<<(unsigned)n_a_rows, 128, fsmem, st>>>(f);
   AURA_CUDA_OK(cudaGetLastError());

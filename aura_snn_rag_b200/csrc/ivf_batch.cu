@@ -570,6 +570,7 @@ __global__ void __launch_bounds__(128) ivf_finish_kernel(const IvfFinishArgs f) 
   RescoreArgs ra;
   ra.out_mul = 1.f;
   ra.rows = f.rows; ra.bf16 = f.bf16; ra.d = f.d; ra.q = f.qn + (size_t)b * f.d; ra.scale = f.scale; ra.bias = f.bias;
+  ra.deep = 0; ra.floor_score = 0.f;
   ra.eps = f.eps_q ? f.eps_q[b] : f.eps; ra.k = f.k; ra.L = f.L; ra.row_base = f.row_base;
   ra.out_idx = f.out_idx + (size_t)b * f.k; ra.out_score = f.out_score + (size_t)b * f.k;
   ra.uncertain = f.uncertain + b;
@@ -1118,7 +1119,7 @@ struct IvfSlotFinishArgs {
 };
 __global__ void __launch_bounds__(128) ivf_slot_finish_kernel(const IvfSlotFinishArgs f) {
   __shared__ u64 keys[IB_MERGE_CAP];
-  __shared__ u64 ex[GT_MAX_L];
+  __shared__ u64 ex[GT_DEEP];
   __shared__ int slot_id[IR_QS_MAX];
   __shared__ int slot_n[IR_QS_MAX];
   __shared__ int hist[IR_HIST];
@@ -1148,7 +1149,9 @@ __global__ void __launch_bounds__(128) ivf_slot_finish_kernel(const IvfSlotFinis
   atomicMax(&s_max, my_max);
   __syncthreads();
   int kept = n_kept;
+  bool refined = false;
   if (kept > IB_MERGE_CAP) {
+    refined = true;
     // the neighbours are spread over many lists, so no single item's L-th best is a tight bound: refine it with a
     // histogram of the scores between the bound and the best score, then collect again
     const unsigned long long range = (unsigned long long)(s_max - g) + 1ull;
@@ -1188,6 +1191,9 @@ __global__ void __launch_bounds__(128) ivf_slot_finish_kernel(const IvfSlotFinis
   RescoreArgs ra;
   ra.out_mul = 1.f;
   ra.rows = f.rows; ra.bf16 = f.bf16; ra.d = f.d; ra.q = f.qn_vec + (size_t)b * f.d; ra.scale = f.scale; ra.bias = f.bias;
+  // every key at or above the final bound of the query (or of the histogram refinement) is in keys[]: second chance allowed
+  ra.deep = 1;
+  { const unsigned fl = refined ? max(g, s_t1) : g; ra.floor_score = fl ? f32_from_orderable(fl) : -INFINITY; }
   ra.eps = f.eps_q ? f.eps_q[b] : f.eps; ra.k = f.k; ra.L = f.L; ra.row_base = f.row_base;
   ra.out_idx = f.out_idx + (size_t)b * f.k; ra.out_score = f.out_score + (size_t)b * f.k;
   ra.uncertain = f.uncertain + b;

@@ -314,7 +314,16 @@ __device__ __forceinline__ float exact_dot_partial(const void* rows, int bf16, i
 
 
 // ---- shared tail of the finish kernels: exact fp32 re-score of the L best tensor-core candidates + certification ----
-// keys[0..n2) sorted descending (approximate keys), ex = GT_MAX_L scratch keys in shared memory; 128 threads.
+// keys[0..n2) sorted descending (approximate keys), ex = GT_DEEP scratch keys in shared memory; 128 threads.
+//
+// Second chance.  A result is certified when its exact k-th best beats (approximate score of the first candidate NOT
+// re-scored) + eps.  With only the L best re-scored that candidate is the (L+1)-th, and on near-tie heavy data the margin
+// of L - k places is sometimes not enough - the caller then pays a full exact scan for the query.  But the finish kernels
+// hold MORE than L candidates: every row whose approximate score exceeds `floor_score` (the largest threshold any list /
+// item ever rejected against: list tails, shared bounds, sampled or seeded start bounds) is present in keys[].  So a
+// query that fails with L re-scores up to GT_DEEP of them and certifies against the first key beyond, or against
+// floor_score itself when everything above it was re-scored.  Only flagged queries take this path.
+static constexpr int GT_DEEP = 512;
 struct RescoreArgs {
   const void* rows; int bf16; int d;
   const float* q;              // this query, normalised fp32
@@ -322,12 +331,14 @@ struct RescoreArgs {
   int k, L; long long row_base;
   long long* out_idx; float* out_score; int* uncertain;   // already offset to this query
   float out_mul;               // written score = exact score * out_mul (all-pairs: 1 / ||row_i||); ranking is unaffected
+  int deep;                    // second chance allowed: keys[] is complete above floor_score
+  float floor_score;
 };
-__device__ __forceinline__ void rescore_and_write(const u64* keys, int n2, u64* ex, const RescoreArgs& f) {
+// exact keys of candidates [0, n_cand) -> ex[0, cap) (zero beyond n_cand / for empty candidates); each warp takes every
+// 4th candidate, four at a time so that their row loads overlap
+__device__ __forceinline__ void rescore_range(const u64* keys, int n_cand, int cap, u64* ex, const RescoreArgs& f) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_cand = min(f.L, n2);
-  // each warp re-scores candidates warp, warp+4, ...; four at a time so that their row loads overlap
-  for (int c0 = warp; c0 < GT_MAX_L; c0 += 16) {
+  for (int c0 = warp; c0 < cap; c0 += 16) {
     float part[4];
     unsigned rowv[4];
     bool live[4];
@@ -348,16 +359,25 @@ __device__ __forceinline__ void rescore_and_write(const u64* keys, int n2, u64* 
         const float sc = f.scale ? f.scale[rowv[u]] : 1.f, bi = f.bias ? f.bias[rowv[u]] : 0.f;
         key = make_key(fmaf(dot, sc, bi), rowv[u]);
       }
-      if (lane == 0 && c < GT_MAX_L) ex[c] = key;
+      if (lane == 0 && c < cap) ex[c] = key;
     }
   }
-  block_bitonic_sort_desc(ex, GT_MAX_L);
+}
+__device__ __forceinline__ void rescore_write_topk(const u64* ex, int cap, const RescoreArgs& f) {
   for (int i = threadIdx.x; i < f.k; i += blockDim.x) {
-    const u64 key = i < GT_MAX_L ? ex[i] : 0ull;
+    const u64 key = i < cap ? ex[i] : 0ull;
     f.out_idx[i] = key ? f.row_base + (long long)key_row(key) : -1ll;
     f.out_score[i] = key ? key_score(key) * f.out_mul : -INFINITY;
   }
-  if (threadIdx.x == 0 && f.uncertain) {
+}
+__device__ __forceinline__ void rescore_and_write(const u64* keys, int n2, u64* ex, const RescoreArgs& f) {
+  __shared__ int s_depth;
+  __shared__ float s_bound;
+  const int n_cand = min(f.L, n2);
+  rescore_range(keys, n_cand, GT_MAX_L, ex, f);
+  block_bitonic_sort_desc(ex, GT_MAX_L);
+  rescore_write_topk(ex, GT_MAX_L, f);
+  if (threadIdx.x == 0) {
     // rows outside the shortlist have approximate score <= s_L (the L-th best approximate score), hence exact
     // score <= s_L + eps: the result is certified when the exact k-th best beats that
     int flag = 0;
@@ -366,7 +386,33 @@ __device__ __forceinline__ void rescore_and_write(const u64* keys, int n2, u64* 
       const u64 kth = ex[min(f.k, GT_MAX_L) - 1];
       if (kth == 0ull || !(key_score(kth) > bound)) flag = 1;
     }
-    *f.uncertain = flag;
+    int depth = 0;
+    if (flag && f.deep) {
+      // second chance: candidates known above the completeness floor, at most GT_DEEP of them
+      int lo = 0, hi = min(n2, GT_DEEP + 1);                      // first index whose key is empty or below the floor
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (keys[mid] != 0ull && key_score(keys[mid]) > f.floor_score) lo = mid + 1; else hi = mid;
+      }
+      if (lo > f.L) {                                               // deeper than the first attempt: worth a second one
+        depth = min(lo, GT_DEEP);
+        // every row not re-scored is either keys[depth...] (approximate score <= that of keys[depth]) or absent from
+        // keys[] (approximate score <= floor_score)
+        s_bound = (lo > GT_DEEP ? key_score(keys[GT_DEEP]) : f.floor_score) + f.eps;
+      }
+    }
+    s_depth = depth;
+    if (f.uncertain) *f.uncertain = flag;
+  }
+  __syncthreads();
+  const int depth = s_depth;
+  if (depth == 0) return;
+  rescore_range(keys, depth, GT_DEEP, ex, f);
+  block_bitonic_sort_desc(ex, GT_DEEP);
+  rescore_write_topk(ex, GT_DEEP, f);
+  if (threadIdx.x == 0 && f.uncertain) {
+    const u64 kth = ex[min(f.k, GT_DEEP) - 1];
+    *f.uncertain = (kth == 0ull || !(key_score(kth) > s_bound)) ? 1 : 0;
   }
 }
 
