@@ -492,12 +492,13 @@ struct IvfFinishArgs {
   const float* eps_q;       // per-query certification bound (bf16 list-major shadow of an fp32 bank), overrides eps
   u64* cand; u64* ceil_out; int round; int* force_flag;   // multi-round mode (see gemm_topk.cu)
   int empty_ok;             // a query without candidates is a valid empty result (row-sharded callers), not a hand-back
+  const unsigned* gthr;     // final shared bounds of the GEMM pass (seed included), part of the completeness floor
   long long* out_idx; float* out_score; int* uncertain;
 };
 
 __global__ void __launch_bounds__(128) ivf_finish_kernel(const IvfFinishArgs f) {
   __shared__ u64 keys[IB_MERGE_CAP];
-  __shared__ u64 ex[GT_MAX_L];
+  __shared__ u64 ex[GT_DEEP];
   const int b = blockIdx.x;
   const bool overflow = *f.n_items > f.cap_items || f.pbase[f.n_lists] > f.cap_plists;
   // Partial lists of this query: one per (probe, chunk of the probed list), each sorted and zero-padded.  Two passes, a
@@ -567,10 +568,26 @@ __global__ void __launch_bounds__(128) ivf_finish_kernel(const IvfFinishArgs f) 
     }
     return;
   }
+  // completeness floor of keys[] (second chance of rescore_and_write): rows absent from keys[] were rejected against a
+  // list tail, the shared / seeded bound of the query, or the head floor above
+  __shared__ unsigned s_floor;
+  if (threadIdx.x == 0) {
+    unsigned fl = (unsigned)(floor_key >> 32);
+    if (f.gthr != nullptr) fl = max(fl, f.gthr[b]);
+    s_floor = fl;
+  }
+  __syncthreads();
+  {
+    unsigned fl = 0u;
+    for (int p = warp; p < f.nprobe; p += 4)
+      for (int j = lane; j < lcnt[p]; j += 32) fl = max(fl, (unsigned)(lptr[p][(size_t)j * lstride[p] + (f.L - 1)] >> 32));
+    if (fl != 0u) atomicMax(&s_floor, fl);
+  }
+  __syncthreads();
   RescoreArgs ra;
   ra.out_mul = 1.f;
   ra.rows = f.rows; ra.bf16 = f.bf16; ra.d = f.d; ra.q = f.qn + (size_t)b * f.d; ra.scale = f.scale; ra.bias = f.bias;
-  ra.deep = 0; ra.floor_score = 0.f;
+  ra.deep = 1; ra.floor_score = s_floor ? f32_from_orderable(s_floor) : -INFINITY;
   ra.eps = f.eps_q ? f.eps_q[b] : f.eps; ra.k = f.k; ra.L = f.L; ra.row_base = f.row_base;
   ra.out_idx = f.out_idx + (size_t)b * f.k; ra.out_score = f.out_score + (size_t)b * f.k;
   ra.uncertain = f.uncertain + b;
@@ -1620,6 +1637,7 @@ extern "C" int aura_ivf_search_batch(const void* rows, int dtype, int64_t n_rows
   f.row_base = row_base; f.spread = a.spread; f.chunk_major = chunk_major; f.out_idx = reinterpret_cast<long long*>(out_idx); f.out_score = out_score; f.uncertain = out_uncertain;
   f.cand = rounds > 1 ? cand : nullptr; f.ceil_out = ceil_buf; f.round = 0; f.force_flag = force;
   f.empty_ok = (flags & AURA_IVF_EMPTY_OK) ? 1 : 0;
+  f.gthr = gthr;
   cudaLaunchConfig_t cfg = {};
   cudaLaunchAttribute cattr[1];
   cattr[0].id = cudaLaunchAttributeClusterDimension;
