@@ -1217,7 +1217,9 @@ extern "C" int aura_batch_topk(const void* rows, int dtype, int64_t n_rows, int 
   // L = 32 certified all 51 200 bench queries, L = 24 handed back 1.7 % of them (each one a 0.45 ms exact scan).
   // AURA_SHADOW_L = 24 | 32 | 48 overrides.
   static const int env_shadow_l = env_int("AURA_SHADOW_L", 0);
-  int shadow_L = k + 14 <= GT_L ? GT_L : GT_L_WIDE;
+  // with the second-chance certificate of the finish kernel (up to 256 candidates re-scored for a query that fails with
+  // L) the 24-entry lists hand nothing back either: k <= 10 keeps 24
+  int shadow_L = k + 14 <= GT_L_SMALL ? GT_L_SMALL : k + 14 <= GT_L ? GT_L : GT_L_WIDE;
   if ((env_shadow_l == GT_L_SMALL || env_shadow_l == GT_L || env_shadow_l == GT_L_WIDE) && k + 14 <= env_shadow_l) shadow_L = env_shadow_l;
   AURA_REQUIRE(make_gemm_plan(n_queries, n_rows, d, bf16 ? 2 : 4, k, true, &p, shadow ? shadow_L : 0), AURA_ERR_UNSUPPORTED,
                "aura_batch_topk: no plan for n_queries=%d k=%d", n_queries, k);

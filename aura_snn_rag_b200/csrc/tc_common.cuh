@@ -321,9 +321,9 @@ __device__ __forceinline__ float exact_dot_partial(const void* rows, int bf16, i
 // of L - k places is sometimes not enough - the caller then pays a full exact scan for the query.  But the finish kernels
 // hold MORE than L candidates: every row whose approximate score exceeds `floor_score` (the largest threshold any list /
 // item ever rejected against: list tails, shared bounds, sampled or seeded start bounds) is present in keys[].  So a
-// query that fails with L re-scores up to GT_DEEP of them and certifies against the first key beyond, or against
+// query that fails with L re-scores up to GT_DEEP (256) of them and certifies against the first key beyond, or against
 // floor_score itself when everything above it was re-scored.  Only flagged queries take this path.
-static constexpr int GT_DEEP = 512;
+static constexpr int GT_DEEP = 256;
 struct RescoreArgs {
   const void* rows; int bf16; int d;
   const float* q;              // this query, normalised fp32

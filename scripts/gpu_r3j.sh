@@ -1,0 +1,20 @@
+#!/bin/bash
+mkdir -p gpurun_out
+python - <<'PY' 2>&1 | tail -3
+import torch, sys
+sys.path.insert(0, ".")
+from aura_snn_rag_b200 import ops
+dev = torch.device("cuda:0")
+g = torch.Generator(device=dev).manual_seed(1234)
+rows = torch.randn(1_000_000, 768, device=dev, generator=g)
+inv = ops.row_inv_norms(rows)
+sh = ops.Bf16Shadow(rows)
+tot = 0
+for it in range(50):
+    q = rows[torch.randint(0, 1_000_000, (1024,), device=dev, generator=g)] + 0.1 * torch.randn(1024, 768, device=dev, generator=g)
+    _, _, fl = ops.batch_topk(rows, q, 10, inv, eps=1.0, shadow=sh)
+    tot += int(fl.sum())
+print("C2 shadow default L: uncertified of 51200:", tot)
+PY
+python scripts/kernel_breakdown.py 100 1000000 2>&1 | tail -1
+python scripts/kernel_breakdown.py 100 125000 2>&1 | tail -1
