@@ -791,6 +791,9 @@ static bool make_gemm_plan(long long n_a_rows, long long n_b_rows, int d, int el
   if (env_groups >= 1 && env_groups <= p->n_ctiles) groups = env_groups;
   if (force_groups) groups = force_groups;
   p->n_groups = groups;
+  // items of many hundred tiles (all-pairs: every A tile walks the whole bank) never notice how their lists warm up,
+  // and a second list per row only doubles the finish work: C3 94.2 ms with two warpgroups against 89.9 ms with one
+  if (p->n_ctiles / groups > 512) p->wg = 1;
   const long long items = (long long)work_rows * groups;
   const long long want = items < units ? items : units;
   p->grid = (int)(p->two_cta ? 2 * want : want);

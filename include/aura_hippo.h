@@ -28,7 +28,8 @@
 extern "C" {
 #endif
 
-#define AURA_HIPPO_VERSION 200 /* 0.2.0 */
+#define AURA_HIPPO_VERSION 300 /* 0.3.0: aura_ivf_search_batch / aura_ivf_pack_lists take the element type of the
+                                  list-major copy (bf16 shadow of an fp32 bank), AURA_IVF_MEASURED_EPS */
 
 enum {
   AURA_OK = 0,

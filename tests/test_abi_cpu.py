@@ -31,7 +31,7 @@ def test_ctypes_table_matches_header():
     from aura_snn_rag_b200 import _lib
     assert sorted(_lib.SIGNATURES) == header_functions()
     lib = _lib.load()
-    assert lib.aura_version() == 200
+    assert lib.aura_version() == 300
     assert lib.aura_last_error_string() is not None
 
 
