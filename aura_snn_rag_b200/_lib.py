@@ -29,6 +29,7 @@ SIGNATURES = {
     "aura_version": (_i, []),
     "aura_last_error_string": (C.c_char_p, []),
     "aura_kernel_launches": (C.c_uint64, []),
+    "aura_debug_last_trap": (_i, [_p]),
     "aura_row_inv_norms": (_i, [_p, _i, _i64, _i, _p, _p]),
     "aura_row_terms": (_i, [_p, _p, _i, _p, _f, _p, _i64, _p, _p, _p]),
     "aura_decay_strength": (_i, [_p, _i64, _f, _p]),

@@ -25,6 +25,7 @@ int  cuda_fail(cudaError_t e, const char* what);
 int  sm_count();
 int  max_smem_optin();
 void note_launches(int n);  // kernels launched by this library in this process (aura_kernel_launches)
+unsigned* trap_trace_device();   // mapped pinned words a watchdog writes before it traps (aura_debug_last_trap); may be null
 int  env_int(const char* name, int dflt);  // tuning knob from the environment (callers cache it in a function-local static)
 
 // scan_topk.cu: shared launcher of aura_scan_topk (probes == nullptr) and aura_ivf_search

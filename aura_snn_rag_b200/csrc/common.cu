@@ -54,8 +54,33 @@ int max_smem_optin() {
   return v > 0 ? v : 232448;
 }
 
+// Where a watchdog trap fired.  The mbarrier / flag waits of the tensor-core kernels trap instead of hanging the GPU when a
+// protocol bug (or a lost co-residency assumption) keeps them waiting; a trap kills the context, so the waiting thread
+// first writes {tag, block, thread, parity} into MAPPED PINNED HOST memory, which the process can still read afterwards.
+static unsigned* g_trace_host = nullptr;
+static unsigned* g_trace_dev = nullptr;
+unsigned* trap_trace_device() {
+  if (g_trace_dev == nullptr) {
+    void* h = nullptr;
+    void* d = nullptr;
+    if (cudaHostAlloc(&h, 64, cudaHostAllocMapped) == cudaSuccess && cudaHostGetDevicePointer(&d, h, 0) == cudaSuccess) {
+      for (int i = 0; i < 16; ++i) reinterpret_cast<unsigned*>(h)[i] = 0u;
+      g_trace_host = reinterpret_cast<unsigned*>(h);
+      g_trace_dev = reinterpret_cast<unsigned*>(d);
+    } else {
+      (void)cudaGetLastError();
+    }
+  }
+  return g_trace_dev;
+}
+
 }  // namespace aura
 
+extern "C" int aura_debug_last_trap(uint32_t out[4]) {
+  if (out == nullptr) return AURA_ERR_INVALID_ARG;
+  for (int i = 0; i < 4; ++i) out[i] = aura::g_trace_host ? aura::g_trace_host[i] : 0u;
+  return AURA_OK;
+}
 extern "C" int aura_version(void) { return AURA_HIPPO_VERSION; }
 extern "C" const char* aura_last_error_string(void) { return aura::g_err; }
 extern "C" uint64_t aura_kernel_launches(void) { return aura::launches(); }

@@ -647,6 +647,7 @@ struct IvfRowsArgs {
   // query b lists its slots in qslots[b][0 .. qn[b])
   u64* slot_keys; int* slot_cnt; int* n_slots; int cap_slots;
   int* qslots; int* qn; int qs_max; int* qflag;
+  unsigned* trace;            // watchdog trace words (mapped pinned host memory), may be null
 };
 
 // chunk geometry of the rows-as-M path: a list is cut into chunks only for load balance, and every (chunk, query) pair
@@ -803,7 +804,7 @@ ivf_rows_kernel(const __grid_constant__ CUtensorMap tmap_lm, const unsigned char
       const int pj = lane & 7, prow = lane >> 3;      // piece = 16 bytes (chunk pj) of B rows prow + 4*i
       for (int item = item_lo + (int)blockIdx.x; item < item_hi; item += (int)gridDim.x, ++item_n) {
         IR_DECODE_ITEM(item)
-        tc::mbar_wait_guarded(bfree, (item_n & 1u) ^ 1u);          // the previous item's MMAs are done with the slabs
+        tc::mbar_wait_traced(bfree, (item_n & 1u) ^ 1u, a.trace, 1u);          // the previous item's MMAs are done with the slabs
         for (int r = prow; r < n_pad; r += 4) {
           const int src_row = min(r, n_live - 1);                  // columns past the group re-load a valid query (threshold +inf)
           const unsigned char* src = qmat + (size_t)(a.pair_of_pos[a0 + src_row] / a.nprobe) * row_pitch + pj * 16;
@@ -819,7 +820,7 @@ ivf_rows_kernel(const __grid_constant__ CUtensorMap tmap_lm, const unsigned char
           for (int cr = r0; cr < r1; cr += IR_BM) {
             for (int kb = 0; kb < a.k_blocks; kb += 2) {
               const int nkb = min(2, a.k_blocks - kb);
-              tc::mbar_wait_guarded(&empty[stage], phase ^ 1u);
+              tc::mbar_wait_traced(&empty[stage], phase ^ 1u, a.trace, 2u);
               mbar_arrive_expect_tx(&full[stage], (unsigned)(nkb * GT_A_BYTES));
               unsigned char* spg = ring + (size_t)stage * stage_bytes;
               for (int h = 0; h < nkb; ++h)
@@ -861,7 +862,7 @@ ivf_rows_kernel(const __grid_constant__ CUtensorMap tmap_lm, const unsigned char
         for (int i = 0; i < 8; ++i) rb[i] = a.list_major ? 0 : a.list_rows[lb + min(cr + prow + 16 * i, r1 - 1)];
         for (int kb = 0; kb < a.k_blocks; kb += 2) {
           const int nkb = min(2, a.k_blocks - kb);
-          tc::mbar_wait_guarded(&empty[stage], phase ^ 1u);
+          tc::mbar_wait_traced(&empty[stage], phase ^ 1u, a.trace, 3u);
           const uint32_t sp = ring_u32 + (uint32_t)stage * stage_bytes;
           bool in_row[2]; size_t ko[2];
 #pragma unroll
@@ -907,17 +908,17 @@ ivf_rows_kernel(const __grid_constant__ CUtensorMap tmap_lm, const unsigned char
         (void)a0;
         const uint32_t idesc = tc::make_idesc(TF32 ? 2 : 1, IR_BM, n_pad);
         if (RB) {
-          tc::mbar_wait_guarded(bfull, item_n & 1u);    // this item's query slabs are resident
+          tc::mbar_wait_traced(bfull, item_n & 1u, a.trace, 4u);    // this item's query slabs are resident
           fence_proxy_async();
         }
         for (int cr = r0; cr < r1; cr += IR_BM, ++tile_n) {
           const unsigned acc = tile_n & 1u, acc_phase = (tile_n >> 1) & 1u;
-          tc::mbar_wait_guarded(&tempty[acc], acc_phase ^ 1u);
+          tc::mbar_wait_traced(&tempty[acc], acc_phase ^ 1u, a.trace, 5u);
           tc::tc_fence_after();
           const uint32_t d_tmem = tmem_base + acc * (uint32_t)NQ;
           for (int kb = 0; kb < a.k_blocks; kb += 2) {
             const int nkb = min(2, a.k_blocks - kb);
-            tc::mbar_wait_guarded(&full[stage], phase);
+            tc::mbar_wait_traced(&full[stage], phase, a.trace, 6u);
             if (!RB) fence_proxy_async();           // cp.async wrote through the generic proxy; the MMA reads through the async proxy
             tc::tc_fence_after();
             const unsigned char* sp = ring + (size_t)stage * stage_bytes;
@@ -967,7 +968,7 @@ ivf_rows_kernel(const __grid_constant__ CUtensorMap tmap_lm, const unsigned char
         const unsigned acc = tile_n & 1u, acc_phase = (tile_n >> 1) & 1u;
         const bool valid_n = cr + IR_BM + te < r1;
         const int rid_n = valid_n ? a.list_rows[lb + cr + IR_BM + te] : 0;
-        tc::mbar_wait_guarded(&tfull[acc], acc_phase);
+        tc::mbar_wait_traced(&tfull[acc], acc_phase, a.trace, 7u);
         tc::tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * (uint32_t)NQ;
         // 32 columns per TMEM load, the next load in flight while the current columns are compared (the epilogue, not the
@@ -1425,6 +1426,7 @@ static int ivf_rows_search(const void* rows, bool bank_bf16, long long n_rows, i
   a.n_slots = reinterpret_cast<int*>(ws + Lo.n_slots); a.cap_slots = Lo.cap_slots;
   a.qslots = reinterpret_cast<int*>(ws + Lo.qslots); a.qn = reinterpret_cast<int*>(ws + Lo.qcnt);
   a.qs_max = IR_QS_MAX; a.qflag = reinterpret_cast<int*>(ws + Lo.qflag);
+  a.trace = trap_trace_device();
   CUtensorMap tmap_lm;
   memset(&tmap_lm, 0, sizeof(tmap_lm));
   a.list_major = 0;

@@ -17,6 +17,20 @@ __device__ __forceinline__ void mbar_wait_guarded(uint64_t* bar, unsigned parity
   }
 }
 
+// same, leaving a trace: {tag, block, thread, parity} in mapped pinned host memory (aura_debug_last_trap)
+__device__ __forceinline__ void mbar_wait_traced(uint64_t* bar, unsigned parity, unsigned* trace, unsigned tag) {
+  unsigned spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 22)) {
+      if (trace != nullptr) {
+        trace[0] = tag; trace[1] = blockIdx.x; trace[2] = threadIdx.x; trace[3] = parity;
+        __threadfence_system();
+      }
+      asm volatile("trap;");
+    }
+  }
+}
+
 // ---- TMA 2-D tiled load, completion on an mbarrier, with an L2 cache-policy hint ----
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar,
                                             uint64_t policy) {

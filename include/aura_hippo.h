@@ -58,6 +58,11 @@ int aura_version(void);
 const char* aura_last_error_string(void);
 /* number of CUDA kernels this library has launched in this process (bench accounting only) */
 uint64_t aura_kernel_launches(void);
+/* {tag, block, thread, parity} of the last watchdog trap of an instrumented kernel wait (the words live in mapped pinned
+ * host memory, so they can be read after the trap has killed the CUDA context); all zero if none fired.
+ * ivf_rows_kernel tags: 1 / 2 resident-mode producer (slabs free / ring slot free), 3 producer ring slot free, 4 MMA
+ * slabs resident, 5 MMA accumulator drained, 6 MMA operands landed, 7 epilogue accumulator complete. */
+int aura_debug_last_trap(uint32_t out[4]);
 
 /* ---- per-row terms maintained at write time / per query -------------------------------- */
 
