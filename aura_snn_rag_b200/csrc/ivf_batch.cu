@@ -625,7 +625,7 @@ __global__ void __launch_bounds__(128) ivf_finish_kernel(const IvfFinishArgs f) 
 static constexpr int IR_THREADS = 288;       // warp 0 MMA, warps 1-4 epilogue, warps 5-8 producers
 static constexpr int IR_BM = 128;            // list rows per tile (TMEM lanes)
 static constexpr int IR_MAX_STAGES = 6;
-static constexpr int IR_MAX_NQ = 128;
+static constexpr int IR_MAX_NQ = 256;       // queries per item of the heaviest section (TMEM: 2 accumulator stages x 256 columns)
 static constexpr int IR_MAX_KPL = 12;        // candidate buffer capacity / 32
 static constexpr int IR_SECTIONS = 3;
 
@@ -745,7 +745,8 @@ ivf_rows_kernel(const __grid_constant__ CUtensorMap tmap_lm, const unsigned char
   int* cnt_s = reinterpret_cast<int*>(thr_s + IR_MAX_NQ);
   int* base_s = cnt_s + IR_MAX_NQ;              // keys in the buffer right after its last compaction
   int* qid_s = base_s + IR_MAX_NQ;
-  uint64_t* full = reinterpret_cast<uint64_t*>(qid_s + IR_MAX_NQ);
+  int* qrow_s = qid_s + IR_MAX_NQ;              // the producers' copy of the group's query rows
+  uint64_t* full = reinterpret_cast<uint64_t*>(qrow_s + IR_MAX_NQ);
   uint64_t* empty = full + IR_MAX_STAGES;
   uint64_t* tfull = empty + IR_MAX_STAGES;
   uint64_t* tempty = tfull + 2;
@@ -759,7 +760,7 @@ ivf_rows_kernel(const __grid_constant__ CUtensorMap tmap_lm, const unsigned char
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int ELEMS_PER_SLAB = TF32 ? 32 : 64;
-  const uint32_t tmem_cols = NQ <= 32 ? 64u : NQ <= 64 ? 128u : 256u;
+  const uint32_t tmem_cols = NQ <= 32 ? 64u : NQ <= 64 ? 128u : NQ <= 128 ? 256u : 512u;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) { mbar_init(&full[s], RB ? 1 : a.list_major ? 129 : 128); mbar_init(&empty[s], 1); }
@@ -845,16 +846,16 @@ ivf_rows_kernel(const __grid_constant__ CUtensorMap tmap_lm, const unsigned char
     int stage = 0; unsigned phase = 0;
     for (int item = item_lo + (int)blockIdx.x; item < item_hi; item += (int)gridDim.x) {
       IR_DECODE_ITEM(item)
-      // query pieces of this thread: piece p = pt + 128*i covers 16 bytes (chunk p & 7) of B row p >> 3
-      const unsigned char* qsrc[IR_MAX_NQ / 16];
-      uint32_t q_dst[IR_MAX_NQ / 16];
-#pragma unroll
-      for (int i = 0; i < IR_MAX_NQ / 16; ++i) {
-        const int row = (pt + 128 * i) >> 3;
-        const int src_row = min(row, n_live - 1);   // columns past the group re-load a valid query (their threshold is +inf)
-        qsrc[i] = row < n_pad ? qmat + (size_t)(a.pair_of_pos[a0 + src_row] / a.nprobe) * row_pitch + pj * 16 : nullptr;
-        q_dst[i] = (uint32_t)(row * GT_SLAB + ((pj ^ (row & 7)) << 4));
+      // query rows of the group, for the gathers below: a table in shared memory, each producer warp filling exactly the
+      // entries it reads (rows 4w + j + 16*i), so a __syncwarp is all the hand-shake it needs.
+      // Piece p = pt + 128*i of a k-block covers 16 bytes (chunk pj) of B row prow + 16*i.
+      __syncwarp();                                 // this warp is done with the previous item's entries
+      for (int idx = lane; idx < (n_pad >> 2); idx += 32) {
+        const int r = (prow & ~3) + (idx & 3) + 16 * (idx >> 2);
+        qrow_s[r] = a.pair_of_pos[a0 + min(r, n_live - 1)] / a.nprobe;   // columns past the group re-load a valid query (threshold +inf)
       }
+      __syncwarp();
+      const int n_pieces = n_pad >> 4;
       const uint64_t pol_b = n_qg > 1 ? pol_keep : pol_stream;   // rows of a list with several query groups are re-read from L2
       for (int cr = r0; cr < r1; cr += IR_BM) {
         int rb[8];
@@ -886,13 +887,17 @@ ivf_rows_kernel(const __grid_constant__ CUtensorMap tmap_lm, const unsigned char
                 if (h < nkb) cp_async16(sp + h * GT_A_BYTES + a_dst + i * 16 * GT_SLAB, src + ko[h], in_row[h] ? 16u : 0u, pol_b);
             }
           }
+          for (int i = 0; i < n_pieces; ++i) {
+            const int row = prow + 16 * i;
+            const unsigned char* src = qmat + (size_t)qrow_s[row] * row_pitch + pj * 16;
+            const uint32_t dst = sp + 2 * GT_A_BYTES + (uint32_t)(row * GT_SLAB + ((pj ^ (row & 7)) << 4));
 #pragma unroll
-          for (int i = 0; i < IR_MAX_NQ / 16; ++i)
-            if (qsrc[i] != nullptr) {
-#pragma unroll
-              for (int h = 0; h < 2; ++h)
-                if (h < nkb) cp_async16(sp + 2 * GT_A_BYTES + h * b_bytes + q_dst[i], qsrc[i] + ko[h], in_row[h] ? 16u : 0u, pol_q);
-            }
+            for (int h = 0; h < 2; ++h)
+              if (h < nkb) cp_async16(dst + h * b_bytes, src + ko[h], in_row[h] ? 16u : 0u);   // no L2 hint: see below
+          }
+          // (the query gathers carry no L2 cache hint: with `.L2::cache_hint` inside this run-time loop the kernel died with
+          // "illegal instruction" on the B200 - any producer variant but the original 8-way unrolled one did - and the
+          // hint was evict_normal, i.e. the default, anyway)
           cp_async_arrive_noinc(&full[stage]);
           if (++stage == S) { stage = 0; phase ^= 1u; }
         }
@@ -949,13 +954,13 @@ ivf_rows_kernel(const __grid_constant__ CUtensorMap tmap_lm, const unsigned char
     for (int item = item_lo + (int)blockIdx.x; item < item_hi; item += (int)gridDim.x) {
       IR_DECODE_ITEM(item)
       tc::named_bar_sync(1, 128);                   // the previous item's flush is complete
-      if (et < NQ) {
-        const bool live = et < n_live;
-        const int b = live ? a.pair_of_pos[a0 + et] / a.nprobe : 0;
-        qid_s[et] = b; cnt_s[et] = 0; base_s[et] = 0;
+      for (int e = et; e < NQ; e += 128) {
+        const bool live = e < n_live;
+        const int b = live ? a.pair_of_pos[a0 + e] / a.nprobe : 0;
+        qid_s[e] = b; cnt_s[e] = 0; base_s[e] = 0;
         float t = INFINITY;                         // dead columns select nothing
         if (live) { const unsigned g = *reinterpret_cast<volatile unsigned*>(a.gthr + b); t = g ? f32_from_orderable(g) : -INFINITY; }
-        thr_s[et] = t;
+        thr_s[e] = t;
       }
       // per-row terms of the first tile; every later tile's are fetched while the previous one is processed
       bool valid = r0 + te < r1;
@@ -1022,29 +1027,31 @@ ivf_rows_kernel(const __grid_constant__ CUtensorMap tmap_lm, const unsigned char
         const bool refresh = ++tiles_since_refresh >= 4;      // pull the bounds other CTAs published every few tiles
         if (need_s[acc] == tile_n + 1u || refresh) {
           tiles_since_refresh = 0;
-          // lane l looks after query q = wi + 4*l
-          const int q = wi + 4 * lane;
-          bool need = false;
-          unsigned g = 0u;
-          if (q < n_live) {
-            g = *reinterpret_cast<volatile unsigned*>(a.gthr + qid_s[q]);
-            const int c = cnt_s[q];
-            if (c > capq) { a.qflag[qid_s[q]] = 1; cnt_s[q] = capq; }    // cannot happen by construction; never silently drop
-            need = c > Lc || (base_s[q] < L && c >= L);
-            if (!need && g != 0u) thr_s[q] = fmaxf(thr_s[q], f32_from_orderable(g));
-          }
-          unsigned todo = __ballot_sync(FULL, need);
-          while (todo) {
-            const int src = __ffs(todo) - 1;
-            todo &= todo - 1u;
-            const int qq = wi + 4 * src;
-            const unsigned gq = __shfl_sync(FULL, g, src);
-            const u64 kth = ir_warp_compact(my_cbuf + (size_t)qq * capq, min(cnt_s[qq], capq), L, lane);
-            if (lane == 0) {
-              const unsigned o = (unsigned)(kth >> 32);
-              cnt_s[qq] = L; base_s[qq] = L;
-              thr_s[qq] = fmaxf(thr_s[qq], f32_from_orderable(o > gq ? o : gq));
-              if (o > gq) atomicMax(a.gthr + qid_s[qq], o);     // L keys of this item alone are at or above it
+          // lane l looks after the queries q = wi + 4*l (+ 128 for the second half of a 256-query item)
+          for (int q0 = 0; q0 < n_live; q0 += 128) {
+            const int q = q0 + wi + 4 * lane;
+            bool need = false;
+            unsigned g = 0u;
+            if (q < n_live) {
+              g = *reinterpret_cast<volatile unsigned*>(a.gthr + qid_s[q]);
+              const int c = cnt_s[q];
+              if (c > capq) { a.qflag[qid_s[q]] = 1; cnt_s[q] = capq; }    // cannot happen by construction; never silently drop
+              need = c > Lc || (base_s[q] < L && c >= L);
+              if (!need && g != 0u) thr_s[q] = fmaxf(thr_s[q], f32_from_orderable(g));
+            }
+            unsigned todo = __ballot_sync(FULL, need);
+            while (todo) {
+              const int src = __ffs(todo) - 1;
+              todo &= todo - 1u;
+              const int qq = q0 + wi + 4 * src;
+              const unsigned gq = __shfl_sync(FULL, g, src);
+              const u64 kth = ir_warp_compact(my_cbuf + (size_t)qq * capq, min(cnt_s[qq], capq), L, lane);
+              if (lane == 0) {
+                const unsigned o = (unsigned)(kth >> 32);
+                cnt_s[qq] = L; base_s[qq] = L;
+                thr_s[qq] = fmaxf(thr_s[qq], f32_from_orderable(o > gq ? o : gq));
+                if (o > gq) atomicMax(a.gthr + qid_s[qq], o);     // L keys of this item alone are at or above it
+              }
             }
           }
           tc::named_bar_sync(1, 128);
@@ -1394,18 +1401,21 @@ static int ivf_rows_search(const void* rows, bool bank_bf16, long long n_rows, i
   static const int env_stages = env_int("AURA_IVF_STAGES", 0), env_rb = env_int("AURA_IVF_RB", 0);
   const int elems = GT_SLAB / eb;
   const int k_blocks = (d + elems - 1) / elems;
-  const size_t fixed = 4 * IR_MAX_NQ * 4 + (2 * IR_MAX_STAGES + 6) * 8 + 16;
+  const size_t fixed = 5 * IR_MAX_NQ * 4 + (2 * IR_MAX_STAGES + 6) * 8 + 16;
   const size_t smem_cap = (size_t)max_smem_optin() - 1024;
   // resident-query mode (bf16 operands, list-major copy; opt-in AURA_IVF_RB=1): ring of 3 x 32 KB row-tile stages +
   // k_blocks slabs of gmax queries (d = 768: 80).  Measured on one C5 shard: 12.28 ms for the heavy section against
   // 10.8 ms with both operands streamed - the groups shrink from 128 to 80 queries, so the rows are streamed 1.6x as
   // often and only 20 % of the L2 -> SM traffic is saved, while a ring of 96 KB covers less latency.  Kept for d <= 512,
   // where all 128 queries fit.
-  int gmax = IR_MAX_NQ;
+  // query-group size of the heavy lists: 256 (M128 x N256 tiles move 18 B per (row, query) pair through the L2 -> SM path,
+  // M128 x N128 tiles 24 B; that path, not HBM or the tensor pipe, bounds those lists - DESIGN 4.6); AURA_IVF_GMAX=128 for A/B
+  static const int env_gmax = env_int("AURA_IVF_GMAX", IR_MAX_NQ);
+  int gmax = env_gmax == 128 ? 128 : IR_MAX_NQ;
   bool rb = false;
   if (env_rb && bf16 && rows_by_list != nullptr && smem_cap > fixed + 3 * 2 * GT_A_BYTES) {
     int fit = (int)((smem_cap - fixed - 3 * 2 * GT_A_BYTES) / ((size_t)k_blocks * GT_SLAB)) & ~15;
-    if (fit > IR_MAX_NQ) fit = IR_MAX_NQ;
+    if (fit > 128) fit = 128;
     if (fit >= 64) { rb = true; gmax = fit; }
   }
   ir_item_count_kernel<<<(n_lists + 255) / 256, 256, 0, st>>>(q_off, list_offsets, n_lists, gmax, items_c);
@@ -1441,7 +1451,7 @@ static int ivf_rows_search(const void* rows, bool bank_bf16, long long n_rows, i
   IrKern kern_rb = ivf_rows_kernel<false, true>;
   int grid = sm_count();
   if (env_grid >= 1 && env_grid <= grid) grid = env_grid;
-  static const int nq_of_section[IR_SECTIONS] = {32, 64, 128};
+  const int nq_of_section[IR_SECTIONS] = {32, 64, rb ? 128 : gmax};
   size_t smem_max = 0, smem_of[IR_SECTIONS];
   int stages_of[IR_SECTIONS];
   for (int s = 0; s < IR_SECTIONS; ++s) {

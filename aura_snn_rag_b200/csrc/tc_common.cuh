@@ -173,8 +173,13 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
 }
 
 // ---- TMEM -> registers: this warp's 32 lanes x 32 consecutive fp32 columns ----
+// (tcgen05.ld / wait::ld are .sync.aligned: every lane of the warp must execute them together.  The epilogues run
+// lane-divergent insertion loops between loads and nothing but the compiler's choice of reconvergence point put the lanes
+// back together - an unrelated change elsewhere in a kernel moved it and the load faulted as an illegal instruction.  So
+// every wrapper reconverges explicitly.)
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float (&v)[32]) {
   uint32_t r[32];
+  __syncwarp();
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -193,6 +198,7 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float (&v)[32]) {
 // Split form for software pipelining: issue the load of the NEXT 32 columns, work on the current ones, then fence.  The
 // fence names the destination registers as read-write operands, so no use of them can be scheduled above it.
 __device__ __forceinline__ void tmem_ld_32x32_issue(uint32_t taddr, uint32_t (&r)[32]) {
+  __syncwarp();
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -205,6 +211,7 @@ __device__ __forceinline__ void tmem_ld_32x32_issue(uint32_t taddr, uint32_t (&r
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_fence(uint32_t (&r)[32]) {
+  __syncwarp();
   asm volatile("tcgen05.wait::ld.sync.aligned;"
                : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
                  "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]),
@@ -217,6 +224,7 @@ __device__ __forceinline__ void tmem_ld_fence(uint32_t (&r)[32]) {
 // this warp's 32 lanes x 16 consecutive fp32 columns
 __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, float (&v)[16]) {
   uint32_t r[16];
+  __syncwarp();
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
