@@ -3,11 +3,11 @@
 mkdir -p gpurun_out
 for N in 8 4 2; do
 T="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2951$N"
-timeout 500 $T bench.py --gpus $N --steps 20 --warmup 3 2>gpurun_out/r02c_scale_err_n$N.log > gpurun_out/r02c_scale_n$N.json; echo "N=$N rc=$?"
-grep -E "Error|error|Traceback" gpurun_out/r02c_scale_err_n$N.log | tail -5
+timeout 500 $T bench.py --gpus $N --steps 20 --warmup 3 2>gpurun_out/r02d_scale_err_n$N.log > gpurun_out/r02d_scale_n$N.json; echo "N=$N rc=$?"
+grep -E "Error|error|Traceback" gpurun_out/r02d_scale_err_n$N.log | tail -5
 python - <<PY
 import json
-d=json.loads(open("gpurun_out/r02c_scale_n$N.json").read().strip().splitlines()[-1])
+d=json.loads(open("gpurun_out/r02d_scale_n$N.json").read().strip().splitlines()[-1])
 print(round(d["value"]), d["ms_per_step"], d["ms_per_step_reps"], "e2e", round(d["e2e"]["value"]), d["exchange"], d["cuda_graph_step"], d["top1_hit_rate"], d.get("uncertified_queries_rerun"))
 c=d.get("c5_sharded"); print({k:c[k] for k in ["build_s","relaxed","strict","recall_at_10_vs_exact","recall_at_100_vs_exact","list_major_copy"]}, c["roofline"]["frac"])
 PY
