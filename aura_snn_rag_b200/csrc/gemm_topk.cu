@@ -1215,13 +1215,11 @@ extern "C" int aura_batch_topk(const void* rows, int dtype, int64_t n_rows, int 
                       (reinterpret_cast<uintptr_t>(shadow_bf16) & 15) == 0;
   const bool bf16 = dtype == AURA_BF16 || shadow;
   GemmPlan p;
-  // shortlist length of the shadow pass: 32 when k + 14 <= 32, else 48.  The list is the epilogue's cost (C2, batch 1024:
-  // 1.28 / 1.51 / 1.63 ms per kernel at L = 24 / 32 / 48), the margin is what certifies: with the measured rounding bound
-  // L = 32 certified all 51 200 bench queries, L = 24 handed back 1.7 % of them (each one a 0.45 ms exact scan).
-  // AURA_SHADOW_L = 24 | 32 | 48 overrides.
+  // shortlist length of the shadow pass: 24 / 32 / 48 for k <= 10 / 18 / 34.  The list is the epilogue's cost, the margin
+  // is what certifies; with the measured rounding bound and the second chance of the finish kernel the 24-entry lists
+  // certified all 51 200 bench queries (before the second chance: 1.7 % handed back at 24, ~0.04 % at 32, each one a
+  // 0.45 ms exact scan).  AURA_SHADOW_L = 24 | 32 | 48 overrides.
   static const int env_shadow_l = env_int("AURA_SHADOW_L", 0);
-  // with the second-chance certificate of the finish kernel (up to 256 candidates re-scored for a query that fails with
-  // L) the 24-entry lists hand nothing back either: k <= 10 keeps 24
   int shadow_L = k + 14 <= GT_L_SMALL ? GT_L_SMALL : k + 14 <= GT_L ? GT_L : GT_L_WIDE;
   if ((env_shadow_l == GT_L_SMALL || env_shadow_l == GT_L || env_shadow_l == GT_L_WIDE) && k + 14 <= env_shadow_l) shadow_L = env_shadow_l;
   AURA_REQUIRE(make_gemm_plan(n_queries, n_rows, d, bf16 ? 2 : 4, k, true, &p, shadow ? shadow_L : 0), AURA_ERR_UNSUPPORTED,

@@ -203,9 +203,11 @@ int aura_ivf_search_batch_items(const void* workspace, int n_queries, int d, int
  * every (query,row) pair and keeps a per-query shortlist; the shortlist is re-scored in exact fp32 and the
  * result certified: out_uncertain[b] = 0 means the top-k of query b is provably the exact fp32 top-k given
  * that tensor-core scores are within `eps` (score units) of the exact ones; 1 means the caller must re-run
- * query b through aura_scan_topk.  Needs d*sizeof(elem) % 16 == 0 and k <= 114.
+ * query b through aura_scan_topk.  A query whose first re-score (the shortlist) cannot be certified is given a second
+ * chance inside the call: up to 256 of the candidates the pass is known to hold completely are re-scored before the
+ * flag is raised.  Needs d*sizeof(elem) % 16 == 0 and k <= 114.
  * shadow_bf16 (may be NULL): a bf16 copy of an fp32 bank (aura_rows_to_bf16, same row order).  The shortlist pass then
- * runs on the copy (kind::f16: half the bytes, twice the tensor rate, 32 candidates per query for k <= 18, 48 for k <= 34) and the re-score
+ * runs on the copy (kind::f16: half the bytes, twice the tensor rate, 24 / 32 / 48 candidates per query for k <= 10 / 18 / 34) and the re-score
  * still reads the fp32 rows, so certified results are the same exact fp32 top-k; `eps` must then bound the bf16 rounding
  * (2^-7 per unit of |scale * ||row|||) - or, with shadow_relerr (DEVICE scalar >= ||bf16(r) - r|| / ||r|| over the bank rows,
  * maintained by aura_rows_to_bf16), `eps` is just that unit, max |scale_r| * ||r||, and the bound is measured per query:
