@@ -48,6 +48,20 @@ def test_argument_validation_without_gpu():
     with pytest.raises(_lib.AuraLibraryError):
         _lib.check(rc, "aura_topk_merge")
     assert lib.aura_scan_topk_workspace_bytes(1000, 64, 4, 10) > 0
+    # list-major copies: the bank's element type, or a bf16 shadow of an fp32 bank (with its rounding-error scalar)
+    F32, BF16 = _lib.AURA_F32, _lib.AURA_BF16
+    rc = lib.aura_ivf_pack_lists(None, BF16, 64, None, 10, None, F32, None, None)
+    assert rc == -1 and b"shadow" in lib.aura_last_error_string()
+    one = ctypes.c_void_p(256)                        # any non-null, 16-byte aligned address: validation only, never dereferenced
+    rc = lib.aura_ivf_search_batch(one, F32, 1000, 64, one, 64, one, 16, 4, one, one, one, BF16, None, None, None, 10, 0, 0,
+                                   0.5, one, one, one, one, 1 << 40, None)
+    assert rc == -1 and b"rounding-error" in lib.aura_last_error_string()
+    rc = lib.aura_ivf_search_batch(one, BF16, 1000, 64, one, 64, one, 16, 4, one, one, one, F32, None, None, None, 10, 0, 0,
+                                   0.5, one, one, one, one, 1 << 40, None)
+    assert rc == -1 and b"list-major copy" in lib.aura_last_error_string()
+    # the watchdog trace words exist (all zero: nothing has trapped)
+    out = (ctypes.c_uint32 * 4)(1, 1, 1, 1)
+    assert lib.aura_debug_last_trap(out) == 0 and list(out) == [0, 0, 0, 0]
 
 
 def test_no_cpu_fallback():
