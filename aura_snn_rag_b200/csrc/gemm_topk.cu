@@ -198,7 +198,8 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               const float2 t = sb[c0 + j];
-              const float sj = fmaf(v[j], t.x, t.y);
+              float sj = fmaf(v[j], t.x, t.y);
+              sj = sj == sj ? sj : -INFINITY;         // a NaN score must not pose as a second copy of the best one
               m2 = fmaxf(m2, fminf(m1, sj));
               m1 = fmaxf(m1, sj);
             }
@@ -209,7 +210,8 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           ++my_tiles;
         }
         const float mine = a.sample_j == 1 ? m1 : m2;
-        if (live && mine > -INFINITY) atomicMin(a.samp_min + (long long)atile * GT_BM + te, f32_orderable(mine));
+        // a list without a finite sample (NaN rows) contributes -inf: the minimum must cover ALL lists to be a bound
+        if (live) atomicMin(a.samp_min + (long long)atile * GT_BM + te, f32_orderable(mine > -INFINITY ? mine : -INFINITY));
         __threadfence();
         tc::named_bar_sync(1 + wg, 128);
         // one thread per warpgroup announces the list and waits (bounded) for the other lists of this A tile; all of
