@@ -393,8 +393,7 @@ __device__ __forceinline__ void rescore_write_topk(const u64* ex, int cap, const
   }
 }
 __device__ __forceinline__ void rescore_and_write(const u64* keys, int n2, u64* ex, const RescoreArgs& f) {
-  __shared__ int s_depth;
-  __shared__ float s_bound;
+  __shared__ int s_flag, s_known;
   const int n_cand = min(f.L, n2);
   rescore_range(keys, n_cand, GT_MAX_L, ex, f);
   block_bitonic_sort_desc(ex, GT_MAX_L);
@@ -408,33 +407,43 @@ __device__ __forceinline__ void rescore_and_write(const u64* keys, int n2, u64* 
       const u64 kth = ex[min(f.k, GT_MAX_L) - 1];
       if (kth == 0ull || !(key_score(kth) > bound)) flag = 1;
     }
-    int depth = 0;
+    int known = 0;
     if (flag && f.deep) {
-      // second chance: candidates known above the completeness floor, at most GT_DEEP of them
-      int lo = 0, hi = min(n2, GT_DEEP + 1);                      // first index whose key is empty or below the floor
+      // second chance: how many candidates are known above the completeness floor (counted up to GT_DEEP + 1)
+      int lo = 0, hi = min(n2, GT_DEEP + 1);                      // first index whose key is empty or at / below the floor
       while (lo < hi) {
         const int mid = (lo + hi) >> 1;
         if (keys[mid] != 0ull && key_score(keys[mid]) > f.floor_score) lo = mid + 1; else hi = mid;
       }
-      if (lo > f.L) {                                               // deeper than the first attempt: worth a second one
-        depth = min(lo, GT_DEEP);
-        // every row not re-scored is either keys[depth...] (approximate score <= that of keys[depth]) or absent from
-        // keys[] (approximate score <= floor_score)
-        s_bound = (lo > GT_DEEP ? key_score(keys[GT_DEEP]) : f.floor_score) + f.eps;
-      }
+      known = lo;
     }
-    s_depth = depth;
+    s_flag = flag; s_known = known;
     if (f.uncertain) *f.uncertain = flag;
   }
   __syncthreads();
-  const int depth = s_depth;
-  if (depth == 0) return;
-  rescore_range(keys, depth, GT_DEEP, ex, f);
-  block_bitonic_sort_desc(ex, GT_DEEP);
-  rescore_write_topk(ex, GT_DEEP, f);
-  if (threadIdx.x == 0 && f.uncertain) {
-    const u64 kth = ex[min(f.k, GT_DEEP) - 1];
-    *f.uncertain = (kth == 0ull || !(key_score(kth) > s_bound)) ? 1 : 0;
+  // two depths: most queries that fail with L pass with 64 candidates (a CTA that re-scores 256 rows is the tail of the
+  // whole finish launch), the rest go to GT_DEEP
+  int done = f.L;
+  for (int round = 0; round < 2; ++round) {
+    const int cap = round == 0 ? 64 : GT_DEEP;
+    const int known = s_known;
+    const int depth = min(known, cap);
+    if (s_flag == 0 || depth <= done) { __syncthreads(); continue; }
+    __syncthreads();                                              // everyone has read s_flag before it is rewritten
+    rescore_range(keys, depth, cap, ex, f);
+    block_bitonic_sort_desc(ex, cap);
+    rescore_write_topk(ex, cap, f);
+    if (threadIdx.x == 0) {
+      // every row not re-scored is either keys[depth...] (approximate score <= that of keys[depth]) or absent from
+      // keys[] (approximate score <= floor_score)
+      const float bound = (known > depth ? key_score(keys[depth]) : f.floor_score) + f.eps;
+      const u64 kth = ex[min(f.k, cap) - 1];
+      const int flag = (kth == 0ull || !(key_score(kth) > bound)) ? 1 : 0;
+      s_flag = flag;
+      if (f.uncertain) *f.uncertain = flag;
+    }
+    done = depth;
+    __syncthreads();
   }
 }
 
